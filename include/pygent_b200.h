@@ -1,0 +1,157 @@
+/*
+ * pygent_b200 -- C ABI of one compiled "problem" (system dynamics + cost), sm_100a.
+ *
+ * This is the drop-in boundary of the simulation-and-planning hot path.  In the reference
+ * (mpritzkoleit/pygent) the only native seam on this path is
+ *
+ *     sympy_to_c.convert_to_c(args, expr, cfilepath=..., use_exisiting_so=False) -> callable
+ *
+ * (call sites: pygent/modeling_scripts/cart_pole.py:159-170, acrobot.py:147-157,
+ *  cart_pole_double_parallel.py:157-168, cart_pole_double_serial.py:170-181,
+ *  cart_pole_triple.py:189-200, pygent/algorithms/ilqr.py:558-571): sympy expressions are
+ * turned into C, compiled into a shared object and called through ctypes, one scalar
+ * evaluation per call.  The B200 replacement compiles the SAME expressions into one shared
+ * library per problem whose entry points below evaluate whole batched loops of the
+ * reference on the GPU:
+ *
+ *   pg_rollout        <- the `for k: environment.step(u_k)` loops (pygent/environments.py:242-276,
+ *                        fast_step :291-322; pygent/algorithms/ilqr.py:501-516 init_trajectory)
+ *   pg_ilqr_forward   <- iLQR.forward_pass for one or all line-search alphas (ilqr.py:187-231, :429-437)
+ *   pg_ilqr_backward  <- iLQR.linearization + cost_lin + backward_pass (ilqr.py:233-346, :518-533, :597-610)
+ *   pg_ilqr_select    <- the line-search bookkeeping, accept/reject, mu schedule and stopping tests of
+ *                        iLQR.run_optim (ilqr.py:418-485, :612-622)
+ *   pg_ilqr_commit    <- "self.xx, self.uu, self.KK, self.kk = best candidate" (ilqr.py:458-464)
+ *   pg_observe        <- helpers.observation (pygent/helpers.py:20-29)
+ *   pg_eval           <- one batched evaluation of f, A, B / the cost expansion (what the reference's
+ *                        generated callables return; used by the parity tests)
+ *
+ * Conventions
+ *   - All array arguments are DEVICE pointers owned by the caller, except where a parameter is
+ *     documented as "host".  Nothing is allocated or retained by the library.
+ *   - Layout is trajectory-minor ("SoA"): the batch index b is the fastest dimension of every array,
+ *     e.g. X[(k*n + i)*B + b].  `dtype` selects the scalar type of every `void*` array.
+ *   - Every function enqueues its work on `stream` (a cudaStream_t passed as void*) and returns
+ *     immediately; return value 0 = success, >0 = cudaError_t of the launch, <0 = PG_E_* below.
+ *   - No CPU fallback exists: without a CUDA device the functions return the CUDA error.
+ */
+#ifndef PYGENT_B200_H
+#define PYGENT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG_ABI_VERSION 1
+
+#define PG_F64 0
+#define PG_F32 1
+
+#define PG_INTEG_RK4 0   /* classical RK4, S substeps per control interval (parity schedule S=4) */
+#define PG_INTEG_EULER 1 /* forward Euler, StateSpaceModel.fast_step (environments.py:291-322)  */
+
+#define PG_E_BADARG (-1)
+#define PG_E_UNSUPPORTED (-2)
+
+#define PG_MAX_ALPHAS 16
+
+/* per-trajectory solver status written by pg_ilqr_select */
+#define PG_ST_RUNNING 0
+#define PG_ST_CONV_FUN 1   /* "Converged: small improvement" (ilqr.py:468-471) */
+#define PG_ST_CONV_GRAD 2  /* "Converged: small gradient"    (ilqr.py:472-475) */
+#define PG_ST_MU_MAX 3     /* "Diverged: no improvement"     (ilqr.py:482-485) */
+#define PG_ST_MAX_ITERS 4
+
+typedef struct {
+    int32_t abi_version;
+    int32_t n;               /* state dimension   */
+    int32_t m;               /* control dimension */
+    int32_t n_obs;           /* observation dimension: angles expand to [cos, sin] */
+    int32_t has_ab;          /* analytic A, B compiled in (else central differences, helpers.py:130-148) */
+    int32_t has_cost_derivs; /* analytic cost expansion compiled in */
+    int32_t cost_uses_xnext; /* running cost depends on x_{k+1} */
+    int32_t reserved;
+    char name[64];
+    char key[32];
+} pg_problem_info_t;
+
+int pg_get_problem_info(pg_problem_info_t* out);
+
+/* Open-loop rollout of B independent environments over T control intervals.
+ *   x0 [n,B]; U [T,m,B] or NULL (u == 0, ilqr.py:505); X [T+1,n,B] or NULL (history, X[0] = x0);
+ *   xN [n,B] or NULL; cost [B] or NULL: sum_k (c(x_k,u_k,x_{k+1},t_{k+1}) + terminal_cost*terminated_{k+1})*dt
+ *   (+ fcost(x_T)*dt if add_final_cost); terminated [B] or NULL: terminate(x_T).
+ *   t0: simulation time of x0 (the reference's env.tt[-1]); time advances by repeated t += dt. */
+int pg_rollout(int dtype, int integrator, int64_t B, int32_t T, int32_t S, double dt, double t0,
+               const void* x0, const void* U, void* X, void* xN, void* cost, uint8_t* terminated,
+               double terminal_cost, int32_t add_final_cost, void* stream);
+
+/* Closed-loop line-search rollouts u_k = K_j (x_k - xbar_j) + alpha k_j + ubar_j, j = min(Tk-1, k).
+ *   alphas: host array of n_alpha values (<= PG_MAX_ALPHAS), all evaluated in one launch;
+ *   alpha_dev [B] or NULL: when given, n_alpha must be 1 and each trajectory uses its own alpha;
+ *   KK [Tk,m,n,B], kk [Tk,m,B]; ulim: host array [m] or NULL -- clip u to +-ulim (constrained=True);
+ *   terminal_cost: the environment's terminal_cost (environments.py:275), 0 by default;
+ *   X_out [n_alpha,T+1,n,B] / U_out [n_alpha,T,m,B] or NULL; cost_out [n_alpha,B];
+ *   diverged_out [n_alpha,B] or NULL: any(x > 1e8) over the rollout (ilqr.py:435);
+ *   terminated_out [n_alpha,B] or NULL; active [B] or NULL: trajectories with active==0 are skipped. */
+int pg_ilqr_forward(int dtype, int integrator, int64_t B, int32_t T, int32_t S, double dt,
+                    int32_t n_alpha, const double* alphas, const void* alpha_dev,
+                    const void* x0, const void* xbar, const void* ubar,
+                    const void* KK, const void* kk, int32_t Tk, const double* ulim, double terminal_cost,
+                    void* X_out, void* U_out, void* cost_out, uint8_t* diverged_out,
+                    uint8_t* terminated_out, const uint8_t* active, void* stream);
+
+/* Backward Riccati pass along (xbar, ubar).
+ *   lin_mode 0: analytic A, B (requires has_ab); 1: central differences eps=1e-3 of f.
+ *   mu [B] per-trajectory regularisation; reg_type 1 or 2 (ilqr.py:291-295);
+ *   ulim host [m] or NULL: box-constrained gains (ilqr.py:304-327, exact-clip restatement);
+ *   outputs: KK [T,m,n,B], kk [T,m,B], dV [2,B] = (sum V1, sum V2), gnorm [B] (ilqr.py:418-420),
+ *   success [B] (0 = Quu not positive definite at some step; KK/kk then incomplete). */
+int pg_ilqr_backward(int dtype, int64_t B, int32_t T, double dt, int32_t reg_type, int32_t lin_mode,
+                     const void* mu, const void* xbar, const void* ubar, const double* ulim,
+                     void* KK, void* kk, void* dV, void* gnorm, uint8_t* success,
+                     const uint8_t* active, void* stream);
+
+typedef struct {
+    int32_t n_alpha;
+    int32_t parallel;     /* iLQR(parallel=...) (ilqr.py:453) */
+    int32_t iteration;    /* 1-based iteration number of this call */
+    int32_t max_iters;
+    double alphas[PG_MAX_ALPHAS];
+    double zmin, tol_fun, tol_grad;
+    double mu_min, mu_max, mu_d0;
+} pg_select_params_t;
+
+/* One line-search decision per trajectory; updates the per-trajectory solver state in place.
+ *   in : cost_cand [n_alpha,B], diverged [n_alpha,B], dV [2,B], gnorm [B], bw_success [B]
+ *   io : cost [B], mu [B], mu_d [B], dcost [B], success_gradient [B] (u8), status [B] (i32), iters [B] (i32)
+ *   out: alpha_best [B], accept [B] (u8), n_active (device int32 counter, incremented per still-running traj) */
+int pg_ilqr_select(int dtype, int64_t B, const pg_select_params_t* params,
+                   const void* cost_cand, const uint8_t* diverged, const void* dV, const void* gnorm,
+                   const uint8_t* bw_success, void* cost, void* mu, void* mu_d, void* dcost,
+                   uint8_t* success_gradient, int32_t* status, int32_t* iters,
+                   void* alpha_best, uint8_t* accept, uint8_t* active, int32_t* n_active, void* stream);
+
+/* For accepted trajectories: re-run the winning alpha and store it as the new nominal trajectory
+ * (xbar, ubar updated in place) and copy the candidate gains into the accepted gains. */
+int pg_ilqr_commit(int dtype, int integrator, int64_t B, int32_t T, int32_t S, double dt,
+                   const void* alpha_best, const uint8_t* accept, const void* x0,
+                   void* xbar, void* ubar, const void* KK, const void* kk, const double* ulim,
+                   void* KK_acc, void* kk_acc, void* stream);
+
+/* o [n_obs,B] = observation(x [n,B]) : angle -> [cos, sin] (helpers.py:20-29). */
+int pg_observe(int dtype, int64_t B, const void* x, void* o, void* stream);
+
+/* Batched point evaluation (parity tests): any output may be NULL.
+ *   x [n,B], u [m,B], t [B] -> f [n,B], A [n,n,B], Bm [n,m,B] (lin_mode as above),
+ *   c [B] running cost (x' = x), cx [n,B], cu [m,B], Cxx [n,n,B], Cuu [m,m,B], Cxu [n,m,B],
+ *   cf [B], cfx [n,B], Cfxx [n,n,B]  (costs NOT multiplied by dt). */
+int pg_eval(int dtype, int64_t B, int32_t lin_mode, const void* x, const void* u, const void* t,
+            void* f, void* A, void* Bm, void* c, void* cx, void* cu, void* Cxx, void* Cuu, void* Cxu,
+            void* cf, void* cfx, void* Cfxx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

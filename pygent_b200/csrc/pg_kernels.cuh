@@ -1,0 +1,881 @@
+// Hand-written sm_100a kernels of the simulation-and-planning hot path, generic over the generated
+// `Problem` (dynamics f, Jacobians A/B, cost and its expansion) and the scalar type T.
+//
+// Work decomposition: ONE THREAD OWNS ONE TRAJECTORY (forward kernels: one thread per
+// (trajectory, line-search alpha)).  The n<=8 state, the m<=2 control, the Jacobians and the Riccati
+// matrices live in registers; all loops over state indices are fully unrolled and skip structural
+// zeros of A, B and the cost Hessians at compile time.  Arrays are trajectory-minor
+// ([..., B] with b fastest), so every global access of a warp is one or two full 128-byte lines.
+// The per-step nominal trajectory and gains are prefetched one control interval ahead into registers,
+// which hides the L2/HBM latency behind the ~1-2k cycle RK4 step.
+#pragma once
+#include <stdint.h>
+
+#include "pg_math.cuh"
+
+namespace pgk {
+
+constexpr int INTEG_RK4 = 0;
+constexpr int INTEG_EULER = 1;
+
+template <typename T, int N>
+__device__ __forceinline__ void copy(T (&d)[N], const T (&s)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; i++) d[i] = s[i];
+}
+
+// ---- integrators --------------------------------------------------------------------------------
+// Classical RK4 with `S` substeps of h = dt/S and the control held constant: the fixed-step parity
+// schedule for StateSpaceModel.step (pygent/environments.py:263).
+template <typename P, typename T>
+__device__ __forceinline__ void rk4_substep(T (&x)[P::N], const T (&u)[P::M], const T h) {
+    constexpr int N = P::N;
+    T k1[N], k2[N], k3[N], k4[N], xt[N];
+    const T hh = T(0.5) * h;
+    P::f(x, u, k1);
+#pragma unroll
+    for (int i = 0; i < N; i++) xt[i] = x[i] + hh * k1[i];
+    P::f(xt, u, k2);
+#pragma unroll
+    for (int i = 0; i < N; i++) xt[i] = x[i] + hh * k2[i];
+    P::f(xt, u, k3);
+#pragma unroll
+    for (int i = 0; i < N; i++) xt[i] = x[i] + h * k3[i];
+    P::f(xt, u, k4);
+    const T h6 = h / T(6);
+#pragma unroll
+    for (int i = 0; i < N; i++) x[i] = x[i] + h6 * (k1[i] + T(2) * k2[i] + T(2) * k3[i] + k4[i]);
+}
+
+// One control interval. INTEG_EULER is StateSpaceModel.fast_step (environments.py:313-315).
+template <typename P, typename T, int INTEG>
+__device__ __forceinline__ void env_step(T (&x)[P::N], const T (&u)[P::M], const T dt, const T h, const int S) {
+    if constexpr (INTEG == INTEG_EULER) {
+        T k1[P::N];
+        P::f(x, u, k1);
+#pragma unroll
+        for (int i = 0; i < P::N; i++) x[i] = x[i] + dt * k1[i];
+    } else {
+        for (int s = 0; s < S; s++) rk4_substep<P, T>(x, u, h);
+    }
+}
+
+// ---- K1: open-loop rollout ----------------------------------------------------------------------
+template <typename T>
+struct RolloutArgs {
+    int64_t B;
+    int T_steps, S;
+    T dt, t0, terminal_cost;
+    int add_final_cost;
+    const T* x0;
+    const T* U;
+    T* X;
+    T* xN;
+    T* cost;
+    uint8_t* terminated;
+};
+
+template <typename P, typename T, int INTEG>
+__global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs<T> a) {
+    constexpr int N = P::N, M = P::M;
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const int64_t B = a.B;
+    T x[N], u[M], un[M];
+#pragma unroll
+    for (int i = 0; i < N; i++) x[i] = a.x0[i * B + b];
+    if (a.X) {
+#pragma unroll
+        for (int i = 0; i < N; i++) a.X[i * B + b] = x[i];
+    }
+    const T h = a.dt / T(a.S);
+    T cost = T(0), t = a.t0;
+    bool term = false;
+#pragma unroll
+    for (int j = 0; j < M; j++) un[j] = (a.U && a.T_steps > 0) ? a.U[j * B + b] : T(0);
+    for (int k = 0; k < a.T_steps; k++) {
+        copy(u, un);
+        if (a.U && k + 1 < a.T_steps) {  // prefetch next control
+#pragma unroll
+            for (int j = 0; j < M; j++) un[j] = a.U[((int64_t)(k + 1) * M + j) * B + b];
+        }
+        T xp[N];
+        copy(xp, x);
+        env_step<P, T, INTEG>(x, u, a.dt, h, a.S);
+        t += a.dt;  // env.tt.extend([tt[-1] + dt]) (environments.py:269)
+        term = P::terminate(x);
+        // c = (cost(x_, u, x, t, np) + terminal_cost*terminated)*dt (environments.py:274-275)
+        cost += (P::cost(xp, u, x, t) + (term ? a.terminal_cost : T(0))) * a.dt;
+        if (a.X) {
+#pragma unroll
+            for (int i = 0; i < N; i++) a.X[((int64_t)(k + 1) * N + i) * B + b] = x[i];
+        }
+    }
+    if (a.add_final_cost) cost += P::fcost(x) * a.dt;  // ilqr.py:513
+    if (a.xN) {
+#pragma unroll
+        for (int i = 0; i < N; i++) a.xN[i * B + b] = x[i];
+    }
+    if (a.cost) a.cost[b] = cost;
+    if (a.terminated) a.terminated[b] = term ? 1 : 0;
+}
+
+// ---- K2: closed-loop line-search rollouts (iLQR.forward_pass, ilqr.py:187-231) ---------------------
+constexpr int MAX_ALPHAS = 16;
+
+template <typename T>
+struct ForwardArgs {
+    int64_t B;
+    int T_steps, S, Tk, n_alpha;
+    T dt, terminal_cost;
+    T alphas[MAX_ALPHAS];
+    const T* alpha_dev;
+    const T* x0;
+    const T* xbar;
+    const T* ubar;
+    const T* KK;
+    const T* kk;
+    int clip;
+    T ulim[2];
+    T* X_out;
+    T* U_out;
+    T* cost_out;
+    uint8_t* diverged_out;
+    uint8_t* terminated_out;
+    const uint8_t* active;
+    // commit mode
+    const uint8_t* accept;
+    T* xbar_io;
+    T* ubar_io;
+    T* KK_acc;
+    T* kk_acc;
+};
+
+template <typename P, typename T>
+struct Nominal {  // gains and nominal point of one control interval
+    T K[P::M * P::N], k[P::M], xb[P::N], ub[P::M];
+    __device__ __forceinline__ void load(const T* KK, const T* kk, const T* xbar, const T* ubar, int j, int64_t B, int64_t b) {
+        constexpr int N = P::N, M = P::M;
+#pragma unroll
+        for (int r = 0; r < M * N; r++) K[r] = KK[((int64_t)j * M * N + r) * B + b];
+#pragma unroll
+        for (int r = 0; r < M; r++) k[r] = kk[((int64_t)j * M + r) * B + b];
+#pragma unroll
+        for (int i = 0; i < N; i++) xb[i] = xbar[((int64_t)j * N + i) * B + b];
+#pragma unroll
+        for (int r = 0; r < M; r++) ub[r] = ubar[((int64_t)j * M + r) * B + b];
+    }
+};
+
+// COMMIT = false: evaluate candidates (cost, flags, optional trajectories).
+// COMMIT = true : re-run the accepted alpha and overwrite the nominal trajectory in place; the
+//                 nominal point of interval k+1 is always loaded BEFORE x_{k+1} is stored, so the
+//                 in-place update never reads its own output (the pointers are deliberately not
+//                 __restrict__).
+template <typename P, typename T, int INTEG, bool COMMIT>
+__global__ void __launch_bounds__(32 * MAX_ALPHAS) ilqr_forward_kernel(const ForwardArgs<T> a) {
+    constexpr int N = P::N, M = P::M;
+    const int64_t B = a.B;
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int ia = threadIdx.y;
+    if (b >= B) return;
+    if constexpr (COMMIT) {
+        if (!a.accept[b]) return;
+    } else {
+        if (a.active && !a.active[b]) return;
+    }
+    const T alpha = a.alpha_dev ? a.alpha_dev[b] : a.alphas[ia];
+    const T* xbar = COMMIT ? a.xbar_io : a.xbar;
+    const T* ubar = COMMIT ? a.ubar_io : a.ubar;
+    T x[N], u[M];
+#pragma unroll
+    for (int i = 0; i < N; i++) x[i] = a.x0[i * B + b];
+    bool div = false;
+#pragma unroll
+    for (int i = 0; i < N; i++) div |= (x[i] > T(1e8));
+    T* Xo = nullptr;
+    T* Uo = nullptr;
+    if constexpr (COMMIT) {
+        Xo = a.xbar_io;
+        Uo = a.ubar_io;
+    } else {
+        if (a.X_out) Xo = a.X_out + (int64_t)ia * (a.T_steps + 1) * N * B;
+        if (a.U_out) Uo = a.U_out + (int64_t)ia * a.T_steps * M * B;
+    }
+    const T h = a.dt / T(a.S);
+    T cost = T(0), t = T(0);  // environment.reset(x0) => tt = [0] (ilqr.py:199)
+    bool term = false;
+    Nominal<P, T> cur, nxt;
+    if (a.T_steps > 0) nxt.load(a.KK, a.kk, xbar, ubar, 0, B, b);
+    if (Xo) {
+#pragma unroll
+        for (int i = 0; i < N; i++) Xo[i * B + b] = x[i];
+    }
+    for (int k = 0; k < a.T_steps; k++) {
+        cur = nxt;
+        if (k + 1 < a.T_steps) {
+            const int j = (k + 1 < a.Tk) ? (k + 1) : (a.Tk - 1);
+            nxt.load(a.KK, a.kk, xbar, ubar, j, B, b);
+        }
+        // u = KK[j] @ (x - xx_[j]) + alpha*kk[j] + uu_[j]   (ilqr.py:206)
+#pragma unroll
+        for (int r = 0; r < M; r++) {
+            T acc = T(0);
+#pragma unroll
+            for (int i = 0; i < N; i++) acc += cur.K[r * N + i] * (x[i] - cur.xb[i]);
+            acc = acc + alpha * cur.k[r];
+            acc = acc + cur.ub[r];
+            if (a.clip) acc = pg::clamp(acc, -a.ulim[r], a.ulim[r]);  // ilqr.py:208-209
+            u[r] = acc;
+        }
+        T xp[N];
+        copy(xp, x);
+        env_step<P, T, INTEG>(x, u, a.dt, h, a.S);
+        t += a.dt;
+        if constexpr (!COMMIT) {
+            term = P::terminate(x);
+            cost += (P::cost(xp, u, x, t) + (term ? a.terminal_cost : T(0))) * a.dt;
+#pragma unroll
+            for (int i = 0; i < N; i++) div |= (x[i] > T(1e8));  // np.any(xx > 1e8) (ilqr.py:435)
+        }
+        if (Xo) {
+#pragma unroll
+            for (int i = 0; i < N; i++) Xo[((int64_t)(k + 1) * N + i) * B + b] = x[i];
+        }
+        if (Uo) {
+#pragma unroll
+            for (int r = 0; r < M; r++) Uo[((int64_t)k * M + r) * B + b] = u[r];
+        }
+        if constexpr (COMMIT) {
+            if (k < a.Tk) {  // self.KK = KK; self.kk = kk (ilqr.py:463-464)
+#pragma unroll
+                for (int r = 0; r < M * N; r++) a.KK_acc[((int64_t)k * M * N + r) * B + b] = cur.K[r];
+#pragma unroll
+                for (int r = 0; r < M; r++) a.kk_acc[((int64_t)k * M + r) * B + b] = cur.k[r];
+            }
+        }
+    }
+    if constexpr (!COMMIT) {
+        cost += P::fcost(x) * a.dt;  // ilqr.py:224
+        const int64_t o = (int64_t)ia * B + b;
+        a.cost_out[o] = cost;
+        if (a.diverged_out) a.diverged_out[o] = div ? 1 : 0;
+        if (a.terminated_out) a.terminated_out[o] = term ? 1 : 0;
+    }
+}
+
+// ---- linearisation ------------------------------------------------------------------------------
+// lin_mode 1: helpers.system_linearization (pygent/helpers.py:130-148), central differences, eps=1e-3.
+template <typename P, typename T>
+__device__ __forceinline__ void fd_AB(const T (&x)[P::N], const T (&u)[P::M], T (&A)[P::N * P::N], T (&Bm)[P::N * P::M]) {
+    constexpr int N = P::N, M = P::M;
+    const T eps = T(1e-3);
+    T fp[N], fm[N], xt[N], ut[M];
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        copy(xt, x);
+        xt[j] = x[j] + eps;
+        P::f(xt, u, fp);
+        xt[j] = x[j] - eps;
+        P::f(xt, u, fm);
+#pragma unroll
+        for (int i = 0; i < N; i++) A[i * N + j] = (fp[i] - fm[i]) / (T(2) * eps);
+    }
+#pragma unroll
+    for (int j = 0; j < M; j++) {
+        copy(ut, u);
+        ut[j] = u[j] + eps;
+        P::f(x, ut, fp);
+        ut[j] = u[j] - eps;
+        P::f(x, ut, fm);
+#pragma unroll
+        for (int i = 0; i < N; i++) Bm[i * M + j] = (fp[i] - fm[i]) / (T(2) * eps);
+    }
+}
+
+// ---- K3: backward Riccati pass (iLQR.backward_pass, ilqr.py:233-346) --------------------------------
+template <typename T>
+struct BackwardArgs {
+    int64_t B;
+    int T_steps, reg_type, constrained;
+    T dt;
+    T ulim[2];
+    const T* mu;
+    const T* xbar;
+    const T* ubar;
+    T* KK;
+    T* kk;
+    T* dV;
+    T* gnorm;
+    uint8_t* success;
+    const uint8_t* active;
+};
+
+template <typename T>
+__device__ __forceinline__ bool np_isclose(T a, T b, T atol) {  // np.isclose(a, b, atol=atol), rtol=1e-5
+    return fabs(a - b) <= atol + T(1e-5) * fabs(b);
+}
+
+template <typename P, typename T, int LIN>
+__global__ void __launch_bounds__(64) ilqr_backward_kernel(const BackwardArgs<T> a) {
+    constexpr int N = P::N, M = P::M;
+    static_assert(M <= 2, "control dimension > 2 not supported by the closed-form Quu solve");
+    const int64_t B = a.B;
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    if (a.active && !a.active[b]) return;
+    const T mu = a.mu[b];
+    const T dt = a.dt;
+    const int Ts = a.T_steps;
+    T x[N], u[M];
+#pragma unroll
+    for (int i = 0; i < N; i++) x[i] = a.xbar[((int64_t)Ts * N + i) * B + b];
+    // vx = cfx(x_N)*dt, Vxx = Cfxx(x_N)*dt (ilqr.py:244-245)
+    T vx[N], Vxx[N * N];
+    P::fcost_derivs(x, vx, Vxx);
+#pragma unroll
+    for (int i = 0; i < N; i++) vx[i] *= dt;
+#pragma unroll
+    for (int i = 0; i < N * N; i++) Vxx[i] = P::cfxx_nz(i) ? Vxx[i] * dt : T(0);
+    T sV1 = T(0), sV2 = T(0);
+    T gmax[M];
+#pragma unroll
+    for (int r = 0; r < M; r++) gmax[r] = T(0);
+    bool ok = true;
+
+    T xn_[N], un_[M];
+    if (Ts > 0) {
+#pragma unroll
+        for (int i = 0; i < N; i++) xn_[i] = a.xbar[((int64_t)(Ts - 1) * N + i) * B + b];
+#pragma unroll
+        for (int r = 0; r < M; r++) un_[r] = a.ubar[((int64_t)(Ts - 1) * M + r) * B + b];
+    }
+    for (int k = Ts - 1; k >= 0; k--) {
+        copy(x, xn_);
+        copy(u, un_);
+        if (k > 0) {  // prefetch the next (earlier) nominal point
+#pragma unroll
+            for (int i = 0; i < N; i++) xn_[i] = a.xbar[((int64_t)(k - 1) * N + i) * B + b];
+#pragma unroll
+            for (int r = 0; r < M; r++) un_[r] = a.ubar[((int64_t)(k - 1) * M + r) * B + b];
+        }
+        // Ad = A*dt + I, Bd = B*dt (ilqr.py:530-531) -- forward-Euler discretisation of the Jacobian
+        T Ad[N * N], Bd[N * M];
+        if constexpr (LIN == 0) {
+            P::AB(x, u, Ad, Bd);
+        } else {
+            fd_AB<P, T>(x, u, Ad, Bd);
+        }
+#pragma unroll
+        for (int i = 0; i < N; i++)
+#pragma unroll
+            for (int j = 0; j < N; j++) Ad[i * N + j] = Ad[i * N + j] * dt + (i == j ? T(1) : T(0));
+#pragma unroll
+        for (int i = 0; i < N * M; i++) Bd[i] = Bd[i] * dt;
+        // structural sparsity known at compile time (analytic Jacobians only)
+        auto adnz = [](int i, int j) constexpr { return LIN != 0 || i == j || P::a_nz(i * N + j); };
+        auto bdnz = [](int i, int r) constexpr { return LIN != 0 || P::b_nz(i * M + r); };
+
+        // cost expansion of c*dt at t_k = k*dt (ilqr.py:162, :236, :597-610)
+        T cx[N], cu[M], Cxx[N * N], Cuu[M * M], Cxu[N * M];
+        P::cost_derivs(x, u, T(k) * dt, cx, cu, Cxx, Cuu, Cxu);
+#pragma unroll
+        for (int i = 0; i < N; i++) cx[i] *= dt;
+#pragma unroll
+        for (int r = 0; r < M; r++) cu[r] *= dt;
+#pragma unroll
+        for (int i = 0; i < M * M; i++) Cuu[i] *= dt;
+
+        // W = Vxx Ad, g = Vxx Bd
+        T W[N * N], g[N * M];
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+#pragma unroll
+            for (int j = 0; j < N; j++) {
+                T acc = T(0);
+#pragma unroll
+                for (int l = 0; l < N; l++)
+                    if (adnz(l, j)) acc += Vxx[i * N + l] * Ad[l * N + j];
+                W[i * N + j] = acc;
+            }
+#pragma unroll
+            for (int r = 0; r < M; r++) {
+                T acc = T(0);
+#pragma unroll
+                for (int l = 0; l < N; l++)
+                    if (bdnz(l, r)) acc += Vxx[i * N + l] * Bd[l * M + r];
+                g[i * M + r] = acc;
+            }
+        }
+        // qx = cx + Ad' vx ; qu = cu + Bd' vx (ilqr.py:283-284)
+        T qx[N], qu[M];
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            T acc = T(0);
+#pragma unroll
+            for (int l = 0; l < N; l++)
+                if (adnz(l, i)) acc += Ad[l * N + i] * vx[l];
+            qx[i] = cx[i] + acc;
+        }
+#pragma unroll
+        for (int r = 0; r < M; r++) {
+            T acc = T(0);
+#pragma unroll
+            for (int l = 0; l < N; l++)
+                if (bdnz(l, r)) acc += Bd[l * M + r] * vx[l];
+            qu[r] = cu[r] + acc;
+        }
+        // Quu = Cuu + Bd' g ; Qux = Cxu' + Bd' W (ilqr.py:288-289)
+        T Quu[M * M], Qux[M * N], QuuR[M * M], QuxR[M * N];
+#pragma unroll
+        for (int r = 0; r < M; r++) {
+#pragma unroll
+            for (int s = 0; s < M; s++) {
+                T acc = T(0);
+#pragma unroll
+                for (int l = 0; l < N; l++)
+                    if (bdnz(l, r)) acc += Bd[l * M + r] * g[l * M + s];
+                Quu[r * M + s] = Cuu[r * M + s] + acc;
+            }
+#pragma unroll
+            for (int j = 0; j < N; j++) {
+                T acc = T(0);
+#pragma unroll
+                for (int l = 0; l < N; l++)
+                    if (bdnz(l, r)) acc += Bd[l * M + r] * W[l * N + j];
+                Qux[r * N + j] = (P::cxu_nz(j * M + r) ? Cxu[j * M + r] * dt : T(0)) + acc;
+            }
+        }
+        // regularisation (ilqr.py:291-295)
+        if (a.reg_type == 1) {
+            // VxxReg = Vxx + mu I  =>  Bd' VxxReg Bd = Bd'(g + mu Bd), Bd' VxxReg Ad = Bd'(W + mu Ad)
+#pragma unroll
+            for (int r = 0; r < M; r++) {
+#pragma unroll
+                for (int s = 0; s < M; s++) {
+                    T acc = T(0);
+#pragma unroll
+                    for (int l = 0; l < N; l++)
+                        if (bdnz(l, r)) acc += Bd[l * M + r] * (g[l * M + s] + mu * Bd[l * M + s]);
+                    QuuR[r * M + s] = Cuu[r * M + s] + acc;
+                }
+#pragma unroll
+                for (int j = 0; j < N; j++) {
+                    T acc = T(0);
+#pragma unroll
+                    for (int l = 0; l < N; l++)
+                        if (bdnz(l, r)) acc += Bd[l * M + r] * (W[l * N + j] + mu * Ad[l * N + j]);
+                    QuxR[r * N + j] = (P::cxu_nz(j * M + r) ? Cxu[j * M + r] * dt : T(0)) + acc;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < M; r++)
+#pragma unroll
+                for (int s = 0; s < M; s++) QuuR[r * M + s] = Quu[r * M + s] + ((a.reg_type == 2 && r == s) ? mu : T(0));
+#pragma unroll
+            for (int i = 0; i < M * N; i++) QuxR[i] = Qux[i];
+        }
+        // positive-definiteness test = np.linalg.cholesky on the lower triangle (ilqr.py:297-302)
+        T kt[M], Kt[M * N];
+        if constexpr (M == 1) {
+            if (!(QuuR[0] > T(0))) ok = false;
+        } else {
+            const T l11sq = QuuR[0];
+            if (!(l11sq > T(0))) {
+                ok = false;
+            } else {
+                const T l21 = QuuR[2] / pg::sqrt(l11sq);
+                if (!(QuuR[3] - l21 * l21 > T(0))) ok = false;
+            }
+        }
+        if (!ok) break;
+        // kt = -QuuReg^-1 qu, Kt = -QuuReg^-1 QuxReg (ilqr.py:330-331)
+        if constexpr (M == 1) {
+            const T q = QuuR[0];
+            kt[0] = -(qu[0] / q);
+#pragma unroll
+            for (int j = 0; j < N; j++) Kt[j] = -(QuxR[j] / q);
+            if (a.constrained) {
+                // box QP in one dimension (ilqr.py:304-327): kt = clip(-qu/Quu, -(lim+u), lim-u);
+                // clamp detection keeps the reference's tolerance AND its lower-bound sign quirk
+                const T up = a.ulim[0] - u[0], lo = a.ulim[0] + u[0];
+                kt[0] = pg::clamp(kt[0], -lo, up);
+                const bool clamped = np_isclose(kt[0], up, T(1e-3)) || np_isclose(kt[0], lo, T(1e-3));
+                if (clamped) {
+#pragma unroll
+                    for (int j = 0; j < N; j++) Kt[j] = T(0);
+                }
+            }
+        } else {
+            // 2x2 solve by LU with partial pivoting (what LAPACK gesv does behind np.linalg.solve)
+            T a00 = QuuR[0], a01 = QuuR[1], a10 = QuuR[2], a11 = QuuR[3];
+            const bool swap = fabs(a10) > fabs(a00);
+            if (swap) {
+                T tmp = a00; a00 = a10; a10 = tmp;
+                tmp = a01; a01 = a11; a11 = tmp;
+            }
+            const T l = a10 / a00;
+            const T u11 = a11 - l * a01;
+            {
+                T b0 = swap ? qu[1] : qu[0], b1 = swap ? qu[0] : qu[1];
+                b1 = b1 - l * b0;
+                const T y1 = b1 / u11;
+                const T y0 = (b0 - a01 * y1) / a00;
+                kt[0] = -y0;
+                kt[1] = -y1;
+            }
+#pragma unroll
+            for (int j = 0; j < N; j++) {
+                T b0 = swap ? QuxR[N + j] : QuxR[j], b1 = swap ? QuxR[j] : QuxR[N + j];
+                b1 = b1 - l * b0;
+                const T y1 = b1 / u11;
+                const T y0 = (b0 - a01 * y1) / a00;
+                Kt[j] = -y0;
+                Kt[N + j] = -y1;
+            }
+            if (a.constrained) {
+                // exact 2-D box QP by active-set enumeration; same clamp tolerance/quirk as above
+                T up[2], lo[2];
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    up[r] = a.ulim[r] - u[r];
+                    lo[r] = a.ulim[r] + u[r];
+                }
+                T best[2] = {kt[0], kt[1]};
+                const bool inside = kt[0] <= up[0] && kt[0] >= -lo[0] && kt[1] <= up[1] && kt[1] >= -lo[1];
+                if (!inside) {
+                    T bestv = T(0);
+                    bool have = false;
+                    auto val = [&](T k0, T k1) {
+                        return T(0.5) * (QuuR[0] * k0 * k0 + (QuuR[1] + QuuR[2]) * k0 * k1 + QuuR[3] * k1 * k1) + qu[0] * k0 + qu[1] * k1;
+                    };
+                    // one coordinate clamped, the other free (then clipped), and both clamped
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {
+#pragma unroll
+                        for (int sgn = 0; sgn < 2; sgn++) {
+                            T kc = sgn ? up[c] : -lo[c];
+                            const int f = 1 - c;
+                            T kf = -(qu[f] + T(0.5) * (QuuR[f * 2 + c] + QuuR[c * 2 + f]) * kc) / QuuR[f * 2 + f];
+                            kf = pg::clamp(kf, -lo[f], up[f]);
+                            const T k0 = c == 0 ? kc : kf, k1 = c == 0 ? kf : kc;
+                            const T v = val(k0, k1);
+                            if (!have || v < bestv) {
+                                have = true;
+                                bestv = v;
+                                best[0] = k0;
+                                best[1] = k1;
+                            }
+                        }
+                    }
+                    kt[0] = best[0];
+                    kt[1] = best[1];
+                }
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    const bool clamped = np_isclose(kt[r], up[r], T(1e-3)) || np_isclose(kt[r], lo[r], T(1e-3));
+                    if (clamped) {
+#pragma unroll
+                        for (int j = 0; j < N; j++) Kt[r * N + j] = T(0);
+                    }
+                }
+            }
+        }
+        // dV1 = kt' qu ; dV2 = 0.5 kt' Quu kt (ilqr.py:337-338)
+        T Qk[M];  // Quu kt
+#pragma unroll
+        for (int r = 0; r < M; r++) {
+            T acc = T(0);
+#pragma unroll
+            for (int s = 0; s < M; s++) acc += Quu[r * M + s] * kt[s];
+            Qk[r] = acc;
+        }
+        T dV1 = T(0), dV2 = T(0);
+#pragma unroll
+        for (int r = 0; r < M; r++) {
+            dV1 += kt[r] * qu[r];
+            dV2 += kt[r] * Qk[r];
+        }
+        sV1 += dV1;
+        sV2 += T(0.5) * dV2;
+        // vx = qx + Kt' Quu kt + Kt' qu + Qux' kt (ilqr.py:334)
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            T t1 = T(0), t2 = T(0), t3 = T(0);
+#pragma unroll
+            for (int r = 0; r < M; r++) {
+                t1 += Kt[r * N + i] * Qk[r];
+                t2 += Kt[r * N + i] * qu[r];
+                t3 += Qux[r * N + i] * kt[r];
+            }
+            vx[i] = ((qx[i] + t1) + t2) + t3;
+        }
+        // Vxx = Qxx + Kt' Quu Kt + Kt' Qux + Qux' Kt, then 0.5 (Vxx + Vxx') (ilqr.py:335-336);
+        // Qxx = Cxx + Ad' W (ilqr.py:287)
+        T QK[M * N];  // Quu Kt
+#pragma unroll
+        for (int r = 0; r < M; r++)
+#pragma unroll
+            for (int j = 0; j < N; j++) {
+                T acc = T(0);
+#pragma unroll
+                for (int s = 0; s < M; s++) acc += Quu[r * M + s] * Kt[s * N + j];
+                QK[r * N + j] = acc;
+            }
+        T Vn[N * N];
+#pragma unroll
+        for (int i = 0; i < N; i++)
+#pragma unroll
+            for (int j = 0; j < N; j++) {
+                T acc = T(0);
+#pragma unroll
+                for (int l = 0; l < N; l++)
+                    if (adnz(l, i)) acc += Ad[l * N + i] * W[l * N + j];
+                T q = (P::cxx_nz(i * N + j) ? Cxx[i * N + j] * dt : T(0)) + acc;
+                T t1 = T(0), t2 = T(0), t3 = T(0);
+#pragma unroll
+                for (int r = 0; r < M; r++) {
+                    t1 += Kt[r * N + i] * QK[r * N + j];
+                    t2 += Kt[r * N + i] * Qux[r * N + j];
+                    t3 += Qux[r * N + i] * Kt[r * N + j];
+                }
+                Vn[i * N + j] = ((q + t1) + t2) + t3;
+            }
+#pragma unroll
+        for (int i = 0; i < N; i++)
+#pragma unroll
+            for (int j = 0; j < N; j++) Vxx[i * N + j] = T(0.5) * (Vn[i * N + j] + Vn[j * N + i]);
+        // gradient norm ingredients: max_k |k| / (|u| + 1) (ilqr.py:418-420)
+#pragma unroll
+        for (int r = 0; r < M; r++) gmax[r] = fmax(gmax[r], fabs(kt[r]) / (fabs(u[r]) + T(1)));
+        // KK.insert(0, Kt); kk.insert(0, kt)
+#pragma unroll
+        for (int r = 0; r < M * N; r++) a.KK[((int64_t)k * M * N + r) * B + b] = Kt[r];
+#pragma unroll
+        for (int r = 0; r < M; r++) a.kk[((int64_t)k * M + r) * B + b] = kt[r];
+    }
+    a.dV[b] = sV1;
+    a.dV[B + b] = sV2;
+    T gsum = T(0);
+#pragma unroll
+    for (int r = 0; r < M; r++) gsum += gmax[r];
+    a.gnorm[b] = gsum / T(M);
+    a.success[b] = ok ? 1 : 0;
+}
+
+// ---- K4: line-search decision, mu schedule, stopping tests (iLQR.run_optim, ilqr.py:407-485) -------
+struct SelectParams {
+    int n_alpha, parallel, iteration, max_iters;
+    double alphas[MAX_ALPHAS];
+    double zmin, tol_fun, tol_grad, mu_min, mu_max, mu_d0;
+};
+
+template <typename T>
+struct SelectArgs {
+    int64_t B;
+    SelectParams p;
+    const T* cost_cand;
+    const uint8_t* diverged;
+    const T* dV;
+    const T* gnorm;
+    const uint8_t* bw_success;
+    T* cost;
+    T* mu;
+    T* mu_d;
+    T* dcost;
+    uint8_t* success_gradient;
+    int32_t* status;
+    int32_t* iters;
+    T* alpha_best;
+    uint8_t* accept;
+    uint8_t* active;
+    int32_t* n_active;
+};
+
+template <typename T>
+__global__ void ilqr_select_kernel(const SelectArgs<T> a) {
+    const int64_t B = a.B;
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    a.accept[b] = 0;
+    if (a.status[b] != 0) {
+        a.active[b] = 0;
+        return;
+    }
+    const SelectParams& p = a.p;
+    T mu = a.mu[b], mu_d = a.mu_d[b];
+    const T mu_d0 = T(p.mu_d0), mu_min = T(p.mu_min), mu_max = T(p.mu_max);
+    auto increase_mu = [&]() {  // ilqr.py:618-622
+        mu_d = fmax(mu_d0, mu_d0 * mu_d);
+        mu = fmax(mu_min, mu * mu_d);
+    };
+    auto decrease_mu = [&]() {  // ilqr.py:612-616
+        mu_d = fmin(mu_d / mu_d0, T(1) / mu_d0);
+        mu = mu * mu_d * (mu > mu_min ? T(1) : T(0));
+    };
+    int status = 0;
+    const int it = a.iters[b] + 1;
+    a.iters[b] = it;
+    if (!a.bw_success[b]) {
+        increase_mu();  // ilqr.py:411-413
+        increase_mu();  // ... and again on the "forward not successful" branch (ilqr.py:478-479)
+        if (mu > mu_max) status = 3;
+    } else {
+        bool sg = a.success_gradient[b] != 0;
+        if (a.gnorm[b] < T(p.tol_grad) && mu < T(1e-5)) {  // ilqr.py:421-423
+            decrease_mu();
+            sg = true;
+        }
+        const T cost_old = a.cost[b];
+        const T sV1 = a.dV[b], sV2 = a.dV[B + b];
+        T dcost = a.dcost[b];
+        bool success_fw = false;
+        int n_tried = 0;
+        for (int i = 0; i < p.n_alpha; i++) {
+            n_tried = i + 1;
+            if (a.diverged[(int64_t)i * B + b]) break;  // 'forward diverged.' (ilqr.py:435-437)
+            const T alpha = T(p.alphas[i]);
+            dcost = cost_old - a.cost_cand[(int64_t)i * B + b];
+            const T expected = -alpha * (sV1 + alpha * sV2);
+            const T z = expected > T(0) ? dcost / expected : pg::sign(dcost);
+            if (z > T(p.zmin)) {
+                success_fw = true;
+                if (!p.parallel) break;
+            }
+        }
+        if (success_fw) {
+            // best_idx = np.argmin(cost_list): first minimum, a NaN wins (ilqr.py:458)
+            int best = 0;
+            T bc = a.cost_cand[b];
+            for (int i = 1; i < n_tried; i++) {
+                const T c = a.cost_cand[(int64_t)i * B + b];
+                if (!(bc != bc) && (c < bc || c != c)) {
+                    bc = c;
+                    best = i;
+                }
+            }
+            a.cost[b] = bc;
+            a.alpha_best[b] = T(p.alphas[best]);
+            a.accept[b] = 1;
+            decrease_mu();
+            if (dcost < T(p.tol_fun)) status = 1;
+            else if (sg) status = 2;
+        } else {
+            increase_mu();
+            if (mu > mu_max) status = 3;
+        }
+        a.dcost[b] = dcost;
+        a.success_gradient[b] = sg ? 1 : 0;
+    }
+    if (status == 0 && it >= p.max_iters) status = 4;
+    a.mu[b] = mu;
+    a.mu_d[b] = mu_d;
+    a.status[b] = status;
+    a.active[b] = status == 0 ? 1 : 0;
+    if (status == 0 && a.n_active) atomicAdd(a.n_active, 1);
+}
+
+// ---- observation (helpers.observation, pygent/helpers.py:20-29) -----------------------------------
+template <typename P, typename T>
+__global__ void observe_kernel(int64_t B, const T* x, T* o) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < P::N; i++) {
+        const T v = x[i * B + b];
+        if (P::x_is_angle(i)) {
+            T s, co;
+            pg::sincos(v, s, co);
+            o[(c++) * B + b] = co;
+            o[(c++) * B + b] = s;
+        } else {
+            o[(c++) * B + b] = v;
+        }
+    }
+}
+
+// ---- batched point evaluation (parity tests) -------------------------------------------------------
+template <typename T>
+struct EvalArgs {
+    int64_t B;
+    int lin_mode;
+    const T* x;
+    const T* u;
+    const T* t;
+    T *f, *A, *Bm, *c, *cx, *cu, *Cxx, *Cuu, *Cxu, *cf, *cfx, *Cfxx;
+};
+
+template <typename P, typename T>
+__global__ void eval_kernel(const EvalArgs<T> a) {
+    constexpr int N = P::N, M = P::M;
+    const int64_t B = a.B;
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    T x[N], u[M];
+#pragma unroll
+    for (int i = 0; i < N; i++) x[i] = a.x[i * B + b];
+#pragma unroll
+    for (int r = 0; r < M; r++) u[r] = a.u[r * B + b];
+    const T t = a.t ? a.t[b] : T(0);
+    if (a.f) {
+        T dx[N];
+        P::f(x, u, dx);
+#pragma unroll
+        for (int i = 0; i < N; i++) a.f[i * B + b] = dx[i];
+    }
+    if (a.A || a.Bm) {
+        T A[N * N], Bm[N * M];
+        if (a.lin_mode == 0) P::AB(x, u, A, Bm);
+        else fd_AB<P, T>(x, u, A, Bm);
+        if (a.A) {
+#pragma unroll
+            for (int i = 0; i < N * N; i++) a.A[i * B + b] = A[i];
+        }
+        if (a.Bm) {
+#pragma unroll
+            for (int i = 0; i < N * M; i++) a.Bm[i * B + b] = Bm[i];
+        }
+    }
+    if (a.c) a.c[b] = P::cost(x, u, x, t);
+    if (a.cx || a.cu || a.Cxx || a.Cuu || a.Cxu) {
+        T cx[N], cu[M], Cxx[N * N], Cuu[M * M], Cxu[N * M];
+        P::cost_derivs(x, u, t, cx, cu, Cxx, Cuu, Cxu);
+        if (a.cx) {
+#pragma unroll
+            for (int i = 0; i < N; i++) a.cx[i * B + b] = cx[i];
+        }
+        if (a.cu) {
+#pragma unroll
+            for (int i = 0; i < M; i++) a.cu[i * B + b] = cu[i];
+        }
+        if (a.Cxx) {
+#pragma unroll
+            for (int i = 0; i < N * N; i++) a.Cxx[i * B + b] = Cxx[i];
+        }
+        if (a.Cuu) {
+#pragma unroll
+            for (int i = 0; i < M * M; i++) a.Cuu[i * B + b] = Cuu[i];
+        }
+        if (a.Cxu) {
+#pragma unroll
+            for (int i = 0; i < N * M; i++) a.Cxu[i * B + b] = Cxu[i];
+        }
+    }
+    if (a.cf) a.cf[b] = P::fcost(x);
+    if (a.cfx || a.Cfxx) {
+        T cfx[N], Cfxx[N * N];
+        P::fcost_derivs(x, cfx, Cfxx);
+        if (a.cfx) {
+#pragma unroll
+            for (int i = 0; i < N; i++) a.cfx[i * B + b] = cfx[i];
+        }
+        if (a.Cfxx) {
+#pragma unroll
+            for (int i = 0; i < N * N; i++) a.Cfxx[i * B + b] = Cfxx[i];
+        }
+    }
+}
+
+}  // namespace pgk

@@ -1,0 +1,403 @@
+"""Batched environments behind pygent's `Environment` API, integrated on the GPU.
+
+Mirrors `pygent/environments.py` (reference): `Environment` (:23-120), `StateSpaceModel` (:182-326)
+and the concrete systems `Pendulum` (:328-357), `AngularPendulum` (:394-423), `CartPole` (:461-482),
+`CartPoleDoubleSerial` (:523-551), `CartPoleDoubleParallel` (:596-615), `CartPoleTriple` (:660-679),
+`Car` (:730-761), `Acrobot` (:763-782), `MarBot` (:826-868) -- same constructor signatures, attribute
+names (`x, x_, x0, xDim, uDim, oDim, o, o_, xIsAngle, uMax, dt, history, tt, terminated`) and methods
+(`reset, step, fast_step, terminate, observe, ode, A, B`).
+
+What is different by design:
+  * `x0` may be one state (list of n) or a batch `[B, n]`; all B environments advance in one kernel
+    launch.  With a single state the attributes have the reference's shapes (`x` is `[n]`,
+    `history` is `[k+1, n]`); with a batch they gain a leading B axis.
+  * `step` integrates with fixed-step RK4, `substeps` per control interval (default 4: within 3e-9 of
+    the reference's adaptive RK45 on these systems) -- the parity schedule.
+  * `rollout(U)` runs a whole control sequence in ONE launch (the reference has only Python loops
+    over `step`, e.g. `pygent/algorithms/ilqr.py:504-512`).
+State lives on the GPU in trajectory-minor layout `[n, B]`; there is no CPU integration path.
+"""
+import numpy as np
+import sympy as sp
+import torch
+
+from . import codegen, lib, tracing
+from .helpers import observation
+from .modeling.systems import SystemModel, get_system
+
+
+def _default_device():
+    if not torch.cuda.is_available():
+        raise lib.PygentB200Error("pygent_b200 needs a CUDA device (B200); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class Environment(object):
+    """Environment base class (reference: environments.py:23-120)."""
+
+    def __init__(self, x0, uDim, dt, device=None, dtype=torch.float64):
+        if callable(x0):
+            self.x0 = x0
+            x0 = x0()
+        else:
+            x0 = np.array(x0, dtype=float)
+            self.x0 = x0
+        x0 = np.array(x0, dtype=float)
+        self.batched = x0.ndim == 2
+        self.batch = x0.shape[0] if self.batched else 1
+        self.xDim = x0.shape[-1]
+        self.oDim = self.xDim
+        self.uDim = uDim
+        self.xIsAngle = np.zeros([self.xDim], dtype=bool)
+        self.uMax = np.ones(uDim)
+        self.dt = dt
+        self.dtype = dtype
+        self._device = device
+        self._set_state(x0)
+
+    # -- device state ---------------------------------------------------------------------------
+    @property
+    def device(self):
+        if self._device is None:
+            self._device = _default_device()
+        return self._device
+
+    def _to_dev(self, a, cols):
+        """host [cols] or [B, cols] -> device [cols, B]"""
+        a = np.asarray(a, dtype=float).reshape(self.batch, cols)
+        return torch.as_tensor(a.T.copy(), dtype=self.dtype, device=self.device).contiguous()
+
+    def _to_host(self, t):
+        """device [c, B] -> numpy [c] (single) or [B, c]"""
+        a = t.detach().to("cpu", torch.float64).numpy().T
+        return a if self.batched else a[0]
+
+    def _set_state(self, x0):
+        self._x0_host = np.array(x0, dtype=float).reshape(self.batch, self.xDim)
+        self._xd = None          # device state, created lazily (so that construction works without a GPU)
+        self._xd_prev = None
+        self._hist = [self._x0_host.copy()]
+        self.tt = [0]
+        self.terminated = False if not self.batched else np.zeros(self.batch, dtype=bool)
+
+    def _state(self):
+        if self._xd is None:
+            self._xd = self._to_dev(self._x0_host, self.xDim)
+            self._xd_prev = self._xd
+        return self._xd
+
+    @property
+    def x(self):
+        return self._to_host(self._state()) if self._xd is not None else (self._x0_host if self.batched else self._x0_host[0])
+
+    @property
+    def x_(self):
+        return self._to_host(self._xd_prev) if self._xd is not None else self.x
+
+    @property
+    def history(self):
+        h = np.stack(self._hist, axis=1)  # [B, k+1, n]
+        return h if self.batched else h[0]
+
+    def get_state(self):
+        return self.x
+
+    def reset(self, x0):
+        """Resets environment to state x0 (list of n, `[B, n]` array, or callable)."""
+        if callable(x0):
+            x0 = x0()
+        x0 = np.array(x0, dtype=float)
+        if x0.ndim == 2 and x0.shape[0] != self.batch:
+            self.batch, self.batched = x0.shape[0], True
+        self._set_state(x0)
+
+    def step(self, *args):
+        raise NotImplementedError
+
+    def observe(self, x):
+        return x
+
+    def save_history(self, filename, path):
+        import pickle
+        with open(path + filename + ".p", "wb") as fh:
+            pickle.dump({"tt": self.tt, "xx": self.history}, fh)
+
+
+class StateSpaceModel(Environment):
+    """dx/dt = f(x, u) environment (reference: environments.py:182-326).
+
+    `ode` is a `SystemModel`, a registered system name, or a callable `ode(t, x, u)` that is traced
+    into sympy (numpy ufuncs inside it are fine)."""
+
+    def __init__(self, ode, cost, x0, uDim, dt, terminal_cost=0., substeps=4, device=None, dtype=torch.float64,
+                 name=None):
+        super(StateSpaceModel, self).__init__(x0, uDim, dt, device=device, dtype=dtype)
+        if isinstance(ode, str):
+            ode = get_system(ode)
+        if isinstance(ode, SystemModel):
+            self.system = ode
+        else:
+            xs = sp.symbols("x1:%d" % (self.xDim + 1))
+            us = sp.symbols("u1:%d" % (uDim + 1))
+            f = tracing.trace(ode, None, list(xs), list(us))
+            self.system = SystemModel(name or "user_%s" % getattr(ode, "__name__", "ode"), f, xs, us, False)
+        if self.system.n != self.xDim or self.system.m != uDim:
+            raise ValueError("system %s has n=%d, m=%d but x0/uDim give n=%d, m=%d"
+                             % (self.system.name, self.system.n, self.system.m, self.xDim, uDim))
+        f_np, A_np, B_np = self.system.numpy_callables()
+        self.ode = f_np
+        if self.system.has_AB:  # like the reference, only systems with symbolic Jacobians expose A, B
+            self.A, self.B = A_np, B_np
+        self._user_cost = cost
+        self.cost = tracing.bind_cost(cost)
+        self.terminal_cost = terminal_cost
+        self.substeps = substeps
+        self.xIsAngle = np.zeros([self.xDim], dtype=bool)
+        self.oDim = self.xDim
+        self._problems = {}
+        self._cost_expr = None
+
+    # -- problem compilation ----------------------------------------------------------------------
+    def _term_limits(self):
+        """[(state index, limit)]: terminated = any(|x_i| > limit); subclasses fill this in."""
+        return []
+
+    def cost_expression(self):
+        """Running cost as a sympy expression in (x, u, x_next, t), obtained like `iLQR.cost_init`
+        does (ilqr.py:539-543): the user's callable evaluated on symbols with mod = sympy."""
+        if self._cost_expr is None:
+            s = self.system
+            xn = sp.symbols("xn1:%d" % (s.n + 1))
+            self._cost_expr = tracing.trace(self.cost, list(s.xs), list(s.us), list(xn), sp.Symbol("t"), sp)
+        return self._cost_expr
+
+    def problem_spec(self, fcost_expr=None):
+        return codegen.ProblemSpec(self.system, self.cost_expression(), fcost_expr, term=self._term_limits(),
+                                   x_is_angle=list(self.xIsAngle))
+
+    def library(self, fcost_expr=None):
+        """The compiled CUDA library of (dynamics, running cost, final cost); built on first use."""
+        key = sp.srepr(sp.sympify(fcost_expr)) if fcost_expr is not None else None
+        key = (key, tuple(self._term_limits()), tuple(bool(a) for a in self.xIsAngle))
+        if key not in self._problems:
+            self._problems[key] = lib.load_problem(self.problem_spec(fcost_expr))
+        return self._problems[key]
+
+    # -- stepping ---------------------------------------------------------------------------------
+    def _advance(self, args, integrator):
+        if len(args) == 2:
+            u, dt = args
+        elif len(args) == 1:
+            u, dt = args[0], self.dt
+        else:
+            raise TypeError("step(u[, dt])")
+        L = self.library()
+        x = self._state()
+        ud = self._to_dev(u, self.uDim).reshape(1, self.uDim, self.batch)
+        r = L.rollout(x, ud, S=self.substeps, dt=dt, t0=float(self.tt[-1]), integrator=integrator,
+                      terminal_cost=float(self.terminal_cost))
+        self._xd_prev, self._xd = x, r["xN"]
+        self._hist.append(r["xN"].detach().to("cpu", torch.float64).numpy().T.copy())
+        self.tt.extend([self.tt[-1] + dt])
+        term = r["terminated"].cpu().numpy().astype(bool)
+        c = r["cost"].to("cpu", torch.float64).numpy()
+        if self.batched:
+            self.terminated = term
+            return c
+        self.terminated = bool(term[0])
+        return float(c[0])
+
+    def step(self, *args):
+        """One control interval `dt` with control `u` (`[m]` or `[B, m]`); returns the transition cost
+        `(cost(x_, u, x, t) + terminal_cost*terminated)*dt` (reference: environments.py:242-276, with
+        solve_ivp replaced by RK4 x `substeps`)."""
+        return self._advance(args, lib.INTEG_RK4)
+
+    def fast_step(self, *args):
+        """Forward-Euler step (reference: environments.py:291-322)."""
+        return self._advance(args, lib.INTEG_EULER)
+
+    def rollout(self, U, history=True, fast=False, add_final_cost=False, fcost_expr=None):
+        """Whole control sequence in one launch.  U: `[T, m]` / `[B, T, m]` host array, or a device
+        tensor already in kernel layout `[T, m, B]`.  Equivalent to `for u in U: step(u)`.
+        Returns dict(X, xN, cost, terminated) as device tensors in kernel layout."""
+        L = self.library(fcost_expr)
+        x = self._state()
+        if torch.is_tensor(U) and U.is_cuda:
+            Ud = U
+        else:
+            U = np.asarray(U, dtype=float)
+            if U.ndim == 2:
+                U = np.broadcast_to(U[None], (self.batch,) + U.shape)
+            Ud = torch.as_tensor(np.ascontiguousarray(U.transpose(1, 2, 0)), dtype=self.dtype, device=self.device)
+        T = Ud.shape[0]
+        r = L.rollout(x, Ud, S=self.substeps, dt=self.dt, t0=float(self.tt[-1]),
+                      integrator=lib.INTEG_EULER if fast else lib.INTEG_RK4, history=history,
+                      terminal_cost=float(self.terminal_cost), add_final_cost=add_final_cost)
+        self._xd_prev, self._xd = x, r["xN"]
+        if history:
+            Xh = r["X"].detach().to("cpu", torch.float64).numpy()  # [T+1, n, B]
+            self._hist.extend([Xh[k].T.copy() for k in range(1, T + 1)])
+        else:
+            self._hist.append(r["xN"].detach().to("cpu", torch.float64).numpy().T.copy())
+        t = self.tt[-1]
+        for _ in range(T):
+            t = t + self.dt
+            self.tt.append(t)
+        term = r["terminated"].cpu().numpy().astype(bool)
+        self.terminated = term if self.batched else bool(term[0])
+        return r
+
+    def terminate(self, x):
+        """True where `x` (`[n]` or `[B, n]`) is a terminal state (reference: environments.py:278-288)."""
+        x = np.asarray(x, dtype=float)
+        out = np.zeros(x.shape[:-1], dtype=bool)
+        for i, lim in self._term_limits():
+            out = out | (np.abs(x[..., i]) > lim)
+        return out if out.ndim else bool(out)
+
+    def observe(self, x):
+        return observation(x, self.xIsAngle)
+
+    @property
+    def o(self):
+        return self.observe(self.x)
+
+    @property
+    def o_(self):
+        return self.observe(self.x_)
+
+
+def _finish(env):
+    env.oDim = int(env.xDim + np.sum(env.xIsAngle))
+
+
+class Pendulum(StateSpaceModel):
+    """reference: environments.py:328-357"""
+
+    def __init__(self, cost, x0, dt, **kw):
+        super(Pendulum, self).__init__(get_system("pendulum"), cost, x0, 1, dt, **kw)
+        self.xIsAngle = [True, False]
+        self.uMax = 3.5 * np.ones(1)
+        _finish(self)
+
+    def _term_limits(self):
+        return [(1, 10.0), (0, 8 * np.pi)]
+
+
+class AngularPendulum(StateSpaceModel):
+    """reference: environments.py:394-423"""
+
+    def __init__(self, cost, x0, dt, **kw):
+        super(AngularPendulum, self).__init__(get_system("angular_pendulum"), cost, x0, 1, dt, **kw)
+        self.xIsAngle = [False, False, False]
+        self.uMax = 3.5 * np.ones(1)
+        _finish(self)
+
+    def _term_limits(self):
+        return [(2, 10.0)]
+
+
+class CartPole(StateSpaceModel):
+    """reference: environments.py:461-482 (`linearized=True`: input = cart acceleration)"""
+
+    def __init__(self, cost, x0, dt, linearized=True, **kw):
+        super(CartPole, self).__init__(get_system("cart_pole_lin" if linearized else "cart_pole"), cost, x0, 1, dt, **kw)
+        self.xIsAngle = [False, True, False, False]
+        self.uMax = (10 if linearized else 100) * np.ones(1)
+        self.x1Max = 1.2
+        self.x3Max = 4.0
+        _finish(self)
+
+    def _term_limits(self):
+        return [(0, self.x1Max), (2, self.x3Max)]
+
+
+class CartPoleDoubleSerial(StateSpaceModel):
+    """reference: environments.py:523-551"""
+
+    def __init__(self, cost, x0, dt, linearized=True, task='swing_up', **kw):
+        name = "cart_pole_double_serial_lin" if linearized else "cart_pole_double_serial"
+        super(CartPoleDoubleSerial, self).__init__(get_system(name), cost, x0, 1, dt, **kw)
+        self.xIsAngle = [False, True, True, False, False, False]
+        self.uMax = (15 if linearized else 100) * np.ones(1)
+        self.task = task
+        self.x1Max = 1.5
+        _finish(self)
+
+    def _term_limits(self):
+        if self.task == 'swing_up':
+            return [(0, self.x1Max), (4, 25.0), (5, 25.0)]
+        if self.task == 'balance':
+            return [(0, self.x1Max), (1, 1.0), (2, 1.0), (4, 25.0), (5, 25.0)]
+        return []
+
+
+class CartPoleDoubleParallel(StateSpaceModel):
+    """reference: environments.py:596-615"""
+
+    def __init__(self, cost, x0, dt, linearized=True, **kw):
+        name = "cart_pole_double_parallel_lin" if linearized else "cart_pole_double_parallel"
+        super(CartPoleDoubleParallel, self).__init__(get_system(name), cost, x0, 1, dt, **kw)
+        self.xIsAngle = [False, True, True, False, False, False]
+        self.uMax = (25 if linearized else 100) * np.ones(1)
+        self.x1Max = 1.5
+        _finish(self)
+
+    def _term_limits(self):
+        return [(0, self.x1Max), (4, 25.0), (5, 25.0)]
+
+
+class CartPoleTriple(StateSpaceModel):
+    """reference: environments.py:660-679 (only the linearised model is shipped)"""
+
+    def __init__(self, cost, x0, dt, linearized=True, **kw):
+        if not linearized:
+            raise NotImplementedError("the reference ships only cart_pole_triple_lin (c_files listing)")
+        super(CartPoleTriple, self).__init__(get_system("cart_pole_triple_lin"), cost, x0, 1, dt, **kw)
+        self.xIsAngle = [False, True, True, True, False, False, False, False]
+        self.uMax = 20 * np.ones(1)
+        self.x1Max = 1.5
+        _finish(self)
+
+    def _term_limits(self):
+        return [(0, self.x1Max)]
+
+
+class Car(StateSpaceModel):
+    """reference: environments.py:730-761 (m = 2)"""
+
+    def __init__(self, cost, x0, dt, **kw):
+        super(Car, self).__init__(get_system("car"), cost, x0, 2, dt, **kw)
+        self.xIsAngle = [False, False, True, False]
+        self.uMax = np.array([.5, 2.])
+        _finish(self)
+
+    def _term_limits(self):
+        return [(0, 5.0), (1, 5.0)]
+
+
+class Acrobot(StateSpaceModel):
+    """reference: environments.py:763-782"""
+
+    def __init__(self, cost, x0, dt, linearized=True, **kw):
+        super(Acrobot, self).__init__(get_system("acrobot_lin" if linearized else "acrobot"), cost, x0, 1, dt, **kw)
+        self.xIsAngle = [True, True, False, False]
+        self.uMax = (50 if linearized else 5) * np.ones(1)
+        _finish(self)
+
+    def _term_limits(self):
+        return [(2, 50.0), (3, 50.0)]
+
+
+class MarBot(StateSpaceModel):
+    """reference: environments.py:826-868"""
+
+    def __init__(self, cost, x0, dt, **kw):
+        super(MarBot, self).__init__(get_system("marbot"), cost, x0, 1, dt, **kw)
+        self.xIsAngle = [False, True, False, False]
+        self.uMax = 2 * np.ones(1)
+        _finish(self)
+
+    def _term_limits(self):
+        return [(0, 1.0)]

@@ -1,0 +1,298 @@
+"""ctypes binding of one compiled problem library (include/pygent_b200.h).
+
+The Python layer passes torch CUDA tensors as raw device pointers + sizes + the current CUDA
+stream; torch is plumbing (memory, streams), the arithmetic is in the library.  Every entry point
+raises on a non-zero return code -- there is no fallback path.
+"""
+import ctypes
+import functools
+
+import torch
+
+from . import build
+
+PG_F64, PG_F32 = 0, 1
+INTEG_RK4, INTEG_EULER = 0, 1
+MAX_ALPHAS = 16
+ST_RUNNING, ST_CONV_FUN, ST_CONV_GRAD, ST_MU_MAX, ST_MAX_ITERS = range(5)
+STATUS_NAMES = {0: "running", 1: "converged: small improvement", 2: "converged: small gradient",
+                3: "diverged: no improvement", 4: "maximum iterations"}
+
+_vp, _i32, _i64, _f64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
+_dp = ctypes.POINTER(ctypes.c_double)
+
+
+class ProblemInfo(ctypes.Structure):
+    _fields_ = [("abi_version", _i32), ("n", _i32), ("m", _i32), ("n_obs", _i32), ("has_ab", _i32),
+                ("has_cost_derivs", _i32), ("cost_uses_xnext", _i32), ("reserved", _i32),
+                ("name", ctypes.c_char * 64), ("key", ctypes.c_char * 32)]
+
+
+class SelectParams(ctypes.Structure):
+    _fields_ = [("n_alpha", _i32), ("parallel", _i32), ("iteration", _i32), ("max_iters", _i32),
+                ("alphas", _f64 * MAX_ALPHAS), ("zmin", _f64), ("tol_fun", _f64), ("tol_grad", _f64),
+                ("mu_min", _f64), ("mu_max", _f64), ("mu_d0", _f64)]
+
+
+# name -> argtypes (restype is always int); mirrors include/pygent_b200.h
+SIGNATURES = {
+    "pg_get_problem_info": [ctypes.POINTER(ProblemInfo)],
+    "pg_rollout": [_i32, _i32, _i64, _i32, _i32, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _i32, _vp],
+    "pg_ilqr_forward": [_i32, _i32, _i64, _i32, _i32, _f64, _i32, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _dp, _f64,
+                        _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pg_ilqr_backward": [_i32, _i64, _i32, _f64, _i32, _i32, _vp, _vp, _vp, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pg_ilqr_select": [_i32, _i64, ctypes.POINTER(SelectParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                       _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pg_ilqr_commit": [_i32, _i32, _i64, _i32, _i32, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _dp, _vp, _vp, _vp],
+    "pg_observe": [_i32, _i64, _vp, _vp, _vp],
+    "pg_eval": [_i32, _i64, _i32] + [_vp] * 16,
+}
+
+
+class PygentB200Error(RuntimeError):
+    pass
+
+
+def _dtype_code(dtype):
+    if dtype == torch.float64:
+        return PG_F64
+    if dtype == torch.float32:
+        return PG_F32
+    raise TypeError("pygent_b200 kernels compute in float64 or float32, got %s" % dtype)
+
+
+def _ptr(t, dtype=None, shape=None, name="tensor"):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL), with shape/dtype checks."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise PygentB200Error("%s must live on a CUDA device (there is no CPU path)" % name)
+    if not t.is_contiguous():
+        raise PygentB200Error("%s must be contiguous" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise PygentB200Error("%s: expected dtype %s, got %s" % (name, dtype, t.dtype))
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise PygentB200Error("%s: expected shape %s, got %s" % (name, tuple(shape), tuple(t.shape)))
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _host_doubles(vals):
+    if vals is None:
+        return None
+    vals = [float(v) for v in vals]
+    return (ctypes.c_double * len(vals))(*vals)
+
+
+class ProblemLibrary:
+    """One loaded `pg_<system>_<key>.so`."""
+
+    def __init__(self, path):
+        self.path = path
+        self.dll = ctypes.CDLL(path)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(self.dll, name)  # AttributeError if the library does not export the ABI
+            fn.argtypes = argtypes
+            fn.restype = ctypes.c_int
+        info = ProblemInfo()
+        self._check(self.dll.pg_get_problem_info(ctypes.byref(info)), "pg_get_problem_info")
+        self.info = info
+        self.n, self.m, self.n_obs = info.n, info.m, info.n_obs
+        self.has_ab = bool(info.has_ab)
+        self.name = info.name.decode()
+        self.key = info.key.decode()
+        self.launches = 0  # kernels launched through this handle (bench.py's gpu_launches)
+
+    @staticmethod
+    def _check(rc, what):
+        if rc == 0:
+            return
+        if rc > 0:
+            raise PygentB200Error("%s: CUDA error %d (%s)" % (what, rc, _cuda_error_name(rc)))
+        raise PygentB200Error("%s: %s" % (what, {-1: "bad argument", -2: "not supported by this problem"}.get(rc, rc)))
+
+    @staticmethod
+    def _stream():
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    # -- K1 ------------------------------------------------------------------------------------
+    def rollout(self, x0, U=None, T=None, S=4, dt=0.02, t0=0.0, integrator=INTEG_RK4, history=False,
+                want_cost=True, terminal_cost=0.0, add_final_cost=False, out=None):
+        """x0 [n,B], U [T,m,B] or None -> dict(xN [n,B], cost [B], terminated [B] u8, X [T+1,n,B])."""
+        n, m = self.n, self.m
+        dtype, dev = x0.dtype, x0.device
+        B = x0.shape[1]
+        if U is not None:
+            T = U.shape[0]
+        if T is None:
+            raise PygentB200Error("rollout needs U or T")
+        out = out or {}
+        xN = out.get("xN")
+        if xN is None:
+            xN = torch.empty((n, B), dtype=dtype, device=dev)
+        cost = out.get("cost")
+        if cost is None and want_cost:
+            cost = torch.empty((B,), dtype=dtype, device=dev)
+        term = out.get("terminated")
+        if term is None:
+            term = torch.empty((B,), dtype=torch.uint8, device=dev)
+        X = out.get("X")
+        if X is None and history:
+            X = torch.empty((T + 1, n, B), dtype=dtype, device=dev)
+        rc = self.dll.pg_rollout(_dtype_code(dtype), integrator, B, T, S, dt, t0,
+                                 _ptr(x0, dtype, (n, B), "x0"), _ptr(U, dtype, (T, m, B), "U"),
+                                 _ptr(X, dtype, (T + 1, n, B), "X"), _ptr(xN, dtype, (n, B), "xN"),
+                                 _ptr(cost, dtype, (B,), "cost"), _ptr(term, torch.uint8, (B,), "terminated"),
+                                 terminal_cost, int(add_final_cost), self._stream())
+        self._check(rc, "pg_rollout")
+        self.launches += 1
+        return {"xN": xN, "cost": cost, "terminated": term, "X": X}
+
+    # -- K2 ------------------------------------------------------------------------------------
+    def ilqr_forward(self, x0, xbar, ubar, KK, kk, alphas=None, alpha_dev=None, S=4, dt=0.02,
+                     integrator=INTEG_RK4, ulim=None, terminal_cost=0.0, want_traj=False, active=None, out=None):
+        n, m = self.n, self.m
+        dtype, dev = x0.dtype, x0.device
+        B = x0.shape[1]
+        T = ubar.shape[0]
+        Tk = KK.shape[0]
+        n_alpha = 1 if alpha_dev is not None else len(alphas)
+        out = out or {}
+        cost = out.get("cost")
+        if cost is None:
+            cost = torch.empty((n_alpha, B), dtype=dtype, device=dev)
+        div = out.get("diverged")
+        if div is None:
+            div = torch.empty((n_alpha, B), dtype=torch.uint8, device=dev)
+        term = out.get("terminated")
+        if term is None:
+            term = torch.empty((n_alpha, B), dtype=torch.uint8, device=dev)
+        X = out.get("X")
+        Uo = out.get("U")
+        if want_traj and X is None:
+            X = torch.empty((n_alpha, T + 1, n, B), dtype=dtype, device=dev)
+            Uo = torch.empty((n_alpha, T, m, B), dtype=dtype, device=dev)
+        rc = self.dll.pg_ilqr_forward(
+            _dtype_code(dtype), integrator, B, T, S, dt, n_alpha, _host_doubles(alphas),
+            _ptr(alpha_dev, dtype, (B,), "alpha_dev"), _ptr(x0, dtype, (n, B), "x0"),
+            _ptr(xbar, dtype, (T + 1, n, B), "xbar"), _ptr(ubar, dtype, (T, m, B), "ubar"),
+            _ptr(KK, dtype, (Tk, m, n, B), "KK"), _ptr(kk, dtype, (Tk, m, B), "kk"), Tk, _host_doubles(ulim),
+            terminal_cost, _ptr(X, dtype, (n_alpha, T + 1, n, B), "X_out"), _ptr(Uo, dtype, (n_alpha, T, m, B), "U_out"),
+            _ptr(cost, dtype, (n_alpha, B), "cost_out"), _ptr(div, torch.uint8, (n_alpha, B), "diverged_out"),
+            _ptr(term, torch.uint8, (n_alpha, B), "terminated_out"), _ptr(active, torch.uint8, (B,), "active"),
+            self._stream())
+        self._check(rc, "pg_ilqr_forward")
+        self.launches += 1
+        return {"cost": cost, "diverged": div, "terminated": term, "X": X, "U": Uo}
+
+    # -- K3 ------------------------------------------------------------------------------------
+    def ilqr_backward(self, xbar, ubar, mu, dt=0.02, reg_type=2, lin_mode=None, ulim=None, active=None, out=None):
+        n, m = self.n, self.m
+        dtype, dev = xbar.dtype, xbar.device
+        T, B = ubar.shape[0], ubar.shape[2]
+        if lin_mode is None:
+            lin_mode = 0 if self.has_ab else 1
+        out = out or {}
+        KK = out.get("KK")
+        if KK is None:
+            KK = torch.zeros((T, m, n, B), dtype=dtype, device=dev)
+        kk = out.get("kk")
+        if kk is None:
+            kk = torch.zeros((T, m, B), dtype=dtype, device=dev)
+        dV = out.get("dV")
+        if dV is None:
+            dV = torch.empty((2, B), dtype=dtype, device=dev)
+        gnorm = out.get("gnorm")
+        if gnorm is None:
+            gnorm = torch.empty((B,), dtype=dtype, device=dev)
+        success = out.get("success")
+        if success is None:
+            success = torch.empty((B,), dtype=torch.uint8, device=dev)
+        rc = self.dll.pg_ilqr_backward(
+            _dtype_code(dtype), B, T, dt, reg_type, lin_mode, _ptr(mu, dtype, (B,), "mu"),
+            _ptr(xbar, dtype, (T + 1, n, B), "xbar"), _ptr(ubar, dtype, (T, m, B), "ubar"), _host_doubles(ulim),
+            _ptr(KK, dtype, (T, m, n, B), "KK"), _ptr(kk, dtype, (T, m, B), "kk"), _ptr(dV, dtype, (2, B), "dV"),
+            _ptr(gnorm, dtype, (B,), "gnorm"), _ptr(success, torch.uint8, (B,), "success"),
+            _ptr(active, torch.uint8, (B,), "active"), self._stream())
+        self._check(rc, "pg_ilqr_backward")
+        self.launches += 1
+        return {"KK": KK, "kk": kk, "dV": dV, "gnorm": gnorm, "success": success}
+
+    # -- K4 ------------------------------------------------------------------------------------
+    def ilqr_select(self, params, cost_cand, diverged, dV, gnorm, bw_success, state, n_active=None):
+        """state: dict of per-trajectory tensors cost, mu, mu_d, dcost, success_gradient, status, iters,
+        alpha_best, accept, active (updated in place)."""
+        dtype = cost_cand.dtype
+        B = cost_cand.shape[1]
+        u8, i32 = torch.uint8, torch.int32
+        rc = self.dll.pg_ilqr_select(
+            _dtype_code(dtype), B, ctypes.byref(params), _ptr(cost_cand, dtype, None, "cost_cand"),
+            _ptr(diverged, u8, tuple(cost_cand.shape), "diverged"), _ptr(dV, dtype, (2, B), "dV"),
+            _ptr(gnorm, dtype, (B,), "gnorm"), _ptr(bw_success, u8, (B,), "bw_success"),
+            _ptr(state["cost"], dtype, (B,), "cost"), _ptr(state["mu"], dtype, (B,), "mu"),
+            _ptr(state["mu_d"], dtype, (B,), "mu_d"), _ptr(state["dcost"], dtype, (B,), "dcost"),
+            _ptr(state["success_gradient"], u8, (B,), "success_gradient"), _ptr(state["status"], i32, (B,), "status"),
+            _ptr(state["iters"], i32, (B,), "iters"), _ptr(state["alpha_best"], dtype, (B,), "alpha_best"),
+            _ptr(state["accept"], u8, (B,), "accept"), _ptr(state["active"], u8, (B,), "active"),
+            _ptr(n_active, i32, None, "n_active"), self._stream())
+        self._check(rc, "pg_ilqr_select")
+        self.launches += 1
+
+    def ilqr_commit(self, x0, xbar, ubar, KK, kk, KK_acc, kk_acc, alpha_best, accept, S=4, dt=0.02,
+                    integrator=INTEG_RK4, ulim=None):
+        n, m = self.n, self.m
+        dtype = x0.dtype
+        B = x0.shape[1]
+        T = ubar.shape[0]
+        rc = self.dll.pg_ilqr_commit(
+            _dtype_code(dtype), integrator, B, T, S, dt, _ptr(alpha_best, dtype, (B,), "alpha_best"),
+            _ptr(accept, torch.uint8, (B,), "accept"), _ptr(x0, dtype, (n, B), "x0"),
+            _ptr(xbar, dtype, (T + 1, n, B), "xbar"), _ptr(ubar, dtype, (T, m, B), "ubar"),
+            _ptr(KK, dtype, (T, m, n, B), "KK"), _ptr(kk, dtype, (T, m, B), "kk"), _host_doubles(ulim),
+            _ptr(KK_acc, dtype, (T, m, n, B), "KK_acc"), _ptr(kk_acc, dtype, (T, m, B), "kk_acc"), self._stream())
+        self._check(rc, "pg_ilqr_commit")
+        self.launches += 1
+
+    def observe(self, x):
+        B = x.shape[1]
+        o = torch.empty((self.n_obs, B), dtype=x.dtype, device=x.device)
+        self._check(self.dll.pg_observe(_dtype_code(x.dtype), B, _ptr(x, None, (self.n, B), "x"), _ptr(o), self._stream()),
+                    "pg_observe")
+        self.launches += 1
+        return o
+
+    def eval(self, x, u, t=None, lin_mode=None, what=("f", "A", "B", "c", "cx", "cu", "Cxx", "Cuu", "Cxu", "cf", "cfx", "Cfxx")):
+        """Point evaluation of the generated functions; returns dict name -> tensor [..., B]."""
+        n, m = self.n, self.m
+        dtype, dev = x.dtype, x.device
+        B = x.shape[1]
+        if lin_mode is None:
+            lin_mode = 0 if self.has_ab else 1
+        shapes = {"f": (n, B), "A": (n, n, B), "B": (n, m, B), "c": (B,), "cx": (n, B), "cu": (m, B), "Cxx": (n, n, B),
+                  "Cuu": (m, m, B), "Cxu": (n, m, B), "cf": (B,), "cfx": (n, B), "Cfxx": (n, n, B)}
+        if not self.info.has_cost_derivs:
+            what = [w for w in what if w not in ("cx", "cu", "Cxx", "Cuu", "Cxu")]
+        outs = {k: torch.empty(shapes[k], dtype=dtype, device=dev) for k in what}
+        order = ["f", "A", "B", "c", "cx", "cu", "Cxx", "Cuu", "Cxu", "cf", "cfx", "Cfxx"]
+        rc = self.dll.pg_eval(_dtype_code(dtype), B, lin_mode, _ptr(x, dtype, (n, B), "x"), _ptr(u, dtype, (m, B), "u"),
+                              _ptr(t, dtype, (B,), "t"), *[_ptr(outs.get(k)) for k in order], self._stream())
+        self._check(rc, "pg_eval")
+        self.launches += 1
+        return outs
+
+
+def _cuda_error_name(rc):
+    try:
+        cudart = torch.cuda.cudart()
+        return cudart.cudaGetErrorString(rc) if hasattr(cudart, "cudaGetErrorString") else "cudaError"
+    except Exception:
+        return "cudaError"
+
+
+@functools.lru_cache(maxsize=None)
+def _load(path):
+    return ProblemLibrary(path)
+
+
+def load_problem(spec):
+    """Build (if needed) and load the library of `spec`; raises if neither is possible."""
+    return _load(build.build_problem(spec))

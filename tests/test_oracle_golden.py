@@ -1,0 +1,98 @@
+"""The oracle (oracle/pygent_oracle.c) against outputs of the UNMODIFIED reference (tests/golden/*.npz,
+made by oracle/make_golden.py).  This is what pins the oracle; the GPU tests then compare the CUDA
+path with the oracle.  CPU only."""
+import numpy as np
+import pytest
+
+import oracle
+from cases import CASES, ILQR_RUNS, oracle_problem
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return float(np.max(np.abs(a - b) / (np.abs(b) + 1.0))) if a.size else 0.0
+
+
+SYSTEMS = sorted({c[2] for c in CASES.values()}) + ["car", "marbot", "angular_pendulum"]
+
+
+@pytest.mark.parametrize("system", SYSTEMS)
+def test_dynamics_and_jacobians_match_reference(golden, system):
+    g = golden("models")
+    xs, us = g[system + "/x"], g[system + "/u"]
+    f = np.array([oracle.f(system, x, u) for x, u in zip(xs, us)])
+    assert rel(f, g[system + "/f"]) < 2e-12
+    if system + "/A" in g.files:
+        AB = [oracle.AB(system, x, u) for x, u in zip(xs, us)]
+        assert rel(np.array([a for a, _ in AB]), g[system + "/A"]) < 2e-11
+        assert rel(np.array([b for _, b in AB]), g[system + "/B"]) < 2e-11
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+@pytest.mark.parametrize("tag,S,integ", [("rk4x1", 1, 0), ("rk4x4", 4, 0), ("euler", 1, 1)])
+def test_fixed_step_rollout_matches_reference(golden, case, tag, S, integ):
+    g = golden("steps")
+    p = oracle_problem(case, S=S, integrator=integ)
+    r = oracle.rollout(p, g[case + "/x0"][None], U=g[case + "/U"][None])
+    Xref, cref = g["%s/%s/X" % (case, tag)], g["%s/%s/c" % (case, tag)]
+    assert rel(r["X"][0], Xref) < 1e-10
+    assert abs(r["cost"][0] - cref.sum()) <= 1e-10 * (abs(cref.sum()) + 1)
+    assert bool(r["terminated"][0]) == bool(g["%s/%s/terminated" % (case, tag)])
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_rk4x4_tracks_native_rk45(golden, case):
+    """north_star tolerance: 1e-6 relative against the reference's own adaptive integrator.  The
+    torque/force-input double pendulums are stiffer: there the gap is the error of the reference's
+    RK45 at its default rtol=1e-3, hence the looser bound."""
+    g = golden("steps")
+    p = oracle_problem(case, S=4)
+    r = oracle.rollout(p, g[case + "/x0"][None], U=g[case + "/U"][None])
+    tol = 1e-6 if case in ("cart_pole", "cart_pole_tv", "pendulum", "acrobot", "double_parallel", "cart_pole_force") else 1e-5
+    assert rel(r["X"][0], g[case + "/rk45/X"]) < tol
+
+
+@pytest.mark.parametrize("run", sorted(ILQR_RUNS))
+def test_ilqr_first_iteration_matches_reference(golden, run):
+    case, T, S, integ, kw = ILQR_RUNS[run]
+    g = golden(run)
+    p = oracle_problem(case, S=S, integrator=integ)
+    q = oracle.ilqr_params(parallel=kw.get("parallel", False), reg_type=kw.get("regType", 2))
+    r0 = oracle.rollout(p, g["x0"][None], T=T, add_final_cost=True)
+    assert rel(r0["X"][0], g["xx0"]) < 1e-10
+    assert abs(r0["cost"][0] - g["cost0"]) < 1e-10 * abs(g["cost0"])
+    KK, kk, s1, s2, gn, ok = oracle.ilqr_backward(p, q, g["xx0"], g["uu0"], 1e-6)
+    assert ok
+    assert rel(KK, g["bw_KK"]) < 1e-8
+    assert rel(kk, g["bw_kk"]) < 1e-8
+    assert rel([s1, s2], g["bw_sumV"]) < 1e-9
+    xo, uo, c, div, term = oracle.ilqr_forward(p, q, 1.0, g["x0"], g["xx0"], g["uu0"], g["bw_KK"], g["bw_kk"])
+    assert rel(xo, g["fw1_xx"]) < 1e-9
+    assert rel(uo, g["fw1_uu"]) < 1e-9
+    assert abs(c - g["fw1_cost"]) < 1e-9 * abs(g["fw1_cost"])
+
+
+@pytest.mark.parametrize("run", sorted(ILQR_RUNS))
+def test_ilqr_solve_matches_reference(golden, run):
+    """Whole run_optim: same iteration count, same per-iteration cost / mu trace, same result."""
+    case, T, S, integ, kw = ILQR_RUNS[run]
+    g = golden(run)
+    p = oracle_problem(case, S=S, integrator=integ)
+    q = oracle.ilqr_params(parallel=kw.get("parallel", False), reg_type=kw.get("regType", 2))
+    out = oracle.ilqr_solve(p, q, g["x0"][None], T, trace=True)
+    iters = int(g["iters"])
+    assert out["iters"][0] == iters
+    tr = out["trace"][0]
+    # golden trace rows: (cost, mu, alpha) at the START of each iteration; ours: after each iteration
+    ours_cost = np.concatenate([[out["cost0"][0]], tr[: iters - 1, 0]])
+    assert rel(ours_cost, g["trace"][:, 0]) < 1e-7
+    ours_mu = np.concatenate([[1e-6], tr[: iters - 1, 2]])
+    assert rel(ours_mu, g["trace"][:, 1]) < 1e-12
+    assert abs(out["cost"][0] - g["cost"]) < 1e-7 * abs(g["cost"])
+    assert rel(out["xx"][0], g["xx"]) < 1e-5
+    assert rel(out["uu"][0], g["uu"]) < 1e-5
+    if float(g["mu"]) <= 1e10:
+        assert rel(out["KK"][0], g["KK"]) < 1e-4
+        assert out["alpha"][0] == pytest.approx(float(g["alpha"]))
+    # else: the reference left through "mu > mu_max" on its last iteration -- a rounding-level
+    # knife edge at mu ~ 1e9 (dcost ~ 1e-12); costs and trajectories above still agree
