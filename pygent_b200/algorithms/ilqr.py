@@ -1,0 +1,362 @@
+"""Batched iLQR on the GPU behind pygent's `iLQR` API.
+
+Mirrors `pygent/algorithms/ilqr.py` (reference): constructor kwargs (:56-75), `init_trajectory`
+(:501-516), `forward_pass` (:187-231), `backward_pass` (:233-346), `run_optim` (:399-499),
+`linearization` (:518-533), `cost_lin` (:597-610), `run` (:348-351), `reset` (:164-171), `save`
+(:646-656).  Every trajectory of the environment's batch is optimised independently, all at once:
+
+    per iteration   K3 pg_ilqr_backward   one thread per trajectory
+                    K2 pg_ilqr_forward    one thread per (trajectory, alpha): all 11 alphas at once
+                    K4 pg_ilqr_select     the reference's serial (or `parallel=True`) line-search
+                                          bookkeeping, accept/reject, mu schedule, stopping tests
+                    K2' pg_ilqr_commit    re-run of the winning alpha -> new nominal trajectory
+
+Evaluating all alphas speculatively changes nothing: K4 replays the reference's control flow on the
+11 costs (first alpha with z > 0 stops a serial search; argmin over the alphas tried so far; dcost
+of the last alpha tried feeds the tolFun test -- SURVEY F7).  Trajectories stop individually
+(`status`), the loop ends when none is running.
+
+Single-plant environments return arrays shaped like the reference's (`xx [T+1,n]`, `uu [T,m]`,
+`KK [T,m,n]`, `kk [T,m,1]`); batched ones gain a leading B axis.
+"""
+import os
+import pickle
+import time
+
+import numpy as np
+import sympy as sp
+import torch
+
+from .. import lib, tracing
+from ..agents import FeedBack
+from .core import Algorithm
+
+
+class iLQR(Algorithm):
+    def __init__(self, environment, t, dt,
+                 maxIters=500,
+                 tolGrad=1e-4,
+                 tolFun=1e-7,
+                 fastForward=False,
+                 path=None,
+                 fcost=None,
+                 constrained=False,
+                 save_interval=10,
+                 printing=True,
+                 log_data=False,
+                 dataset_size=1e6,
+                 regType=2,
+                 finite_diff=False,
+                 file_prefix='',
+                 init=True,
+                 reset_mu=True,
+                 saving=True,
+                 parallel=False,
+                 final_backpass=False,
+                 check_every=4):
+        self.uDim = environment.uDim
+        self.xDim = environment.xDim
+        self.saving = path is not None
+        self.path = path
+        if self.saving:
+            for sub in ("", "plots/", "animations/", "data/", "c_files/"):
+                os.makedirs(path + sub, exist_ok=True)
+        self.fastForward = fastForward
+        batch = environment.batch if environment.batched else None
+        super(iLQR, self).__init__(environment, FeedBack(None, self.uDim, batch), t, dt)
+        self.xIsAngle = self.environment.xIsAngle
+        if finite_diff:
+            raise NotImplementedError("finite_diff=True (central-difference cost expansion, helpers.py:41-128) "
+                                      "is not on the GPU path yet; the analytic expansion is generated from the cost")
+        if final_backpass:
+            raise NotImplementedError("final_backpass (equilibrium + DARE terminal gain, ilqr.py:246-260, :487-494) "
+                                      "is not implemented; pass final_backpass=False")
+        self.finite_diff = finite_diff
+        self.final_backpass = final_backpass
+        # final cost expression: fcost(x) or fcost(x, mod) called on symbols (ilqr.py:119-125, :552)
+        xs = list(environment.system.xs)
+        if fcost is None:
+            # the reference's default, cost_fnc(x, 0, t, mod) = cost*dt, then scaled by dt again
+            c = environment.cost_expression()
+            zero_u = {u: 0 for u in environment.system.us}
+            self._fcost_expr = sp.sympify(c).subs(zero_u).subs(sp.Symbol("t"), t) * dt
+        else:
+            self._fcost_expr = tracing.trace(tracing.bind_fcost(fcost), xs, sp)
+        self.lib = environment.library(self._fcost_expr)
+        if not self.lib.info.has_cost_derivs:
+            raise ValueError("iLQR needs a running cost c(x, u[, t]) that does not depend on the next state "
+                             "(the reference evaluates it with x' = None, ilqr.py:183)")
+        self.integrator = lib.INTEG_EULER if fastForward else lib.INTEG_RK4
+        self.substeps = environment.substeps
+        self.lin_mode = 0 if self.lib.has_ab else 1
+        self.dtype = environment.dtype
+        self.B = environment.batch
+        self.batched = environment.batched
+        self.reset_mu = reset_mu
+        self.init = init
+        self.printing = printing
+        self.file_prefix = file_prefix
+        self.check_every = max(1, int(check_every))
+
+        # algorithm parameters (ilqr.py:141-162)
+        self.success_fw = False
+        self.max_iters = maxIters
+        self.mu_min = 1e-6
+        self.mu_max = 1e10
+        self.mu_d0 = 1.6
+        self.mu0 = 1.e-6
+        self.alphas = 10 ** np.linspace(0, -3, 11)
+        self.zmin = 0.
+        self.tolGrad = tolGrad
+        self.tolFun = tolFun
+        self.constrained = constrained
+        self.regType = regType
+        self.save_interval = save_interval
+        self.parallel = parallel
+        self.tt = np.arange(0, self.t, self.dt)
+        self.iterations = 0
+        self._alloc()
+        if init:
+            self.init_trajectory()
+
+    # -- device state -------------------------------------------------------------------------------
+    @property
+    def lims(self):
+        return np.asarray(self.environment.uMax, dtype=float)  # read at use: examples rescale env.uMax
+
+    def _alloc(self):
+        T, n, m, B = self.steps, self.xDim, self.uDim, self.B
+        dev, dt_ = self.environment.device, self.dtype
+        z = lambda *s: torch.zeros(s, dtype=dt_, device=dev)
+        self._xbar, self._ubar = z(T + 1, n, B), z(T, m, B)
+        self._KK, self._kk = z(T, m, n, B), z(T, m, B)            # accepted gains (self.KK / self.kk)
+        self._KKc, self._kkc = z(T, m, n, B), z(T, m, B)          # candidate gains of the current backward pass
+        self._x0 = self.environment._to_dev(self.environment._x0_host, n)
+        u8 = lambda *s: torch.zeros(s, dtype=torch.uint8, device=dev)
+        i32 = lambda *s: torch.zeros(s, dtype=torch.int32, device=dev)
+        self._st = {"cost": z(B), "mu": z(B) + self.mu0, "mu_d": z(B) + 1.0, "dcost": z(B),
+                    "success_gradient": u8(B), "status": i32(B), "iters": i32(B), "alpha_best": z(B) + 1.0,
+                    "accept": u8(B), "active": u8(B) + 1}
+        A = len(self.alphas)
+        self._bw = {"KK": self._KKc, "kk": self._kkc, "dV": z(2, B), "gnorm": z(B), "success": u8(B)}
+        self._fw = {"cost": z(A, B), "diverged": u8(A, B), "terminated": u8(A, B)}
+        self._n_active = i32(1)
+        self._have_gains = False
+
+    def _host(self, t, batch_axis_last=True):
+        a = t.detach().to("cpu", torch.float64).numpy()
+        a = np.moveaxis(a, -1, 0)  # [B, ...]
+        return a if self.batched else a[0]
+
+    # reference-shaped views ------------------------------------------------------------------------
+    @property
+    def xx(self):
+        return self._host(self._xbar)
+
+    @property
+    def uu(self):
+        return self._host(self._ubar)
+
+    @property
+    def KK(self):
+        return self._host(self._KK) if self._have_gains else []
+
+    @property
+    def kk(self):
+        return self._host(self._kk)[..., None] if self._have_gains else []
+
+    @property
+    def cost(self):
+        c = self._st["cost"].to("cpu", torch.float64).numpy()
+        return c if self.batched else float(c[0])
+
+    @property
+    def mu(self):
+        v = self._st["mu"].to("cpu", torch.float64).numpy()
+        return v if self.batched else float(v[0])
+
+    @property
+    def current_alpha(self):
+        v = self._st["alpha_best"].to("cpu", torch.float64).numpy()
+        return v if self.batched else float(v[0])
+
+    @property
+    def status(self):
+        v = self._st["status"].cpu().numpy()
+        return v if self.batched else int(v[0])
+
+    @property
+    def iters(self):
+        v = self._st["iters"].cpu().numpy()
+        return v if self.batched else int(v[0])
+
+    def _ulim(self):
+        return list(self.lims) if self.constrained else None
+
+    # -- the reference's methods ---------------------------------------------------------------------
+    def init_trajectory(self):
+        """Initial trajectory with u = 0 (ilqr.py:501-516): cost = sum c*dt + fcost(x_N)*dt."""
+        self._x0 = self.environment._to_dev(self.environment._x0_host, self.xDim)
+        self._ubar.zero_()
+        self.lib.rollout(self._x0, None, T=self.steps, S=self.substeps, dt=self.dt, integrator=self.integrator,
+                         terminal_cost=float(self.environment.terminal_cost), add_final_cost=True,
+                         out={"X": self._xbar, "cost": self._st["cost"]})
+        self.agent.reset()
+
+    def reset(self):
+        self._have_gains = False
+        self._KK.zero_()
+        self._kk.zero_()
+        self._st["mu"].fill_(self.mu0)
+        self._st["mu_d"].fill_(1.0)
+        self._st["status"].zero_()
+        self._st["iters"].zero_()
+        self._st["active"].fill_(1)
+        self._st["success_gradient"].zero_()
+        if self.init:
+            self.init_trajectory()
+
+    def cost_fnc(self, x, u, t, mod):
+        return self.environment.cost(x, u, None, t, mod) * self.dt
+
+    def _gains_to_dev(self, KK, kk):
+        T, n, m, B = self.steps, self.xDim, self.uDim, self.B
+        KK = np.asarray(KK, dtype=float).reshape((B, -1, m, n) if self.batched else (1, -1, m, n))
+        kk = np.asarray(kk, dtype=float).reshape((B, -1, m) if self.batched else (1, -1, m))
+        dev = self.environment.device
+        return (torch.as_tensor(np.ascontiguousarray(np.moveaxis(KK, 0, -1)), dtype=self.dtype, device=dev),
+                torch.as_tensor(np.ascontiguousarray(np.moveaxis(kk, 0, -1)), dtype=self.dtype, device=dev))
+
+    def forward_pass(self, alpha, KK, kk, optim=True):
+        """Closed-loop rollout for one alpha from environment.x0 (ilqr.py:187-231).
+        Returns xx, uu, cost, terminated (host arrays, reference shapes)."""
+        if len(KK) == 0:
+            raise ValueError("forward_pass needs gains (run backward_pass or run_optim first)")
+        KKd, kkd = (KK, kk) if torch.is_tensor(KK) else self._gains_to_dev(KK, kk)
+        r = self.lib.ilqr_forward(self._x0, self._xbar, self._ubar, KKd, kkd, alphas=[float(alpha)], S=self.substeps,
+                                  dt=self.dt, integrator=self.integrator, ulim=self._ulim(),
+                                  terminal_cost=float(self.environment.terminal_cost), want_traj=True)
+        xx, uu = self._host(r["X"][0]), self._host(r["U"][0])
+        cost = r["cost"][0].to("cpu", torch.float64).numpy()
+        term = r["terminated"][0].cpu().numpy().astype(bool)
+        self.agent.set_history(uu)
+        return (xx, uu, cost, term) if self.batched else (xx, uu, float(cost[0]), bool(term[0]))
+
+    def backward_pass(self, final=False):
+        """Riccati sweep along (xx, uu) (ilqr.py:233-346).  Returns V1, V2, success, KK, kk where V1, V2
+        are the SUMS of the reference's per-step lists (only their sums are ever used, ilqr.py:442)."""
+        if final:
+            raise NotImplementedError("final backward pass (DARE terminal value) is not implemented")
+        r = self.lib.ilqr_backward(self._xbar, self._ubar, self._st["mu"], dt=self.dt, reg_type=self.regType,
+                                   lin_mode=self.lin_mode, ulim=self._ulim(), out=self._bw)
+        dV = r["dV"].to("cpu", torch.float64).numpy()
+        ok = r["success"].cpu().numpy().astype(bool)
+        KK, kk = self._host(r["KK"]), self._host(r["kk"])[..., None]
+        if self.batched:
+            return dV[0], dV[1], ok, KK, kk
+        return float(dV[0, 0]), float(dV[1, 0]), bool(ok[0]), KK, kk
+
+    def linearization(self, x, u):
+        """Ad = I + A dt, Bd = B dt, fd = 0 (ilqr.py:518-533) at one point or a batch of points."""
+        x, u = np.atleast_2d(np.asarray(x, dtype=float)), np.atleast_2d(np.asarray(u, dtype=float))
+        dev = self.environment.device
+        xd = torch.as_tensor(x.T.copy(), dtype=self.dtype, device=dev)
+        ud = torch.as_tensor(u.T.copy(), dtype=self.dtype, device=dev)
+        r = self.lib.eval(xd, ud, lin_mode=self.lin_mode, what=("A", "B"))
+        A = np.moveaxis(r["A"].to("cpu", torch.float64).numpy(), -1, 0)
+        Bm = np.moveaxis(r["B"].to("cpu", torch.float64).numpy(), -1, 0)
+        Ad = A * self.dt + np.eye(self.xDim)
+        Bd = Bm * self.dt
+        fd = np.zeros((len(x), self.xDim, 1))
+        return (Ad[0], Bd[0], fd[0]) if len(x) == 1 else (Ad, Bd, fd)
+
+    def cost_lin(self, x, u, t):
+        """Second-order expansion of c*dt: Cxx, Cuu, Cxu, cx, cu (ilqr.py:597-610)."""
+        x, u = np.atleast_2d(np.asarray(x, dtype=float)), np.atleast_2d(np.asarray(u, dtype=float))
+        dev = self.environment.device
+        xd = torch.as_tensor(x.T.copy(), dtype=self.dtype, device=dev)
+        ud = torch.as_tensor(u.T.copy(), dtype=self.dtype, device=dev)
+        td = torch.as_tensor(np.broadcast_to(np.asarray(t, dtype=float), (len(x),)).copy(), dtype=self.dtype, device=dev)
+        r = self.lib.eval(xd, ud, td, what=("cx", "cu", "Cxx", "Cuu", "Cxu"))
+        g = lambda k: np.moveaxis(r[k].to("cpu", torch.float64).numpy(), -1, 0) * self.dt
+        out = (g("Cxx"), g("Cuu"), g("Cxu"), g("cx")[..., None], g("cu")[..., None])
+        return tuple(o[0] for o in out) if len(x) == 1 else out
+
+    def _select_params(self):
+        p = lib.SelectParams()
+        p.n_alpha, p.parallel, p.max_iters = len(self.alphas), int(self.parallel), int(self.max_iters)
+        for i, a in enumerate(self.alphas):
+            p.alphas[i] = float(a)
+        p.zmin, p.tol_fun, p.tol_grad = self.zmin, self.tolFun, self.tolGrad
+        p.mu_min, p.mu_max, p.mu_d0 = self.mu_min, self.mu_max, self.mu_d0
+        return p
+
+    def iterate(self):
+        """One loop body of run_optim (ilqr.py:407-485) for every running trajectory: 4 launches, no sync."""
+        st = self._st
+        L = self.lib
+        L.ilqr_backward(self._xbar, self._ubar, st["mu"], dt=self.dt, reg_type=self.regType, lin_mode=self.lin_mode,
+                        ulim=self._ulim(), active=st["active"], out=self._bw)
+        L.ilqr_forward(self._x0, self._xbar, self._ubar, self._KKc, self._kkc, alphas=self.alphas, S=self.substeps,
+                       dt=self.dt, integrator=self.integrator, ulim=self._ulim(),
+                       terminal_cost=float(self.environment.terminal_cost), active=st["active"], out=self._fw)
+        self._n_active.zero_()
+        L.ilqr_select(self._sel, self._fw["cost"], self._fw["diverged"], self._bw["dV"], self._bw["gnorm"],
+                      self._bw["success"], st, self._n_active)
+        L.ilqr_commit(self._x0, self._xbar, self._ubar, self._KKc, self._kkc, self._KK, self._kk, st["alpha_best"],
+                      st["accept"], S=self.substeps, dt=self.dt, integrator=self.integrator, ulim=self._ulim())
+        self._have_gains = True
+
+    def run_optim(self):
+        """Trajectory optimisation (ilqr.py:399-499).  Returns (xx, uu, cost)."""
+        start_time = time.time()
+        st = self._st
+        if self.reset_mu:
+            st["mu"].fill_(self.mu0)
+            st["mu_d"].fill_(1.0)
+        # a new call re-arms every trajectory: `for _ in range(1, max_iters + 1)` starts over
+        st["status"].zero_()
+        st["iters"].zero_()
+        st["active"].fill_(1)
+        st["success_gradient"].zero_()
+        self._sel = self._select_params()
+        it = 0
+        while it < self.max_iters:
+            self.iterate()
+            it += 1
+            if it % self.check_every == 0 or it == self.max_iters:
+                if int(self._n_active.item()) == 0:  # the only host<->device sync of the loop
+                    break
+        self.iterations = int(st["iters"].max().item())
+        xx, uu = self.xx, self.uu
+        self.agent.set_history(uu)
+        if self.printing:
+            stat = np.atleast_1d(self.status)
+            print('Iterations: %d | Final Cost-to-Go: %.2f | Runtime: %.2f min. | %s'
+                  % (self.iterations, float(np.mean(self.cost)), (time.time() - start_time) / 60,
+                     ", ".join("%s: %d" % (lib.STATUS_NAMES[s], int((stat == s).sum())) for s in sorted(set(stat.tolist())))))
+        if self.saving:
+            self.save()
+        return xx, uu, self.cost
+
+    def run(self, x0):
+        """Apply the stored time-varying controller from x0 (ilqr.py:348-351)."""
+        self.environment.reset(x0)
+        self._x0 = self.environment._to_dev(self.environment._x0_host, self.xDim)
+        r = self.lib.ilqr_forward(self._x0, self._xbar, self._ubar, self._KK, self._kk, alphas=[1.0], S=self.substeps,
+                                  dt=self.dt, integrator=self.integrator, ulim=self._ulim(),
+                                  terminal_cost=float(self.environment.terminal_cost), want_traj=True)
+        self._xbar.copy_(r["X"][0])
+        self._ubar.copy_(r["U"][0])
+        self._st["cost"].copy_(r["cost"][0])
+
+    def save(self):
+        """Controller on disk in the reference's format (ilqr.py:646-656)."""
+        d = self.path + 'data/'
+        np.save(d + 'K_', self.KK)
+        np.save(d + 'k', self.kk)
+        np.save(d + 'uu', self.uu)
+        np.save(d + 'xx', self.xx)
+        np.save(d + 'alpha', self.current_alpha)
+        with open(d + 'time_info.p', 'wb') as fh:
+            pickle.dump(list(np.arange(0, self.steps + 1) * self.dt), fh)

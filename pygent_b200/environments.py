@@ -144,10 +144,6 @@ class StateSpaceModel(Environment):
         if self.system.n != self.xDim or self.system.m != uDim:
             raise ValueError("system %s has n=%d, m=%d but x0/uDim give n=%d, m=%d"
                              % (self.system.name, self.system.n, self.system.m, self.xDim, uDim))
-        f_np, A_np, B_np = self.system.numpy_callables()
-        self.ode = f_np
-        if self.system.has_AB:  # like the reference, only systems with symbolic Jacobians expose A, B
-            self.A, self.B = A_np, B_np
         self._user_cost = cost
         self.cost = tracing.bind_cost(cost)
         self.terminal_cost = terminal_cost
@@ -156,6 +152,17 @@ class StateSpaceModel(Environment):
         self.oDim = self.xDim
         self._problems = {}
         self._cost_expr = None
+
+    def __getattr__(self, name):
+        # numpy callables `ode(t, x, u)`, `A(x, u)`, `B(x, u)` of the reference API, lambdified on first use;
+        # like the reference, only systems with symbolic Jacobians expose A and B (ilqr.py:523)
+        if name in ("ode", "A", "B") and "system" in self.__dict__:
+            f_np, A_np, B_np = self.system.numpy_callables()
+            if name == "ode":
+                return f_np
+            if self.system.has_AB:
+                return A_np if name == "A" else B_np
+        raise AttributeError(name)
 
     # -- problem compilation ----------------------------------------------------------------------
     def _term_limits(self):

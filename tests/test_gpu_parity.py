@@ -1,0 +1,329 @@
+"""CUDA path vs the oracle and vs the reference's golden outputs.  Everything here goes through the
+C ABI of the compiled problem libraries (pygent_b200/lib.py -> include/pygent_b200.h)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from cases import CASES, ILQR_RUNS, oracle_problem
+from pygent_b200 import lib as pglib
+from pygent_b200.examples import make_env, make_ilqr
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return float(np.max(np.abs(a - b) / (np.abs(b) + 1.0))) if a.size else 0.0
+
+
+def dev(a, dtype=torch.float64):
+    """host [B, ...] -> device [..., B]"""
+    return torch.as_tensor(np.ascontiguousarray(np.moveaxis(np.asarray(a, dtype=float), 0, -1)), dtype=dtype, device="cuda")
+
+
+def dev_U(U, dtype=torch.float64):
+    """host [B, T, m] -> device [T, m, B]"""
+    return torch.as_tensor(np.ascontiguousarray(np.asarray(U, dtype=float).transpose(1, 2, 0)), dtype=dtype, device="cuda")
+
+
+def host(t):
+    """device [..., B] -> host [B, ...]"""
+    return np.moveaxis(t.detach().to("cpu", torch.float64).numpy(), -1, 0)
+
+
+def solver(case, T, x0=None, **kw):
+    return make_ilqr(case, T, x0=x0, **kw)
+
+
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_generated_functions_match_oracle(case):
+    """f, A, B and the cost expansion of the generated device code at random points."""
+    alg = solver(case, 10)
+    L = alg.lib
+    n, m = L.n, L.m
+    rng = np.random.default_rng(1)
+    P = 257
+    xs, us, ts = rng.uniform(-2.5, 2.5, (P, n)), rng.uniform(-3, 3, (P, m)), rng.uniform(0, 2, P)
+    if case == "triple":
+        xs[:, 4:] *= 0.3
+    r = L.eval(dev(xs), dev(us), torch.as_tensor(ts, device="cuda"))
+    system = CASES[case][2]
+    f = np.array([oracle.f(system, x, u) for x, u in zip(xs, us)])
+    assert rel(host(r["f"]), f) < 1e-11
+    AB = [oracle.AB(system, x, u, fd=not L.has_ab) for x, u in zip(xs, us)]
+    assert rel(host(r["A"]), np.array([a for a, _ in AB])) < 1e-9
+    assert rel(host(r["B"]), np.array([b for _, b in AB])) < 1e-9
+    cp = CASES[case][3]()[2]
+    qx, qf = np.array(cp["qx"]), np.array(cp["qf"])
+    ru = np.array(cp["ru"])[None] + np.array(cp.get("re", [0.0] * m))[None] * np.exp(-cp.get("rd", 0.0) * ts)[:, None]
+    assert rel(host(r["c"]), (qx * xs ** 2).sum(1) + (ru * us ** 2).sum(1)) < 1e-12
+    assert rel(host(r["cx"]), 2 * qx * xs) < 1e-12
+    assert rel(host(r["cu"]), 2 * ru * us) < 1e-12
+    assert rel(host(r["Cxx"]), np.broadcast_to(np.diag(2 * qx), (P, n, n))) < 1e-12
+    assert rel(host(r["Cuu"])[:, 0, 0], 2 * ru[:, 0]) < 1e-12
+    assert rel(host(r["Cxu"]), 0) == 0
+    assert rel(host(r["cf"]), (qf * xs ** 2).sum(1)) < 1e-12
+    assert rel(host(r["cfx"]), 2 * qf * xs) < 1e-12
+    assert rel(host(r["Cfxx"]), np.broadcast_to(np.diag(2 * qf), (P, n, n))) < 1e-12
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+@pytest.mark.parametrize("S,integ", [(1, 0), (4, 0), (1, 1)])
+def test_rollout_matches_oracle(case, S, integ):
+    alg = solver(case, 10)
+    L = alg.lib
+    n, m = L.n, L.m
+    rng = np.random.default_rng(2)
+    B, T = 96, 60
+    x0 = np.array(CASES[case][4]) + rng.uniform(-0.2, 0.2, (B, n))
+    umax = float(np.ravel(alg.environment.uMax)[0])
+    U = rng.uniform(-umax, umax, (B, T, m)) * 0.5
+    dt = CASES[case][5]
+    r = L.rollout(dev(x0), dev_U(U), S=S, dt=dt, integrator=integ, history=True, add_final_cost=True)
+    p = oracle_problem(case, S=S, integrator=integ)
+    ro = oracle.rollout(p, x0, U=U, add_final_cost=True)
+    X = np.moveaxis(r["X"].cpu().numpy(), -1, 0)  # [B, T+1, n]
+    assert rel(X, ro["X"]) < 1e-9
+    assert rel(host(r["xN"]), ro["xN"]) < 1e-9
+    assert rel(r["cost"].cpu().numpy(), ro["cost"]) < 1e-9
+    assert np.array_equal(r["terminated"].cpu().numpy(), ro["terminated"])
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_rollout_matches_reference_golden(golden, case):
+    """Same inputs as the unmodified reference: RK4x4 (1e-10), RK4x1, Euler, and native RK45 (1e-6)."""
+    g = golden("steps")
+    alg = solver(case, 10)
+    L = alg.lib
+    dt = CASES[case][5]
+    x0 = dev(g[case + "/x0"][None])
+    U = torch.as_tensor(np.ascontiguousarray(g[case + "/U"][:, :, None]), device="cuda")
+    for tag, S, integ, tol in (("rk4x4", 4, 0, 1e-10), ("rk4x1", 1, 0, 1e-10), ("euler", 1, 1, 1e-10), ("rk45", 4, 0, None)):
+        r = L.rollout(x0, U, S=S, dt=dt, integrator=integ, history=True)
+        X = r["X"].cpu().numpy()[:, :, 0]
+        if tol is None:
+            tol = 1e-6 if case in ("cart_pole", "cart_pole_tv", "pendulum", "acrobot", "double_parallel", "cart_pole_force") else 1e-5
+        assert rel(X, g["%s/%s/X" % (case, tag)]) < tol, tag
+        if tag != "rk45":
+            c = g["%s/%s/c" % (case, tag)].sum()
+            assert abs(r["cost"].item() - c) < 1e-10 * (abs(c) + 1)
+
+
+def test_rollout_edge_cases():
+    alg = solver("cart_pole", 10)
+    L = alg.lib
+    # empty batch and zero-length horizon
+    r = L.rollout(torch.zeros((4, 0), dtype=torch.float64, device="cuda"), T=5, S=4, dt=0.02)
+    assert r["xN"].shape == (4, 0)
+    x0 = dev(np.array([[0.1, 3.0, 0.0, 0.2]] * 3))
+    r = L.rollout(x0, T=0, S=4, dt=0.02, history=True)
+    assert torch.equal(r["xN"], x0) and torch.equal(r["X"][0], x0) and float(r["cost"].abs().max()) == 0.0
+    # ragged batch (not a multiple of the CTA size) and u == 0 when U is NULL
+    B = 131
+    rng = np.random.default_rng(3)
+    xs = np.array([0, np.pi, 0, 0]) + rng.uniform(-0.1, 0.1, (B, 4))
+    r1 = L.rollout(dev(xs), T=20, S=4, dt=0.02)
+    r2 = L.rollout(dev(xs), torch.zeros((20, 1, B), dtype=torch.float64, device="cuda"), S=4, dt=0.02)
+    assert torch.equal(r1["xN"], r2["xN"]) and torch.equal(r1["cost"], r2["cost"])
+    # termination box and terminal cost
+    xs = np.array([[1.19, np.pi, 3.0, 0.0], [0.0, np.pi, 0.0, 0.0]])
+    r = L.rollout(dev(xs), T=3, S=4, dt=0.02, terminal_cost=7.0)
+    r0 = L.rollout(dev(xs), T=3, S=4, dt=0.02, terminal_cost=0.0)
+    assert r["terminated"].cpu().tolist() == [1, 0]
+    extra = (r["cost"] - r0["cost"]).cpu().numpy()
+    assert extra[1] == 0 and extra[0] == pytest.approx(7.0 * 0.02 * 3, rel=1e-12)
+    # wrong device / dtype / shape fail loudly
+    with pytest.raises(pglib.PygentB200Error):
+        L.rollout(torch.zeros((4, 2), dtype=torch.float64), T=1)
+    with pytest.raises(pglib.PygentB200Error):
+        L.rollout(torch.zeros((5, 2), dtype=torch.float64, device="cuda"), T=1)
+    with pytest.raises(TypeError):
+        L.rollout(torch.zeros((4, 2), dtype=torch.float16, device="cuda"), T=1)
+
+
+@pytest.mark.parametrize("run", sorted(ILQR_RUNS))
+def test_ilqr_backward_and_forward_match_golden(golden, run):
+    """First backward pass (K, k, sum V1, sum V2) and the alpha = 1 forward pass of the reference."""
+    case, T, S, integ, kw = ILQR_RUNS[run]
+    g = golden(run)
+    alg = solver(case, T, x0=g["x0"], env_kw={"substeps": S}, fastForward=bool(integ), regType=kw.get("regType", 2))
+    assert rel(alg.xx, g["xx0"]) < 1e-10
+    assert alg.cost == pytest.approx(float(g["cost0"]), rel=1e-11)
+    V1, V2, ok, KK, kk = alg.backward_pass()
+    assert ok
+    assert rel(KK, g["bw_KK"]) < 1e-8
+    assert rel(kk[..., 0], g["bw_kk"]) < 1e-8
+    assert rel([V1, V2], g["bw_sumV"]) < 1e-9
+    xx, uu, cost, term = alg.forward_pass(1.0, g["bw_KK"], g["bw_kk"])
+    assert rel(xx, g["fw1_xx"]) < 1e-9
+    assert rel(uu, g["fw1_uu"]) < 1e-9
+    assert cost == pytest.approx(float(g["fw1_cost"]), rel=1e-9)
+
+
+@pytest.mark.parametrize("run", sorted(ILQR_RUNS))
+def test_ilqr_solve_matches_reference(golden, run):
+    """Whole run_optim of the unmodified reference: iteration count, final cost, trajectory, gains."""
+    case, T, S, integ, kw = ILQR_RUNS[run]
+    g = golden(run)
+    alg = solver(case, T, x0=g["x0"], env_kw={"substeps": S}, fastForward=bool(integ), regType=kw.get("regType", 2),
+                 parallel=kw.get("parallel", False))
+    xx, uu, cost = alg.run_optim()
+    assert alg.iters == int(g["iters"])
+    assert cost == pytest.approx(float(g["cost"]), rel=1e-7)
+    assert rel(xx, g["xx"]) < 1e-5
+    assert rel(uu, g["uu"]) < 1e-5
+    if float(g["mu"]) <= 1e10:
+        assert rel(alg.KK, g["KK"]) < 1e-4
+        assert alg.current_alpha == pytest.approx(float(g["alpha"]))
+        assert alg.mu == pytest.approx(float(g["mu"]), rel=1e-9)
+
+
+@pytest.mark.parametrize("case,T,parallel,constrained", [
+    ("cart_pole", 100, False, False), ("cart_pole", 100, True, False), ("cart_pole", 60, False, True),
+    ("acrobot", 80, True, False), ("double_parallel", 100, True, False), ("double_serial", 60, False, False),
+    ("pendulum", 60, False, True), ("cart_pole_tv", 100, False, False)])
+def test_ilqr_batch_matches_oracle(case, T, parallel, constrained):
+    """A batch of random initial states: every trajectory must take the oracle's path (same number of
+    iterations, same stopping reason, same accepted alpha) and land on the same optimum."""
+    rng = np.random.default_rng(5)
+    n = len(CASES[case][4])
+    B = 48
+    x0 = np.array(CASES[case][4]) + rng.uniform(-0.3, 0.3, (B, n))
+    alg = solver(case, T, x0=x0, parallel=parallel, constrained=constrained, maxIters=150)
+    alg.run_optim()
+    p = oracle_problem(case, S=4)
+    q = oracle.ilqr_params(max_iters=150, parallel=parallel, constrained=constrained, lims=list(alg.lims))
+    so = oracle.ilqr_solve(p, q, x0, T, nthreads=8)
+    # chaotic swing-ups can amplify rounding differences into a different line-search decision; require the
+    # overwhelming majority to follow the identical path and all to reach an equally good optimum
+    same = (alg.iters == so["iters"]) & (alg.status == so["status"])
+    assert same.mean() >= 0.9, (alg.iters, so["iters"])
+    assert rel(alg.cost[same], so["cost"][same]) < 1e-6
+    assert rel(alg.xx[same], so["xx"][same]) < 1e-4
+    assert rel(alg.mu[same], so["mu"][same]) < 1e-9
+    assert np.all(alg.cost <= so["cost0"] * (1 + 1e-12))
+
+
+def test_ilqr_per_trajectory_control_flow():
+    """Trajectories that stop early must not be touched again, and a sharded batch must give exactly the
+    bits of the full batch (pure data parallelism)."""
+    rng = np.random.default_rng(6)
+    B, T = 40, 60
+    x0 = np.array([0, np.pi, 0, 0]) + rng.uniform(-0.3, 0.3, (B, 4))
+    x0[3] = [0, 0, 0, 0]  # already at the optimum: no alpha improves, mu runs away within a few iterations
+    full = solver("cart_pole", T, x0=x0, maxIters=60)
+    full.run_optim()
+    assert full.status[3] == pglib.ST_MU_MAX and full.iters[3] < full.iters.max()
+    parts = []
+    for sl in (slice(0, 17), slice(17, 40)):
+        part = solver("cart_pole", T, x0=x0[sl], maxIters=60)
+        part.run_optim()
+        parts.append(part)
+    for name in ("xx", "uu", "KK", "cost", "mu", "iters", "status"):
+        assert np.array_equal(getattr(full, name), np.concatenate([getattr(p, name) for p in parts])), name
+
+
+@pytest.mark.parametrize("case", ["cart_pole", "acrobot", "double_parallel"])
+def test_fp32_rollout_within_stated_tolerance(case):
+    """fp32 instantiation of the same kernels: 5e-3 relative on states over 100 control intervals, stated
+    (north_star asks for a stated looser tolerance; measured values are recorded in DESIGN.md)."""
+    rng = np.random.default_rng(7)
+    n = len(CASES[case][4])
+    B, T = 256, 100
+    x0 = np.array(CASES[case][4]) + rng.uniform(-0.05, 0.05, (B, n))
+    alg = solver(case, 10)
+    umax = float(np.ravel(alg.environment.uMax)[0])
+    U = rng.uniform(-umax, umax, (B, T, 1)) * 0.2
+    dt = CASES[case][5]
+    r64 = alg.lib.rollout(dev(x0), dev_U(U), S=4, dt=dt, history=True)
+    r32 = alg.lib.rollout(dev(x0, torch.float32), dev_U(U, torch.float32), S=4, dt=dt, history=True)
+    err = rel(r32["X"].double().cpu().numpy(), r64["X"].cpu().numpy())
+    assert err < 5e-3, err
+    assert rel(r32["cost"].double().cpu().numpy(), r64["cost"].cpu().numpy()) < 5e-3
+
+
+def test_observation_kernel():
+    env = make_env("cart_pole")
+    L = env.library()
+    rng = np.random.default_rng(8)
+    xs = rng.uniform(-4, 4, (33, 4))
+    o = host(L.observe(dev(xs)))
+    want = np.stack([xs[:, 0], np.cos(xs[:, 1]), np.sin(xs[:, 1]), xs[:, 2], xs[:, 3]], axis=1)
+    assert rel(o, want) < 1e-15
+    assert rel(env.observe(xs), want) < 1e-15
+
+
+# ---- properties at the benchmark's full size (BASELINE.json config 2) ---------------------------------
+def test_full_size_rollout_properties():
+    """65,536 envs x 500 steps: determinism, batch-permutation equivariance, horizon composition and
+    history on/off -- all bit-exact -- plus an oracle check on a random subset."""
+    B, T = 65536, 500
+    alg = solver("cart_pole", 10)
+    L = alg.lib
+    gen = torch.Generator(device="cpu").manual_seed(0)
+    x0 = torch.zeros((4, B), dtype=torch.float64)
+    x0[0] = (torch.rand(B, generator=gen, dtype=torch.float64) - 0.5) * 0.1
+    x0[1] = np.pi + (torch.rand(B, generator=gen, dtype=torch.float64) - 0.5) * 0.1
+    U = (torch.rand((T, 1, B), generator=gen, dtype=torch.float64) * 2 - 1) * 10.0
+    x0d, Ud = x0.cuda(), U.cuda()
+    r = L.rollout(x0d, Ud, S=4, dt=0.02)
+    r2 = L.rollout(x0d, Ud, S=4, dt=0.02)
+    assert torch.equal(r["xN"], r2["xN"]) and torch.equal(r["cost"], r2["cost"])
+    perm = torch.randperm(B, generator=gen).cuda()
+    rp = L.rollout(x0d[:, perm].contiguous(), Ud[:, :, perm].contiguous(), S=4, dt=0.02)
+    assert torch.equal(rp["xN"], r["xN"][:, perm]) and torch.equal(rp["cost"], r["cost"][perm])
+    ra = L.rollout(x0d, Ud[:250].contiguous(), S=4, dt=0.02)
+    rb = L.rollout(ra["xN"], Ud[250:].contiguous(), S=4, dt=0.02, t0=float(np.sum(np.full(250, 0.02))))
+    assert torch.equal(rb["xN"], r["xN"])
+    assert float(((ra["cost"] + rb["cost"]) - r["cost"]).abs().max()) < 1e-9 * float(r["cost"].abs().max())
+    rh = L.rollout(x0d[:, :4096].contiguous(), Ud[:, :, :4096].contiguous(), S=4, dt=0.02, history=True)
+    assert torch.equal(rh["xN"], r["xN"][:, :4096]) and torch.equal(rh["X"][-1], rh["xN"])
+    idx = np.random.default_rng(9).choice(B, 64, replace=False)
+    p = oracle_problem("cart_pole", S=4)
+    ro = oracle.rollout(p, x0.numpy().T[idx], U=U.numpy()[:, :, idx].transpose(2, 0, 1), nthreads=8)
+    assert rel(host(r["xN"])[idx], ro["xN"]) < 1e-8
+    assert rel(r["cost"].cpu().numpy()[idx], ro["cost"]) < 1e-9
+
+
+# ---- the reference-facing Python API -----------------------------------------------------------------
+def test_environment_api_single_plant():
+    """One plant, stepped like the reference's examples: shapes, history, tt, costs."""
+    g = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "steps.npz"))
+    env = make_env("cart_pole", x0=g["cart_pole/x0"])
+    assert env.xDim == 4 and env.uDim == 1 and env.oDim == 5
+    U = g["cart_pole/U"]
+    costs = [env.step(U[k]) for k in range(10)]
+    assert isinstance(costs[0], float) and np.shape(env.x) == (4,)
+    assert env.history.shape == (11, 4) and len(env.tt) == 11
+    assert rel(env.history, g["cart_pole/rk4x4/X"][:11]) < 1e-10
+    assert rel(costs, g["cart_pole/rk4x4/c"][:10]) < 1e-10
+    assert rel(env.x_, g["cart_pole/rk4x4/X"][9]) < 1e-10
+    assert np.shape(env.o) == (5,) and env.terminated in (False, True)
+    env.reset(g["cart_pole/x0"])
+    env.rollout(U[:10])
+    assert rel(env.history, g["cart_pole/rk4x4/X"][:11]) < 1e-10
+    # numpy callables of the reference API
+    assert rel(env.ode(0, [0.1, 0.7, -0.3, 1.1], [2.5]), [-0.3, 1.1, 2.5, 12.096269276790501]) < 1e-14
+    assert env.A([0.1, 0.7, -0.3, 1.1], [2.5])[3, 1] == pytest.approx(8.708529569078923, rel=1e-13)
+    assert env.B([0.1, 0.7, -0.3, 1.1], [2.5])[3, 0] == pytest.approx(1.1303497074638655, rel=1e-13)
+
+
+def test_environment_api_batched_and_user_ode():
+    rng = np.random.default_rng(10)
+    x0 = np.array([np.pi, 0]) + rng.uniform(-0.1, 0.1, (7, 2))
+    env = make_env("pendulum", x0=x0)
+    U = rng.uniform(-3, 3, (7, 12, 1))
+    cs = np.array([env.step(U[:, k]) for k in range(12)])
+    assert cs.shape == (12, 7) and env.history.shape == (7, 13, 2)
+    p = oracle_problem("pendulum", S=4)
+    ro = oracle.rollout(p, x0, U=U)
+    assert rel(env.history, ro["X"]) < 1e-10
+    assert rel(cs.sum(0), ro["cost"]) < 1e-10
+    assert not hasattr(env, "A")
+    # a user-defined StateSpaceModel with numpy ufuncs in its ODE (like the reference's Pendulum.ode)
+    from pygent_b200.examples import user_ode_env
+    env2 = user_ode_env(x0)
+    env2.rollout(U)
+    assert rel(env2.history, ro["X"]) < 1e-10
