@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: batched cart-pole RK4 rollouts (BASELINE.json config 2) + batched iLQR.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the rollout kernel over the whole batch: 65,536 environments x 500 control
+intervals x 4 RK4 substeps per GPU, random actions, fp64 (workload is per GPU: weak scaling; ranks share
+nothing on the data path).  Prints ONE JSON line (rank 0):
+  value      env-steps/s over all GPUs with inputs resident in HBM (CUDA events, max over ranks)
+  e2e        the same through the public API (`env.rollout`) from pinned HOST buffers: H2D of x0 and U,
+             kernel, D2H of the per-environment cost and final state, all inside the timed region
+  roofline   FP64 FMA pipe: algorithmic flops per launch / mean launch duration vs the DFMA peak measured
+             on this pool's B200 (profiles/fp_peak_b200.json), plus the HBM view of the same launch
+  cpu_baseline  the CPU oracle (C port of the reference's step loop) on a bounded sample, all host threads
+  ilqr       iLQR iterations/s on 16,384 cart-pole swing-ups per GPU (BASELINE.json config 3), to convergence
+`--impl reference` times the reference's algorithm on the host cores (the C oracle port -- the reference
+itself is pure Python and does not travel to the GPU box) on the same config/metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_ENVS, T_STEPS, SUBSTEPS, DT, U_MAX = 65536, 500, 4, 0.02, 10.0
+FLOPS_PER_SUBSTEP = 228   # 4 f-evals (8 arith + 36 sincos) + 13n combine, n = 4, fp64
+FLOPS_COST = 14           # quadratic running cost per control interval
+ILQR_B, ILQR_T = 16384, 100
+CONFIG = {"workload": "batched cart-pole RK4 rollouts, 65,536 envs x 500 steps per GPU, random actions "
+                      "(BASELINE.json configs[1])",
+          "system": "CartPole(linearized=True)", "envs_per_gpu": B_ENVS, "horizon": T_STEPS, "substeps": SUBSTEPS,
+          "dt": DT, "integrator": "RK4", "cost": "examples/nmpc/cart_pole.py c_k",
+          "l2_policy": "inputs larger than L2: U is 262 MB per GPU and is re-read from HBM every step"}
+
+
+def algorithmic_flops_per_launch():
+    return B_ENVS * T_STEPS * (SUBSTEPS * FLOPS_PER_SUBSTEP + FLOPS_COST)
+
+
+def synthetic_inputs(seed, B=B_ENVS, T=T_STEPS):
+    """x0 = [U(-.05,.05), pi+U(-.05,.05), 0, 0], u ~ U(-uMax, uMax); host, kernel layout."""
+    import torch
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    x0 = torch.zeros((4, B), dtype=torch.float64)
+    x0[0] = (torch.rand(B, generator=gen, dtype=torch.float64) - 0.5) * 0.1
+    x0[1] = np.pi + (torch.rand(B, generator=gen, dtype=torch.float64) - 0.5) * 0.1
+    U = (torch.rand((T, 1, B), generator=gen, dtype=torch.float64) * 2 - 1) * U_MAX
+    return x0, U
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [c.strip() for c in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s in sm if s > 0.5 * max(mx)] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def fp64_peak():
+    p = os.path.join(ROOT, "profiles", "fp_peak_b200.json")
+    if os.path.isfile(p):
+        with open(p) as fh:
+            return float(json.load(fh)["fp64_fma_tflops"]), "measured DFMA microbenchmark on this pool's B200 (profiles/fp_peak_b200.json, tools/fp_peak.cu)"
+    return 37.2, "nominal 148 SM x 64 lanes x 2 x 1.965 GHz (no measurement committed)"
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_rollout_baseline(n_envs, threads, seed=0):
+    """The oracle's step loop (RK4 x 4) on the first `n_envs` environments of the workload."""
+    import oracle
+    from pygent_b200.examples import CASES
+    _, _, cp = CASES["cart_pole"][3]()
+    p = oracle.make_problem("cart_pole_lin", DT, S=SUBSTEPS, term_lim=[1.2, 0, 4.0, 0], **cp)
+    x0, U = synthetic_inputs(seed, B=n_envs)
+    x0h = np.ascontiguousarray(x0.numpy().T)
+    Uh = np.ascontiguousarray(U.numpy().transpose(2, 0, 1))
+    t0 = time.perf_counter()
+    oracle.rollout(p, x0h, U=Uh, history=False, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return n_envs * T_STEPS / dt, dt
+
+
+def run_reference(args, rank):
+    """Reference arm: the reference's algorithm on the host cores (oracle port), same metric and config."""
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    threads = os.cpu_count() or 1
+    n = 8192
+    for _ in range(args.warmup):
+        cpu_rollout_baseline(n, threads)
+    el = 0.0
+    for _ in range(args.steps):
+        el += cpu_rollout_baseline(n, threads)[1]
+    value = n * T_STEPS * args.steps / el
+    sample = "%d of the 65,536 envs x 500 steps per step (RK4 x 4), OpenMP over all host threads" % n
+    print(json.dumps({
+        "impl": "reference", "metric": "rk4_env_steps_per_s", "value": value, "unit": "env-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": CONFIG,
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-ilqr", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pygent_b200 import lib as pglib
+    from pygent_b200.examples import make_ilqr
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # the public objects a user would build: a batched CartPole and its iLQR (the compiled library is shared)
+    x0_h, U_h = synthetic_inputs(seed=rank)
+    alg = make_ilqr("cart_pole", ILQR_T, x0=np.zeros((2, 4)))   # only to obtain the problem library
+    L = alg.lib
+    x0 = x0_h.to(dev)
+    U = U_h.to(dev)
+    out = {"xN": torch.empty((4, B_ENVS), dtype=torch.float64, device=dev),
+           "cost": torch.empty((B_ENVS,), dtype=torch.float64, device=dev),
+           "terminated": torch.empty((B_ENVS,), dtype=torch.uint8, device=dev)}
+
+    def step():
+        L.rollout(x0, U, S=SUBSTEPS, dt=DT, out=out)
+
+    # ---- device-resident throughput ------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = L.launches
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for e0, e1 in evs:
+        e0.record()
+        step()
+        e1.record()
+    t_end.record()
+    barrier()
+    clocks = sampler.stop()
+    gpu_launches = L.launches - launches0
+    elapsed_ms = t_start.elapsed_time(t_end)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    if world > 1:
+        tmax = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(tmax.item())
+    value = world * B_ENVS * T_STEPS * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the public API, host buffers --------------------------------------------
+    from pygent_b200.examples import make_env
+    env = make_env("cart_pole", x0=np.ascontiguousarray(x0_h.numpy().T), device=dev)
+    U_pin, x0_pin = U_h.pin_memory(), x0_h.pin_memory()
+    cost_pin = torch.empty((B_ENVS,), dtype=torch.float64).pin_memory()
+    xN_pin = torch.empty((4, B_ENVS), dtype=torch.float64).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        r = env.rollout_host(x0_pin, U_pin, cost_out=cost_pin, xN_out=xN_pin)
+        return r
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tmax = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_s = float(tmax.item())
+    e2e_value = world * B_ENVS * T_STEPS * e2e_steps / e2e_s
+    assert torch.equal(xN_pin, out["xN"].cpu()), "e2e path and resident path disagree on the final states"
+    assert torch.allclose(cost_pin, out["cost"].cpu(), rtol=1e-12, atol=0), "e2e path and resident path disagree"
+
+    # ---- final cost / argmin gather: the only collective of the path -----------------------
+    cmin, imin = torch.min(out["cost"], dim=0)
+    key = torch.stack([cmin, (imin + rank * B_ENVS).to(torch.float64)])
+    if world > 1:
+        keys = [torch.empty_like(key) for _ in range(world)]
+        dist.all_gather(keys, key)
+        key = min(keys, key=lambda k: float(k[0]))
+    best = {"cost": float(key[0]), "env": int(key[1])}
+
+    # ---- iLQR iterations/s (config 3 sized per GPU) ---------------------------------------------------
+    ilqr = None
+    if not args.no_ilqr:
+        rng = np.random.default_rng(1000 + rank)
+        xi = np.array([0, np.pi, 0, 0]) + rng.uniform(-1, 1, (ILQR_B, 4)) * np.array([.5, .3, .5, .5])
+        solver = make_ilqr("cart_pole", ILQR_T, x0=xi, env_kw={"device": dev}, maxIters=500)
+        solver.run_optim()  # warm-up solve (same work)
+        solver.environment.reset(xi)
+        solver.reset()
+        barrier()
+        l0 = solver.lib.launches
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        solver.run_optim()
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b)
+        total_iters = int(solver.iters.sum())
+        if world > 1:
+            t = torch.tensor([ms, -float(total_iters)], dtype=torch.float64, device=dev)
+            tm = t.clone()
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ts = t.clone()
+            dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+            ms, total_iters = float(tm[0]), int(-ts[1])
+        st = solver.status
+        ilqr = {"metric": "ilqr_iterations_per_s", "value": total_iters / (ms * 1e-3), "unit": "iLQR iterations/s",
+                "trajectories_per_gpu": ILQR_B, "horizon": ILQR_T, "substeps": SUBSTEPS, "ms": ms,
+                "iterations_total": total_iters, "iterations_max": int(solver.iters.max()),
+                "gpu_launches": solver.lib.launches - l0,
+                "converged_frac": float(np.mean((st == pglib.ST_CONV_FUN) | (st == pglib.ST_CONV_GRAD))),
+                "mean_final_cost": float(np.mean(solver.cost)), "line_search": "serial semantics, 11 alphas evaluated per launch"}
+
+    if rank == 0:
+        peak_tf, peak_src = fp64_peak()
+        hbm_gbs, hbm_src = hbm_peak()
+        flops = algorithmic_flops_per_launch()
+        achieved = flops / (kernel_ms * 1e-3) / 1e12
+        hbm_bytes = U.numel() * 8 + x0.numel() * 8 + B_ENVS * (8 * 4 + 8 + 1)
+        res = {
+            "metric": "rk4_env_steps_per_s", "value": value, "unit": "env-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": CONFIG, "clocks": clocks, "gpu_launches": gpu_launches,
+            "e2e": {"value": e2e_value, "unit": "env-steps/s",
+                    "h2d_bytes_per_step": int(U_pin.numel() * 8 + x0_pin.numel() * 8),
+                    "d2h_bytes_per_step": int(cost_pin.numel() * 8 + xN_pin.numel() * 8), "steps": e2e_steps},
+            "roofline": {"bound": "fp64", "kernel": "rollout_kernel<Problem,double,RK4>", "achieved": achieved,
+                         "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "peak_source": peak_src,
+                         "flops_per_launch": flops, "kernel_ms": kernel_ms, "traffic": None,
+                         "hbm": {"achieved": hbm_bytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_gbs, "unit": "GB/s",
+                                 "frac": hbm_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_gbs, "bytes_per_launch": hbm_bytes,
+                                 "peak_source": hbm_src}},
+            "best": best,
+        }
+        if ilqr is not None:
+            res["ilqr"] = ilqr
+        if not args.no_cpu:
+            import oracle
+            oracle.build()
+            threads = os.cpu_count() or 1
+            n = 16384
+            v, secs = cpu_rollout_baseline(n, threads)
+            v1, secs1 = cpu_rollout_baseline(1024, 1)
+            res["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port",
+                                   "sample": "first %d of the 65,536 envs x 500 steps (RK4 x 4), C oracle, OpenMP; %.1f s" % (n, secs),
+                                   "single_core": v1}
+        print(json.dumps(res))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -51,6 +51,9 @@ extern "C" {
 #define PG_INTEG_RK4 0   /* classical RK4, S substeps per control interval (parity schedule S=4) */
 #define PG_INTEG_EULER 1 /* forward Euler, StateSpaceModel.fast_step (environments.py:291-322)  */
 
+#define PG_ROLLOUT_FINAL_COST 1 /* add fcost(x_T)*dt to the cost (ilqr.py:513) */
+#define PG_ROLLOUT_ACCUMULATE 2 /* cost[b] holds the sum of earlier time segments of the same rollout */
+
 #define PG_E_BADARG (-1)
 #define PG_E_UNSUPPORTED (-2)
 
@@ -81,11 +84,13 @@ int pg_get_problem_info(pg_problem_info_t* out);
 /* Open-loop rollout of B independent environments over T control intervals.
  *   x0 [n,B]; U [T,m,B] or NULL (u == 0, ilqr.py:505); X [T+1,n,B] or NULL (history, X[0] = x0);
  *   xN [n,B] or NULL; cost [B] or NULL: sum_k (c(x_k,u_k,x_{k+1},t_{k+1}) + terminal_cost*terminated_{k+1})*dt
- *   (+ fcost(x_T)*dt if add_final_cost); terminated [B] or NULL: terminate(x_T).
+ *   (+ fcost(x_T)*dt with PG_ROLLOUT_FINAL_COST; added to the incoming cost[b] with PG_ROLLOUT_ACCUMULATE,
+ *   which lets a long rollout be fed in time segments while the next segment's controls are still in
+ *   flight from the host); terminated [B] or NULL: terminate(x_T).
  *   t0: simulation time of x0 (the reference's env.tt[-1]); time advances by repeated t += dt. */
 int pg_rollout(int dtype, int integrator, int64_t B, int32_t T, int32_t S, double dt, double t0,
                const void* x0, const void* U, void* X, void* xN, void* cost, uint8_t* terminated,
-               double terminal_cost, int32_t add_final_cost, void* stream);
+               double terminal_cost, int32_t flags, void* stream);
 
 /* Closed-loop line-search rollouts u_k = K_j (x_k - xbar_j) + alpha k_j + ubar_j, j = min(Tk-1, k).
  *   alphas: host array of n_alpha values (<= PG_MAX_ALPHAS), all evaluated in one launch;

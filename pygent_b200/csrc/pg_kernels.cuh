@@ -66,7 +66,7 @@ struct RolloutArgs {
     int64_t B;
     int T_steps, S;
     T dt, t0, terminal_cost;
-    int add_final_cost;
+    int add_final_cost, accumulate_cost;
     const T* x0;
     const T* U;
     T* X;
@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs<T> a) {
         for (int i = 0; i < N; i++) a.X[i * B + b] = x[i];
     }
     const T h = a.dt / T(a.S);
-    T cost = T(0), t = a.t0;
+    // accumulate_cost: this launch continues a rollout split into time segments (cost[b] carries the sum)
+    T cost = (a.accumulate_cost && a.cost) ? a.cost[b] : T(0), t = a.t0;
     bool term = false;
 #pragma unroll
     for (int j = 0; j < M; j++) un[j] = (a.U && a.T_steps > 0) ? a.U[j * B + b] : T(0);

@@ -255,6 +255,54 @@ class StateSpaceModel(Environment):
         self.terminated = term if self.batched else bool(term[0])
         return r
 
+    def rollout_host(self, x0, U, cost_out=None, xN_out=None, segments=10, fast=False):
+        """End-to-end rollout from HOST buffers in kernel layout: x0 `[n, B]`, U `[T, m, B]` (pinned torch
+        tensors), results into the pinned `cost_out [B]` / `xN_out [n, B]`.  The horizon is fed in `segments`
+        time slices: while slice k integrates, slice k+1 crosses PCIe on a second stream (double buffered),
+        so the wall time approaches max(copy, compute) instead of their sum.  Synchronises before returning."""
+        L = self.library()
+        T, m, B = U.shape
+        n = self.xDim
+        dev, dt_ = self.device, self.dtype
+        seg = (T + segments - 1) // segments
+        st = getattr(self, "_host_pipe", None)
+        if st is None or st["shape"] != (seg, m, B):
+            st = {"shape": (seg, m, B), "copy": torch.cuda.Stream(device=dev),
+                  "buf": [torch.empty((seg, m, B), dtype=dt_, device=dev) for _ in range(2)],
+                  "x": [torch.empty((n, B), dtype=dt_, device=dev) for _ in range(2)],
+                  "cost": torch.empty((B,), dtype=dt_, device=dev),
+                  "term": torch.empty((B,), dtype=torch.uint8, device=dev)}
+            self._host_pipe = st
+        comp = torch.cuda.current_stream(dev)
+        copy = st["copy"]
+        copy.wait_stream(comp)
+        with torch.cuda.stream(copy):
+            st["x"][0].copy_(x0, non_blocking=True)
+        done = [None, None]   # compute-done events per U buffer
+        t0, k, i = 0.0, 0, 0
+        while k < T:
+            k1 = min(T, k + seg)
+            b = i % 2
+            with torch.cuda.stream(copy):
+                if done[b] is not None:
+                    copy.wait_event(done[b])
+                st["buf"][b][: k1 - k].copy_(U[k:k1], non_blocking=True)
+                ready = copy.record_event()
+            comp.wait_event(ready)
+            L.rollout(st["x"][i % 2], st["buf"][b][: k1 - k], S=self.substeps, dt=self.dt, t0=t0,
+                      integrator=lib.INTEG_EULER if fast else lib.INTEG_RK4, terminal_cost=float(self.terminal_cost),
+                      accumulate_cost=i > 0, out={"xN": st["x"][(i + 1) % 2], "cost": st["cost"], "terminated": st["term"]})
+            done[b] = comp.record_event()
+            for _ in range(k1 - k):
+                t0 = t0 + self.dt
+            k, i = k1, i + 1
+        if cost_out is not None:
+            cost_out.copy_(st["cost"], non_blocking=True)
+        if xN_out is not None:
+            xN_out.copy_(st["x"][i % 2], non_blocking=True)
+        comp.synchronize()
+        return {"cost": cost_out, "xN": xN_out}
+
     def terminate(self, x):
         """True where `x` (`[n]` or `[B, n]`) is a terminal state (reference: environments.py:278-288)."""
         x = np.asarray(x, dtype=float)

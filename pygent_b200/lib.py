@@ -116,7 +116,7 @@ class ProblemLibrary:
 
     # -- K1 ------------------------------------------------------------------------------------
     def rollout(self, x0, U=None, T=None, S=4, dt=0.02, t0=0.0, integrator=INTEG_RK4, history=False,
-                want_cost=True, terminal_cost=0.0, add_final_cost=False, out=None):
+                want_cost=True, terminal_cost=0.0, add_final_cost=False, accumulate_cost=False, out=None):
         """x0 [n,B], U [T,m,B] or None -> dict(xN [n,B], cost [B], terminated [B] u8, X [T+1,n,B])."""
         n, m = self.n, self.m
         dtype, dev = x0.dtype, x0.device
@@ -142,7 +142,7 @@ class ProblemLibrary:
                                  _ptr(x0, dtype, (n, B), "x0"), _ptr(U, dtype, (T, m, B), "U"),
                                  _ptr(X, dtype, (T + 1, n, B), "X"), _ptr(xN, dtype, (n, B), "xN"),
                                  _ptr(cost, dtype, (B,), "cost"), _ptr(term, torch.uint8, (B,), "terminated"),
-                                 terminal_cost, int(add_final_cost), self._stream())
+                                 terminal_cost, int(add_final_cost) | (2 if accumulate_cost else 0), self._stream())
         self._check(rc, "pg_rollout")
         self.launches += 1
         return {"xN": xN, "cost": cost, "terminated": term, "X": X}
