@@ -155,7 +155,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-ilqr", action="store_true")
@@ -199,11 +199,13 @@ def main():
         L.rollout(x0, U, S=SUBSTEPS, dt=DT, out=out)
 
     # ---- device-resident throughput ------------------------------------------------------------------
+    # clocks are sampled from before the warm-up until the last GPU phase ends: the timed region proper can be
+    # shorter than one nvidia-smi period when the driver asks for few steps
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
     launches0 = L.launches
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -214,7 +216,6 @@ def main():
         e1.record()
     t_end.record()
     barrier()
-    clocks = sampler.stop()
     gpu_launches = L.launches - launches0
     elapsed_ms = t_start.elapsed_time(t_end)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
@@ -294,6 +295,7 @@ def main():
                 "converged_frac": float(np.mean((st == pglib.ST_CONV_FUN) | (st == pglib.ST_CONV_GRAD))),
                 "mean_final_cost": float(np.mean(solver.cost)), "line_search": "serial semantics, 11 alphas evaluated per launch"}
 
+    clocks = sampler.stop()
     if rank == 0:
         peak_tf, peak_src = fp64_peak()
         hbm_gbs, hbm_src = hbm_peak()
