@@ -20,6 +20,7 @@ import sympy as sp
 from sympy.printing.c import C99CodePrinter
 
 ABI_VERSION = 1
+CODEGEN_VERSION = 3  # bump to invalidate cached libraries when the emitted code changes
 
 _FUNCS = {"sin": "pg::sin", "cos": "pg::cos", "tan": "pg::tan", "exp": "pg::exp", "log": "pg::log",
           "sqrt": "pg::sqrt", "asin": "pg::asin", "acos": "pg::acos", "atan": "pg::atan",
@@ -103,23 +104,48 @@ def _pair_trig(exprs, prefix):
     return exprs, defs
 
 
-def emit_body(outputs, sym_names, prefix="w"):
+def _needs_register(fl):
+    """A double literal whose low 32 bits are non-zero cannot be an instruction immediate."""
+    import struct
+    return struct.unpack("<Q", struct.pack("<d", float(fl)))[0] & 0xFFFFFFFF != 0
+
+
+def hoistable_constants(exprs, limit=8):
+    """Float literals of the hot expressions that are worth keeping in registers (Ctx::kN)."""
+    found = []
+    for e in exprs:
+        for fl in sorted(sp.sympify(e).atoms(sp.Float), key=lambda v: float(v)):
+            if _needs_register(fl) and all(float(fl) != float(o) for o in found):
+                found.append(fl)
+    return found[:limit]
+
+
+def emit_body(outputs, sym_names, prefix="w", hoisted=()):
     """C++ statements computing `outputs` = [(lhs_string, sympy expr)].
 
     sym_names: {sympy Symbol: C++ lvalue string}.  Zero expressions are still assigned (callers
-    rely on every output being written)."""
+    rely on every output being written).  `hoisted` float literals are read from the context
+    (`m.kN`) instead of being emitted as immediates."""
     ren = {s: sp.Symbol(n) for s, n in sym_names.items()}
     exprs = [sp.sympify(e).xreplace(ren) for _, e in outputs]
+    if hoisted:
+        hmap = {}
+        for e in exprs:
+            for fl in e.atoms(sp.Float):
+                for i, h in enumerate(hoisted):
+                    if float(fl) == float(h):
+                        hmap[fl] = sp.Symbol("m.k%d" % i)
+        exprs = [e.xreplace(hmap) for e in exprs]
     exprs, trig = _pair_trig(exprs, prefix)
     lines = []
     # trig arguments may share sub-expressions with the algebra; keep it simple: emit them first
     for arg, s, c in trig:
         if s is not None and c is not None:
-            lines.append("T %s, %s; pg::sincos(%s, %s, %s);" % (s, c, _cxx(arg), s, c))
+            lines.append("T %s, %s; m.sincos(%s, %s, %s);" % (s, c, _cxx(arg), s, c))
         elif s is not None:
-            lines.append("const T %s = pg::sin(%s);" % (s, _cxx(arg)))
+            lines.append("const T %s = m.sin(%s);" % (s, _cxx(arg)))
         else:
-            lines.append("const T %s = pg::cos(%s);" % (c, _cxx(arg)))
+            lines.append("const T %s = m.cos(%s);" % (c, _cxx(arg)))
     repl, red = sp.cse(exprs, symbols=sp.numbered_symbols(prefix + "t"), optimizations="basic", order="none")
     for s, e in repl:
         lines.append("const T %s = %s;" % (s, _cxx(e)))
@@ -137,7 +163,9 @@ def _mask_fn(name, mat):
 
 
 def _fn(sig, body_lines, indent="    "):
-    out = [indent + "template <typename T> __device__ __forceinline__ static " + sig + " {"]
+    name, rest = sig.split("(", 1)
+    sig = name + "(const Ctx<T>& m, " + rest
+    out = [indent + "template <typename T> __device__ __forceinline__ static " + sig + " {", indent + "    (void)m;"]
     out += [indent + "    " + l for l in body_lines]
     out.append(indent + "}")
     return out
@@ -175,7 +203,7 @@ class ProblemSpec:
     def key(self, extra=""):
         h = hashlib.sha1()
         s = self.system
-        parts = [str(ABI_VERSION), s.name, sp.srepr(s.f), sp.srepr(s.A), sp.srepr(s.B), str(s.has_AB),
+        parts = [str(ABI_VERSION), str(CODEGEN_VERSION), s.name, sp.srepr(s.f), sp.srepr(s.A), sp.srepr(s.B), str(s.has_AB),
                  sp.srepr(self.cost), sp.srepr(self.fcost), repr(self.term), repr(self.x_is_angle), extra]
         h.update("\n".join(parts).encode())
         return h.hexdigest()[:16]
@@ -205,6 +233,7 @@ class ProblemSpec:
 
         L = ["// generated by pygent_b200.codegen -- do not edit", "#pragma once",
              '#define PG_PROBLEM_NAME "%s"' % s.name, '#define PG_PROBLEM_KEY "%s"' % key,
+             "__device__ const double PG_PROBLEM_CONSTS[%d] = {%s};" % (max(1, len(hoistable_constants(list(s.f)))), ", ".join(repr(float(h)) for h in hoistable_constants(list(s.f))) or "0.0"),
              "struct Problem {",
              "    static constexpr int N = %d, M = %d, NOBS = %d;" % (n, m, n_obs),
              "    static constexpr bool HAS_AB = %s;" % ("true" if s.has_AB else "false"),
@@ -218,8 +247,16 @@ class ProblemSpec:
             L += [_mask_fn("cxx_nz", [1] * (n * n)), _mask_fn("cuu_nz", [1] * (m * m)), _mask_fn("cxu_nz", [1] * (n * m))]
         L.append(_mask_fn("cfxx_nz", Cfxx))
 
+        # per-thread context: sin/cos coefficients (pg::MathCtx) + the literals of f, all held in registers
+        hoisted = hoistable_constants(list(s.f))
+        L += ["    template <typename T> struct Ctx : pg::MathCtx<T> {"]
+        if hoisted:
+            L += ["        T %s;" % ", ".join("k%d" % i for i in range(len(hoisted)))]
+        L += ["        __device__ __forceinline__ Ctx() {"]
+        L += ["            k%d = pg::hoist(PG_PROBLEM_CONSTS, %d, T(%r));" % (i, i, float(h)) for i, h in enumerate(hoisted)]
+        L += ["        }", "    };"]
         L += _fn("void f(const T (&x)[N], const T (&u)[M], T (&dx)[N])",
-                 emit_body([("dx[%d]" % i, s.f[i]) for i in range(n)], names))
+                 emit_body([("dx[%d]" % i, s.f[i]) for i in range(n)], names, hoisted=hoisted))
         ab_out = [("A[%d]" % (i * n + j), s.A[i, j]) for i in range(n) for j in range(n)]
         ab_out += [("B[%d]" % (i * m + j), s.B[i, j]) for i in range(n) for j in range(m)]
         L += _fn("void AB(const T (&x)[N], const T (&u)[M], T (&A)[N * N], T (&B)[N * M])", emit_body(ab_out, names))

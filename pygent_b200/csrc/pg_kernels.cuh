@@ -28,20 +28,20 @@ __device__ __forceinline__ void copy(T (&d)[N], const T (&s)[N]) {
 // Classical RK4 with `S` substeps of h = dt/S and the control held constant: the fixed-step parity
 // schedule for StateSpaceModel.step (pygent/environments.py:263).
 template <typename P, typename T>
-__device__ __forceinline__ void rk4_substep(T (&x)[P::N], const T (&u)[P::M], const T h) {
+__device__ __forceinline__ void rk4_substep(const typename P::template Ctx<T>& m, T (&x)[P::N], const T (&u)[P::M], const T h) {
     constexpr int N = P::N;
     T k1[N], k2[N], k3[N], k4[N], xt[N];
     const T hh = T(0.5) * h;
-    P::f(x, u, k1);
+    P::f(m, x, u, k1);
 #pragma unroll
     for (int i = 0; i < N; i++) xt[i] = x[i] + hh * k1[i];
-    P::f(xt, u, k2);
+    P::f(m, xt, u, k2);
 #pragma unroll
     for (int i = 0; i < N; i++) xt[i] = x[i] + hh * k2[i];
-    P::f(xt, u, k3);
+    P::f(m, xt, u, k3);
 #pragma unroll
     for (int i = 0; i < N; i++) xt[i] = x[i] + h * k3[i];
-    P::f(xt, u, k4);
+    P::f(m, xt, u, k4);
     const T h6 = h / T(6);
 #pragma unroll
     for (int i = 0; i < N; i++) x[i] = x[i] + h6 * (k1[i] + T(2) * k2[i] + T(2) * k3[i] + k4[i]);
@@ -49,14 +49,14 @@ __device__ __forceinline__ void rk4_substep(T (&x)[P::N], const T (&u)[P::M], co
 
 // One control interval. INTEG_EULER is StateSpaceModel.fast_step (environments.py:313-315).
 template <typename P, typename T, int INTEG>
-__device__ __forceinline__ void env_step(T (&x)[P::N], const T (&u)[P::M], const T dt, const T h, const int S) {
+__device__ __forceinline__ void env_step(const typename P::template Ctx<T>& m, T (&x)[P::N], const T (&u)[P::M], const T dt, const T h, const int S) {
     if constexpr (INTEG == INTEG_EULER) {
         T k1[P::N];
-        P::f(x, u, k1);
+        P::f(m, x, u, k1);
 #pragma unroll
         for (int i = 0; i < P::N; i++) x[i] = x[i] + dt * k1[i];
     } else {
-        for (int s = 0; s < S; s++) rk4_substep<P, T>(x, u, h);
+        for (int s = 0; s < S; s++) rk4_substep<P, T>(m, x, u, h);
     }
 }
 
@@ -77,6 +77,7 @@ struct RolloutArgs {
 
 template <typename P, typename T, int INTEG>
 __global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs<T> a) {
+    const typename P::template Ctx<T> m;
     constexpr int N = P::N, M = P::M;
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.B) return;
@@ -102,17 +103,17 @@ __global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs<T> a) {
         }
         T xp[N];
         copy(xp, x);
-        env_step<P, T, INTEG>(x, u, a.dt, h, a.S);
+        env_step<P, T, INTEG>(m, x, u, a.dt, h, a.S);
         t += a.dt;  // env.tt.extend([tt[-1] + dt]) (environments.py:269)
-        term = P::terminate(x);
+        term = P::terminate(m, x);
         // c = (cost(x_, u, x, t, np) + terminal_cost*terminated)*dt (environments.py:274-275)
-        cost += (P::cost(xp, u, x, t) + (term ? a.terminal_cost : T(0))) * a.dt;
+        cost += (P::cost(m, xp, u, x, t) + (term ? a.terminal_cost : T(0))) * a.dt;
         if (a.X) {
 #pragma unroll
             for (int i = 0; i < N; i++) a.X[((int64_t)(k + 1) * N + i) * B + b] = x[i];
         }
     }
-    if (a.add_final_cost) cost += P::fcost(x) * a.dt;  // ilqr.py:513
+    if (a.add_final_cost) cost += P::fcost(m, x) * a.dt;  // ilqr.py:513
     if (a.xN) {
 #pragma unroll
         for (int i = 0; i < N; i++) a.xN[i * B + b] = x[i];
@@ -175,6 +176,7 @@ struct Nominal {  // gains and nominal point of one control interval
 //                 __restrict__).
 template <typename P, typename T, int INTEG, bool COMMIT>
 __global__ void __launch_bounds__(32 * MAX_ALPHAS) ilqr_forward_kernel(const ForwardArgs<T> a) {
+    const typename P::template Ctx<T> m;
     constexpr int N = P::N, M = P::M;
     const int64_t B = a.B;
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -231,11 +233,11 @@ __global__ void __launch_bounds__(32 * MAX_ALPHAS) ilqr_forward_kernel(const For
         }
         T xp[N];
         copy(xp, x);
-        env_step<P, T, INTEG>(x, u, a.dt, h, a.S);
+        env_step<P, T, INTEG>(m, x, u, a.dt, h, a.S);
         t += a.dt;
         if constexpr (!COMMIT) {
-            term = P::terminate(x);
-            cost += (P::cost(xp, u, x, t) + (term ? a.terminal_cost : T(0))) * a.dt;
+            term = P::terminate(m, x);
+            cost += (P::cost(m, xp, u, x, t) + (term ? a.terminal_cost : T(0))) * a.dt;
 #pragma unroll
             for (int i = 0; i < N; i++) div |= (x[i] > T(1e8));  // np.any(xx > 1e8) (ilqr.py:435)
         }
@@ -257,7 +259,7 @@ __global__ void __launch_bounds__(32 * MAX_ALPHAS) ilqr_forward_kernel(const For
         }
     }
     if constexpr (!COMMIT) {
-        cost += P::fcost(x) * a.dt;  // ilqr.py:224
+        cost += P::fcost(m, x) * a.dt;  // ilqr.py:224
         const int64_t o = (int64_t)ia * B + b;
         a.cost_out[o] = cost;
         if (a.diverged_out) a.diverged_out[o] = div ? 1 : 0;
@@ -268,7 +270,7 @@ __global__ void __launch_bounds__(32 * MAX_ALPHAS) ilqr_forward_kernel(const For
 // ---- linearisation ------------------------------------------------------------------------------
 // lin_mode 1: helpers.system_linearization (pygent/helpers.py:130-148), central differences, eps=1e-3.
 template <typename P, typename T>
-__device__ __forceinline__ void fd_AB(const T (&x)[P::N], const T (&u)[P::M], T (&A)[P::N * P::N], T (&Bm)[P::N * P::M]) {
+__device__ __forceinline__ void fd_AB(const typename P::template Ctx<T>& m, const T (&x)[P::N], const T (&u)[P::M], T (&A)[P::N * P::N], T (&Bm)[P::N * P::M]) {
     constexpr int N = P::N, M = P::M;
     const T eps = T(1e-3);
     T fp[N], fm[N], xt[N], ut[M];
@@ -276,9 +278,9 @@ __device__ __forceinline__ void fd_AB(const T (&x)[P::N], const T (&u)[P::M], T 
     for (int j = 0; j < N; j++) {
         copy(xt, x);
         xt[j] = x[j] + eps;
-        P::f(xt, u, fp);
+        P::f(m, xt, u, fp);
         xt[j] = x[j] - eps;
-        P::f(xt, u, fm);
+        P::f(m, xt, u, fm);
 #pragma unroll
         for (int i = 0; i < N; i++) A[i * N + j] = (fp[i] - fm[i]) / (T(2) * eps);
     }
@@ -286,9 +288,9 @@ __device__ __forceinline__ void fd_AB(const T (&x)[P::N], const T (&u)[P::M], T 
     for (int j = 0; j < M; j++) {
         copy(ut, u);
         ut[j] = u[j] + eps;
-        P::f(x, ut, fp);
+        P::f(m, x, ut, fp);
         ut[j] = u[j] - eps;
-        P::f(x, ut, fm);
+        P::f(m, x, ut, fm);
 #pragma unroll
         for (int i = 0; i < N; i++) Bm[i * M + j] = (fp[i] - fm[i]) / (T(2) * eps);
     }
@@ -319,6 +321,7 @@ __device__ __forceinline__ bool np_isclose(T a, T b, T atol) {  // np.isclose(a,
 
 template <typename P, typename T, int LIN>
 __global__ void __launch_bounds__(64) ilqr_backward_kernel(const BackwardArgs<T> a) {
+    const typename P::template Ctx<T> m;
     constexpr int N = P::N, M = P::M;
     static_assert(M <= 2, "control dimension > 2 not supported by the closed-form Quu solve");
     const int64_t B = a.B;
@@ -333,7 +336,7 @@ __global__ void __launch_bounds__(64) ilqr_backward_kernel(const BackwardArgs<T>
     for (int i = 0; i < N; i++) x[i] = a.xbar[((int64_t)Ts * N + i) * B + b];
     // vx = cfx(x_N)*dt, Vxx = Cfxx(x_N)*dt (ilqr.py:244-245)
     T vx[N], Vxx[N * N];
-    P::fcost_derivs(x, vx, Vxx);
+    P::fcost_derivs(m, x, vx, Vxx);
 #pragma unroll
     for (int i = 0; i < N; i++) vx[i] *= dt;
 #pragma unroll
@@ -363,9 +366,9 @@ __global__ void __launch_bounds__(64) ilqr_backward_kernel(const BackwardArgs<T>
         // Ad = A*dt + I, Bd = B*dt (ilqr.py:530-531) -- forward-Euler discretisation of the Jacobian
         T Ad[N * N], Bd[N * M];
         if constexpr (LIN == 0) {
-            P::AB(x, u, Ad, Bd);
+            P::AB(m, x, u, Ad, Bd);
         } else {
-            fd_AB<P, T>(x, u, Ad, Bd);
+            fd_AB<P, T>(m, x, u, Ad, Bd);
         }
 #pragma unroll
         for (int i = 0; i < N; i++)
@@ -379,7 +382,7 @@ __global__ void __launch_bounds__(64) ilqr_backward_kernel(const BackwardArgs<T>
 
         // cost expansion of c*dt at t_k = k*dt (ilqr.py:162, :236, :597-610)
         T cx[N], cu[M], Cxx[N * N], Cuu[M * M], Cxu[N * M];
-        P::cost_derivs(x, u, T(k) * dt, cx, cu, Cxx, Cuu, Cxu);
+        P::cost_derivs(m, x, u, T(k) * dt, cx, cu, Cxx, Cuu, Cxu);
 #pragma unroll
         for (int i = 0; i < N; i++) cx[i] *= dt;
 #pragma unroll
@@ -788,7 +791,7 @@ __global__ void observe_kernel(int64_t B, const T* x, T* o) {
         const T v = x[i * B + b];
         if (P::x_is_angle(i)) {
             T s, co;
-            pg::sincos(v, s, co);
+            pg::MathCtx<T>().sincos(v, s, co);
             o[(c++) * B + b] = co;
             o[(c++) * B + b] = s;
         } else {
@@ -810,6 +813,7 @@ struct EvalArgs {
 
 template <typename P, typename T>
 __global__ void eval_kernel(const EvalArgs<T> a) {
+    const typename P::template Ctx<T> m;
     constexpr int N = P::N, M = P::M;
     const int64_t B = a.B;
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -822,14 +826,14 @@ __global__ void eval_kernel(const EvalArgs<T> a) {
     const T t = a.t ? a.t[b] : T(0);
     if (a.f) {
         T dx[N];
-        P::f(x, u, dx);
+        P::f(m, x, u, dx);
 #pragma unroll
         for (int i = 0; i < N; i++) a.f[i * B + b] = dx[i];
     }
     if (a.A || a.Bm) {
         T A[N * N], Bm[N * M];
-        if (a.lin_mode == 0) P::AB(x, u, A, Bm);
-        else fd_AB<P, T>(x, u, A, Bm);
+        if (a.lin_mode == 0) P::AB(m, x, u, A, Bm);
+        else fd_AB<P, T>(m, x, u, A, Bm);
         if (a.A) {
 #pragma unroll
             for (int i = 0; i < N * N; i++) a.A[i * B + b] = A[i];
@@ -839,10 +843,10 @@ __global__ void eval_kernel(const EvalArgs<T> a) {
             for (int i = 0; i < N * M; i++) a.Bm[i * B + b] = Bm[i];
         }
     }
-    if (a.c) a.c[b] = P::cost(x, u, x, t);
+    if (a.c) a.c[b] = P::cost(m, x, u, x, t);
     if (a.cx || a.cu || a.Cxx || a.Cuu || a.Cxu) {
         T cx[N], cu[M], Cxx[N * N], Cuu[M * M], Cxu[N * M];
-        P::cost_derivs(x, u, t, cx, cu, Cxx, Cuu, Cxu);
+        P::cost_derivs(m, x, u, t, cx, cu, Cxx, Cuu, Cxu);
         if (a.cx) {
 #pragma unroll
             for (int i = 0; i < N; i++) a.cx[i * B + b] = cx[i];
@@ -864,10 +868,10 @@ __global__ void eval_kernel(const EvalArgs<T> a) {
             for (int i = 0; i < N * M; i++) a.Cxu[i * B + b] = Cxu[i];
         }
     }
-    if (a.cf) a.cf[b] = P::fcost(x);
+    if (a.cf) a.cf[b] = P::fcost(m, x);
     if (a.cfx || a.Cfxx) {
         T cfx[N], Cfxx[N * N];
-        P::fcost_derivs(x, cfx, Cfxx);
+        P::fcost_derivs(m, x, cfx, Cfxx);
         if (a.cfx) {
 #pragma unroll
             for (int i = 0; i < N; i++) a.cfx[i * B + b] = cfx[i];
