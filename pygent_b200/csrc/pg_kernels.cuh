@@ -55,6 +55,9 @@ __device__ __forceinline__ void env_step(const typename P::template Ctx<T>& m, T
         P::f(m, x, u, k1);
 #pragma unroll
         for (int i = 0; i < P::N; i++) x[i] = x[i] + dt * k1[i];
+    } else if (S == 4) {  // the parity schedule: fully unrolled, no loop-carried register copies
+#pragma unroll
+        for (int s = 0; s < 4; s++) rk4_substep<P, T>(m, x, u, h);
     } else {
         for (int s = 0; s < S; s++) rk4_substep<P, T>(m, x, u, h);
     }

@@ -83,7 +83,10 @@ struct MathCtx<double> {
         P3 = opaque_load(t + 15);
     }
     __device__ __forceinline__ void sincos(double x, double& s, double& c) const {
-        if (!(fabs(x) < 1073741824.0)) x = __longlong_as_double(0x7ff8000000000000LL);
+        {  // out-of-domain (|x| >= 2^30, inf, nan) -> NaN, decided on the exponent bits (integer pipe)
+            const int hi = __double2hiint(x);
+            x = __hiloint2double(((hi & 0x7fffffff) < 0x41d00000) ? hi : 0x7ff80000, __double2loint(x));
+        }
         const double magic = 6755399441055744.0;  // 1.5 * 2^52
         const double qd = fma(x, TWO_OVER_PI, magic);
         const int q = __double2loint(qd);

@@ -138,7 +138,8 @@ def test_codegen_pairs_sincos_and_masks():
     x1, x2, x3, x4 = s.xs
     spec = ProblemSpec(s, x1 ** 2 + s.us[0] ** 2, x2 ** 2, term=[(0, 1.2)], x_is_angle=[0, 1, 0, 0])
     h = spec.header("k")
-    assert h.count("pg::sincos(x[1]") == 2  # once in f, once in AB
+    assert h.count("m.sincos(x[1]") == 2  # once in f, once in AB
+    assert "k1 = pg::hoist(PG_PROBLEM_CONSTS, 1, T(1.477886191760791));" in h and "m.k1*" in h
     assert "a_nz(int i) { constexpr unsigned char m[16] = {0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 1, 0, 1}" in h
     assert "NOBS = 5" in h and "HAS_AB = true" in h
     assert spec.key() != ProblemSpec(s, x1 ** 2 + 2 * s.us[0] ** 2, x2 ** 2).key()
