@@ -254,13 +254,9 @@ def main():
     assert torch.allclose(cost_pin, out["cost"].cpu(), rtol=1e-12, atol=0), "e2e path and resident path disagree"
 
     # ---- final cost / argmin gather: the only collective of the path -----------------------
-    cmin, imin = torch.min(out["cost"], dim=0)
-    key = torch.stack([cmin, (imin + rank * B_ENVS).to(torch.float64)])
-    if world > 1:
-        keys = [torch.empty_like(key) for _ in range(world)]
-        dist.all_gather(keys, key)
-        key = min(keys, key=lambda k: float(k[0]))
-    best = {"cost": float(key[0]), "env": int(key[1])}
+    from pygent_b200 import distributed as pgd
+    bc, bi, br = pgd.gather_best(out["cost"], offset=rank * B_ENVS)
+    best = {"cost": bc, "env": bi, "rank": br}
 
     # ---- iLQR iterations/s (config 3 sized per GPU) ---------------------------------------------------
     ilqr = None
