@@ -92,6 +92,17 @@ int pg_rollout(int dtype, int integrator, int64_t B, int32_t T, int32_t S, doubl
                const void* x0, const void* U, void* X, void* xN, void* cost, uint8_t* terminated,
                double terminal_cost, int32_t flags, void* stream);
 
+/* The same rollout, load-balanced for large batches: persistent worker warps (4 per warp scheduler) pull
+ * (32-trajectory group, 25-step time chunk) units from a ticket queue, so that all schedulers carry the same
+ * load even when B/32 is not a multiple of the scheduler count (65,536 envs: 3.46 warps per scheduler).
+ * Results are bit-identical to pg_rollout.  xN and cost are required (they carry the state between chunks);
+ * workspace: device scratch of at least pg_rollout_workspace_bytes(B, T) bytes, contents irrelevant.
+ * workspace[8..12) holds an error flag afterwards (non-zero: a worker gave up waiting -- never expected). */
+int64_t pg_rollout_workspace_bytes(int64_t B, int32_t T);
+int pg_rollout_balanced(int dtype, int integrator, int64_t B, int32_t T, int32_t S, double dt, double t0,
+                        const void* x0, const void* U, void* X, void* xN, void* cost, uint8_t* terminated,
+                        double terminal_cost, int32_t flags, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Closed-loop line-search rollouts u_k = K_j (x_k - xbar_j) + alpha k_j + ubar_j, j = min(Tk-1, k).
  *   alphas: host array of n_alpha values (<= PG_MAX_ALPHAS), all evaluated in one launch;
  *   alpha_dev [B] or NULL: when given, n_alpha must be 1 and each trajectory uses its own alpha;

@@ -125,6 +125,121 @@ __global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs<T> a) {
     if (a.terminated) a.terminated[b] = term ? 1 : 0;
 }
 
+// ---- K1b: the same rollout, load-balanced ---------------------------------------------------------
+// At the benchmark size (65,536 envs = 2,048 warps on 592 warp schedulers) every scheduler holds 3 or 4
+// warps and the kernel ends with the 4-warp ones: 13.5% of the FP64 pipe idles (measured: 65,536 envs take
+// exactly as long as 75,776).  Here 4 persistent worker warps sit on EVERY scheduler and pull (group of 32
+// trajectories, time chunk) units from a global ticket queue; a group is re-queued after each chunk, so
+// every worker is busy the same fraction of the time and all schedulers carry the same average load.
+//   ticket s < n_groups      : group s, first chunk (implicit, nothing to wait for)
+//   ticket s >= n_groups     : wait until queue[s - n_groups] is published by whichever worker finished a chunk
+// The state of a group between chunks lives in xN / cost (L2: written with a release fence, read with
+// ld.cg, because another SM's L1 may hold a stale copy), the group's clock in tq, its next chunk in progress.
+template <typename T>
+struct QueueArgs {
+    RolloutArgs<T> r;
+    int n_groups, n_chunks, chunk;
+    int* counters;   // [0] next ticket, [1] next free queue slot, [2] error flag
+    int* queue;      // [n_groups * (n_chunks - 1)], zero = not yet published, else group + 1
+    int* progress;   // [n_groups] next chunk of the group
+    T* tq;           // [n_groups] simulation time of the group
+};
+
+template <typename P, typename T, int INTEG>
+__global__ void __launch_bounds__(128) rollout_queue_kernel(const QueueArgs<T> q) {
+    const typename P::template Ctx<T> m;
+    constexpr int N = P::N, M = P::M;
+    const RolloutArgs<T>& a = q.r;
+    const int64_t B = a.B;
+    const int lane = threadIdx.x & 31;
+    const T h = a.dt / T(a.S);
+    const int total = q.n_groups * q.n_chunks;
+    for (;;) {
+        int g = -1;
+        if (lane == 0) {
+            const int s = atomicAdd(&q.counters[0], 1);
+            if (s < q.n_groups) {
+                g = s;
+            } else if (s < total) {
+                volatile int* slot = q.queue + (s - q.n_groups);
+                int v = 0, spins = 0;
+                while ((v = *slot) == 0) {
+                    __nanosleep(128);
+                    if (++spins > (1 << 24)) {  // ~2 s: something is wrong, do not hang the GPU
+                        atomicExch(&q.counters[2], 1);
+                        break;
+                    }
+                }
+                g = v - 1;
+                __threadfence();  // acquire: the producer's state stores are visible after this
+            }
+        }
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g < 0) return;
+        const int c = (g < 0) ? 0 : __ldcg(&q.progress[g]);
+        const int64_t b = (int64_t)g * 32 + lane;
+        const bool valid = b < B;
+        const int64_t bb = valid ? b : B - 1;  // ragged last group: idle lanes shadow the last trajectory
+        const int k0 = c * q.chunk, k1 = min(a.T_steps, k0 + q.chunk);
+        T x[N], u[M], un[M];
+        T cost, t;
+        if (c == 0) {
+#pragma unroll
+            for (int i = 0; i < N; i++) x[i] = a.x0[i * B + bb];
+            cost = (a.accumulate_cost) ? __ldcg(&a.cost[bb]) : T(0);
+            t = a.t0;
+            if (a.X && valid) {
+#pragma unroll
+                for (int i = 0; i < N; i++) a.X[i * B + b] = x[i];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < N; i++) x[i] = __ldcg(&a.xN[i * B + bb]);
+            cost = __ldcg(&a.cost[bb]);
+            t = __ldcg(&q.tq[g]);
+        }
+        bool term = false;
+#pragma unroll
+        for (int j = 0; j < M; j++) un[j] = (a.U && k0 < k1) ? a.U[((int64_t)k0 * M + j) * B + bb] : T(0);
+        for (int k = k0; k < k1; k++) {
+            copy(u, un);
+            if (a.U && k + 1 < k1) {
+#pragma unroll
+                for (int j = 0; j < M; j++) un[j] = a.U[((int64_t)(k + 1) * M + j) * B + bb];
+            }
+            T xp[N];
+            copy(xp, x);
+            env_step<P, T, INTEG>(m, x, u, a.dt, h, a.S);
+            t += a.dt;
+            term = P::terminate(m, x);
+            cost += (P::cost(m, xp, u, x, t) + (term ? a.terminal_cost : T(0))) * a.dt;
+            if (a.X && valid) {
+#pragma unroll
+                for (int i = 0; i < N; i++) a.X[((int64_t)(k + 1) * N + i) * B + b] = x[i];
+            }
+        }
+        const bool last = k1 >= a.T_steps;
+        if (last && a.add_final_cost) cost += P::fcost(m, x) * a.dt;
+        if (valid) {
+#pragma unroll
+            for (int i = 0; i < N; i++) a.xN[i * B + b] = x[i];
+            a.cost[b] = cost;
+            if (last && a.terminated) a.terminated[b] = term ? 1 : 0;
+        }
+        if (!last) {
+            __threadfence();  // release: state before the ticket
+            __syncwarp();
+            if (lane == 0) {
+                q.tq[g] = t;
+                q.progress[g] = c + 1;
+                __threadfence();
+                const int p = atomicAdd(&q.counters[1], 1);
+                atomicExch(&q.queue[p], g + 1);
+            }
+        }
+    }
+}
+
 // ---- K2: closed-loop line-search rollouts (iLQR.forward_pass, ilqr.py:187-231) ---------------------
 constexpr int MAX_ALPHAS = 16;
 

@@ -38,6 +38,7 @@ class SelectParams(ctypes.Structure):
 SIGNATURES = {
     "pg_get_problem_info": [ctypes.POINTER(ProblemInfo)],
     "pg_rollout": [_i32, _i32, _i64, _i32, _i32, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _i32, _vp],
+    "pg_rollout_balanced": [_i32, _i32, _i64, _i32, _i32, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _i32, _vp, _i64, _vp],
     "pg_ilqr_forward": [_i32, _i32, _i64, _i32, _i32, _f64, _i32, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _dp, _f64,
                         _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "pg_ilqr_backward": [_i32, _i64, _i32, _f64, _i32, _i32, _vp, _vp, _vp, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
@@ -93,6 +94,9 @@ class ProblemLibrary:
             fn = getattr(self.dll, name)  # AttributeError if the library does not export the ABI
             fn.argtypes = argtypes
             fn.restype = ctypes.c_int
+        self.dll.pg_rollout_workspace_bytes.argtypes = [_i64, _i32]
+        self.dll.pg_rollout_workspace_bytes.restype = _i64
+        self._workspace = {}
         info = ProblemInfo()
         self._check(self.dll.pg_get_problem_info(ctypes.byref(info)), "pg_get_problem_info")
         self.info = info
@@ -116,8 +120,12 @@ class ProblemLibrary:
 
     # -- K1 ------------------------------------------------------------------------------------
     def rollout(self, x0, U=None, T=None, S=4, dt=0.02, t0=0.0, integrator=INTEG_RK4, history=False,
-                want_cost=True, terminal_cost=0.0, add_final_cost=False, accumulate_cost=False, out=None):
-        """x0 [n,B], U [T,m,B] or None -> dict(xN [n,B], cost [B], terminated [B] u8, X [T+1,n,B])."""
+                want_cost=True, terminal_cost=0.0, add_final_cost=False, accumulate_cost=False, out=None,
+                balanced=None):
+        """x0 [n,B], U [T,m,B] or None -> dict(xN [n,B], cost [B], terminated [B] u8, X [T+1,n,B]).
+
+        balanced: use the work-queue kernel (pg_rollout_balanced); default: when the batch fills the GPU but
+        is not a whole number of warps per scheduler and the horizon has several chunks."""
         n, m = self.n, self.m
         dtype, dev = x0.dtype, x0.device
         B = x0.shape[1]
@@ -138,11 +146,27 @@ class ProblemLibrary:
         X = out.get("X")
         if X is None and history:
             X = torch.empty((T + 1, n, B), dtype=dtype, device=dev)
+        flags = int(add_final_cost) | (2 if accumulate_cost else 0)
+        if balanced is None:
+            balanced = use_balanced_rollout(B, T, dev)
+        if balanced and cost is not None and T >= 1 and B > 0:
+            nbytes = int(self.dll.pg_rollout_workspace_bytes(B, T))
+            ws = self._workspace.get(dev)
+            if ws is None or ws.numel() < nbytes:
+                ws = self._workspace[dev] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            rc = self.dll.pg_rollout_balanced(_dtype_code(dtype), integrator, B, T, S, dt, t0,
+                                              _ptr(x0, dtype, (n, B), "x0"), _ptr(U, dtype, (T, m, B), "U"),
+                                              _ptr(X, dtype, (T + 1, n, B), "X"), _ptr(xN, dtype, (n, B), "xN"),
+                                              _ptr(cost, dtype, (B,), "cost"), _ptr(term, torch.uint8, (B,), "terminated"),
+                                              terminal_cost, flags, _ptr(ws), nbytes, self._stream())
+            self._check(rc, "pg_rollout_balanced")
+            self.launches += 1
+            return {"xN": xN, "cost": cost, "terminated": term, "X": X}
         rc = self.dll.pg_rollout(_dtype_code(dtype), integrator, B, T, S, dt, t0,
                                  _ptr(x0, dtype, (n, B), "x0"), _ptr(U, dtype, (T, m, B), "U"),
                                  _ptr(X, dtype, (T + 1, n, B), "X"), _ptr(xN, dtype, (n, B), "xN"),
                                  _ptr(cost, dtype, (B,), "cost"), _ptr(term, torch.uint8, (B,), "terminated"),
-                                 terminal_cost, int(add_final_cost) | (2 if accumulate_cost else 0), self._stream())
+                                 terminal_cost, flags, self._stream())
         self._check(rc, "pg_rollout")
         self.launches += 1
         return {"xN": xN, "cost": cost, "terminated": term, "X": X}
@@ -278,6 +302,22 @@ class ProblemLibrary:
         self._check(rc, "pg_eval")
         self.launches += 1
         return outs
+
+
+@functools.lru_cache(maxsize=None)
+def _sm_count(index):
+    return torch.cuda.get_device_properties(index).multi_processor_count
+
+
+def use_balanced_rollout(B, T, dev):
+    """Work-queue kernel pays off when the GPU is full (>= 2 warps per scheduler) but the warps do not divide
+    evenly over the 4 x SM schedulers, and the horizon spans several 25-step chunks."""
+    sched = 4 * _sm_count(dev.index if dev.index is not None else torch.cuda.current_device())
+    warps = (B + 31) // 32
+    if warps < 2 * sched or T < 100:
+        return False
+    per = warps / sched
+    return (-(-warps // sched)) / per > 1.04
 
 
 def _cuda_error_name(rc):
