@@ -92,8 +92,8 @@ int pg_rollout(int dtype, int integrator, int64_t B, int32_t T, int32_t S, doubl
                const void* x0, const void* U, void* X, void* xN, void* cost, uint8_t* terminated,
                double terminal_cost, int32_t flags, void* stream);
 
-/* The same rollout, load-balanced for large batches: persistent worker warps (4 per warp scheduler) pull
- * (32-trajectory group, 25-step time chunk) units from a ticket queue, so that all schedulers carry the same
+/* The same rollout, load-balanced for large batches: persistent worker warps (3 per warp scheduler) pull
+ * (32-trajectory group, 20-step time chunk) units from a ticket queue, so that all schedulers carry the same
  * load even when B/32 is not a multiple of the scheduler count (65,536 envs: 3.46 warps per scheduler).
  * Results are bit-identical to pg_rollout.  xN and cost are required (they carry the state between chunks);
  * workspace: device scratch of at least pg_rollout_workspace_bytes(B, T) bytes, contents irrelevant.

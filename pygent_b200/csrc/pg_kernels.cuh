@@ -128,9 +128,9 @@ __global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs<T> a) {
 // ---- K1b: the same rollout, load-balanced ---------------------------------------------------------
 // At the benchmark size (65,536 envs = 2,048 warps on 592 warp schedulers) every scheduler holds 3 or 4
 // warps and the kernel ends with the 4-warp ones: 13.5% of the FP64 pipe idles (measured: 65,536 envs take
-// exactly as long as 75,776).  Here 4 persistent worker warps sit on EVERY scheduler and pull (group of 32
+// exactly as long as 75,776).  Here 3 persistent worker warps sit on EVERY scheduler and pull (group of 32
 // trajectories, time chunk) units from a global ticket queue; a group is re-queued after each chunk, so
-// every worker is busy the same fraction of the time and all schedulers carry the same average load.
+// every scheduler is fed the same share of the work.
 //   ticket s < n_groups      : group s, first chunk (implicit, nothing to wait for)
 //   ticket s >= n_groups     : wait until queue[s - n_groups] is published by whichever worker finished a chunk
 // The state of a group between chunks lives in xN / cost (L2: written with a release fence, read with

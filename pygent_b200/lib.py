@@ -312,6 +312,8 @@ def _sm_count(index):
 def use_balanced_rollout(B, T, dev):
     """Work-queue kernel pays off when the GPU is full (>= 2 warps per scheduler) but the warps do not divide
     evenly over the 4 x SM schedulers, and the horizon spans several 25-step chunks."""
+    if dev.type != "cuda":
+        return False
     sched = 4 * _sm_count(dev.index if dev.index is not None else torch.cuda.current_device())
     warps = (B + 31) // 32
     if warps < 2 * sched or T < 100:

@@ -29,6 +29,8 @@ def test_header_declares_what_the_library_exports(built):
     hdr = open(os.path.join(ROOT, "include", "pygent_b200.h")).read()
     declared = set(re.findall(r"^int (pg_\w+)\(", hdr, flags=re.M))
     assert declared == set(lib.SIGNATURES), declared ^ set(lib.SIGNATURES)
+    declared |= set(re.findall(r"^int64_t (pg_\w+)\(", hdr, flags=re.M))
+    assert "pg_rollout_workspace_bytes" in declared
     specs, paths = built
     for p in paths:
         dll = ctypes.CDLL(p)
@@ -58,7 +60,7 @@ def test_no_cpu_fallback():
         env.step([0.0])
     L = env.library()
     with pytest.raises(lib.PygentB200Error):
-        L.rollout(torch.zeros((4, 2), dtype=torch.float64), T=1)
+        L.rollout(torch.zeros((4, 2), dtype=torch.float64), T=1, balanced=False)
 
 
 def test_product_never_imports_the_oracle():
