@@ -110,13 +110,16 @@ int pg_rollout_balanced(int dtype, int integrator, int64_t B, int32_t T, int32_t
  *   terminal_cost: the environment's terminal_cost (environments.py:275), 0 by default;
  *   X_out [n_alpha,T+1,n,B] / U_out [n_alpha,T,m,B] or NULL; cost_out [n_alpha,B];
  *   diverged_out [n_alpha,B] or NULL: any(x > 1e8) over the rollout (ilqr.py:435);
- *   terminated_out [n_alpha,B] or NULL; active [B] or NULL: trajectories with active==0 are skipped. */
+ *   terminated_out [n_alpha,B] or NULL; active [B] or NULL: trajectories with active==0 are skipped;
+ *   index [<=B] (i32) + count [1] (i32, device) or both NULL: compacted work list -- only trajectories
+ *   index[0..*count) are processed (written by pg_ilqr_select; late iLQR iterations touch few trajectories). */
 int pg_ilqr_forward(int dtype, int integrator, int64_t B, int32_t T, int32_t S, double dt,
                     int32_t n_alpha, const double* alphas, const void* alpha_dev,
                     const void* x0, const void* xbar, const void* ubar,
                     const void* KK, const void* kk, int32_t Tk, const double* ulim, double terminal_cost,
                     void* X_out, void* U_out, void* cost_out, uint8_t* diverged_out,
-                    uint8_t* terminated_out, const uint8_t* active, void* stream);
+                    uint8_t* terminated_out, const uint8_t* active,
+                    const int32_t* index, const int32_t* count, void* stream);
 
 /* Backward Riccati pass along (xbar, ubar).
  *   lin_mode 0: analytic A, B (requires has_ab); 1: central differences eps=1e-3 of f.
@@ -127,7 +130,7 @@ int pg_ilqr_forward(int dtype, int integrator, int64_t B, int32_t T, int32_t S, 
 int pg_ilqr_backward(int dtype, int64_t B, int32_t T, double dt, int32_t reg_type, int32_t lin_mode,
                      const void* mu, const void* xbar, const void* ubar, const double* ulim,
                      void* KK, void* kk, void* dV, void* gnorm, uint8_t* success,
-                     const uint8_t* active, void* stream);
+                     const uint8_t* active, const int32_t* index, const int32_t* count, void* stream);
 
 typedef struct {
     int32_t n_alpha;
@@ -142,19 +145,22 @@ typedef struct {
 /* One line-search decision per trajectory; updates the per-trajectory solver state in place.
  *   in : cost_cand [n_alpha,B], diverged [n_alpha,B], dV [2,B], gnorm [B], bw_success [B]
  *   io : cost [B], mu [B], mu_d [B], dcost [B], success_gradient [B] (u8), status [B] (i32), iters [B] (i32)
- *   out: alpha_best [B], accept [B] (u8), n_active (device int32 counter, incremented per still-running traj) */
+ *   out: alpha_best [B], accept [B] (u8), active [B] (u8), n_active (device int32 counter: += trajectories still
+ *        running), index_out [B] or NULL: their indices, compacted (the next iteration's work list);
+ *   index_in / count_in: this iteration's work list or NULL (all B). */
 int pg_ilqr_select(int dtype, int64_t B, const pg_select_params_t* params,
                    const void* cost_cand, const uint8_t* diverged, const void* dV, const void* gnorm,
                    const uint8_t* bw_success, void* cost, void* mu, void* mu_d, void* dcost,
                    uint8_t* success_gradient, int32_t* status, int32_t* iters,
-                   void* alpha_best, uint8_t* accept, uint8_t* active, int32_t* n_active, void* stream);
+                   void* alpha_best, uint8_t* accept, uint8_t* active, int32_t* n_active,
+                   const int32_t* index_in, const int32_t* count_in, int32_t* index_out, void* stream);
 
 /* For accepted trajectories: re-run the winning alpha and store it as the new nominal trajectory
  * (xbar, ubar updated in place) and copy the candidate gains into the accepted gains. */
 int pg_ilqr_commit(int dtype, int integrator, int64_t B, int32_t T, int32_t S, double dt,
                    const void* alpha_best, const uint8_t* accept, const void* x0,
                    void* xbar, void* ubar, const void* KK, const void* kk, const double* ulim,
-                   void* KK_acc, void* kk_acc, void* stream);
+                   void* KK_acc, void* kk_acc, const int32_t* index, const int32_t* count, void* stream);
 
 /* o [n_obs,B] = observation(x [n,B]) : angle -> [cos, sin] (helpers.py:20-29). */
 int pg_observe(int dtype, int64_t B, const void* x, void* o, void* stream);

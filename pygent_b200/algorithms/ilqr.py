@@ -140,7 +140,11 @@ class iLQR(Algorithm):
         A = len(self.alphas)
         self._bw = {"KK": self._KKc, "kk": self._kkc, "dV": z(2, B), "gnorm": z(B), "success": u8(B)}
         self._fw = {"cost": z(A, B), "diverged": u8(A, B), "terminated": u8(A, B)}
-        self._n_active = i32(1)
+        # compacted work lists (ping-pong): trajectories still running, written by the select kernel
+        self._idx = [torch.arange(B, dtype=torch.int32, device=dev), i32(B)]
+        self._cnt = [i32(1) + B, i32(1)]
+        self._cur = 0
+        self._n_active = self._cnt[1]
         self._have_gains = False
 
     def _host(self, t, batch_axis_last=True):
@@ -291,20 +295,32 @@ class iLQR(Algorithm):
         p.mu_min, p.mu_max, p.mu_d0 = self.mu_min, self.mu_max, self.mu_d0
         return p
 
+    def _rearm(self):
+        """Every trajectory back on the work list (start of run_optim)."""
+        self._cur = 0
+        self._idx[0].copy_(torch.arange(self.B, dtype=torch.int32, device=self._idx[0].device))
+        self._cnt[0].fill_(self.B)
+        self._n_active = self._cnt[0]
+
     def iterate(self):
-        """One loop body of run_optim (ilqr.py:407-485) for every running trajectory: 4 launches, no sync."""
+        """One loop body of run_optim (ilqr.py:407-485) for every running trajectory: 4 launches, no sync.
+        The kernels walk the compacted list of running trajectories; select writes the next list."""
         st = self._st
         L = self.lib
+        cur, nxt = self._cur, 1 - self._cur
+        work = (self._idx[cur], self._cnt[cur])
         L.ilqr_backward(self._xbar, self._ubar, st["mu"], dt=self.dt, reg_type=self.regType, lin_mode=self.lin_mode,
-                        ulim=self._ulim(), active=st["active"], out=self._bw)
+                        ulim=self._ulim(), out=self._bw, work=work)
         L.ilqr_forward(self._x0, self._xbar, self._ubar, self._KKc, self._kkc, alphas=self.alphas, S=self.substeps,
                        dt=self.dt, integrator=self.integrator, ulim=self._ulim(),
-                       terminal_cost=float(self.environment.terminal_cost), active=st["active"], out=self._fw)
-        self._n_active.zero_()
+                       terminal_cost=float(self.environment.terminal_cost), out=self._fw, work=work)
+        self._cnt[nxt].zero_()
         L.ilqr_select(self._sel, self._fw["cost"], self._fw["diverged"], self._bw["dV"], self._bw["gnorm"],
-                      self._bw["success"], st, self._n_active)
+                      self._bw["success"], st, self._cnt[nxt], work=work, index_out=self._idx[nxt])
         L.ilqr_commit(self._x0, self._xbar, self._ubar, self._KKc, self._kkc, self._KK, self._kk, st["alpha_best"],
-                      st["accept"], S=self.substeps, dt=self.dt, integrator=self.integrator, ulim=self._ulim())
+                      st["accept"], S=self.substeps, dt=self.dt, integrator=self.integrator, ulim=self._ulim(), work=work)
+        self._cur = nxt
+        self._n_active = self._cnt[nxt]
         self._have_gains = True
 
     def run_optim(self):
@@ -319,6 +335,7 @@ class iLQR(Algorithm):
         st["iters"].zero_()
         st["active"].fill_(1)
         st["success_gradient"].zero_()
+        self._rearm()
         self._sel = self._select_params()
         it = 0
         while it < self.max_iters:

@@ -263,6 +263,8 @@ struct ForwardArgs {
     uint8_t* diverged_out;
     uint8_t* terminated_out;
     const uint8_t* active;
+    const int32_t* index;  // optional work list: thread i handles trajectory index[i], i < *count
+    const int32_t* count;
     // commit mode
     const uint8_t* accept;
     T* xbar_io;
@@ -297,9 +299,15 @@ __global__ void __launch_bounds__(32 * MAX_ALPHAS) ilqr_forward_kernel(const For
     const typename P::template Ctx<T> m;
     constexpr int N = P::N, M = P::M;
     const int64_t B = a.B;
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int ia = threadIdx.y;
-    if (b >= B) return;
+    int64_t b = tid;
+    if (a.index) {  // compacted list of running trajectories (written by ilqr_select_kernel)
+        if (tid >= *a.count) return;
+        b = a.index[tid];
+    } else if (b >= B) {
+        return;
+    }
     if constexpr (COMMIT) {
         if (!a.accept[b]) return;
     } else {
@@ -430,6 +438,8 @@ struct BackwardArgs {
     T* gnorm;
     uint8_t* success;
     const uint8_t* active;
+    const int32_t* index;
+    const int32_t* count;
 };
 
 template <typename T>
@@ -443,8 +453,14 @@ __global__ void __launch_bounds__(64) ilqr_backward_kernel(const BackwardArgs<T>
     constexpr int N = P::N, M = P::M;
     static_assert(M <= 2, "control dimension > 2 not supported by the closed-form Quu solve");
     const int64_t B = a.B;
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t b = tid;
+    if (a.index) {
+        if (tid >= *a.count) return;
+        b = a.index[tid];
+    } else if (b >= B) {
+        return;
+    }
     if (a.active && !a.active[b]) return;
     const T mu = a.mu[b];
     const T dt = a.dt;
@@ -813,17 +829,18 @@ struct SelectArgs {
     uint8_t* accept;
     uint8_t* active;
     int32_t* n_active;
+    const int32_t* index_in;  // optional work list of this iteration ...
+    const int32_t* count_in;
+    int32_t* index_out;       // ... and the compacted list of trajectories still running after it
 };
 
 template <typename T>
-__global__ void ilqr_select_kernel(const SelectArgs<T> a) {
+__device__ __forceinline__ int select_one(const SelectArgs<T>& a, const int64_t b) {
     const int64_t B = a.B;
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
     a.accept[b] = 0;
     if (a.status[b] != 0) {
         a.active[b] = 0;
-        return;
+        return a.status[b];
     }
     const SelectParams& p = a.p;
     T mu = a.mu[b], mu_d = a.mu_d[b];
@@ -895,7 +912,33 @@ __global__ void ilqr_select_kernel(const SelectArgs<T> a) {
     a.mu_d[b] = mu_d;
     a.status[b] = status;
     a.active[b] = status == 0 ? 1 : 0;
-    if (status == 0 && a.n_active) atomicAdd(a.n_active, 1);
+    return status;
+}
+
+template <typename T>
+__global__ void ilqr_select_kernel(const SelectArgs<T> a) {
+    const int64_t B = a.B;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t b = tid;
+    bool valid = true;
+    if (a.index_in) {
+        valid = tid < *a.count_in;
+        b = valid ? a.index_in[tid] : 0;
+    } else {
+        valid = b < B;
+    }
+    int status = 1;
+    if (valid) status = select_one(a, b);
+    // compaction: trajectories still running are appended to index_out (warp-aggregated, order kept in a warp)
+    const bool keep = valid && status == 0;
+    const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+    if (ballot && a.n_active) {
+        const int lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == __ffs(ballot) - 1) base = atomicAdd(a.n_active, __popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
+        if (keep && a.index_out) a.index_out[base + __popc(ballot & ((1u << lane) - 1))] = (int32_t)b;
+    }
 }
 
 // ---- observation (helpers.observation, pygent/helpers.py:20-29) -----------------------------------

@@ -40,11 +40,13 @@ SIGNATURES = {
     "pg_rollout": [_i32, _i32, _i64, _i32, _i32, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _i32, _vp],
     "pg_rollout_balanced": [_i32, _i32, _i64, _i32, _i32, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _i32, _vp, _i64, _vp],
     "pg_ilqr_forward": [_i32, _i32, _i64, _i32, _i32, _f64, _i32, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _dp, _f64,
-                        _vp, _vp, _vp, _vp, _vp, _vp, _vp],
-    "pg_ilqr_backward": [_i32, _i64, _i32, _f64, _i32, _i32, _vp, _vp, _vp, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+                        _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pg_ilqr_backward": [_i32, _i64, _i32, _f64, _i32, _i32, _vp, _vp, _vp, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                         _vp],
     "pg_ilqr_select": [_i32, _i64, ctypes.POINTER(SelectParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                       _vp, _vp, _vp, _vp, _vp, _vp, _vp],
-    "pg_ilqr_commit": [_i32, _i32, _i64, _i32, _i32, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _dp, _vp, _vp, _vp],
+                       _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pg_ilqr_commit": [_i32, _i32, _i64, _i32, _i32, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _dp, _vp, _vp, _vp, _vp,
+                       _vp],
     "pg_observe": [_i32, _i64, _vp, _vp, _vp],
     "pg_eval": [_i32, _i64, _i32] + [_vp] * 16,
 }
@@ -115,6 +117,13 @@ class ProblemLibrary:
         raise PygentB200Error("%s: %s" % (what, {-1: "bad argument", -2: "not supported by this problem"}.get(rc, rc)))
 
     @staticmethod
+    def _work(work, B):
+        if work is None:
+            return None, None
+        index, count = work
+        return _ptr(index, torch.int32, (B,), "work index"), _ptr(count, torch.int32, (1,), "work count")
+
+    @staticmethod
     def _stream():
         return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -173,7 +182,9 @@ class ProblemLibrary:
 
     # -- K2 ------------------------------------------------------------------------------------
     def ilqr_forward(self, x0, xbar, ubar, KK, kk, alphas=None, alpha_dev=None, S=4, dt=0.02,
-                     integrator=INTEG_RK4, ulim=None, terminal_cost=0.0, want_traj=False, active=None, out=None):
+                     integrator=INTEG_RK4, ulim=None, terminal_cost=0.0, want_traj=False, active=None, out=None,
+                     work=None):
+        """work: (index i32 [B], count i32 [1]) compacted list of trajectories to process, or None (all)."""
         n, m = self.n, self.m
         dtype, dev = x0.dtype, x0.device
         B = x0.shape[1]
@@ -203,13 +214,14 @@ class ProblemLibrary:
             terminal_cost, _ptr(X, dtype, (n_alpha, T + 1, n, B), "X_out"), _ptr(Uo, dtype, (n_alpha, T, m, B), "U_out"),
             _ptr(cost, dtype, (n_alpha, B), "cost_out"), _ptr(div, torch.uint8, (n_alpha, B), "diverged_out"),
             _ptr(term, torch.uint8, (n_alpha, B), "terminated_out"), _ptr(active, torch.uint8, (B,), "active"),
-            self._stream())
+            *self._work(work, B), self._stream())
         self._check(rc, "pg_ilqr_forward")
         self.launches += 1
         return {"cost": cost, "diverged": div, "terminated": term, "X": X, "U": Uo}
 
     # -- K3 ------------------------------------------------------------------------------------
-    def ilqr_backward(self, xbar, ubar, mu, dt=0.02, reg_type=2, lin_mode=None, ulim=None, active=None, out=None):
+    def ilqr_backward(self, xbar, ubar, mu, dt=0.02, reg_type=2, lin_mode=None, ulim=None, active=None, out=None,
+                      work=None):
         n, m = self.n, self.m
         dtype, dev = xbar.dtype, xbar.device
         T, B = ubar.shape[0], ubar.shape[2]
@@ -236,13 +248,14 @@ class ProblemLibrary:
             _ptr(xbar, dtype, (T + 1, n, B), "xbar"), _ptr(ubar, dtype, (T, m, B), "ubar"), _host_doubles(ulim),
             _ptr(KK, dtype, (T, m, n, B), "KK"), _ptr(kk, dtype, (T, m, B), "kk"), _ptr(dV, dtype, (2, B), "dV"),
             _ptr(gnorm, dtype, (B,), "gnorm"), _ptr(success, torch.uint8, (B,), "success"),
-            _ptr(active, torch.uint8, (B,), "active"), self._stream())
+            _ptr(active, torch.uint8, (B,), "active"), *self._work(work, B), self._stream())
         self._check(rc, "pg_ilqr_backward")
         self.launches += 1
         return {"KK": KK, "kk": kk, "dV": dV, "gnorm": gnorm, "success": success}
 
     # -- K4 ------------------------------------------------------------------------------------
-    def ilqr_select(self, params, cost_cand, diverged, dV, gnorm, bw_success, state, n_active=None):
+    def ilqr_select(self, params, cost_cand, diverged, dV, gnorm, bw_success, state, n_active=None, work=None,
+                    index_out=None):
         """state: dict of per-trajectory tensors cost, mu, mu_d, dcost, success_gradient, status, iters,
         alpha_best, accept, active (updated in place)."""
         dtype = cost_cand.dtype
@@ -257,12 +270,13 @@ class ProblemLibrary:
             _ptr(state["success_gradient"], u8, (B,), "success_gradient"), _ptr(state["status"], i32, (B,), "status"),
             _ptr(state["iters"], i32, (B,), "iters"), _ptr(state["alpha_best"], dtype, (B,), "alpha_best"),
             _ptr(state["accept"], u8, (B,), "accept"), _ptr(state["active"], u8, (B,), "active"),
-            _ptr(n_active, i32, None, "n_active"), self._stream())
+            _ptr(n_active, i32, None, "n_active"), *self._work(work, B), _ptr(index_out, i32, (B,), "index_out"),
+            self._stream())
         self._check(rc, "pg_ilqr_select")
         self.launches += 1
 
     def ilqr_commit(self, x0, xbar, ubar, KK, kk, KK_acc, kk_acc, alpha_best, accept, S=4, dt=0.02,
-                    integrator=INTEG_RK4, ulim=None):
+                    integrator=INTEG_RK4, ulim=None, work=None):
         n, m = self.n, self.m
         dtype = x0.dtype
         B = x0.shape[1]
@@ -272,7 +286,8 @@ class ProblemLibrary:
             _ptr(accept, torch.uint8, (B,), "accept"), _ptr(x0, dtype, (n, B), "x0"),
             _ptr(xbar, dtype, (T + 1, n, B), "xbar"), _ptr(ubar, dtype, (T, m, B), "ubar"),
             _ptr(KK, dtype, (T, m, n, B), "KK"), _ptr(kk, dtype, (T, m, B), "kk"), _host_doubles(ulim),
-            _ptr(KK_acc, dtype, (T, m, n, B), "KK_acc"), _ptr(kk_acc, dtype, (T, m, B), "kk_acc"), self._stream())
+            _ptr(KK_acc, dtype, (T, m, n, B), "KK_acc"), _ptr(kk_acc, dtype, (T, m, B), "kk_acc"), *self._work(work, B),
+            self._stream())
         self._check(rc, "pg_ilqr_commit")
         self.launches += 1
 

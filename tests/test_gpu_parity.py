@@ -279,6 +279,7 @@ def test_ilqr_iterations_in_lockstep_with_oracle(case, T, parallel, constrained,
     p = oracle_problem(case, S=4)
     q = oracle.ilqr_params(parallel=parallel, constrained=constrained, lims=list(alg.lims), reg_type=reg)
     alg._sel = alg._select_params()
+    alg._rearm()
     st = [dict(mu=1e-6, mu_d=1.0, cost=float(alg.cost[b]), dcost=0.0, sg=False, iters=0, alpha=1.0) for b in range(B)]
     status = np.zeros(B, dtype=int)
     for it in range(25):
