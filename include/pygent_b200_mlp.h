@@ -1,0 +1,70 @@
+/*
+ * pygent_b200 -- C ABI of the learned-MLP dynamics path (BASELINE.json config 5), sm_100a.
+ *
+ * Reference: pygent/nn_models.py:152-202 (NNDynamics: (oDim+uDim) -> 500 -> ReLU -> 500 -> ReLU -> dxDim, fp32,
+ * input/output standardisation) and pygent/algorithms/mbrl.py:125-130 (MBRL.ode with sparse_dyn:
+ * rhs = [x[n/2:], nn(obs(x), u) / dt]), integrated with forward Euler (StateSpaceModel.fast_step,
+ * pygent/environments.py:291-322; MBRL builds its planner with fastForward=True, mbrl.py:81).
+ *
+ * One control interval for a batch of rows (trajectories, line-search candidates, finite-difference points):
+ *     o  = (observation(x) - oMean) / oVar                     fp64 -> fp32   (helpers.py:20-29, nn_models.py:193-197)
+ *     h1 = relu(W1 [o; (u - uMean)/uVar] + b1)                 CUDA cores (K <= 16)
+ *     h2 = relu(W2 h1 + b2)                                    500 x 500: the dense GEMM of this path
+ *     dv = (W3 h2 + b3) * dxVar + dxMean                       CUDA cores (N <= 4)
+ *     x' = x + dt * [x[n/2:], dv / dt]                         fp64
+ * precision PG_MLP_FP32: layer 2 in fp32 FFMA (tracks the reference's fp32 torch path to ~1e-6);
+ * precision PG_MLP_BF16: layer 2 on the 5th-generation tensor cores (tcgen05.mma, bf16 operands, fp32
+ *                        accumulation in TMEM), weights streamed from L2 by bulk async copies.
+ *
+ * All pointers are device pointers owned by the caller; state arrays are trajectory-minor ([n, R], R fastest),
+ * fp64; every function enqueues on `stream` and returns 0 / a cudaError_t / a negative PG_E_* code.
+ */
+#ifndef PYGENT_B200_MLP_H
+#define PYGENT_B200_MLP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG_MLP_FP32 0
+#define PG_MLP_BF16 1
+
+#define PG_MLP_HIDDEN 500     /* the reference's layer width (nn_models.py:179-181) */
+#define PG_MLP_HPAD 512       /* padded width used by the kernels */
+#define PG_MLP_MAX_IN 16      /* n_obs + m */
+#define PG_MLP_MAX_DX 4       /* outputs (n/2 with sparse_dyn) */
+
+typedef struct {
+    int32_t n, m, n_obs, dx_dim; /* state, control, observation, network output dimensions; dx_dim == n/2 */
+    uint8_t is_angle[8];         /* xIsAngle: angle states enter the network as [cos, sin] */
+} pg_mlp_dims_t;
+
+/* Size of the packed parameter block, and packing from the torch layout (host pointers, fp32):
+ *   W1 [500, n_obs+m], b1 [500], W2 [500, 500], b2 [500], W3 [dx_dim, 500], b3 [dx_dim],
+ *   o_mean/o_var [n_obs], u_mean/u_var [m], dx_mean/dx_var [dx_dim].
+ * `packed_host` receives the block; copy it to the device (any 1024-byte aligned address). */
+int64_t pg_mlp_packed_bytes(void);
+int pg_mlp_pack(const pg_mlp_dims_t* dims, const float* W1, const float* b1, const float* W2, const float* b2,
+                const float* W3, const float* b3, const float* o_mean, const float* o_var, const float* u_mean,
+                const float* u_var, const float* dx_mean, const float* dx_var, void* packed_host);
+
+/* rhs [n, R] = MBRL.ode(x [n, R], u [m, R]) : batched evaluation of the learned dynamics (used for the
+ * finite-difference linearisation, helpers.py:130-148, and by the parity tests). */
+int pg_mlp_ode(int precision, const pg_mlp_dims_t* dims, const void* packed, int64_t R, double dt,
+               const double* x, const double* u, double* rhs, void* stream);
+
+/* Euler rollout of B trajectories through the learned dynamics, T control intervals.
+ *   open loop   : U [T, m, B] (or NULL: u = 0);
+ *   closed loop : KK [T, m, n, B], kk [T, m, B], xbar [T+1, n, B], ubar [T, m, B], alpha -- iLQR.forward_pass
+ *                 (ilqr.py:206): u_k = K_k (x_k - xbar_k) + alpha k_k + ubar_k; ulim [m] host or NULL clips u.
+ *   X [T+1, n, B] receives the trajectory (X[0] = x0), U_out [T, m, B] or NULL the applied controls. */
+int pg_mlp_rollout(int precision, const pg_mlp_dims_t* dims, const void* packed, int64_t B, int32_t T, double dt,
+                   const double* x0, const double* U, const double* KK, const double* kk, const double* xbar,
+                   const double* ubar, double alpha, const double* ulim, double* X, double* U_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

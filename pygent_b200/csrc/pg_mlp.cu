@@ -1,0 +1,571 @@
+// Learned-MLP dynamics (NNDynamics / MBRL.ode) on the B200: see include/pygent_b200_mlp.h.
+//
+//   mlp_fp32_kernel : 64 rows per CTA, layer 2 as a register-tiled fp32 FFMA GEMM (reference precision).
+//   mlp_bf16_kernel : 128 rows per CTA = one UMMA M tile.  Per control interval and CTA:
+//        layer 1 (K <= 16) on CUDA cores -> H1 as bf16 straight into the 128B-swizzled K-major smem
+//        image tcgen05.mma reads (A operand, 128 x 512);
+//        layer 2: 64 x tcgen05.mma.cta_group::1.kind::f16 (M128 N256 K16), accumulators in TMEM
+//        (128 lanes x 512 fp32 columns = all of it), W2 streamed from L2 in pre-swizzled 32 KB chunks by
+//        cp.async.bulk through a 3-stage mbarrier ring (no tensor map needed: the chunks are stored in
+//        global memory already in their smem image);
+//        epilogue: tcgen05.ld (row = TMEM lane = thread) -> +b2, ReLU, layer 3 (N <= 4) -> Euler update (fp64).
+//   Rows are trajectories / line-search candidates / finite-difference points; a CTA carries its rows
+//   through all T control intervals, the state never leaves registers.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/pygent_b200_mlp.h"
+#include "pg_math.cuh"
+
+#define PG_E_BADARG (-1)
+
+namespace {
+
+constexpr int H = PG_MLP_HPAD;      // 512
+constexpr int HID = PG_MLP_HIDDEN;  // 500
+constexpr int MAXIN = PG_MLP_MAX_IN;
+constexpr int MAXDX = PG_MLP_MAX_DX;
+constexpr int CHUNK_BYTES = 256 * 64 * 2;  // one W2 chunk image: 256 n-rows x 64 k bf16 = 32 KB
+constexpr int N_CHUNKS = 16;               // 8 k-blocks x 2 n-halves
+
+struct alignas(1024) MlpPacked {
+    uint16_t W2b[N_CHUNKS][CHUNK_BYTES / 2];  // bf16, 128B-swizzled K-major images, chunk = kb * 2 + half
+    float W2t[H][H];                          // [k][n] fp32 (FFMA path)
+    float W1[H][MAXIN];                       // [k][input]
+    float b1[H];
+    float b2[H];
+    float W3[H][MAXDX];                       // [k][output]
+    float b3[MAXDX];
+    float o_mean[MAXIN], o_var[MAXIN];
+    float u_mean[2], u_var[2];
+    float dx_mean[MAXDX], dx_var[MAXDX];
+};
+
+inline uint16_t f32_to_bf16(float f) {  // round to nearest even
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+
+struct MlpArgs {
+    pg_mlp_dims_t d;
+    const MlpPacked* w;
+    int64_t R;
+    int T;
+    double dt;
+    int rollout;  // 0: rhs = ode(x, u) for given points; 1: Euler rollout
+    const double* x0;
+    const double* U;
+    const double* KK;
+    const double* kk;
+    const double* xbar;
+    const double* ubar;
+    double alpha;
+    int clip;
+    double ulim[2];
+    double* X;
+    double* U_out;
+    double* rhs;
+};
+
+// ---- per-row pieces shared by both kernels ---------------------------------------------------------------
+__device__ __forceinline__ void control_of_row(const MlpArgs& a, int k, int64_t r, const double (&x)[8], double (&u)[2]) {
+    const int n = a.d.n, m = a.d.m;
+    const int64_t R = a.R;
+    for (int j = 0; j < m; j++) {
+        double v = 0.0;
+        if (a.KK) {  // u = K (x - xbar) + alpha k + ubar (ilqr.py:206)
+            double acc = 0.0;
+            for (int i = 0; i < n; i++) acc += a.KK[(((int64_t)k * m + j) * n + i) * R + r] * (x[i] - a.xbar[((int64_t)k * n + i) * R + r]);
+            v = acc + a.alpha * a.kk[((int64_t)k * m + j) * R + r];
+            v = v + a.ubar[((int64_t)k * m + j) * R + r];
+        } else if (a.U) {
+            v = a.U[((int64_t)k * m + j) * R + r];
+        }
+        if (a.clip) v = fmin(fmax(v, -a.ulim[j]), a.ulim[j]);
+        u[j] = v;
+    }
+}
+
+// network input: observation (angles -> [cos, sin], fp64) cast to fp32, then standardised (nn_models.py:193-198)
+__device__ __forceinline__ void network_input(const MlpArgs& a, const pg::MathCtx<double>& mc, const double (&x)[8],
+                                              const double (&u)[2], float (&in)[MAXIN]) {
+    const MlpPacked* w = a.w;
+    int c = 0;
+    for (int i = 0; i < a.d.n; i++) {
+        if (a.d.is_angle[i]) {
+            double s, co;
+            mc.sincos(x[i], s, co);
+            in[c] = ((float)co - w->o_mean[c]) / w->o_var[c];
+            c++;
+            in[c] = ((float)s - w->o_mean[c]) / w->o_var[c];
+            c++;
+        } else {
+            in[c] = ((float)x[i] - w->o_mean[c]) / w->o_var[c];
+            c++;
+        }
+    }
+    for (int j = 0; j < a.d.m; j++) {
+        in[c] = ((float)u[j] - w->u_mean[j]) / w->u_var[j];
+        c++;
+    }
+    for (; c < MAXIN; c++) in[c] = 0.0f;
+}
+
+// rhs = [x[n/2:], float32(1/dt) * (y * dxVar + dxMean)]  (mbrl.py:126-128, nn_models.py:200-201), Euler update
+__device__ __forceinline__ void finish_row(const MlpArgs& a, int64_t r, bool valid, int k, const float (&y)[MAXDX],
+                                           double (&x)[8], const double (&u)[2]) {
+    const int n = a.d.n, nh = a.d.n / 2, m = a.d.m;
+    const MlpPacked* w = a.w;
+    const float inv_dt = (float)(1.0 / a.dt);
+    double rhs[8];
+    for (int i = 0; i < nh; i++) rhs[i] = x[nh + i];
+    for (int j = 0; j < nh; j++) {
+        const float dv = (y[j] + w->b3[j]) * w->dx_var[j] + w->dx_mean[j];
+        rhs[nh + j] = (double)(inv_dt * dv);
+    }
+    if (!a.rollout) {
+        if (valid)
+            for (int i = 0; i < n; i++) a.rhs[(int64_t)i * a.R + r] = rhs[i];
+        return;
+    }
+    for (int i = 0; i < n; i++) x[i] = x[i] + a.dt * rhs[i];  // fast_step (environments.py:313-315)
+    if (valid) {
+        for (int i = 0; i < n; i++) a.X[((int64_t)(k + 1) * n + i) * a.R + r] = x[i];
+        if (a.U_out)
+            for (int j = 0; j < m; j++) a.U_out[((int64_t)k * m + j) * a.R + r] = u[j];
+    }
+}
+
+__device__ __forceinline__ void load_row(const MlpArgs& a, int64_t r, bool valid, double (&x)[8], double (&u)[2]) {
+    for (int i = 0; i < 8; i++) x[i] = 0.0;
+    u[0] = u[1] = 0.0;
+    if (!valid) return;
+    for (int i = 0; i < a.d.n; i++) x[i] = a.x0[(int64_t)i * a.R + r];
+    if (a.rollout) {
+        for (int i = 0; i < a.d.n; i++) a.X[(int64_t)i * a.R + r] = x[i];
+    } else {
+        for (int j = 0; j < a.d.m; j++) u[j] = a.U[(int64_t)j * a.R + r];
+    }
+}
+
+// ---- fp32 FFMA kernel --------------------------------------------------------------------------------------
+constexpr int F_ROWS = 64, F_HSTR = 513;
+
+__global__ void __launch_bounds__(256) mlp_fp32_kernel(const MlpArgs a) {
+    extern __shared__ float fsm[];
+    float* H1s = fsm;                        // [64][513]
+    float* ins = H1s + F_ROWS * F_HSTR;      // [64][16]
+    float* ys = ins + F_ROWS * MAXIN;        // [64][4]
+    const MlpPacked* w = a.w;
+    const int t = threadIdx.x;
+    const int64_t r = (int64_t)blockIdx.x * F_ROWS + t;
+    const bool owner = t < F_ROWS, valid = owner && r < a.R;
+    const pg::MathCtx<double> mc;
+    double x[8], u[2];
+    if (owner) load_row(a, r, valid, x, u);
+    const int steps = a.rollout ? a.T : 1;
+    for (int k = 0; k < steps; k++) {
+        if (owner) {
+            if (a.rollout && valid) control_of_row(a, k, r, x, u);
+            float in[MAXIN];
+            network_input(a, mc, x, u, in);
+#pragma unroll
+            for (int j = 0; j < MAXIN; j++) ins[t * MAXIN + j] = in[j];
+        }
+        __syncthreads();
+        {  // layer 1: thread -> (row, quarter of the hidden units)
+            const int row = t & 63, q = t >> 6;
+            float in[MAXIN];
+#pragma unroll
+            for (int j = 0; j < MAXIN; j++) in[j] = ins[row * MAXIN + j];
+            for (int kk = q * 128; kk < q * 128 + 128; kk++) {
+                float acc = w->b1[kk];
+#pragma unroll
+                for (int j = 0; j < MAXIN; j++) acc = fmaf(w->W1[kk][j], in[j], acc);
+                H1s[row * F_HSTR + kk] = kk < HID ? fmaxf(acc, 0.0f) : 0.0f;
+            }
+        }
+        __syncthreads();
+        {  // layers 2 + 3: thread -> 4 rows x 4 columns of each 64-column panel
+            const int ty = t >> 4, tx = t & 15;
+            float yp[4][MAXDX];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < MAXDX; j++) yp[i][j] = 0.0f;
+            for (int p = 0; p < H / 64; p++) {
+                const int n0 = p * 64 + tx * 4;
+                float acc[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) acc[i][c] = 0.0f;
+                const float* h = H1s + (ty * 4) * F_HSTR;
+#pragma unroll 4
+                for (int kk = 0; kk < HID; kk++) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(&w->W2t[kk][n0]));
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const float av = h[i * F_HSTR + kk];
+                        acc[i][0] = fmaf(av, b.x, acc[i][0]);
+                        acc[i][1] = fmaf(av, b.y, acc[i][1]);
+                        acc[i][2] = fmaf(av, b.z, acc[i][2]);
+                        acc[i][3] = fmaf(av, b.w, acc[i][3]);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const float bb = w->b2[n0 + c];
+                    const float4 w3 = *reinterpret_cast<const float4*>(&w->W3[n0 + c][0]);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const float h2 = fmaxf(acc[i][c] + bb, 0.0f);
+                        yp[i][0] = fmaf(h2, w3.x, yp[i][0]);
+                        yp[i][1] = fmaf(h2, w3.y, yp[i][1]);
+                        yp[i][2] = fmaf(h2, w3.z, yp[i][2]);
+                        yp[i][3] = fmaf(h2, w3.w, yp[i][3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < MAXDX; j++) {
+                    float v = yp[i][j];
+                    v += __shfl_xor_sync(0xffffffffu, v, 8);
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    if (tx == 0) ys[(ty * 4 + i) * MAXDX + j] = v;
+                }
+        }
+        __syncthreads();
+        if (owner) {
+            float y[MAXDX];
+#pragma unroll
+            for (int j = 0; j < MAXDX; j++) y[j] = ys[t * MAXDX + j];
+            finish_row(a, r, valid, k, y, x, u);
+        }
+        __syncthreads();
+    }
+}
+
+// ---- tcgen05 helpers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok = 0;
+    for (uint32_t spins = 0; !ok; spins++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!ok && spins > (1u << 26)) __trap();  // a lost arrival must not hang the GPU
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// K-major, 128-byte swizzle: 8-row groups 1024 B apart (SBO), LBO field 1 (unused for swizzled K-major), version 1
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// D (fp32) = A (bf16, K-major) x B (bf16, K-major), M = 128, N = 256
+constexpr uint32_t UMMA_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(UMMA_IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+constexpr int T_ROWS = 128, T_STAGES = 3;
+constexpr int T_A_BYTES = T_ROWS * H * 2;  // 128 KB: 8 k-blocks of [128 rows x 64 k] bf16
+constexpr int T_SMEM = T_A_BYTES + T_STAGES * CHUNK_BYTES + 256;
+
+__global__ void __launch_bounds__(128, 1) mlp_bf16_kernel(const MlpArgs a) {
+    extern __shared__ __align__(1024) uint8_t tsm[];
+    uint8_t* As = tsm;
+    uint8_t* Bs = tsm + T_A_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(tsm + T_A_BYTES + T_STAGES * CHUNK_BYTES);
+    uint64_t* empty = full + T_STAGES;
+    uint64_t* accum = empty + T_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+    const MlpPacked* w = a.w;
+    const int t = threadIdx.x, warp = t >> 5;
+    const int64_t r = (int64_t)blockIdx.x * T_ROWS + t;
+    const bool valid = r < a.R;
+    const pg::MathCtx<double> mc;
+
+    if (t == 0) {
+        for (int s = 0; s < T_STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {  // the whole accumulator file of the SM: 128 lanes x 512 fp32 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    double x[8], u[2];
+    load_row(a, r, valid, x, u);
+    uint32_t chunk_no = 0;  // producer (thread 0) and MMA issuer (thread 32) count chunks the same way
+    const int steps = a.rollout ? a.T : 1;
+    for (int k = 0; k < steps; k++) {
+        if (a.rollout && valid) control_of_row(a, k, r, x, u);
+        float in[MAXIN];
+        network_input(a, mc, x, u, in);
+        // layer 1 -> bf16 -> swizzled K-major A image: element (row, kk) of k-block kb lives at
+        //   kb * 16 KB + (row / 8) * 1024 + (row % 8) * 128 + (((kk / 8) ^ (row % 8)) * 16) + (kk % 8) * 2
+        {
+            uint8_t* rowp = As + (t >> 3) * 1024 + (t & 7) * 128;
+            for (int g = 0; g < H / 8; g++) {  // 8 hidden units = one 16-byte chunk
+                uint32_t packed[4];
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) {
+                    float h2[2];
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        const int kk = g * 8 + e + q;
+                        float acc = w->b1[kk];
+#pragma unroll
+                        for (int j = 0; j < MAXIN; j++) acc = fmaf(w->W1[kk][j], in[j], acc);
+                        h2[q] = kk < HID ? fmaxf(acc, 0.0f) : 0.0f;
+                    }
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(packed[e >> 1]) : "f"(h2[1]), "f"(h2[0]));
+                }
+                const int kb = g >> 3, cidx = (g & 7) ^ (t & 7);
+                *reinterpret_cast<uint4*>(rowp + kb * (T_ROWS * 128) + cidx * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA unit
+        __syncthreads();
+        if (t == 0) {  // producer: W2 chunks, L2 -> smem ring
+            uint32_t c = chunk_no;
+            for (int i = 0; i < N_CHUNKS; i++, c++) {
+                const uint32_t s = c % T_STAGES, use = c / T_STAGES;
+                mbar_wait(&empty[s], (use & 1) ^ 1);
+                mbar_expect_tx(&full[s], CHUNK_BYTES);
+                bulk_g2s(Bs + s * CHUNK_BYTES, &w->W2b[i][0], CHUNK_BYTES, &full[s]);
+            }
+        } else if (t == 32) {  // MMA issuer: one thread drives the tensor core for the whole CTA
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t c = chunk_no;
+            for (int i = 0; i < N_CHUNKS; i++, c++) {
+                const uint32_t s = c % T_STAGES, use = c / T_STAGES;
+                mbar_wait(&full[s], use & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const int kb = i >> 1, half = i & 1;
+                const uint32_t a_addr = smem_u32(As + kb * (T_ROWS * 128));
+                const uint32_t b_addr = smem_u32(Bs + s * CHUNK_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < 4; ks++)  // K = 16 per instruction = 32 bytes along the swizzled row
+                    umma_bf16(tmem_base + half * 256, umma_desc_sw128(a_addr + ks * 32), umma_desc_sw128(b_addr + ks * 32),
+                              (kb > 0 || ks > 0) ? 1u : 0u);
+                umma_commit(&empty[s]);  // frees the stage when these MMAs have read it
+            }
+            umma_commit(accum);  // all 64 MMAs of this control interval done -> accumulators readable
+        }
+        chunk_no += N_CHUNKS;
+        mbar_wait(accum, k & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // epilogue: thread = row = TMEM lane; +b2, ReLU, layer 3
+        float y[MAXDX] = {0.0f, 0.0f, 0.0f, 0.0f};
+        for (int cb = 0; cb < H / 32; cb++) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + cb * 32, v);
+#pragma unroll
+            for (int c = 0; c < 32; c++) {
+                const int nn = cb * 32 + c;
+                const float h2 = fmaxf(__uint_as_float(v[c]) + w->b2[nn], 0.0f);
+                const float4 w3 = *reinterpret_cast<const float4*>(&w->W3[nn][0]);
+                y[0] = fmaf(h2, w3.x, y[0]);
+                y[1] = fmaf(h2, w3.y, y[1]);
+                y[2] = fmaf(h2, w3.z, y[2]);
+                y[3] = fmaf(h2, w3.w, y[3]);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();  // every lane has read its accumulators before the next interval's MMAs overwrite them
+        finish_row(a, r, valid, k, y, x, u);
+    }
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
+int launch(int precision, const MlpArgs& a, cudaStream_t st) {
+    if (a.R == 0) return 0;
+    if (precision == PG_MLP_FP32) {
+        const int smem = (F_ROWS * F_HSTR + F_ROWS * MAXIN + F_ROWS * MAXDX) * 4;
+        static bool set = false;
+        if (!set) {
+            cudaError_t e = cudaFuncSetAttribute(mlp_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return (int)e;
+            set = true;
+        }
+        mlp_fp32_kernel<<<(unsigned)((a.R + F_ROWS - 1) / F_ROWS), 256, smem, st>>>(a);
+    } else if (precision == PG_MLP_BF16) {
+        static bool set = false;
+        if (!set) {
+            cudaError_t e = cudaFuncSetAttribute(mlp_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM);
+            if (e != cudaSuccess) return (int)e;
+            set = true;
+        }
+        mlp_bf16_kernel<<<(unsigned)((a.R + T_ROWS - 1) / T_ROWS), 128, T_SMEM, st>>>(a);
+    } else {
+        return PG_E_BADARG;
+    }
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+bool dims_ok(const pg_mlp_dims_t* d) {
+    if (!d || d->n < 2 || d->n > 8 || (d->n & 1) || d->m < 1 || d->m > 2) return false;
+    int no = 0;
+    for (int i = 0; i < d->n; i++) no += d->is_angle[i] ? 2 : 1;
+    return no == d->n_obs && d->n_obs + d->m <= MAXIN && d->dx_dim == d->n / 2 && d->dx_dim <= MAXDX;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t pg_mlp_packed_bytes(void) { return (int64_t)sizeof(MlpPacked); }
+
+int pg_mlp_pack(const pg_mlp_dims_t* d, const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
+                const float* b3, const float* o_mean, const float* o_var, const float* u_mean, const float* u_var,
+                const float* dx_mean, const float* dx_var, void* packed_host) {
+    if (!dims_ok(d) || !W1 || !b1 || !W2 || !b2 || !W3 || !b3 || !packed_host) return PG_E_BADARG;
+    MlpPacked* p = (MlpPacked*)packed_host;
+    memset(p, 0, sizeof(MlpPacked));
+    const int nin = d->n_obs + d->m;
+    for (int k = 0; k < HID; k++) {
+        for (int j = 0; j < nin; j++) p->W1[k][j] = W1[k * nin + j];
+        p->b1[k] = b1[k];
+        p->b2[k] = b2[k];
+        for (int j = 0; j < d->dx_dim; j++) p->W3[k][j] = W3[j * HID + k];
+        for (int n = 0; n < HID; n++) p->W2t[k][n] = W2[n * HID + k];  // W2 is [out n][in k]
+    }
+    for (int j = 0; j < d->dx_dim; j++) {
+        p->b3[j] = b3[j];
+        p->dx_mean[j] = dx_mean ? dx_mean[j] : 0.0f;
+        p->dx_var[j] = dx_var ? dx_var[j] : 1.0f;
+    }
+    for (int j = 0; j < MAXIN; j++) {
+        p->o_mean[j] = (o_mean && j < d->n_obs) ? o_mean[j] : 0.0f;
+        p->o_var[j] = (o_var && j < d->n_obs) ? o_var[j] : 1.0f;
+    }
+    for (int j = 0; j < 2; j++) {
+        p->u_mean[j] = (u_mean && j < d->m) ? u_mean[j] : 0.0f;
+        p->u_var[j] = (u_var && j < d->m) ? u_var[j] : 1.0f;
+    }
+    // bf16 chunk images: chunk = kb * 2 + half holds W2[n = half*256 + nl][k = kb*64 + kk] at the swizzled offset
+    for (int kb = 0; kb < 8; kb++)
+        for (int half = 0; half < 2; half++) {
+            uint16_t* img = p->W2b[kb * 2 + half];
+            for (int nl = 0; nl < 256; nl++)
+                for (int kk = 0; kk < 64; kk++) {
+                    const int n = half * 256 + nl, k = kb * 64 + kk;
+                    const float v = (n < HID && k < HID) ? W2[n * HID + k] : 0.0f;
+                    const int off = (nl >> 3) * 1024 + (nl & 7) * 128 + (((kk >> 3) ^ (nl & 7)) << 4) + (kk & 7) * 2;
+                    img[off >> 1] = f32_to_bf16(v);
+                }
+        }
+    return 0;
+}
+
+int pg_mlp_ode(int precision, const pg_mlp_dims_t* dims, const void* packed, int64_t R, double dt, const double* x,
+               const double* u, double* rhs, void* stream) {
+    if (R == 0) return 0;
+    if (!dims_ok(dims) || !packed || R < 0 || !x || !u || !rhs || !(dt > 0)) return PG_E_BADARG;
+    MlpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.d = *dims;
+    a.w = (const MlpPacked*)packed;
+    a.R = R;
+    a.T = 1;
+    a.dt = dt;
+    a.rollout = 0;
+    a.x0 = x;
+    a.U = u;
+    a.rhs = rhs;
+    return launch(precision, a, (cudaStream_t)stream);
+}
+
+int pg_mlp_rollout(int precision, const pg_mlp_dims_t* dims, const void* packed, int64_t B, int32_t T, double dt,
+                   const double* x0, const double* U, const double* KK, const double* kk, const double* xbar,
+                   const double* ubar, double alpha, const double* ulim, double* X, double* U_out, void* stream) {
+    if (B == 0) return 0;
+    if (!dims_ok(dims) || !packed || B < 0 || T < 0 || !x0 || !X || !(dt > 0)) return PG_E_BADARG;
+    if (KK && (!kk || !xbar || !ubar)) return PG_E_BADARG;
+    MlpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.d = *dims;
+    a.w = (const MlpPacked*)packed;
+    a.R = B;
+    a.T = T;
+    a.dt = dt;
+    a.rollout = 1;
+    a.x0 = x0;
+    a.U = U;
+    a.KK = KK;
+    a.kk = kk;
+    a.xbar = xbar;
+    a.ubar = ubar;
+    a.alpha = alpha;
+    a.clip = ulim != nullptr;
+    for (int j = 0; j < dims->m && ulim; j++) a.ulim[j] = ulim[j];
+    a.X = X;
+    a.U_out = U_out;
+    return launch(precision, a, (cudaStream_t)stream);
+}
+
+}  // extern "C"

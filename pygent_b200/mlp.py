@@ -1,0 +1,172 @@
+"""GPU path of the learned-MLP dynamics (include/pygent_b200_mlp.h): library build, ctypes binding, and the
+environment that integrates `MBRL.ode` (pygent/algorithms/mbrl.py:125-130) with forward Euler.
+
+`precision="fp32"`: layer 2 in fp32 FFMA -- tracks the reference's fp32 torch network to ~1e-6;
+`precision="bf16"`: layer 2 on the tcgen05 tensor cores (bf16 operands, fp32 accumulation in TMEM).
+"""
+import ctypes
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import torch
+
+from . import build as pgbuild
+from .lib import PygentB200Error
+
+PRECISIONS = {"fp32": 0, "bf16": 1}
+_SRC = [os.path.join(pgbuild.CSRC, "pg_mlp.cu"), os.path.join(pgbuild.CSRC, "pg_math.cuh"),
+        os.path.join(pgbuild.INCLUDE, "pygent_b200_mlp.h")]
+
+
+class Dims(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_int32), ("m", ctypes.c_int32), ("n_obs", ctypes.c_int32), ("dx_dim", ctypes.c_int32),
+                ("is_angle", ctypes.c_uint8 * 8)]
+
+
+def library_path():
+    h = hashlib.sha1()
+    for p in _SRC:
+        with open(p, "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(pgbuild.NVCC_FLAGS).encode())
+    return os.path.join(pgbuild.CACHE, "pg_mlp_%s.so" % h.hexdigest()[:12])
+
+
+def build_library(force=False):
+    so = library_path()
+    if os.path.isfile(so) and not force:
+        return so
+    nvcc = pgbuild.find_nvcc()
+    if nvcc is None:
+        raise RuntimeError("pygent_b200: %s is missing and nvcc was not found; there is no CPU fallback" % so)
+    os.makedirs(pgbuild.CACHE, exist_ok=True)
+    tmp = so + ".tmp%d" % os.getpid()
+    res = subprocess.run([nvcc] + pgbuild.NVCC_FLAGS + [_SRC[0], "-o", tmp], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed for pg_mlp.cu:\n" + res.stderr[-4000:])
+    os.replace(tmp, so)
+    return so
+
+
+_vp, _i32, _i64, _f64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
+_fp = ctypes.POINTER(ctypes.c_float)
+_dims_p = ctypes.POINTER(Dims)
+SIGNATURES = {
+    "pg_mlp_pack": [_dims_p] + [_fp] * 12 + [_vp],
+    "pg_mlp_ode": [_i32, _dims_p, _vp, _i64, _f64, _vp, _vp, _vp, _vp],
+    "pg_mlp_rollout": [_i32, _dims_p, _vp, _i64, _i32, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _f64,
+                       ctypes.POINTER(ctypes.c_double), _vp, _vp, _vp],
+}
+_dll = None
+
+
+def dll():
+    global _dll
+    if _dll is None:
+        _dll = ctypes.CDLL(build_library())
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(_dll, name)
+            fn.argtypes, fn.restype = argtypes, ctypes.c_int
+        _dll.pg_mlp_packed_bytes.restype = ctypes.c_int64
+    return _dll
+
+
+def _check(rc, what):
+    if rc:
+        raise PygentB200Error("%s failed: %s" % (what, "bad argument" if rc < 0 else "CUDA error %d" % rc))
+
+
+def _dev(a, device):
+    """host [R, c] -> device [c, R] fp64"""
+    return torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype=float).T), dtype=torch.float64, device=device)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float64):
+        raise PygentB200Error("MLP path expects contiguous fp64 CUDA tensors")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class MLPDynamics:
+    """Packed network + moments on the device."""
+
+    def __init__(self, dims, packed, device):
+        self.dims, self.packed, self.device = dims, packed, device
+        self.n, self.m = dims.n, dims.m
+        self.launches = 0
+
+    @classmethod
+    def from_arrays(cls, n, m, is_angle, W1, b1, W2, b2, W3, b3, o_mean=None, o_var=None, u_mean=None, u_var=None,
+                    dx_mean=None, dx_var=None, device=None):
+        if device is None:
+            if not torch.cuda.is_available():
+                raise PygentB200Error("pygent_b200 needs a CUDA device (B200); there is no CPU fallback")
+            device = torch.device("cuda", torch.cuda.current_device())
+        d = Dims()
+        d.n, d.m = n, m
+        d.n_obs = int(n + np.sum(np.asarray(is_angle, dtype=bool)))
+        d.dx_dim = n // 2
+        for i, a in enumerate(is_angle):
+            d.is_angle[i] = 1 if a else 0
+        f = lambda a: None if a is None else np.ascontiguousarray(np.asarray(a, dtype=np.float32).ravel())
+        arrs = [f(a) for a in (W1, b1, W2, b2, W3, b3, o_mean, o_var, u_mean, u_var, dx_mean, dx_var)]
+        nbytes = int(dll().pg_mlp_packed_bytes())
+        host = torch.empty(nbytes + 1024, dtype=torch.uint8)
+        off = (-host.data_ptr()) % 1024
+        ptrs = [None if a is None else a.ctypes.data_as(_fp) for a in arrs]
+        _check(dll().pg_mlp_pack(ctypes.byref(d), *ptrs, ctypes.c_void_p(host.data_ptr() + off)), "pg_mlp_pack")
+        raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+        doff = (-raw.data_ptr()) % 1024
+        packed = raw[doff:doff + nbytes]
+        packed.copy_(host[off:off + nbytes])
+        obj = cls(d, packed, device)
+        obj._raw = raw
+        return obj
+
+    @classmethod
+    def from_module(cls, net, device=None):
+        """net: `pygent_b200.nn_models.NNDynamics` (or the reference's): layer1/2/3 + moments."""
+        g = lambda t: t.detach().cpu().numpy()
+        assert net.dxDim == net.xDim // 2, "only sparse_dyn networks (velocity half, mbrl.py:54-57) are supported"
+        return cls.from_arrays(net.xDim, net.uDim, net.xIsAngle, g(net.layer1.weight), g(net.layer1.bias),
+                               g(net.layer2.weight), g(net.layer2.bias), g(net.layer3.weight), g(net.layer3.bias),
+                               g(net.oMean), g(net.oVar), g(net.uMean), g(net.uVar), g(net.dxMean), g(net.dxVar), device)
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def ode_device(self, x, u, dt, precision="fp32"):
+        """x [n, R], u [m, R] device fp64 -> rhs [n, R] = MBRL.ode."""
+        R = x.shape[1]
+        rhs = torch.empty_like(x)
+        _check(dll().pg_mlp_ode(PRECISIONS[precision], ctypes.byref(self.dims), ctypes.c_void_p(self.packed.data_ptr()),
+                                R, dt, _ptr(x), _ptr(u), _ptr(rhs), self._stream()), "pg_mlp_ode")
+        self.launches += 1
+        return rhs
+
+    def ode(self, x, u, dt, precision="fp32"):
+        """host x [R, n], u [R, m] -> rhs [R, n]"""
+        rhs = self.ode_device(_dev(x, self.device), _dev(u, self.device), dt, precision)
+        return rhs.cpu().numpy().T
+
+    def rollout_device(self, x0, dt, T=None, U=None, gains=None, alpha=1.0, ulim=None, precision="fp32", want_u=False):
+        """x0 [n, B]; open loop U [T, m, B] (None: u = 0) or closed loop gains = (KK, kk, xbar, ubar).
+        Returns X [T+1, n, B] (and the applied controls [T, m, B] if want_u)."""
+        B = x0.shape[1]
+        if U is not None:
+            T = U.shape[0]
+        if gains is not None:
+            T = gains[3].shape[0]
+        X = torch.empty((T + 1, self.n, B), dtype=torch.float64, device=self.device)
+        Uo = torch.empty((T, self.m, B), dtype=torch.float64, device=self.device) if want_u else None
+        KK, kk, xbar, ubar = gains if gains is not None else (None, None, None, None)
+        lim = None if ulim is None else (ctypes.c_double * len(ulim))(*[float(v) for v in ulim])
+        _check(dll().pg_mlp_rollout(PRECISIONS[precision], ctypes.byref(self.dims), ctypes.c_void_p(self.packed.data_ptr()),
+                                    B, T, dt, _ptr(x0), _ptr(U), _ptr(KK), _ptr(kk), _ptr(xbar), _ptr(ubar), alpha, lim,
+                                    _ptr(X), _ptr(Uo), self._stream()), "pg_mlp_rollout")
+        self.launches += 1
+        return (X, Uo) if want_u else X
