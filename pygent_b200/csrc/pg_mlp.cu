@@ -320,22 +320,31 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-constexpr int T_ROWS = 128, T_STAGES = 3;
+constexpr int T_ROWS = 128, T_STAGES = 2, T_THREADS = 512, T_SPLIT = T_THREADS / T_ROWS;
 constexpr int T_A_BYTES = T_ROWS * H * 2;  // 128 KB: 8 k-blocks of [128 rows x 64 k] bf16
-constexpr int T_SMEM = T_A_BYTES + T_STAGES * CHUNK_BYTES + 256;
+constexpr int T_INS_BYTES = T_ROWS * MAXIN * 4;            // network inputs of the 128 rows
+constexpr int T_YP_BYTES = T_SPLIT * T_ROWS * MAXDX * 4;   // partial layer-3 sums
+constexpr int T_SMEM = T_A_BYTES + T_STAGES * CHUNK_BYTES + T_INS_BYTES + T_YP_BYTES + 256;
 
-__global__ void __launch_bounds__(128, 1) mlp_bf16_kernel(const MlpArgs a) {
+// 512 threads per CTA: thread t works on row (t & 127); the four threads of a row split the hidden units
+// (layer 1) and the accumulator columns (epilogue) four ways.  Warp w reads TMEM lanes 32 (w % 4) .. +31, which
+// is exactly the row quarter (t & 127) >> 5 of its threads.  Threads 0..127 own the fp64 state of their row.
+__global__ void __launch_bounds__(T_THREADS, 1) mlp_bf16_kernel(const MlpArgs a) {
     extern __shared__ __align__(1024) uint8_t tsm[];
     uint8_t* As = tsm;
     uint8_t* Bs = tsm + T_A_BYTES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(tsm + T_A_BYTES + T_STAGES * CHUNK_BYTES);
+    float* ins = reinterpret_cast<float*>(tsm + T_A_BYTES + T_STAGES * CHUNK_BYTES);
+    float* yp = ins + T_ROWS * MAXIN;
+    uint64_t* full = reinterpret_cast<uint64_t*>(yp + T_SPLIT * T_ROWS * MAXDX);
     uint64_t* empty = full + T_STAGES;
     uint64_t* accum = empty + T_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
     const MlpPacked* w = a.w;
-    const int t = threadIdx.x, warp = t >> 5;
-    const int64_t r = (int64_t)blockIdx.x * T_ROWS + t;
-    const bool valid = r < a.R;
+    const int t = threadIdx.x, warp = t >> 5, row = t & (T_ROWS - 1), part = t >> 7;
+    const bool owner = t < T_ROWS;
+    const int64_t r = (int64_t)blockIdx.x * T_ROWS + row;
+    const bool valid = owner && r < a.R;
+    const int nin = a.d.n_obs + a.d.m;
     const pg::MathCtx<double> mc;
 
     if (t == 0) {
@@ -356,33 +365,44 @@ __global__ void __launch_bounds__(128, 1) mlp_bf16_kernel(const MlpArgs a) {
     const uint32_t tmem_base = *tmem_slot;
 
     double x[8], u[2];
-    load_row(a, r, valid, x, u);
+    if (owner) load_row(a, r, valid, x, u);
     uint32_t chunk_no = 0;  // producer (thread 0) and MMA issuer (thread 32) count chunks the same way
     const int steps = a.rollout ? a.T : 1;
     for (int k = 0; k < steps; k++) {
-        if (a.rollout && valid) control_of_row(a, k, r, x, u);
-        float in[MAXIN];
-        network_input(a, mc, x, u, in);
+        if (owner) {
+            if (a.rollout && valid) control_of_row(a, k, r, x, u);
+            float in[MAXIN];
+            network_input(a, mc, x, u, in);
+#pragma unroll
+            for (int j = 0; j < MAXIN; j++) ins[row * MAXIN + j] = in[j];
+        }
+        __syncthreads();
         // layer 1 -> bf16 -> swizzled K-major A image: element (row, kk) of k-block kb lives at
         //   kb * 16 KB + (row / 8) * 1024 + (row % 8) * 128 + (((kk / 8) ^ (row % 8)) * 16) + (kk % 8) * 2
         {
-            uint8_t* rowp = As + (t >> 3) * 1024 + (t & 7) * 128;
-            for (int g = 0; g < H / 8; g++) {  // 8 hidden units = one 16-byte chunk
+            float in[MAXIN];
+#pragma unroll
+            for (int j = 0; j < MAXIN; j++) in[j] = ins[row * MAXIN + j];
+            uint8_t* rowp = As + (row >> 3) * 1024 + (row & 7) * 128;
+            for (int g = part * (H / 8 / T_SPLIT); g < (part + 1) * (H / 8 / T_SPLIT); g++) {  // 8 hidden units = one 16-byte chunk
+                float acc[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) acc[e] = w->b1[g * 8 + e];
+#pragma unroll
+                for (int j = 0; j < MAXIN; j++) {
+                    if (j < nin) {
+#pragma unroll
+                        for (int e = 0; e < 8; e++) acc[e] = fmaf(w->W1[g * 8 + e][j], in[j], acc[e]);
+                    }
+                }
                 uint32_t packed[4];
 #pragma unroll
                 for (int e = 0; e < 8; e += 2) {
-                    float h2[2];
-#pragma unroll
-                    for (int q = 0; q < 2; q++) {
-                        const int kk = g * 8 + e + q;
-                        float acc = w->b1[kk];
-#pragma unroll
-                        for (int j = 0; j < MAXIN; j++) acc = fmaf(w->W1[kk][j], in[j], acc);
-                        h2[q] = kk < HID ? fmaxf(acc, 0.0f) : 0.0f;
-                    }
-                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(packed[e >> 1]) : "f"(h2[1]), "f"(h2[0]));
+                    const float lo = (g * 8 + e) < HID ? fmaxf(acc[e], 0.0f) : 0.0f;
+                    const float hi = (g * 8 + e + 1) < HID ? fmaxf(acc[e + 1], 0.0f) : 0.0f;
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(packed[e >> 1]) : "f"(hi), "f"(lo));
                 }
-                const int kb = g >> 3, cidx = (g & 7) ^ (t & 7);
+                const int kb = g >> 3, cidx = (g & 7) ^ (row & 7);
                 *reinterpret_cast<uint4*>(rowp + kb * (T_ROWS * 128) + cidx * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
             }
         }
@@ -417,25 +437,38 @@ __global__ void __launch_bounds__(128, 1) mlp_bf16_kernel(const MlpArgs a) {
         chunk_no += N_CHUNKS;
         mbar_wait(accum, k & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // epilogue: thread = row = TMEM lane; +b2, ReLU, layer 3
-        float y[MAXDX] = {0.0f, 0.0f, 0.0f, 0.0f};
-        for (int cb = 0; cb < H / 32; cb++) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + cb * 32, v);
+        // epilogue: TMEM lane = row; this thread's quarter of the 512 columns: +b2, ReLU, layer 3
+        {
+            float y[MAXDX] = {0.0f, 0.0f, 0.0f, 0.0f};
+            for (int cb = part * (H / 32 / T_SPLIT); cb < (part + 1) * (H / 32 / T_SPLIT); cb++) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + cb * 32, v);
 #pragma unroll
-            for (int c = 0; c < 32; c++) {
-                const int nn = cb * 32 + c;
-                const float h2 = fmaxf(__uint_as_float(v[c]) + w->b2[nn], 0.0f);
-                const float4 w3 = *reinterpret_cast<const float4*>(&w->W3[nn][0]);
-                y[0] = fmaf(h2, w3.x, y[0]);
-                y[1] = fmaf(h2, w3.y, y[1]);
-                y[2] = fmaf(h2, w3.z, y[2]);
-                y[3] = fmaf(h2, w3.w, y[3]);
+                for (int c = 0; c < 32; c++) {
+                    const int nn = cb * 32 + c;
+                    const float h2 = fmaxf(__uint_as_float(v[c]) + w->b2[nn], 0.0f);
+                    const float4 w3 = *reinterpret_cast<const float4*>(&w->W3[nn][0]);
+                    y[0] = fmaf(h2, w3.x, y[0]);
+                    y[1] = fmaf(h2, w3.y, y[1]);
+                    y[2] = fmaf(h2, w3.z, y[2]);
+                    y[3] = fmaf(h2, w3.w, y[3]);
+                }
             }
+            *reinterpret_cast<float4*>(&yp[(part * T_ROWS + row) * MAXDX]) = make_float4(y[0], y[1], y[2], y[3]);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();  // every lane has read its accumulators before the next interval's MMAs overwrite them
-        finish_row(a, r, valid, k, y, x, u);
+        if (owner) {
+            float y[MAXDX];
+#pragma unroll
+            for (int j = 0; j < MAXDX; j++) {
+                float v = 0.0f;
+#pragma unroll
+                for (int q = 0; q < T_SPLIT; q++) v += yp[(q * T_ROWS + row) * MAXDX + j];
+                y[j] = v;
+            }
+            finish_row(a, r, valid, k, y, x, u);
+        }
     }
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
@@ -459,7 +492,7 @@ int launch(int precision, const MlpArgs& a, cudaStream_t st) {
             if (e != cudaSuccess) return (int)e;
             set = true;
         }
-        mlp_bf16_kernel<<<(unsigned)((a.R + T_ROWS - 1) / T_ROWS), 128, T_SMEM, st>>>(a);
+        mlp_bf16_kernel<<<(unsigned)((a.R + T_ROWS - 1) / T_ROWS), T_THREADS, T_SMEM, st>>>(a);
     } else {
         return PG_E_BADARG;
     }
