@@ -20,7 +20,7 @@ import sympy as sp
 from sympy.printing.c import C99CodePrinter
 
 ABI_VERSION = 1
-CODEGEN_VERSION = 3  # bump to invalidate cached libraries when the emitted code changes
+CODEGEN_VERSION = 4  # bump to invalidate cached libraries when the emitted code changes
 
 _FUNCS = {"sin": "pg::sin", "cos": "pg::cos", "tan": "pg::tan", "exp": "pg::exp", "log": "pg::log",
           "sqrt": "pg::sqrt", "asin": "pg::asin", "acos": "pg::acos", "atan": "pg::atan",
@@ -120,7 +120,24 @@ def hoistable_constants(exprs, limit=8):
     return found[:limit]
 
 
-def emit_body(outputs, sym_names, prefix="w", hoisted=()):
+def anchored_trig_args(f_exprs, xs):
+    """The sin/cos arguments of the ODE right-hand side if ALL of them are affine in the state with numeric
+    coefficients (x2, x1 + x2, ...): [(arg, needs_sin, needs_cos)], in the order `emit_body` numbers them;
+    else [].  For such systems the integrator keeps sin/cos of each argument as an "anchor" and obtains the
+    values at the RK stages by rotating the anchor through the small argument increment (pg_math.cuh)."""
+    xs = list(xs)
+    _, trig = _pair_trig([sp.sympify(e) for e in f_exprs], "w")
+    out = []
+    for arg, s, c in trig:
+        if not arg.free_symbols or not arg.free_symbols <= set(xs):
+            return []
+        if arg.atoms(sp.Function) or not all(sp.diff(arg, x).is_number for x in xs):
+            return []
+        out.append((arg, s is not None, c is not None))
+    return out
+
+
+def emit_body(outputs, sym_names, prefix="w", hoisted=(), given_trig=False):
     """C++ statements computing `outputs` = [(lhs_string, sympy expr)].
 
     sym_names: {sympy Symbol: C++ lvalue string}.  Zero expressions are still assigned (callers
@@ -139,8 +156,13 @@ def emit_body(outputs, sym_names, prefix="w", hoisted=()):
     exprs, trig = _pair_trig(exprs, prefix)
     lines = []
     # trig arguments may share sub-expressions with the algebra; keep it simple: emit them first
-    for arg, s, c in trig:
-        if s is not None and c is not None:
+    for j, (arg, s, c) in enumerate(trig):
+        if given_trig:  # sin/cos of the j-th argument are inputs (sn[j], cs[j])
+            if s is not None:
+                lines.append("const T %s = sn[%d];" % (s, j))
+            if c is not None:
+                lines.append("const T %s = cs[%d];" % (c, j))
+        elif s is not None and c is not None:
             lines.append("T %s, %s; m.sincos(%s, %s, %s);" % (s, c, _cxx(arg), s, c))
         elif s is not None:
             lines.append("const T %s = m.sin(%s);" % (s, _cxx(arg)))
@@ -257,6 +279,24 @@ class ProblemSpec:
         L += ["        }", "    };"]
         L += _fn("void f(const T (&x)[N], const T (&u)[M], T (&dx)[N])",
                  emit_body([("dx[%d]" % i, s.f[i]) for i in range(n)], names, hoisted=hoisted))
+        # anchored trig (see anchored_trig_args): argument values, their increment between two states, and f
+        # with sin/cos given
+        targs = anchored_trig_args(list(s.f), xs)
+        nt = len(targs)
+        L.insert(L.index("struct Problem {") + 1, "    static constexpr int NTRIG = %d, NTRIG_ = %d;" % (nt, max(1, nt)))
+        xren = {x: sp.Symbol("x[%d]" % i) for i, x in enumerate(xs)}
+        dren = {x: sp.Symbol("(xb[%d] - xa[%d])" % (i, i)) for i, x in enumerate(xs)}
+        L += _fn("void trig_arg(const T (&x)[N], T (&a)[NTRIG_])",
+                 ["(void)x; (void)a;"] + ["a[%d] = %s;" % (j, _cxx(a.xreplace(xren))) for j, (a, _, _) in enumerate(targs)])
+        L += _fn("void trig_inc(const T (&xa)[N], const T (&xb)[N], T (&d)[NTRIG_])",
+                 ["(void)xa; (void)xb; (void)d;"] +
+                 ["d[%d] = %s;" % (j, _cxx(sum(sp.diff(a, x) * dren[x] for x in xs if sp.diff(a, x) != 0)))
+                  for j, (a, _, _) in enumerate(targs)])
+        if nt:
+            body = emit_body([("dx[%d]" % i, s.f[i]) for i in range(n)], names, hoisted=hoisted, given_trig=True)
+        else:
+            body = ["(void)sn; (void)cs;", "f(m, x, u, dx);"]
+        L += _fn("void f_trig(const T (&x)[N], const T (&u)[M], const T (&sn)[NTRIG_], const T (&cs)[NTRIG_], T (&dx)[N])", body)
         ab_out = [("A[%d]" % (i * n + j), s.A[i, j]) for i in range(n) for j in range(n)]
         ab_out += [("B[%d]" % (i * m + j), s.B[i, j]) for i in range(n) for j in range(m)]
         L += _fn("void AB(const T (&x)[N], const T (&u)[M], T (&A)[N * N], T (&B)[N * M])", emit_body(ab_out, names))

@@ -47,6 +47,58 @@ __device__ __forceinline__ void rk4_substep(const typename P::template Ctx<T>& m
     for (int i = 0; i < N; i++) x[i] = x[i] + h6 * (k1[i] + T(2) * k2[i] + T(2) * k3[i] + k4[i]);
 }
 
+// The same substep for systems whose sin/cos arguments are all affine in the state (Problem::NTRIG > 0, every
+// shipped model): (sn, cs) hold sin/cos of the arguments at x (the anchor); the three intermediate stages and,
+// with ADVANCE, the new anchor at x_{n+1} are rotations of it through the argument increment, which is computed
+// from the rounded states (xt - x is exact), so the rotation sees exactly the angle a fresh evaluation would.
+// `big` collects the largest increment magnitude (see MathCtx::rotate).
+template <typename P, typename T, bool ADVANCE>
+__device__ __forceinline__ void rk4_substep_anchored(const typename P::template Ctx<T>& m, T (&x)[P::N], const T (&u)[P::M], const T h,
+                                                     T (&sn)[P::NTRIG_], T (&cs)[P::NTRIG_], int& big) {
+    constexpr int N = P::N, NT = P::NTRIG_;
+    T k1[N], k2[N], k3[N], k4[N], xt[N], d[NT], s1[NT], c1[NT];
+    const T hh = T(0.5) * h;
+    auto stage = [&](const T (&k)[N], const T w) {
+#pragma unroll
+        for (int i = 0; i < N; i++) xt[i] = x[i] + w * k[i];
+        P::trig_inc(m, x, xt, d);
+#pragma unroll
+        for (int j = 0; j < NT; j++) {
+            big = max(big, m.mag(d[j]));
+            m.rotate(d[j], sn[j], cs[j], s1[j], c1[j]);
+        }
+    };
+    P::f_trig(m, x, u, sn, cs, k1);
+    stage(k1, hh);
+    P::f_trig(m, xt, u, s1, c1, k2);
+    stage(k2, hh);
+    P::f_trig(m, xt, u, s1, c1, k3);
+    stage(k3, h);
+    P::f_trig(m, xt, u, s1, c1, k4);
+    const T h6 = h / T(6);
+#pragma unroll
+    for (int i = 0; i < N; i++) xt[i] = x[i] + h6 * (k1[i] + T(2) * k2[i] + T(2) * k3[i] + k4[i]);
+    if constexpr (ADVANCE) {
+        P::trig_inc(m, x, xt, d);
+#pragma unroll
+        for (int j = 0; j < NT; j++) {
+            big = max(big, m.mag(d[j]));
+            m.rotate(d[j], sn[j], cs[j], sn[j], cs[j]);
+        }
+    }
+    copy(x, xt);
+}
+
+template <typename P, typename T>
+__device__ __forceinline__ void rk4_interval_plain(const typename P::template Ctx<T>& m, T (&x)[P::N], const T (&u)[P::M], const T h, const int S) {
+    if (S == 4) {  // the parity schedule: fully unrolled, no loop-carried register copies
+#pragma unroll
+        for (int s = 0; s < 4; s++) rk4_substep<P, T>(m, x, u, h);
+    } else {
+        for (int s = 0; s < S; s++) rk4_substep<P, T>(m, x, u, h);
+    }
+}
+
 // One control interval. INTEG_EULER is StateSpaceModel.fast_step (environments.py:313-315).
 template <typename P, typename T, int INTEG>
 __device__ __forceinline__ void env_step(const typename P::template Ctx<T>& m, T (&x)[P::N], const T (&u)[P::M], const T dt, const T h, const int S) {
@@ -55,11 +107,31 @@ __device__ __forceinline__ void env_step(const typename P::template Ctx<T>& m, T
         P::f(m, x, u, k1);
 #pragma unroll
         for (int i = 0; i < P::N; i++) x[i] = x[i] + dt * k1[i];
-    } else if (S == 4) {  // the parity schedule: fully unrolled, no loop-carried register copies
+    } else if constexpr (P::NTRIG > 0) {
+        // anchor: one fresh sin/cos per argument and control interval, then rotations (15 of the 16 evaluations
+        // of the S = 4 schedule).  Speculative: if any increment was outside the rotation's domain, the interval
+        // is redone from the saved state with fresh evaluations (never on the example horizons; large |thetadot|).
+        T x0[P::N], sn[P::NTRIG_], cs[P::NTRIG_], a[P::NTRIG_];
+        copy(x0, x);
+        P::trig_arg(m, x, a);
 #pragma unroll
-        for (int s = 0; s < 4; s++) rk4_substep<P, T>(m, x, u, h);
+        for (int j = 0; j < P::NTRIG_; j++) m.sincos(a[j], sn[j], cs[j]);
+        int big = 0;
+        if (S == 4) {
+            rk4_substep_anchored<P, T, true>(m, x, u, h, sn, cs, big);
+            rk4_substep_anchored<P, T, true>(m, x, u, h, sn, cs, big);
+            rk4_substep_anchored<P, T, true>(m, x, u, h, sn, cs, big);
+            rk4_substep_anchored<P, T, false>(m, x, u, h, sn, cs, big);
+        } else {
+            for (int s = 0; s + 1 < S; s++) rk4_substep_anchored<P, T, true>(m, x, u, h, sn, cs, big);
+            rk4_substep_anchored<P, T, false>(m, x, u, h, sn, cs, big);
+        }
+        if (big >= pg::MathCtx<T>::ROT_LIMIT) {
+            copy(x, x0);
+            rk4_interval_plain<P, T>(m, x, u, h, S);
+        }
     } else {
-        for (int s = 0; s < S; s++) rk4_substep<P, T>(m, x, u, h);
+        rk4_interval_plain<P, T>(m, x, u, h, S);
     }
 }
 
