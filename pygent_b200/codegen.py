@@ -20,7 +20,7 @@ import sympy as sp
 from sympy.printing.c import C99CodePrinter
 
 ABI_VERSION = 1
-CODEGEN_VERSION = 4  # bump to invalidate cached libraries when the emitted code changes
+CODEGEN_VERSION = 5  # bump to invalidate cached libraries when the emitted code changes
 
 _FUNCS = {"sin": "pg::sin", "cos": "pg::cos", "tan": "pg::tan", "exp": "pg::exp", "log": "pg::log",
           "sqrt": "pg::sqrt", "asin": "pg::asin", "acos": "pg::acos", "atan": "pg::atan",
@@ -285,12 +285,13 @@ class ProblemSpec:
         nt = len(targs)
         L.insert(L.index("struct Problem {") + 1, "    static constexpr int NTRIG = %d, NTRIG_ = %d;" % (nt, max(1, nt)))
         xren = {x: sp.Symbol("x[%d]" % i) for i, x in enumerate(xs)}
-        dren = {x: sp.Symbol("(xb[%d] - xa[%d])" % (i, i)) for i, x in enumerate(xs)}
+        kren = {x: sp.Symbol("k[%d]" % i) for i, x in enumerate(xs)}
         L += _fn("void trig_arg(const T (&x)[N], T (&a)[NTRIG_])",
                  ["(void)x; (void)a;"] + ["a[%d] = %s;" % (j, _cxx(a.xreplace(xren))) for j, (a, _, _) in enumerate(targs)])
-        L += _fn("void trig_inc(const T (&xa)[N], const T (&xb)[N], T (&d)[NTRIG_])",
-                 ["(void)xa; (void)xb; (void)d;"] +
-                 ["d[%d] = %s;" % (j, _cxx(sum(sp.diff(a, x) * dren[x] for x in xs if sp.diff(a, x) != 0)))
+        # increment of every argument when the state moves by w*k (the arguments are affine: exact)
+        L += _fn("void trig_inc(const T (&k)[N], const T w, T (&d)[NTRIG_])",
+                 ["(void)k; (void)w; (void)d;"] +
+                 ["d[%d] = w*(%s);" % (j, _cxx(sum(sp.diff(a, x) * kren[x] for x in xs if sp.diff(a, x) != 0)))
                   for j, (a, _, _) in enumerate(targs)])
         if nt:
             body = emit_body([("dx[%d]" % i, s.f[i]) for i in range(n)], names, hoisted=hoisted, given_trig=True)

@@ -49,44 +49,66 @@ __device__ __forceinline__ void rk4_substep(const typename P::template Ctx<T>& m
 
 // The same substep for systems whose sin/cos arguments are all affine in the state (Problem::NTRIG > 0, every
 // shipped model): (sn, cs) hold sin/cos of the arguments at x (the anchor); the three intermediate stages and,
-// with ADVANCE, the new anchor at x_{n+1} are rotations of it through the argument increment, which is computed
-// from the rounded states (xt - x is exact), so the rotation sees exactly the angle a fresh evaluation would.
+// with ADVANCE, the new anchor at x_{n+1} are rotations of it through the argument increment w*k (the arguments
+// are affine in x; the angle component of the stage state itself is then dead code).
 // `big` collects the largest increment magnitude (see MathCtx::rotate).
-template <typename P, typename T, bool ADVANCE>
-__device__ __forceinline__ void rk4_substep_anchored(const typename P::template Ctx<T>& m, T (&x)[P::N], const T (&u)[P::M], const T h,
-                                                     T (&sn)[P::NTRIG_], T (&cs)[P::NTRIG_], int& big) {
+// E trajectories per thread, interleaved stage by stage: the FP64 pipe of the B200 reaches its peak only with
+// independent instructions from the SAME warp (profiles/fp_peak_b200.json: ILP 1 saturates at 72% of peak however
+// many warps are resident, ILP 4 at 100% with one warp per scheduler), and one RK4 chain has little ILP.
+template <typename P, typename T, int E, bool ADVANCE>
+__device__ __forceinline__ void rk4_substep_anchored(const typename P::template Ctx<T>& m, T (&x)[E][P::N], const T (&u)[E][P::M], const T h,
+                                                     T (&sn)[E][P::NTRIG_], T (&cs)[E][P::NTRIG_], int& big) {
     constexpr int N = P::N, NT = P::NTRIG_;
-    T k1[N], k2[N], k3[N], k4[N], xt[N], d[NT], s1[NT], c1[NT];
+    T k1[E][N], k2[E][N], k3[E][N], k4[E][N], xt[E][N], d[E][NT], s1[E][NT], c1[E][NT];
     const T hh = T(0.5) * h;
-    auto stage = [&](const T (&k)[N], const T w) {
+    auto stage = [&](const T (&k)[E][N], const T w) {
 #pragma unroll
-        for (int i = 0; i < N; i++) xt[i] = x[i] + w * k[i];
-        P::trig_inc(m, x, xt, d);
+        for (int e = 0; e < E; e++) {
 #pragma unroll
-        for (int j = 0; j < NT; j++) {
-            big = max(big, m.mag(d[j]));
-            m.rotate(d[j], sn[j], cs[j], s1[j], c1[j]);
+            for (int i = 0; i < N; i++) xt[e][i] = x[e][i] + w * k[e][i];
+            P::trig_inc(m, k[e], w, d[e]);
         }
+#pragma unroll
+        for (int e = 0; e < E; e++)
+#pragma unroll
+            for (int j = 0; j < NT; j++) {
+                big = max(big, m.mag(d[e][j]));
+                m.rotate(d[e][j], sn[e][j], cs[e][j], s1[e][j], c1[e][j]);
+            }
     };
-    P::f_trig(m, x, u, sn, cs, k1);
+#pragma unroll
+    for (int e = 0; e < E; e++) P::f_trig(m, x[e], u[e], sn[e], cs[e], k1[e]);
     stage(k1, hh);
-    P::f_trig(m, xt, u, s1, c1, k2);
+#pragma unroll
+    for (int e = 0; e < E; e++) P::f_trig(m, xt[e], u[e], s1[e], c1[e], k2[e]);
     stage(k2, hh);
-    P::f_trig(m, xt, u, s1, c1, k3);
+#pragma unroll
+    for (int e = 0; e < E; e++) P::f_trig(m, xt[e], u[e], s1[e], c1[e], k3[e]);
     stage(k3, h);
-    P::f_trig(m, xt, u, s1, c1, k4);
+#pragma unroll
+    for (int e = 0; e < E; e++) P::f_trig(m, xt[e], u[e], s1[e], c1[e], k4[e]);
     const T h6 = h / T(6);
+    T ks[E][N];
 #pragma unroll
-    for (int i = 0; i < N; i++) xt[i] = x[i] + h6 * (k1[i] + T(2) * k2[i] + T(2) * k3[i] + k4[i]);
-    if constexpr (ADVANCE) {
-        P::trig_inc(m, x, xt, d);
+    for (int e = 0; e < E; e++)
 #pragma unroll
-        for (int j = 0; j < NT; j++) {
-            big = max(big, m.mag(d[j]));
-            m.rotate(d[j], sn[j], cs[j], sn[j], cs[j]);
+        for (int i = 0; i < N; i++) {
+            ks[e][i] = k1[e][i] + T(2) * k2[e][i] + T(2) * k3[e][i] + k4[e][i];
+            xt[e][i] = x[e][i] + h6 * ks[e][i];
         }
+    if constexpr (ADVANCE) {
+#pragma unroll
+        for (int e = 0; e < E; e++) P::trig_inc(m, ks[e], h6, d[e]);
+#pragma unroll
+        for (int e = 0; e < E; e++)
+#pragma unroll
+            for (int j = 0; j < NT; j++) {
+                big = max(big, m.mag(d[e][j]));
+                m.rotate(d[e][j], sn[e][j], cs[e][j], sn[e][j], cs[e][j]);
+            }
     }
-    copy(x, xt);
+#pragma unroll
+    for (int e = 0; e < E; e++) copy(x[e], xt[e]);
 }
 
 template <typename P, typename T>
@@ -99,40 +121,59 @@ __device__ __forceinline__ void rk4_interval_plain(const typename P::template Ct
     }
 }
 
-// One control interval. INTEG_EULER is StateSpaceModel.fast_step (environments.py:313-315).
-template <typename P, typename T, int INTEG>
-__device__ __forceinline__ void env_step(const typename P::template Ctx<T>& m, T (&x)[P::N], const T (&u)[P::M], const T dt, const T h, const int S) {
+// One control interval of E trajectories held by one thread.  INTEG_EULER is StateSpaceModel.fast_step
+// (environments.py:313-315).
+template <typename P, typename T, int INTEG, int E>
+__device__ __forceinline__ void env_step_multi(const typename P::template Ctx<T>& m, T (&x)[E][P::N], const T (&u)[E][P::M], const T dt, const T h,
+                                               const int S) {
     if constexpr (INTEG == INTEG_EULER) {
-        T k1[P::N];
-        P::f(m, x, u, k1);
 #pragma unroll
-        for (int i = 0; i < P::N; i++) x[i] = x[i] + dt * k1[i];
+        for (int e = 0; e < E; e++) {
+            T k1[P::N];
+            P::f(m, x[e], u[e], k1);
+#pragma unroll
+            for (int i = 0; i < P::N; i++) x[e][i] = x[e][i] + dt * k1[i];
+        }
     } else if constexpr (P::NTRIG > 0) {
         // anchor: one fresh sin/cos per argument and control interval, then rotations (15 of the 16 evaluations
         // of the S = 4 schedule).  Speculative: if any increment was outside the rotation's domain, the interval
         // is redone from the saved state with fresh evaluations (never on the example horizons; large |thetadot|).
-        T x0[P::N], sn[P::NTRIG_], cs[P::NTRIG_], a[P::NTRIG_];
-        copy(x0, x);
-        P::trig_arg(m, x, a);
+        T x0[E][P::N], sn[E][P::NTRIG_], cs[E][P::NTRIG_], a[E][P::NTRIG_];
 #pragma unroll
-        for (int j = 0; j < P::NTRIG_; j++) m.sincos(a[j], sn[j], cs[j]);
+        for (int e = 0; e < E; e++) {
+            copy(x0[e], x[e]);
+            P::trig_arg(m, x[e], a[e]);
+        }
+#pragma unroll
+        for (int e = 0; e < E; e++)
+#pragma unroll
+            for (int j = 0; j < P::NTRIG_; j++) m.sincos(a[e][j], sn[e][j], cs[e][j]);
         int big = 0;
         if (S == 4) {
-            rk4_substep_anchored<P, T, true>(m, x, u, h, sn, cs, big);
-            rk4_substep_anchored<P, T, true>(m, x, u, h, sn, cs, big);
-            rk4_substep_anchored<P, T, true>(m, x, u, h, sn, cs, big);
-            rk4_substep_anchored<P, T, false>(m, x, u, h, sn, cs, big);
+            rk4_substep_anchored<P, T, E, true>(m, x, u, h, sn, cs, big);
+            rk4_substep_anchored<P, T, E, true>(m, x, u, h, sn, cs, big);
+            rk4_substep_anchored<P, T, E, true>(m, x, u, h, sn, cs, big);
+            rk4_substep_anchored<P, T, E, false>(m, x, u, h, sn, cs, big);
         } else {
-            for (int s = 0; s + 1 < S; s++) rk4_substep_anchored<P, T, true>(m, x, u, h, sn, cs, big);
-            rk4_substep_anchored<P, T, false>(m, x, u, h, sn, cs, big);
+            for (int s = 0; s + 1 < S; s++) rk4_substep_anchored<P, T, E, true>(m, x, u, h, sn, cs, big);
+            rk4_substep_anchored<P, T, E, false>(m, x, u, h, sn, cs, big);
         }
         if (big >= pg::MathCtx<T>::ROT_LIMIT) {
-            copy(x, x0);
-            rk4_interval_plain<P, T>(m, x, u, h, S);
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                copy(x[e], x0[e]);
+                rk4_interval_plain<P, T>(m, x[e], u[e], h, S);
+            }
         }
     } else {
-        rk4_interval_plain<P, T>(m, x, u, h, S);
+#pragma unroll
+        for (int e = 0; e < E; e++) rk4_interval_plain<P, T>(m, x[e], u[e], h, S);
     }
+}
+
+template <typename P, typename T, int INTEG>
+__device__ __forceinline__ void env_step(const typename P::template Ctx<T>& m, T (&x)[P::N], const T (&u)[P::M], const T dt, const T h, const int S) {
+    env_step_multi<P, T, INTEG, 1>(m, reinterpret_cast<T(&)[1][P::N]>(x), reinterpret_cast<const T(&)[1][P::M]>(u), dt, h, S);
 }
 
 // ---- K1: open-loop rollout ----------------------------------------------------------------------
@@ -205,20 +246,26 @@ __global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs<T> a) {
 // every scheduler is fed the same share of the work.
 //   ticket s < n_groups      : group s, first chunk (implicit, nothing to wait for)
 //   ticket s >= n_groups     : wait until queue[s - n_groups] is published by whichever worker finished a chunk
+// Chunk boundaries come from a table (uniform 20-step chunks by default, see queue_schedule() in pg_abi.cu); the
+// per-unit hand-off costs 6-7 L2 round trips (~15% of the stall samples at 20 steps per unit).
 // The state of a group between chunks lives in xN / cost (L2: written with a release fence, read with
 // ld.cg, because another SM's L1 may hold a stale copy), the group's clock in tq, its next chunk in progress.
+constexpr int MAX_CHUNKS = 255;
+
 template <typename T>
 struct QueueArgs {
     RolloutArgs<T> r;
-    int n_groups, n_chunks, chunk;
+    int n_groups, n_chunks;
+    int bounds[MAX_CHUNKS + 1];  // chunk c covers control intervals [bounds[c], bounds[c + 1])
     int* counters;   // [0] next ticket, [1] next free queue slot, [2] error flag
     int* queue;      // [n_groups * (n_chunks - 1)], zero = not yet published, else group + 1
     int* progress;   // [n_groups] next chunk of the group
     T* tq;           // [n_groups] simulation time of the group
 };
 
-template <typename P, typename T, int INTEG>
-__global__ void __launch_bounds__(128) rollout_queue_kernel(const QueueArgs<T> q) {
+template <typename P, typename T, int INTEG, int E>
+__global__ void __launch_bounds__(128, 3) rollout_queue_kernel(const QueueArgs<T> q) {
+    // a group = 32 * E trajectories: lane l holds trajectories g*32*E + e*32 + l, e < E (every access coalesced)
     const typename P::template Ctx<T> m;
     constexpr int N = P::N, M = P::M;
     const RolloutArgs<T>& a = q.r;
@@ -248,55 +295,73 @@ __global__ void __launch_bounds__(128) rollout_queue_kernel(const QueueArgs<T> q
         }
         g = __shfl_sync(0xffffffffu, g, 0);
         if (g < 0) return;
-        const int c = (g < 0) ? 0 : __ldcg(&q.progress[g]);
-        const int64_t b = (int64_t)g * 32 + lane;
-        const bool valid = b < B;
-        const int64_t bb = valid ? b : B - 1;  // ragged last group: idle lanes shadow the last trajectory
-        const int k0 = c * q.chunk, k1 = min(a.T_steps, k0 + q.chunk);
-        T x[N], u[M], un[M];
-        T cost, t;
-        if (c == 0) {
+        const int c = __ldcg(&q.progress[g]);
+        int64_t b[E], bb[E];
+        bool valid[E];
 #pragma unroll
-            for (int i = 0; i < N; i++) x[i] = a.x0[i * B + bb];
-            cost = (a.accumulate_cost) ? __ldcg(&a.cost[bb]) : T(0);
-            t = a.t0;
-            if (a.X && valid) {
-#pragma unroll
-                for (int i = 0; i < N; i++) a.X[i * B + b] = x[i];
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < N; i++) x[i] = __ldcg(&a.xN[i * B + bb]);
-            cost = __ldcg(&a.cost[bb]);
-            t = __ldcg(&q.tq[g]);
+        for (int e = 0; e < E; e++) {
+            b[e] = ((int64_t)g * E + e) * 32 + lane;
+            valid[e] = b[e] < B;
+            bb[e] = valid[e] ? b[e] : B - 1;  // ragged last group: idle slots shadow the last trajectory
         }
-        bool term = false;
+        const int k0 = q.bounds[c], k1 = q.bounds[c + 1];
+        T x[E][N], u[E][M], un[E][M], cost[E];
+        T t;
 #pragma unroll
-        for (int j = 0; j < M; j++) un[j] = (a.U && k0 < k1) ? a.U[((int64_t)k0 * M + j) * B + bb] : T(0);
-        for (int k = k0; k < k1; k++) {
-            copy(u, un);
-            if (a.U && k + 1 < k1) {
+        for (int e = 0; e < E; e++) {
+            if (c == 0) {
 #pragma unroll
-                for (int j = 0; j < M; j++) un[j] = a.U[((int64_t)(k + 1) * M + j) * B + bb];
+                for (int i = 0; i < N; i++) x[e][i] = a.x0[i * B + bb[e]];
+                cost[e] = (a.accumulate_cost) ? __ldcg(&a.cost[bb[e]]) : T(0);
+                if (a.X && valid[e]) {
+#pragma unroll
+                    for (int i = 0; i < N; i++) a.X[i * B + b[e]] = x[e][i];
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < N; i++) x[e][i] = __ldcg(&a.xN[i * B + bb[e]]);
+                cost[e] = __ldcg(&a.cost[bb[e]]);
             }
-            T xp[N];
-            copy(xp, x);
-            env_step<P, T, INTEG>(m, x, u, a.dt, h, a.S);
-            t += a.dt;
-            term = P::terminate(m, x);
-            cost += (P::cost(m, xp, u, x, t) + (term ? a.terminal_cost : T(0))) * a.dt;
-            if (a.X && valid) {
 #pragma unroll
-                for (int i = 0; i < N; i++) a.X[((int64_t)(k + 1) * N + i) * B + b] = x[i];
+            for (int j = 0; j < M; j++) un[e][j] = (a.U && k0 < k1) ? a.U[((int64_t)k0 * M + j) * B + bb[e]] : T(0);
+        }
+        t = (c == 0) ? a.t0 : __ldcg(&q.tq[g]);
+        bool term[E];
+#pragma unroll
+        for (int e = 0; e < E; e++) term[e] = false;
+        for (int k = k0; k < k1; k++) {
+            T xp[E][N];
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                copy(u[e], un[e]);
+                if (a.U && k + 1 < k1) {
+#pragma unroll
+                    for (int j = 0; j < M; j++) un[e][j] = a.U[((int64_t)(k + 1) * M + j) * B + bb[e]];
+                }
+                copy(xp[e], x[e]);
+            }
+            env_step_multi<P, T, INTEG, E>(m, x, u, a.dt, h, a.S);
+            t += a.dt;
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                term[e] = P::terminate(m, x[e]);
+                cost[e] += (P::cost(m, xp[e], u[e], x[e], t) + (term[e] ? a.terminal_cost : T(0))) * a.dt;
+                if (a.X && valid[e]) {
+#pragma unroll
+                    for (int i = 0; i < N; i++) a.X[((int64_t)(k + 1) * N + i) * B + b[e]] = x[e][i];
+                }
             }
         }
         const bool last = k1 >= a.T_steps;
-        if (last && a.add_final_cost) cost += P::fcost(m, x) * a.dt;
-        if (valid) {
 #pragma unroll
-            for (int i = 0; i < N; i++) a.xN[i * B + b] = x[i];
-            a.cost[b] = cost;
-            if (last && a.terminated) a.terminated[b] = term ? 1 : 0;
+        for (int e = 0; e < E; e++) {
+            if (last && a.add_final_cost) cost[e] += P::fcost(m, x[e]) * a.dt;
+            if (valid[e]) {
+#pragma unroll
+                for (int i = 0; i < N; i++) a.xN[i * B + b[e]] = x[e][i];
+                a.cost[b[e]] = cost[e];
+                if (last && a.terminated) a.terminated[b[e]] = term[e] ? 1 : 0;
+            }
         }
         if (!last) {
             __threadfence();  // release: state before the ticket

@@ -108,7 +108,7 @@ struct MathCtx<double> {
         c = __hiloint2double(__double2hiint(b) ^ (((q + 1) & 2) << 30), __double2loint(b));
     }
     // sin/cos(a0 + d) from the "anchor" (s0, c0) = sin/cos(a0) by the angle-addition formulas, for the small
-    // argument increments of the RK4 stages (|d| = h |thetadot|, a few 1e-2): 15 FP64 instructions and no integer
+    // argument increments of the RK4 stages (|d| = h |thetadot|, a few 1e-2): 13 FP64 instructions and no integer
     // work instead of 22 + ~12.  sin d and cos d - 1 are the fdlibm polynomials cut after z^3 (their next terms
     // are < 4e-17 resp. 3e-19 for |d| < 2^-4), so the result is within ~1 ulp of a fresh evaluation plus the
     // anchor's own error.  Valid for |d| < 2^-4 only: callers collect mag(d) (integer pipe) and redo the control
@@ -120,8 +120,8 @@ struct MathCtx<double> {
         const double z = d * d;
         const double sd = fma(fma(fma(S3, z, S2), z, S1), d * z, d);    // sin d
         const double cm = fma(fma(fma(C3, z, C2), z, C1), z, -0.5) * z;  // cos d - 1
-        s = s0 + fma(c0, sd, s0 * cm);
-        c = c0 + fma(-s0, sd, c0 * cm);
+        s = fma(c0, sd, fma(s0, cm, s0));
+        c = fma(-s0, sd, fma(c0, cm, c0));
     }
     __device__ __forceinline__ double sin(double x) const {
         double s, c;
@@ -145,8 +145,8 @@ struct MathCtx<float> {
         const float z = d * d;
         const float sd = fmaf(fmaf(8.3333333333e-3f, z, -1.6666666667e-1f), d * z, d);
         const float cm = fmaf(fmaf(-1.3888888889e-3f, z, 4.1666666667e-2f), z, -0.5f) * z;
-        s = s0 + fmaf(c0, sd, s0 * cm);
-        c = c0 + fmaf(-s0, sd, c0 * cm);
+        s = fmaf(c0, sd, fmaf(s0, cm, s0));
+        c = fmaf(-s0, sd, fmaf(c0, cm, c0));
     }
     __device__ __forceinline__ float sin(float x) const { return ::sinf(x); }
     __device__ __forceinline__ float cos(float x) const { return ::cosf(x); }
