@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define PG_ABI_VERSION 1
+#define PG_ABI_VERSION 2
 
 #define PG_F64 0
 #define PG_F32 1
@@ -161,6 +161,33 @@ int pg_ilqr_commit(int dtype, int integrator, int64_t B, int32_t T, int32_t S, d
                    const void* alpha_best, const uint8_t* accept, const void* x0,
                    void* xbar, void* ubar, const void* KK, const void* kk, const double* ulim,
                    void* KK_acc, void* kk_acc, const int32_t* index, const int32_t* count, void* stream);
+
+/* --- iLQR over dynamics integrated and linearised OUTSIDE this library (the learned-MLP model of MBRL,
+ * include/pygent_b200_mlp.h; reference: pygent/algorithms/mbrl.py:76-93 builds its NMPC/iLQR planner on
+ * StateSpaceModel(self.ode, ...), whose iLQR.linearization falls back to finite differences, ilqr.py:526).  The
+ * problem library still owns the cost (sympy -> CUDA), the Riccati recursion and the line-search logic. */
+
+/* pg_ilqr_backward with caller-supplied CONTINUOUS-time Jacobians A [T,n,n,B], Bm [T,n,m,B] of the dynamics along
+ * (xbar, ubar); discretised like the reference, Ad = I + A dt, Bd = B dt (ilqr.py:530-531). */
+int pg_ilqr_backward_ext(int dtype, int64_t B, int32_t T, double dt, int32_t reg_type, const void* mu,
+                         const void* xbar, const void* ubar, const void* A, const void* Bm, const double* ulim,
+                         void* KK, void* kk, void* dV, void* gnorm, uint8_t* success,
+                         const int32_t* index, const int32_t* count, void* stream);
+
+/* Cost of candidate trajectories produced elsewhere: X [n_alpha,T+1,n,B], U [n_alpha,T,m,B] ->
+ * cost_out [n_alpha,B] = sum_k (c(x_k,u_k,x_{k+1},t_{k+1}) + terminal_cost*terminated_{k+1}) dt + fcost(x_T) dt
+ * (ilqr.py:213-224; t_0 = t0, time advances by repeated t += dt), diverged_out / terminated_out [n_alpha,B] as in
+ * pg_ilqr_forward. */
+int pg_traj_cost(int dtype, int64_t B, int32_t T, double dt, double t0, int32_t n_alpha, const void* X, const void* U,
+                 double terminal_cost, void* cost_out, uint8_t* diverged_out, uint8_t* terminated_out,
+                 const int32_t* index, const int32_t* count, void* stream);
+
+/* pg_ilqr_commit without re-integration: for accepted trajectories copy candidate alpha_best[b] (looked up in the
+ * host array alphas [n_alpha]) from X_cand / U_cand into xbar / ubar and the candidate gains into the accepted ones. */
+int pg_ilqr_commit_copy(int dtype, int64_t B, int32_t T, int32_t n_alpha, const double* alphas,
+                        const void* alpha_best, const uint8_t* accept, const void* X_cand, const void* U_cand,
+                        void* xbar, void* ubar, const void* KK, const void* kk, void* KK_acc, void* kk_acc,
+                        const int32_t* index, const int32_t* count, void* stream);
 
 /* o [n_obs,B] = observation(x [n,B]) : angle -> [cos, sin] (helpers.py:20-29). */
 int pg_observe(int dtype, int64_t B, const void* x, void* o, void* stream);

@@ -64,6 +64,29 @@ int pg_mlp_rollout(int precision, const pg_mlp_dims_t* dims, const void* packed,
                    const double* x0, const double* U, const double* KK, const double* kk, const double* xbar,
                    const double* ubar, double alpha, const double* ulim, double* X, double* U_out, void* stream);
 
+/* iLQR.forward_pass for n_alpha line-search candidates at once (ilqr.py:187-231, :429-437) -- and pg_mlp_rollout is its
+ * n_alpha = 1 case: rows of the launch are (candidate, trajectory) pairs.
+ *   alphas: host array [n_alpha <= 16];  X [n_alpha, T+1, n, B], U_out [n_alpha, T, m, B] or NULL;
+ *   index [<= B] (i32) + count [1] (i32, device) or both NULL: compacted work list of trajectory numbers (the one
+ *   pg_ilqr_select writes) -- only those trajectories are rolled out, other slots of X / U_out are left untouched.
+ *   The costs of the candidates are evaluated from X / U_out by the problem library (pg_traj_cost). */
+int pg_mlp_forward(int precision, const pg_mlp_dims_t* dims, const void* packed, int64_t B, int32_t T, double dt,
+                   int32_t n_alpha, const double* alphas, const double* x0, const double* U, const double* KK,
+                   const double* kk, const double* xbar, const double* ubar, const double* ulim, double* X, double* U_out,
+                   const int32_t* index, const int32_t* count, void* stream);
+
+/* Continuous-time Jacobians of MBRL.ode along a trajectory, for iLQR.linearization (ilqr.py:518-533):
+ *   A [T, n, n, B], Bm [T, n, m, B] at (xbar_k, ubar_k), k < T;  xbar [T+1, n, B], ubar [T, m, B].
+ *   PG_MLP_LIN_FD       central differences with eps = 1e-3 through 2(n+m) network evaluations -- what the reference does
+ *                       (helpers.system_linearization, pygent/helpers.py:130-148); any precision, meant for PG_MLP_FP32;
+ *   PG_MLP_LIN_ANALYTIC the exact derivative of the piecewise-linear network by the chain rule, on the tensor cores
+ *                       (PG_MLP_BF16 only): one forward GEMM for the ReLU masks + one transposed GEMM per output. */
+#define PG_MLP_LIN_ANALYTIC 0
+#define PG_MLP_LIN_FD 1
+int pg_mlp_linearize(int precision, int lin_mode, const pg_mlp_dims_t* dims, const void* packed, int64_t B, int32_t T,
+                     double dt, const double* xbar, const double* ubar, double* A, double* Bm, const int32_t* index,
+                     const int32_t* count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

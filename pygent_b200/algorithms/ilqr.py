@@ -16,6 +16,15 @@ Evaluating all alphas speculatively changes nothing: K4 replays the reference's 
 of the last alpha tried feeds the tolFun test -- SURVEY F7).  Trajectories stop individually
 (`status`), the loop ends when none is running.
 
+Learned dynamics (`environments.LearnedStateSpaceModel`, the reference's MBRL planner, mbrl.py:76-93): the same loop
+with the dynamics' own library in place of the generated ODE --
+
+    per iteration   pg_mlp_linearize      Jacobians along the nominal trajectory (analytic chain on the tensor
+                                          cores, or the reference's central differences)
+                    pg_ilqr_backward_ext  Riccati sweep on those Jacobians
+                    pg_mlp_forward        all 11 closed-loop Euler rollouts through the network
+                    pg_traj_cost          their costs;  K4 as above;  pg_ilqr_commit_copy instead of a re-run
+
 Single-plant environments return arrays shaped like the reference's (`xx [T+1,n]`, `uu [T,m]`,
 `KK [T,m,n]`, `kk [T,m,1]`); batched ones gain a leading B axis.
 """
@@ -82,13 +91,17 @@ class iLQR(Algorithm):
             self._fcost_expr = sp.sympify(c).subs(zero_u).subs(sp.Symbol("t"), t) * dt
         else:
             self._fcost_expr = tracing.trace(tracing.bind_fcost(fcost), xs, sp)
+        self.learned = bool(getattr(environment, "learned", False))
+        if self.learned and not fastForward:
+            raise NotImplementedError("a learned model predicts one Euler step per control interval: construct the "
+                                      "planner with fastForward=True, as MBRL does (mbrl.py:81)")
         self.lib = environment.library(self._fcost_expr)
         if not self.lib.info.has_cost_derivs:
             raise ValueError("iLQR needs a running cost c(x, u[, t]) that does not depend on the next state "
                              "(the reference evaluates it with x' = None, ilqr.py:183)")
         self.integrator = lib.INTEG_EULER if fastForward else lib.INTEG_RK4
         self.substeps = environment.substeps
-        self.lin_mode = 0 if self.lib.has_ab else 1
+        self.lin_mode = 2 if self.learned else (0 if self.lib.has_ab else 1)
         self.dtype = environment.dtype
         self.B = environment.batch
         self.batched = environment.batched
@@ -146,6 +159,9 @@ class iLQR(Algorithm):
         self._cur = 0
         self._n_active = self._cnt[1]
         self._have_gains = False
+        if self.learned:  # Jacobians along the nominal trajectory and the candidate trajectories of the line search
+            self._lin = {"A": z(T, n, n, B), "B": z(T, n, m, B)}
+            self._cand = {"X": z(A, T + 1, n, B), "U": z(A, T, m, B)}
 
     def _host(self, t, batch_axis_last=True):
         a = t.detach().to("cpu", torch.float64).numpy()
@@ -202,6 +218,14 @@ class iLQR(Algorithm):
         """Initial trajectory with u = 0 (ilqr.py:501-516): cost = sum c*dt + fcost(x_N)*dt."""
         self._x0 = self.environment._to_dev(self.environment._x0_host, self.xDim)
         self._ubar.zero_()
+        if self.learned:
+            env = self.environment
+            X = env.dynamics.rollout_device(self._x0, self.dt, T=self.steps, precision=env.precision)
+            self._xbar.copy_(X)
+            c = self.lib.traj_cost(X[None], self._ubar[None], dt=self.dt, terminal_cost=float(env.terminal_cost))
+            self._st["cost"].copy_(c["cost"][0])
+            self.agent.reset()
+            return
         self.lib.rollout(self._x0, None, T=self.steps, S=self.substeps, dt=self.dt, integrator=self.integrator,
                          terminal_cost=float(self.environment.terminal_cost), add_final_cost=True,
                          out={"X": self._xbar, "cost": self._st["cost"]})
@@ -237,22 +261,42 @@ class iLQR(Algorithm):
         if len(KK) == 0:
             raise ValueError("forward_pass needs gains (run backward_pass or run_optim first)")
         KKd, kkd = (KK, kk) if torch.is_tensor(KK) else self._gains_to_dev(KK, kk)
-        r = self.lib.ilqr_forward(self._x0, self._xbar, self._ubar, KKd, kkd, alphas=[float(alpha)], S=self.substeps,
-                                  dt=self.dt, integrator=self.integrator, ulim=self._ulim(),
-                                  terminal_cost=float(self.environment.terminal_cost), want_traj=True)
+        r = self._forward_candidates([float(alpha)], KKd, kkd)
         xx, uu = self._host(r["X"][0]), self._host(r["U"][0])
         cost = r["cost"][0].to("cpu", torch.float64).numpy()
         term = r["terminated"][0].cpu().numpy().astype(bool)
         self.agent.set_history(uu)
         return (xx, uu, cost, term) if self.batched else (xx, uu, float(cost[0]), bool(term[0]))
 
+    def _forward_candidates(self, alphas, KKd, kkd, out=None, cand=None, work=None):
+        """Closed-loop rollouts for `alphas` from x0 with trajectories: dict(X, U, cost, diverged, terminated)."""
+        env = self.environment
+        if self.learned:
+            X, U = env.dynamics.forward_device(self._x0, self.dt, alphas, (KKd, kkd, self._xbar, self._ubar), ulim=self._ulim(),
+                                               precision=env.precision, out=cand, work=work)
+            r = self.lib.traj_cost(X, U, dt=self.dt, terminal_cost=float(env.terminal_cost), out=out, work=work)
+            r.update(X=X, U=U)
+            return r
+        return self.lib.ilqr_forward(self._x0, self._xbar, self._ubar, KKd, kkd, alphas=alphas, S=self.substeps, dt=self.dt,
+                                     integrator=self.integrator, ulim=self._ulim(),
+                                     terminal_cost=float(env.terminal_cost), want_traj=True, out=out, work=work)
+
+    def _backward(self, work=None):
+        if self.learned:
+            env = self.environment
+            env.dynamics.linearize_device(self._xbar, self._ubar, self.dt, mode=env.linearization, precision=env.precision,
+                                          out=self._lin, work=work)
+            return self.lib.ilqr_backward_ext(self._xbar, self._ubar, self._st["mu"], self._lin["A"], self._lin["B"], dt=self.dt,
+                                              reg_type=self.regType, ulim=self._ulim(), out=self._bw, work=work)
+        return self.lib.ilqr_backward(self._xbar, self._ubar, self._st["mu"], dt=self.dt, reg_type=self.regType,
+                                      lin_mode=self.lin_mode, ulim=self._ulim(), out=self._bw, work=work)
+
     def backward_pass(self, final=False):
         """Riccati sweep along (xx, uu) (ilqr.py:233-346).  Returns V1, V2, success, KK, kk where V1, V2
         are the SUMS of the reference's per-step lists (only their sums are ever used, ilqr.py:442)."""
         if final:
             raise NotImplementedError("final backward pass (DARE terminal value) is not implemented")
-        r = self.lib.ilqr_backward(self._xbar, self._ubar, self._st["mu"], dt=self.dt, reg_type=self.regType,
-                                   lin_mode=self.lin_mode, ulim=self._ulim(), out=self._bw)
+        r = self._backward()
         dV = r["dV"].to("cpu", torch.float64).numpy()
         ok = r["success"].cpu().numpy().astype(bool)
         KK, kk = self._host(r["KK"]), self._host(r["kk"])[..., None]
@@ -266,7 +310,13 @@ class iLQR(Algorithm):
         dev = self.environment.device
         xd = torch.as_tensor(x.T.copy(), dtype=self.dtype, device=dev)
         ud = torch.as_tensor(u.T.copy(), dtype=self.dtype, device=dev)
-        r = self.lib.eval(xd, ud, lin_mode=self.lin_mode, what=("A", "B"))
+        if self.learned:
+            env = self.environment
+            Ad_, Bd_ = env.dynamics.linearize_device(torch.stack([xd, xd]), ud[None], self.dt, mode=env.linearization,
+                                                     precision=env.precision)
+            r = {"A": Ad_[0], "B": Bd_[0]}
+        else:
+            r = self.lib.eval(xd, ud, lin_mode=self.lin_mode, what=("A", "B"))
         A = np.moveaxis(r["A"].to("cpu", torch.float64).numpy(), -1, 0)
         Bm = np.moveaxis(r["B"].to("cpu", torch.float64).numpy(), -1, 0)
         Ad = A * self.dt + np.eye(self.xDim)
@@ -309,16 +359,22 @@ class iLQR(Algorithm):
         L = self.lib
         cur, nxt = self._cur, 1 - self._cur
         work = (self._idx[cur], self._cnt[cur])
-        L.ilqr_backward(self._xbar, self._ubar, st["mu"], dt=self.dt, reg_type=self.regType, lin_mode=self.lin_mode,
-                        ulim=self._ulim(), out=self._bw, work=work)
-        L.ilqr_forward(self._x0, self._xbar, self._ubar, self._KKc, self._kkc, alphas=self.alphas, S=self.substeps,
-                       dt=self.dt, integrator=self.integrator, ulim=self._ulim(),
-                       terminal_cost=float(self.environment.terminal_cost), out=self._fw, work=work)
+        self._backward(work=work)
+        if self.learned:
+            self._forward_candidates(list(self.alphas), self._KKc, self._kkc, out=self._fw, cand=self._cand, work=work)
+        else:
+            L.ilqr_forward(self._x0, self._xbar, self._ubar, self._KKc, self._kkc, alphas=self.alphas, S=self.substeps,
+                           dt=self.dt, integrator=self.integrator, ulim=self._ulim(),
+                           terminal_cost=float(self.environment.terminal_cost), out=self._fw, work=work)
         self._cnt[nxt].zero_()
         L.ilqr_select(self._sel, self._fw["cost"], self._fw["diverged"], self._bw["dV"], self._bw["gnorm"],
                       self._bw["success"], st, self._cnt[nxt], work=work, index_out=self._idx[nxt])
-        L.ilqr_commit(self._x0, self._xbar, self._ubar, self._KKc, self._kkc, self._KK, self._kk, st["alpha_best"],
-                      st["accept"], S=self.substeps, dt=self.dt, integrator=self.integrator, ulim=self._ulim(), work=work)
+        if self.learned:
+            L.ilqr_commit_copy(list(self.alphas), st["alpha_best"], st["accept"], self._cand["X"], self._cand["U"], self._xbar,
+                               self._ubar, self._KKc, self._kkc, self._KK, self._kk, work=work)
+        else:
+            L.ilqr_commit(self._x0, self._xbar, self._ubar, self._KKc, self._kkc, self._KK, self._kk, st["alpha_best"],
+                          st["accept"], S=self.substeps, dt=self.dt, integrator=self.integrator, ulim=self._ulim(), work=work)
         self._cur = nxt
         self._n_active = self._cnt[nxt]
         self._have_gains = True
@@ -360,9 +416,7 @@ class iLQR(Algorithm):
         """Apply the stored time-varying controller from x0 (ilqr.py:348-351)."""
         self.environment.reset(x0)
         self._x0 = self.environment._to_dev(self.environment._x0_host, self.xDim)
-        r = self.lib.ilqr_forward(self._x0, self._xbar, self._ubar, self._KK, self._kk, alphas=[1.0], S=self.substeps,
-                                  dt=self.dt, integrator=self.integrator, ulim=self._ulim(),
-                                  terminal_cost=float(self.environment.terminal_cost), want_traj=True)
+        r = self._forward_candidates([1.0], self._KK, self._kk)
         self._xbar.copy_(r["X"][0])
         self._ubar.copy_(r["U"][0])
         self._st["cost"].copy_(r["cost"][0])

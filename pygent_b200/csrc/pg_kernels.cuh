@@ -577,6 +577,8 @@ struct BackwardArgs {
     const uint8_t* active;
     const int32_t* index;
     const int32_t* count;
+    const T* A_ext;  // LIN == 2: continuous-time Jacobians supplied by the caller, [T, n, n, B] and [T, n, m, B]
+    const T* B_ext;
 };
 
 template <typename T>
@@ -638,8 +640,13 @@ __global__ void __launch_bounds__(64) ilqr_backward_kernel(const BackwardArgs<T>
         T Ad[N * N], Bd[N * M];
         if constexpr (LIN == 0) {
             P::AB(m, x, u, Ad, Bd);
-        } else {
+        } else if constexpr (LIN == 1) {
             fd_AB<P, T>(m, x, u, Ad, Bd);
+        } else {  // learned dynamics: linearised by its own library (pg_mlp_linearize)
+#pragma unroll
+            for (int i = 0; i < N * N; i++) Ad[i] = a.A_ext[((int64_t)k * N * N + i) * B + b];
+#pragma unroll
+            for (int i = 0; i < N * M; i++) Bd[i] = a.B_ext[((int64_t)k * N * M + i) * B + b];
         }
 #pragma unroll
         for (int i = 0; i < N; i++)
@@ -1076,6 +1083,111 @@ __global__ void ilqr_select_kernel(const SelectArgs<T> a) {
         base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
         if (keep && a.index_out) a.index_out[base + __popc(ballot & ((1u << lane) - 1))] = (int32_t)b;
     }
+}
+
+// ---- cost of given candidate trajectories (forward passes integrated elsewhere: learned dynamics) -----------------
+// cost[a, b] = sum_k (c(x_k, u_k, x_{k+1}, t_{k+1}) + terminal_cost * terminated_{k+1}) dt + fcost(x_T) dt, with the
+// time accumulated like the environment does (fast_step, environments.py:313-322; ilqr.py:213-224).
+template <typename T>
+struct TrajCostArgs {
+    int64_t B;
+    int T_steps, n_alpha;
+    T dt, t0, terminal_cost;
+    const T* X;  // [n_alpha, T+1, n, B]
+    const T* U;  // [n_alpha, T, m, B]
+    T* cost_out;
+    uint8_t* diverged_out;
+    uint8_t* terminated_out;
+    const int32_t* index;
+    const int32_t* count;
+};
+
+template <typename P, typename T>
+__global__ void traj_cost_kernel(const TrajCostArgs<T> a) {
+    const typename P::template Ctx<T> m;
+    constexpr int N = P::N, M = P::M;
+    const int64_t B = a.B;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int ia = blockIdx.y;
+    int64_t b = tid;
+    if (a.index) {
+        if (tid >= *a.count) return;
+        b = a.index[tid];
+    } else if (b >= B) {
+        return;
+    }
+    const T* X = a.X + (int64_t)ia * (a.T_steps + 1) * N * B;
+    const T* U = a.U + (int64_t)ia * a.T_steps * M * B;
+    T x[N], xn[N], u[M];
+    bool div = false, term = false;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        xn[i] = X[i * B + b];
+        div |= (xn[i] > T(1e8));
+    }
+    T cost = T(0), t = a.t0;
+    for (int k = 0; k < a.T_steps; k++) {
+        copy(x, xn);
+#pragma unroll
+        for (int i = 0; i < N; i++) xn[i] = X[((int64_t)(k + 1) * N + i) * B + b];
+#pragma unroll
+        for (int r = 0; r < M; r++) u[r] = U[((int64_t)k * M + r) * B + b];
+        t += a.dt;
+        term = P::terminate(m, xn);
+        cost += (P::cost(m, x, u, xn, t) + (term ? a.terminal_cost : T(0))) * a.dt;
+#pragma unroll
+        for (int i = 0; i < N; i++) div |= (xn[i] > T(1e8));
+    }
+    cost += P::fcost(m, xn) * a.dt;
+    const int64_t o = (int64_t)ia * B + b;
+    a.cost_out[o] = cost;
+    if (a.diverged_out) a.diverged_out[o] = div ? 1 : 0;
+    if (a.terminated_out) a.terminated_out[o] = term ? 1 : 0;
+}
+
+// ---- commit by copy: the winning candidate becomes the nominal trajectory (ilqr.py:458-464) -------------------------
+template <typename T>
+struct CommitCopyArgs {
+    int64_t B;
+    int T_steps, n_alpha, N, M;
+    T alphas[MAX_ALPHAS];
+    const T* alpha_best;
+    const uint8_t* accept;
+    const T* X_cand;
+    const T* U_cand;
+    T* xbar;
+    T* ubar;
+    const T* KK;
+    const T* kk;
+    T* KK_acc;
+    T* kk_acc;
+    const int32_t* index;
+    const int32_t* count;
+};
+
+template <typename T>
+__global__ void commit_copy_kernel(const CommitCopyArgs<T> a) {
+    const int64_t B = a.B;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t b = tid;
+    if (a.index) {
+        if (tid >= *a.count) return;
+        b = a.index[tid];
+    } else if (b >= B) {
+        return;
+    }
+    if (!a.accept[b]) return;
+    const T ab = a.alpha_best[b];
+    int ia = 0;
+    for (int i = 0; i < a.n_alpha; i++)
+        if (a.alphas[i] == ab) ia = i;
+    const int N = a.N, M = a.M, Ts = a.T_steps;
+    const T* X = a.X_cand + (int64_t)ia * (Ts + 1) * N * B;
+    const T* U = a.U_cand + (int64_t)ia * Ts * M * B;
+    for (int64_t r = 0; r < (int64_t)(Ts + 1) * N; r++) a.xbar[r * B + b] = X[r * B + b];
+    for (int64_t r = 0; r < (int64_t)Ts * M; r++) a.ubar[r * B + b] = U[r * B + b];
+    for (int64_t r = 0; r < (int64_t)Ts * M * N; r++) a.KK_acc[r * B + b] = a.KK[r * B + b];
+    for (int64_t r = 0; r < (int64_t)Ts * M; r++) a.kk_acc[r * B + b] = a.kk[r * B + b];
 }
 
 // ---- observation (helpers.observation, pygent/helpers.py:20-29) -----------------------------------

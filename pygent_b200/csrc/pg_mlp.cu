@@ -11,6 +11,11 @@
 //        epilogue: tcgen05.ld (row = TMEM lane = thread) -> +b2, ReLU, layer 3 (N <= 4) -> Euler update (fp64).
 //   Rows are trajectories / line-search candidates / finite-difference points; a CTA carries its rows
 //   through all T control intervals, the state never leaves registers.
+//   mlp_jac_kernel  : analytic Jacobian of the learned dynamics for iLQR's backward pass, 128 rows per CTA, three
+//        GEMM passes on the same tcgen05 pipeline: forward (ReLU masks of both hidden layers), then per network
+//        output j one pass G1_j = (W3[j,:] * mask2) x W2 against the TRANSPOSED weight images, epilogue
+//        (* mask1) x W1 and the chain rule through standardisation and the [cos, sin] observation.  Replaces
+//        the 2(n+m) = 10 network evaluations of the reference's central differences (helpers.py:130-148).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -32,6 +37,7 @@ constexpr int N_CHUNKS = 16;               // 8 k-blocks x 2 n-halves
 
 struct alignas(1024) MlpPacked {
     uint16_t W2b[N_CHUNKS][CHUNK_BYTES / 2];  // bf16, 128B-swizzled K-major images, chunk = kb * 2 + half
+    uint16_t W2bT[N_CHUNKS][CHUNK_BYTES / 2];  // the same for W2^T (contraction over layer 2's OUTPUT index)
     float W2t[H][H];                          // [k][n] fp32 (FFMA path)
     float W1[H][MAXIN];                       // [k][input]
     float b1[H];
@@ -51,40 +57,94 @@ inline uint16_t f32_to_bf16(float f) {  // round to nearest even
     return (uint16_t)(u >> 16);
 }
 
+constexpr int MODE_ODE = 0, MODE_ROLLOUT = 1, MODE_LIN_FD = 2, MODE_LIN_AN = 3;
+constexpr int MAX_ALPHAS = 16;
+
 struct MlpArgs {
     pg_mlp_dims_t d;
     const MlpPacked* w;
-    int64_t R;
+    int mode;
+    int64_t R;   // work items without a work list: points (ODE) or trajectories (ROLLOUT, LIN_*)
+    int64_t Bs;  // batch stride of every [..., B] array
     int T;
     double dt;
-    int rollout;  // 0: rhs = ode(x, u) for given points; 1: Euler rollout
+    int n_alpha;
+    double alphas[MAX_ALPHAS];
+    const int32_t* index;  // optional compacted work list (trajectory numbers) and its device-side length
+    const int32_t* count;
     const double* x0;
     const double* U;
     const double* KK;
     const double* kk;
     const double* xbar;
     const double* ubar;
-    double alpha;
     int clip;
     double ulim[2];
     double* X;
     double* U_out;
     double* rhs;
+    double* A;
+    double* Bm;
 };
 
-// ---- per-row pieces shared by both kernels ---------------------------------------------------------------
-__device__ __forceinline__ void control_of_row(const MlpArgs& a, int k, int64_t r, const double (&x)[8], double (&u)[2]) {
+// Row r of the launch -> what it computes.  ROLLOUT: r = ia * cnt + w (line-search candidate ia of work item w);
+// LIN_*: r = k * cnt + w (control interval k of work item w); cnt = *count or R; trajectory b = index[w] or w.
+struct Row {
+    bool valid;
+    int64_t b;
+    int ia, k;
+    double alpha;
+};
+
+__device__ __forceinline__ int64_t work_count(const MlpArgs& a) { return a.count ? (int64_t)*a.count : a.R; }
+
+__device__ __forceinline__ int64_t total_rows(const MlpArgs& a) {
+    const int64_t cnt = work_count(a);
+    if (a.mode == MODE_ROLLOUT) return cnt * a.n_alpha;
+    if (a.mode == MODE_LIN_FD || a.mode == MODE_LIN_AN) return cnt * a.T;
+    return cnt;
+}
+
+__device__ __forceinline__ Row decode_row(const MlpArgs& a, int64_t r) {
+    Row row;
+    const int64_t cnt = work_count(a);
+    row.valid = r < total_rows(a);
+    row.ia = row.k = 0;
+    row.alpha = 1.0;
+    int64_t w = r;
+    if (row.valid && cnt > 0) {
+        if (a.mode == MODE_ROLLOUT) {
+            row.ia = (int)(r / cnt);
+            w = r - (int64_t)row.ia * cnt;
+            row.alpha = a.alphas[row.ia];
+        } else if (a.mode != MODE_ODE) {
+            row.k = (int)(r / cnt);
+            w = r - (int64_t)row.k * cnt;
+        }
+    }
+    row.b = (row.valid && a.index) ? (int64_t)a.index[w] : w;
+    return row;
+}
+
+__device__ __forceinline__ int steps_of(const MlpArgs& a) {
+    if (a.mode == MODE_ROLLOUT) return a.T;
+    if (a.mode == MODE_LIN_FD) return 2 * (a.d.n + a.d.m);  // x_i +- eps, u_j +- eps (helpers.py:139-146)
+    return 1;
+}
+
+// ---- per-row pieces shared by the kernels -----------------------------------------------------------------
+__device__ __forceinline__ void control_of_row(const MlpArgs& a, const Row& row, int k, const double (&x)[8], double (&u)[2]) {
     const int n = a.d.n, m = a.d.m;
-    const int64_t R = a.R;
+    const int64_t B = a.Bs, b = row.b;
     for (int j = 0; j < m; j++) {
         double v = 0.0;
         if (a.KK) {  // u = K (x - xbar) + alpha k + ubar (ilqr.py:206)
             double acc = 0.0;
-            for (int i = 0; i < n; i++) acc += a.KK[(((int64_t)k * m + j) * n + i) * R + r] * (x[i] - a.xbar[((int64_t)k * n + i) * R + r]);
-            v = acc + a.alpha * a.kk[((int64_t)k * m + j) * R + r];
-            v = v + a.ubar[((int64_t)k * m + j) * R + r];
+            for (int i = 0; i < n; i++) acc += a.KK[(((int64_t)k * m + j) * n + i) * B + b] * (x[i] - a.xbar[((int64_t)k * n + i) * B + b]);
+            v = acc + row.alpha * a.kk[((int64_t)k * m + j) * B + b];
+            v = v + a.ubar[((int64_t)k * m + j) * B + b];
         } else if (a.U) {
-            v = a.U[((int64_t)k * m + j) * R + r];
+            v = a.U[((int64_t)k * m + j) * B + b];
         }
         if (a.clip) v = fmin(fmax(v, -a.ulim[j]), a.ulim[j]);
         u[j] = v;
@@ -116,40 +176,78 @@ __device__ __forceinline__ void network_input(const MlpArgs& a, const pg::MathCt
     for (; c < MAXIN; c++) in[c] = 0.0f;
 }
 
-// rhs = [x[n/2:], float32(1/dt) * (y * dxVar + dxMean)]  (mbrl.py:126-128, nn_models.py:200-201), Euler update
-__device__ __forceinline__ void finish_row(const MlpArgs& a, int64_t r, bool valid, int k, const float (&y)[MAXDX],
-                                           double (&x)[8], const double (&u)[2]) {
+__device__ __forceinline__ void load_row(const MlpArgs& a, const Row& row, double (&x)[8], double (&u)[2]) {
+    for (int i = 0; i < 8; i++) x[i] = 0.0;
+    u[0] = u[1] = 0.0;
+    if (!row.valid) return;
+    const int n = a.d.n, m = a.d.m;
+    const int64_t B = a.Bs, b = row.b;
+    if (a.mode == MODE_ROLLOUT) {
+        for (int i = 0; i < n; i++) {
+            x[i] = a.x0[(int64_t)i * B + b];
+            a.X[(((int64_t)row.ia * (a.T + 1)) * n + i) * B + b] = x[i];
+        }
+    } else if (a.mode == MODE_ODE) {
+        for (int i = 0; i < n; i++) x[i] = a.x0[(int64_t)i * B + b];
+        for (int j = 0; j < m; j++) u[j] = a.U[(int64_t)j * B + b];
+    } else {  // linearisation point (xbar_k, ubar_k)
+        for (int i = 0; i < n; i++) x[i] = a.xbar[((int64_t)row.k * n + i) * B + b];
+        for (int j = 0; j < m; j++) u[j] = a.ubar[((int64_t)row.k * m + j) * B + b];
+    }
+}
+
+constexpr double FD_EPS = 1e-3;  // helpers.system_linearization (pygent/helpers.py:130)
+
+// Before the network evaluation of step s: the point (xe, ue) it is evaluated at.
+__device__ __forceinline__ void pre_step(const MlpArgs& a, const Row& row, int s, const double (&x)[8], double (&u)[2],
+                                         double (&xe)[8], double (&ue)[2]) {
+    if (a.mode == MODE_ROLLOUT && row.valid) control_of_row(a, row, s, x, u);
+    for (int i = 0; i < 8; i++) xe[i] = x[i];
+    ue[0] = u[0];
+    ue[1] = u[1];
+    if (a.mode == MODE_LIN_FD) {
+        const int j = s >> 1;
+        const double e = (s & 1) ? -FD_EPS : FD_EPS;
+        if (j < a.d.n) xe[j] = x[j] + e;
+        else ue[j - a.d.n] = u[j - a.d.n] + e;
+    }
+}
+
+// After it: rhs = [x[n/2:], float32(1/dt) * (y * dxVar + dxMean)] (mbrl.py:126-128, nn_models.py:200-201), then the
+// Euler update (fast_step, environments.py:313-315), the plain right-hand side, or one central-difference column.
+__device__ __forceinline__ void post_step(const MlpArgs& a, const Row& row, int s, const float (&y)[MAXDX], double (&x)[8],
+                                          const double (&u)[2], const double (&xe)[8], double (&fplus)[8]) {
     const int n = a.d.n, nh = a.d.n / 2, m = a.d.m;
+    const int64_t B = a.Bs, b = row.b;
     const MlpPacked* w = a.w;
     const float inv_dt = (float)(1.0 / a.dt);
     double rhs[8];
-    for (int i = 0; i < nh; i++) rhs[i] = x[nh + i];
+    for (int i = 0; i < nh; i++) rhs[i] = xe[nh + i];
     for (int j = 0; j < nh; j++) {
         const float dv = (y[j] + w->b3[j]) * w->dx_var[j] + w->dx_mean[j];
         rhs[nh + j] = (double)(inv_dt * dv);
     }
-    if (!a.rollout) {
-        if (valid)
-            for (int i = 0; i < n; i++) a.rhs[(int64_t)i * a.R + r] = rhs[i];
-        return;
-    }
-    for (int i = 0; i < n; i++) x[i] = x[i] + a.dt * rhs[i];  // fast_step (environments.py:313-315)
-    if (valid) {
-        for (int i = 0; i < n; i++) a.X[((int64_t)(k + 1) * n + i) * a.R + r] = x[i];
-        if (a.U_out)
-            for (int j = 0; j < m; j++) a.U_out[((int64_t)k * m + j) * a.R + r] = u[j];
-    }
-}
-
-__device__ __forceinline__ void load_row(const MlpArgs& a, int64_t r, bool valid, double (&x)[8], double (&u)[2]) {
-    for (int i = 0; i < 8; i++) x[i] = 0.0;
-    u[0] = u[1] = 0.0;
-    if (!valid) return;
-    for (int i = 0; i < a.d.n; i++) x[i] = a.x0[(int64_t)i * a.R + r];
-    if (a.rollout) {
-        for (int i = 0; i < a.d.n; i++) a.X[(int64_t)i * a.R + r] = x[i];
-    } else {
-        for (int j = 0; j < a.d.m; j++) u[j] = a.U[(int64_t)j * a.R + r];
+    if (a.mode == MODE_ODE) {
+        if (row.valid)
+            for (int i = 0; i < n; i++) a.rhs[(int64_t)i * B + b] = rhs[i];
+    } else if (a.mode == MODE_ROLLOUT) {
+        for (int i = 0; i < n; i++) x[i] = x[i] + a.dt * rhs[i];
+        if (row.valid) {
+            for (int i = 0; i < n; i++) a.X[(((int64_t)row.ia * (a.T + 1) + s + 1) * n + i) * B + b] = x[i];
+            if (a.U_out)
+                for (int j = 0; j < m; j++) a.U_out[(((int64_t)row.ia * a.T + s) * m + j) * B + b] = u[j];
+        }
+    } else {  // MODE_LIN_FD: (f(p + e) - f(p - e)) / (2 eps)
+        if ((s & 1) == 0) {
+            for (int i = 0; i < n; i++) fplus[i] = rhs[i];
+        } else if (row.valid) {
+            const int j = s >> 1;
+            for (int i = 0; i < n; i++) {
+                const double col = (fplus[i] - rhs[i]) / (2 * FD_EPS);
+                if (j < n) a.A[(((int64_t)row.k * n + i) * n + j) * B + b] = col;
+                else a.Bm[(((int64_t)row.k * n + i) * m + (j - n)) * B + b] = col;
+            }
+        }
     }
 }
 
@@ -163,17 +261,19 @@ __global__ void __launch_bounds__(256) mlp_fp32_kernel(const MlpArgs a) {
     float* ys = ins + F_ROWS * MAXIN;        // [64][4]
     const MlpPacked* w = a.w;
     const int t = threadIdx.x;
-    const int64_t r = (int64_t)blockIdx.x * F_ROWS + t;
-    const bool owner = t < F_ROWS, valid = owner && r < a.R;
+    if ((int64_t)blockIdx.x * F_ROWS >= total_rows(a)) return;  // compacted work list: surplus CTAs
+    const bool owner = t < F_ROWS;
+    Row row = decode_row(a, (int64_t)blockIdx.x * F_ROWS + (owner ? t : 0));
+    row.valid = row.valid && owner;
     const pg::MathCtx<double> mc;
-    double x[8], u[2];
-    if (owner) load_row(a, r, valid, x, u);
-    const int steps = a.rollout ? a.T : 1;
+    double x[8], u[2], xe[8], ue[2], fplus[8];
+    if (owner) load_row(a, row, x, u);
+    const int steps = steps_of(a);
     for (int k = 0; k < steps; k++) {
         if (owner) {
-            if (a.rollout && valid) control_of_row(a, k, r, x, u);
+            pre_step(a, row, k, x, u, xe, ue);
             float in[MAXIN];
-            network_input(a, mc, x, u, in);
+            network_input(a, mc, xe, ue, in);
 #pragma unroll
             for (int j = 0; j < MAXIN; j++) ins[t * MAXIN + j] = in[j];
         }
@@ -249,7 +349,7 @@ __global__ void __launch_bounds__(256) mlp_fp32_kernel(const MlpArgs a) {
             float y[MAXDX];
 #pragma unroll
             for (int j = 0; j < MAXDX; j++) y[j] = ys[t * MAXDX + j];
-            finish_row(a, r, valid, k, y, x, u);
+            post_step(a, row, k, y, x, u, xe, fplus);
         }
         __syncthreads();
     }
@@ -326,6 +426,53 @@ constexpr int T_INS_BYTES = T_ROWS * MAXIN * 4;            // network inputs of 
 constexpr int T_YP_BYTES = T_SPLIT * T_ROWS * MAXDX * 4;   // partial layer-3 sums
 constexpr int T_SMEM = T_A_BYTES + T_STAGES * CHUNK_BYTES + T_INS_BYTES + T_YP_BYTES + 256;
 
+// One 128 x 512 x 512 GEMM of the CTA: D (TMEM, fp32) = A (smem image, bf16) x B (16 chunk images streamed from L2).
+// Thread 0 produces the chunk ring, thread 32 issues the 64 MMAs; everybody returns when the accumulators are
+// readable.  `img` selects the weight images (W2b: forward, W2bT: transposed).
+struct GemmPipe {
+    uint8_t* As;
+    uint8_t* Bs;
+    uint64_t* full;
+    uint64_t* empty;
+    uint64_t* accum;
+    uint32_t tmem_base;
+    uint32_t chunk_no;  // producer and issuer count chunks the same way
+    uint32_t passes;
+};
+
+__device__ __forceinline__ void gemm_pass(GemmPipe& p, const uint16_t (*img)[CHUNK_BYTES / 2], int t) {
+    if (t == 0) {  // producer: weight chunks, L2 -> smem ring
+        uint32_t c = p.chunk_no;
+        for (int i = 0; i < N_CHUNKS; i++, c++) {
+            const uint32_t s = c % T_STAGES, use = c / T_STAGES;
+            mbar_wait(&p.empty[s], (use & 1) ^ 1);
+            mbar_expect_tx(&p.full[s], CHUNK_BYTES);
+            bulk_g2s(p.Bs + s * CHUNK_BYTES, &img[i][0], CHUNK_BYTES, &p.full[s]);
+        }
+    } else if (t == 32) {  // MMA issuer: one thread drives the tensor core for the whole CTA
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t c = p.chunk_no;
+        for (int i = 0; i < N_CHUNKS; i++, c++) {
+            const uint32_t s = c % T_STAGES, use = c / T_STAGES;
+            mbar_wait(&p.full[s], use & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int kb = i >> 1, half = i & 1;
+            const uint32_t a_addr = smem_u32(p.As + kb * (T_ROWS * 128));
+            const uint32_t b_addr = smem_u32(p.Bs + s * CHUNK_BYTES);
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++)  // K = 16 per instruction = 32 bytes along the swizzled row
+                umma_bf16(p.tmem_base + half * 256, umma_desc_sw128(a_addr + ks * 32), umma_desc_sw128(b_addr + ks * 32),
+                          (kb > 0 || ks > 0) ? 1u : 0u);
+            umma_commit(&p.empty[s]);  // frees the stage when these MMAs have read it
+        }
+        umma_commit(p.accum);  // all 64 MMAs of this pass done -> accumulators readable
+    }
+    p.chunk_no += N_CHUNKS;
+    mbar_wait(p.accum, p.passes & 1);
+    p.passes++;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
 // 512 threads per CTA: thread t works on row (t & 127); the four threads of a row split the hidden units
 // (layer 1) and the accumulator columns (epilogue) four ways.  Warp w reads TMEM lanes 32 (w % 4) .. +31, which
 // is exactly the row quarter (t & 127) >> 5 of its threads.  Threads 0..127 own the fp64 state of their row.
@@ -341,9 +488,10 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_bf16_kernel(const MlpArgs a)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
     const MlpPacked* w = a.w;
     const int t = threadIdx.x, warp = t >> 5, row = t & (T_ROWS - 1), part = t >> 7;
+    if ((int64_t)blockIdx.x * T_ROWS >= total_rows(a)) return;  // compacted work list: surplus CTAs
     const bool owner = t < T_ROWS;
-    const int64_t r = (int64_t)blockIdx.x * T_ROWS + row;
-    const bool valid = owner && r < a.R;
+    Row rw = decode_row(a, (int64_t)blockIdx.x * T_ROWS + row);
+    rw.valid = rw.valid && owner;
     const int nin = a.d.n_obs + a.d.m;
     const pg::MathCtx<double> mc;
 
@@ -364,15 +512,15 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_bf16_kernel(const MlpArgs a)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    double x[8], u[2];
-    if (owner) load_row(a, r, valid, x, u);
-    uint32_t chunk_no = 0;  // producer (thread 0) and MMA issuer (thread 32) count chunks the same way
-    const int steps = a.rollout ? a.T : 1;
+    double x[8], u[2], xe[8], ue[2], fplus[8];
+    if (owner) load_row(a, rw, x, u);
+    GemmPipe pipe = {As, Bs, full, empty, accum, tmem_base, 0u, 0u};
+    const int steps = steps_of(a);
     for (int k = 0; k < steps; k++) {
         if (owner) {
-            if (a.rollout && valid) control_of_row(a, k, r, x, u);
+            pre_step(a, rw, k, x, u, xe, ue);
             float in[MAXIN];
-            network_input(a, mc, x, u, in);
+            network_input(a, mc, xe, ue, in);
 #pragma unroll
             for (int j = 0; j < MAXIN; j++) ins[row * MAXIN + j] = in[j];
         }
@@ -408,35 +556,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_bf16_kernel(const MlpArgs a)
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA unit
         __syncthreads();
-        if (t == 0) {  // producer: W2 chunks, L2 -> smem ring
-            uint32_t c = chunk_no;
-            for (int i = 0; i < N_CHUNKS; i++, c++) {
-                const uint32_t s = c % T_STAGES, use = c / T_STAGES;
-                mbar_wait(&empty[s], (use & 1) ^ 1);
-                mbar_expect_tx(&full[s], CHUNK_BYTES);
-                bulk_g2s(Bs + s * CHUNK_BYTES, &w->W2b[i][0], CHUNK_BYTES, &full[s]);
-            }
-        } else if (t == 32) {  // MMA issuer: one thread drives the tensor core for the whole CTA
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t c = chunk_no;
-            for (int i = 0; i < N_CHUNKS; i++, c++) {
-                const uint32_t s = c % T_STAGES, use = c / T_STAGES;
-                mbar_wait(&full[s], use & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const int kb = i >> 1, half = i & 1;
-                const uint32_t a_addr = smem_u32(As + kb * (T_ROWS * 128));
-                const uint32_t b_addr = smem_u32(Bs + s * CHUNK_BYTES);
-#pragma unroll
-                for (int ks = 0; ks < 4; ks++)  // K = 16 per instruction = 32 bytes along the swizzled row
-                    umma_bf16(tmem_base + half * 256, umma_desc_sw128(a_addr + ks * 32), umma_desc_sw128(b_addr + ks * 32),
-                              (kb > 0 || ks > 0) ? 1u : 0u);
-                umma_commit(&empty[s]);  // frees the stage when these MMAs have read it
-            }
-            umma_commit(accum);  // all 64 MMAs of this control interval done -> accumulators readable
-        }
-        chunk_no += N_CHUNKS;
-        mbar_wait(accum, k & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        gemm_pass(pipe, w->W2b, t);
         // epilogue: TMEM lane = row; this thread's quarter of the 512 columns: +b2, ReLU, layer 3
         {
             float y[MAXDX] = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -467,16 +587,242 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_bf16_kernel(const MlpArgs a)
                 for (int q = 0; q < T_SPLIT; q++) v += yp[(q * T_ROWS + row) * MAXDX + j];
                 y[j] = v;
             }
-            finish_row(a, r, valid, k, y, x, u);
+            post_step(a, rw, k, y, x, u, xe, fplus);
         }
     }
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
+// ---- analytic Jacobian on the tensor cores ---------------------------------------------------------------------
+// rhs = [x[n/2:], (1/dt) (dxVar * y(in(x, u)) + dxMean)],  y = W3 relu(W2 relu(W1 in + b1) + b2) + b3, so for output j
+//   dy_j/din = ((W3[j,:] * m2) W2 * m1) W1,   m1 = [h1 > 0], m2 = [h2 > 0]
+// and d in/d(x, u) is diagonal except for the angle states, which enter as [cos, sin].  Three GEMM passes per 128-row
+// tile: forward (masks only), then one pass per output against the transposed weight images.  The accumulators and the
+// A image are reused between passes; after a pass has completed the A image doubles as scratch for the partial sums.
+constexpr int J_MASK_WORDS = H / 32;                          // 16 mask words per row and layer
+constexpr int J_MASK_BYTES = 2 * T_ROWS * J_MASK_WORDS * 4;   // both hidden layers
+constexpr int J_SMEM = T_A_BYTES + T_STAGES * CHUNK_BYTES + T_INS_BYTES + J_MASK_BYTES + 256;
+
+__global__ void __launch_bounds__(T_THREADS, 1) mlp_jac_kernel(const MlpArgs a) {
+    extern __shared__ __align__(1024) uint8_t tsm[];
+    uint8_t* As = tsm;
+    uint8_t* Bs = tsm + T_A_BYTES;
+    float* ins = reinterpret_cast<float*>(tsm + T_A_BYTES + T_STAGES * CHUNK_BYTES);
+    uint32_t* m1 = reinterpret_cast<uint32_t*>(ins + T_ROWS * MAXIN);
+    uint32_t* m2 = m1 + T_ROWS * J_MASK_WORDS;
+    uint64_t* full = reinterpret_cast<uint64_t*>(m2 + T_ROWS * J_MASK_WORDS);
+    uint64_t* empty = full + T_STAGES;
+    uint64_t* accum = empty + T_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+    const MlpPacked* w = a.w;
+    const int t = threadIdx.x, warp = t >> 5, row = t & (T_ROWS - 1), part = t >> 7;
+    if ((int64_t)blockIdx.x * T_ROWS >= total_rows(a)) return;
+    const bool owner = t < T_ROWS;
+    Row rw = decode_row(a, (int64_t)blockIdx.x * T_ROWS + row);
+    rw.valid = rw.valid && owner;
+    const int n = a.d.n, nh = a.d.n / 2, m = a.d.m, nin = a.d.n_obs + a.d.m;
+    const pg::MathCtx<double> mc;
+
+    if (t == 0) {
+        for (int s = 0; s < T_STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    GemmPipe pipe = {As, Bs, full, empty, accum, tmem_base, 0u, 0u};
+
+    double x[8], u[2];
+    if (owner) {
+        load_row(a, rw, x, u);
+        float in[MAXIN];
+        network_input(a, mc, x, u, in);
+#pragma unroll
+        for (int j = 0; j < MAXIN; j++) ins[row * MAXIN + j] = in[j];
+    }
+    __syncthreads();
+    uint8_t* rowp = As + (row >> 3) * 1024 + (row & 7) * 128;
+    constexpr int G0 = H / 8 / T_SPLIT;  // 16 groups of 8 hidden units per thread
+    {  // pass 0, A image: layer 1 (as in mlp_bf16_kernel) + its ReLU mask
+        float in[MAXIN];
+#pragma unroll
+        for (int j = 0; j < MAXIN; j++) in[j] = ins[row * MAXIN + j];
+        uint32_t mw = 0;
+        for (int gi = 0; gi < G0; gi++) {
+            const int g = part * G0 + gi;
+            float acc[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) acc[e] = w->b1[g * 8 + e];
+#pragma unroll
+            for (int j = 0; j < MAXIN; j++) {
+                if (j < nin) {
+#pragma unroll
+                    for (int e = 0; e < 8; e++) acc[e] = fmaf(w->W1[g * 8 + e][j], in[j], acc[e]);
+                }
+            }
+            uint32_t packed[4];
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+                const bool plo = (g * 8 + e) < HID && acc[e] > 0.0f, phi = (g * 8 + e + 1) < HID && acc[e + 1] > 0.0f;
+                const float lo = plo ? acc[e] : 0.0f, hi = phi ? acc[e + 1] : 0.0f;
+                mw |= (plo ? 1u : 0u) << ((gi & 3) * 8 + e);
+                mw |= (phi ? 1u : 0u) << ((gi & 3) * 8 + e + 1);
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(packed[e >> 1]) : "f"(hi), "f"(lo));
+            }
+            const int kb = g >> 3, cidx = (g & 7) ^ (row & 7);
+            *reinterpret_cast<uint4*>(rowp + kb * (T_ROWS * 128) + cidx * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            if ((gi & 3) == 3) {  // hidden units 32 w .. 32 w + 31 -> mask word w = g / 4
+                m1[row * J_MASK_WORDS + (g >> 2)] = mw;
+                mw = 0;
+            }
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    gemm_pass(pipe, w->W2b, t);
+    // mask of layer 2: [acc + b2 > 0]
+    for (int cb = part * (H / 32 / T_SPLIT); cb < (part + 1) * (H / 32 / T_SPLIT); cb++) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + cb * 32, v);
+        uint32_t mw = 0;
+#pragma unroll
+        for (int c = 0; c < 32; c++) {
+            const int nn = cb * 32 + c;
+            mw |= ((nn < HID && __uint_as_float(v[c]) + w->b2[nn] > 0.0f) ? 1u : 0u) << c;
+        }
+        m2[row * J_MASK_WORDS + cb] = mw;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+
+    double sx[8], cx[8];  // sin/cos of the angle states for the chain rule
+    if (owner) {
+        for (int i = 0; i < n; i++) {
+            sx[i] = 0.0;
+            cx[i] = 1.0;
+            if (a.d.is_angle[i]) mc.sincos(x[i], sx[i], cx[i]);
+        }
+    }
+    float* partial = reinterpret_cast<float*>(As);  // [T_SPLIT][T_ROWS][MAXIN], valid between a pass and the next image
+    for (int j = 0; j < nh; j++) {
+        // A image: g2 = W3[j, :] * m2 (bf16), same swizzled layout as H1
+        for (int gi = 0; gi < G0; gi++) {
+            const int g = part * G0 + gi;
+            const uint32_t bits = (m2[row * J_MASK_WORDS + (g >> 2)] >> ((g & 3) * 8)) & 0xffu;
+            uint32_t packed[4];
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+                const float lo = ((bits >> e) & 1u) ? w->W3[g * 8 + e][j] : 0.0f;
+                const float hi = ((bits >> (e + 1)) & 1u) ? w->W3[g * 8 + e + 1][j] : 0.0f;
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(packed[e >> 1]) : "f"(hi), "f"(lo));
+            }
+            const int kb = g >> 3, cidx = (g & 7) ^ (row & 7);
+            *reinterpret_cast<uint4*>(rowp + kb * (T_ROWS * 128) + cidx * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        gemm_pass(pipe, w->W2bT, t);
+        // epilogue: g1 = acc * m1, gin = g1 W1 (this thread's quarter of the hidden units)
+        {
+            float gin[MAXIN];
+#pragma unroll
+            for (int c = 0; c < MAXIN; c++) gin[c] = 0.0f;
+            for (int cb = part * (H / 32 / T_SPLIT); cb < (part + 1) * (H / 32 / T_SPLIT); cb++) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + cb * 32, v);
+                const uint32_t mw = m1[row * J_MASK_WORDS + cb];
+#pragma unroll
+                for (int c = 0; c < 32; c++) {
+                    const float g1 = ((mw >> c) & 1u) ? __uint_as_float(v[c]) : 0.0f;
+                    const float4* w1 = reinterpret_cast<const float4*>(&w->W1[cb * 32 + c][0]);
+#pragma unroll
+                    for (int q = 0; q < MAXIN / 4; q++) {
+                        if (q * 4 < nin) {
+                            const float4 ww = w1[q];
+                            gin[q * 4 + 0] = fmaf(g1, ww.x, gin[q * 4 + 0]);
+                            gin[q * 4 + 1] = fmaf(g1, ww.y, gin[q * 4 + 1]);
+                            gin[q * 4 + 2] = fmaf(g1, ww.z, gin[q * 4 + 2]);
+                            gin[q * 4 + 3] = fmaf(g1, ww.w, gin[q * 4 + 3]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < MAXIN; c++) partial[(part * T_ROWS + row) * MAXIN + c] = gin[c];
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (rw.valid) {
+            float gin[MAXIN];
+#pragma unroll
+            for (int c = 0; c < MAXIN; c++) {
+                float v = 0.0f;
+#pragma unroll
+                for (int q = 0; q < T_SPLIT; q++) v += partial[(q * T_ROWS + row) * MAXIN + c];
+                gin[c] = v;
+            }
+            // d rhs[nh + j] / d(x, u) = (1/dt) dxVar_j * sum_c gin_c * d in_c / d(x, u)
+            const double sc = (double)((float)(1.0 / a.dt) * w->dx_var[j]);
+            const int64_t B = a.Bs, b = rw.b;
+            int c = 0;
+            for (int i = 0; i < n; i++) {
+                double dcol;
+                if (a.d.is_angle[i]) {
+                    dcol = (double)gin[c] * (-sx[i]) / (double)w->o_var[c] + (double)gin[c + 1] * cx[i] / (double)w->o_var[c + 1];
+                    c += 2;
+                } else {
+                    dcol = (double)gin[c] / (double)w->o_var[c];
+                    c++;
+                }
+                a.A[(((int64_t)rw.k * n + nh + j) * n + i) * B + b] = sc * dcol;
+            }
+            for (int jj = 0; jj < m; jj++) {
+                a.Bm[(((int64_t)rw.k * n + nh + j) * m + jj) * B + b] = sc * (double)gin[c] / (double)w->u_var[jj];
+                c++;
+            }
+        }
+        __syncthreads();  // the partial sums are consumed before the next pass writes its image over them
+    }
+    if (rw.valid) {  // position half: d x[nh + i] / dx
+        const int64_t B = a.Bs, b = rw.b;
+        for (int i = 0; i < nh; i++) {
+            for (int c = 0; c < n; c++) a.A[(((int64_t)rw.k * n + i) * n + c) * B + b] = (c == nh + i) ? 1.0 : 0.0;
+            for (int jj = 0; jj < m; jj++) a.Bm[(((int64_t)rw.k * n + i) * m + jj) * B + b] = 0.0;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
+int64_t max_rows(const MlpArgs& a) {  // upper bound of total_rows() known on the host (the work list may be shorter)
+    if (a.mode == MODE_ROLLOUT) return a.R * a.n_alpha;
+    if (a.mode == MODE_LIN_FD || a.mode == MODE_LIN_AN) return a.R * a.T;
+    return a.R;
+}
+
 int launch(int precision, const MlpArgs& a, cudaStream_t st) {
-    if (a.R == 0) return 0;
-    if (precision == PG_MLP_FP32) {
+    const int64_t rows = max_rows(a);
+    if (rows == 0) return 0;
+    if (a.mode == MODE_LIN_AN) {
+        if (precision != PG_MLP_BF16) return PG_E_BADARG;  // the analytic chain exists on the tensor-core path only
+        static bool set = false;
+        if (!set) {
+            cudaError_t e = cudaFuncSetAttribute(mlp_jac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, J_SMEM);
+            if (e != cudaSuccess) return (int)e;
+            set = true;
+        }
+        mlp_jac_kernel<<<(unsigned)((rows + T_ROWS - 1) / T_ROWS), T_THREADS, J_SMEM, st>>>(a);
+    } else if (precision == PG_MLP_FP32) {
         const int smem = (F_ROWS * F_HSTR + F_ROWS * MAXIN + F_ROWS * MAXDX) * 4;
         static bool set = false;
         if (!set) {
@@ -484,7 +830,7 @@ int launch(int precision, const MlpArgs& a, cudaStream_t st) {
             if (e != cudaSuccess) return (int)e;
             set = true;
         }
-        mlp_fp32_kernel<<<(unsigned)((a.R + F_ROWS - 1) / F_ROWS), 256, smem, st>>>(a);
+        mlp_fp32_kernel<<<(unsigned)((rows + F_ROWS - 1) / F_ROWS), 256, smem, st>>>(a);
     } else if (precision == PG_MLP_BF16) {
         static bool set = false;
         if (!set) {
@@ -492,7 +838,7 @@ int launch(int precision, const MlpArgs& a, cudaStream_t st) {
             if (e != cudaSuccess) return (int)e;
             set = true;
         }
-        mlp_bf16_kernel<<<(unsigned)((a.R + T_ROWS - 1) / T_ROWS), T_THREADS, T_SMEM, st>>>(a);
+        mlp_bf16_kernel<<<(unsigned)((rows + T_ROWS - 1) / T_ROWS), T_THREADS, T_SMEM, st>>>(a);
     } else {
         return PG_E_BADARG;
     }
@@ -551,6 +897,15 @@ int pg_mlp_pack(const pg_mlp_dims_t* d, const float* W1, const float* b1, const 
                     const int off = (nl >> 3) * 1024 + (nl & 7) * 128 + (((kk >> 3) ^ (nl & 7)) << 4) + (kk & 7) * 2;
                     img[off >> 1] = f32_to_bf16(v);
                 }
+            // transposed: output column kcol = half*256 + nl, contraction index nn = kb*64 + kk -> W2[nn][kcol]
+            uint16_t* imgT = p->W2bT[kb * 2 + half];
+            for (int nl = 0; nl < 256; nl++)
+                for (int kk = 0; kk < 64; kk++) {
+                    const int kcol = half * 256 + nl, nn = kb * 64 + kk;
+                    const float v = (nn < HID && kcol < HID) ? W2[nn * HID + kcol] : 0.0f;
+                    const int off = (nl >> 3) * 1024 + (nl & 7) * 128 + (((kk >> 3) ^ (nl & 7)) << 4) + (kk & 7) * 2;
+                    imgT[off >> 1] = f32_to_bf16(v);
+                }
         }
     return 0;
 }
@@ -563,10 +918,11 @@ int pg_mlp_ode(int precision, const pg_mlp_dims_t* dims, const void* packed, int
     memset(&a, 0, sizeof(a));
     a.d = *dims;
     a.w = (const MlpPacked*)packed;
-    a.R = R;
+    a.mode = MODE_ODE;
+    a.R = a.Bs = R;
     a.T = 1;
+    a.n_alpha = 1;
     a.dt = dt;
-    a.rollout = 0;
     a.x0 = x;
     a.U = u;
     a.rhs = rhs;
@@ -576,28 +932,66 @@ int pg_mlp_ode(int precision, const pg_mlp_dims_t* dims, const void* packed, int
 int pg_mlp_rollout(int precision, const pg_mlp_dims_t* dims, const void* packed, int64_t B, int32_t T, double dt,
                    const double* x0, const double* U, const double* KK, const double* kk, const double* xbar,
                    const double* ubar, double alpha, const double* ulim, double* X, double* U_out, void* stream) {
+    return pg_mlp_forward(precision, dims, packed, B, T, dt, 1, &alpha, x0, U, KK, kk, xbar, ubar, ulim, X, U_out, nullptr,
+                          nullptr, stream);
+}
+
+int pg_mlp_forward(int precision, const pg_mlp_dims_t* dims, const void* packed, int64_t B, int32_t T, double dt,
+                   int32_t n_alpha, const double* alphas, const double* x0, const double* U, const double* KK,
+                   const double* kk, const double* xbar, const double* ubar, const double* ulim, double* X, double* U_out,
+                   const int32_t* index, const int32_t* count, void* stream) {
     if (B == 0) return 0;
     if (!dims_ok(dims) || !packed || B < 0 || T < 0 || !x0 || !X || !(dt > 0)) return PG_E_BADARG;
+    if (n_alpha < 1 || n_alpha > MAX_ALPHAS || !alphas) return PG_E_BADARG;
     if (KK && (!kk || !xbar || !ubar)) return PG_E_BADARG;
+    if ((index == nullptr) != (count == nullptr)) return PG_E_BADARG;
     MlpArgs a;
     memset(&a, 0, sizeof(a));
     a.d = *dims;
     a.w = (const MlpPacked*)packed;
-    a.R = B;
+    a.mode = MODE_ROLLOUT;
+    a.R = a.Bs = B;
     a.T = T;
     a.dt = dt;
-    a.rollout = 1;
+    a.n_alpha = n_alpha;
+    for (int i = 0; i < n_alpha; i++) a.alphas[i] = alphas[i];
+    a.index = index;
+    a.count = count;
     a.x0 = x0;
     a.U = U;
     a.KK = KK;
     a.kk = kk;
     a.xbar = xbar;
     a.ubar = ubar;
-    a.alpha = alpha;
     a.clip = ulim != nullptr;
     for (int j = 0; j < dims->m && ulim; j++) a.ulim[j] = ulim[j];
     a.X = X;
     a.U_out = U_out;
+    return launch(precision, a, (cudaStream_t)stream);
+}
+
+int pg_mlp_linearize(int precision, int lin_mode, const pg_mlp_dims_t* dims, const void* packed, int64_t B, int32_t T,
+                     double dt, const double* xbar, const double* ubar, double* A, double* Bm, const int32_t* index,
+                     const int32_t* count, void* stream) {
+    if (B == 0 || T == 0) return 0;
+    if (!dims_ok(dims) || !packed || B < 0 || T < 0 || !xbar || !ubar || !A || !Bm || !(dt > 0)) return PG_E_BADARG;
+    if (lin_mode != PG_MLP_LIN_ANALYTIC && lin_mode != PG_MLP_LIN_FD) return PG_E_BADARG;
+    if ((index == nullptr) != (count == nullptr)) return PG_E_BADARG;
+    MlpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.d = *dims;
+    a.w = (const MlpPacked*)packed;
+    a.mode = lin_mode == PG_MLP_LIN_FD ? MODE_LIN_FD : MODE_LIN_AN;
+    a.R = a.Bs = B;
+    a.T = T;
+    a.dt = dt;
+    a.n_alpha = 1;
+    a.index = index;
+    a.count = count;
+    a.xbar = xbar;
+    a.ubar = ubar;
+    a.A = A;
+    a.Bm = Bm;
     return launch(precision, a, (cudaStream_t)stream);
 }
 

@@ -323,6 +323,106 @@ class StateSpaceModel(Environment):
         return self.observe(self.x_)
 
 
+class LearnedStateSpaceModel(StateSpaceModel):
+    """Environment whose dynamics are a learned MLP: the reference's `MBRL.nn_environment =
+    StateSpaceModel(self.ode, environment.cost, x0, uDim, dt)` with `MBRL.ode = [x[n/2:], 1/dt * nn_dynamics.ode(x, u)]`
+    (pygent/algorithms/mbrl.py:76, :125-130), integrated with forward Euler (`fast_step`; the planner is built with
+    fastForward=True, mbrl.py:81).
+
+    `net` is a `pygent_b200.nn_models.NNDynamics` (sparse_dyn: dxDim = xDim / 2).  Rollouts and linearisation run in
+    the learned-dynamics library (include/pygent_b200_mlp.h); the problem library compiled from `cost` supplies the
+    cost, its expansion and the iLQR kernels.  precision "fp32" follows the reference's fp32 network, "bf16" puts the
+    500 x 500 layer on the tensor cores; linearization "fd" is the reference's central differences, "analytic" the
+    chain rule on the tensor cores (bf16 only)."""
+
+    def __init__(self, net, cost, x0, uDim, dt, terminal_cost=0., precision="bf16", linearization=None, device=None):
+        n = int(np.array(x0() if callable(x0) else x0).shape[-1])
+        if net.xDim != n or net.uDim != uDim or net.dxDim * 2 != n:
+            raise ValueError("network dimensions (x %d, u %d, dx %d) do not match the environment (n %d, m %d, sparse_dyn)"
+                             % (net.xDim, net.uDim, net.dxDim, n, uDim))
+        xs = sp.symbols("x1:%d" % (n + 1))
+        us = sp.symbols("u1:%d" % (uDim + 1))
+        # structural stand-in for the compiled problem: position rates are the velocities, the learned part is NOT
+        # in this library (its rollout kernels are never used for this environment)
+        f = list(xs[n // 2:]) + [sp.Integer(0)] * (n // 2)
+        system = SystemModel("learned_n%d_m%d" % (n, uDim), f, xs, us, False)
+        super(LearnedStateSpaceModel, self).__init__(system, cost, x0, uDim, dt, terminal_cost=terminal_cost, substeps=1,
+                                                     device=device, dtype=torch.float64)
+        self.net = net
+        self.precision = precision
+        self.linearization = linearization or ("analytic" if precision == "bf16" else "fd")
+        if self.linearization == "analytic" and precision != "bf16":
+            raise ValueError("the analytic Jacobian chain runs on the tensor-core path (precision='bf16'); use linearization='fd'")
+        self.learned = True
+
+    @property
+    def dynamics(self):
+        """Packed device copy of the network (rebuilt after `net.invalidate()`)."""
+        return self.net.device_model(self.device)
+
+    def ode(self, t, x, u):
+        """MBRL.ode (mbrl.py:125-130) for one state or a batch of states, evaluated on the GPU."""
+        x, u = np.asarray(x, dtype=float), np.asarray(u, dtype=float)
+        rhs = self.dynamics.ode(np.atleast_2d(x), np.atleast_2d(u), self.dt, precision=self.precision)
+        return rhs[0] if x.ndim == 1 else rhs
+
+    def _advance(self, args, integrator):
+        if len(args) == 2:
+            u, dt = args
+        elif len(args) == 1:
+            u, dt = args[0], self.dt
+        else:
+            raise TypeError("step(u[, dt])")
+        if abs(dt - self.dt) > 1e-15:
+            raise ValueError("the learned model predicts one control interval dt = %g (mbrl.py:126)" % self.dt)
+        x = self._state()
+        ud = self._to_dev(u, self.uDim).reshape(1, self.uDim, self.batch)
+        X, Uo = self._open_loop(x, ud)
+        xn = X[0, 1].contiguous()
+        c = self.library().traj_cost(X, Uo, dt=dt, t0=float(self.tt[-1]), terminal_cost=float(self.terminal_cost))
+        self._xd_prev, self._xd = x, xn
+        self._hist.append(xn.detach().to("cpu", torch.float64).numpy().T.copy())
+        self.tt.extend([self.tt[-1] + dt])
+        term = np.asarray(self.terminate(self._hist[-1]))
+        cost = c["cost"][0].to("cpu", torch.float64).numpy()
+        # traj_cost adds fcost(x_T)*dt, which is zero for the plain environment library
+        if self.batched:
+            self.terminated = term
+            return cost
+        self.terminated = bool(term[0]) if term.ndim else bool(term)
+        return float(cost[0])
+
+    def _open_loop(self, x, Ud):
+        """Euler rollout along given controls Ud [T, m, B]: (X [1,T+1,n,B], U [1,T,m,B])."""
+        X = self.dynamics.rollout_device(x, self.dt, U=Ud, precision=self.precision)
+        return X[None], Ud[None]
+
+    def step(self, *args):
+        """The learned model has one integrator: forward Euler over one control interval."""
+        return self._advance(args, lib.INTEG_EULER)
+
+    fast_step = step
+
+    def rollout(self, U, history=True, fast=True, add_final_cost=False, fcost_expr=None):
+        x = self._state()
+        if torch.is_tensor(U) and U.is_cuda:
+            Ud = U
+        else:
+            U = np.asarray(U, dtype=float)
+            if U.ndim == 2:
+                U = np.broadcast_to(U[None], (self.batch,) + U.shape)
+            Ud = torch.as_tensor(np.ascontiguousarray(U.transpose(1, 2, 0)), dtype=self.dtype, device=self.device)
+        X, Uo = self._open_loop(x, Ud)
+        c = self.library(fcost_expr).traj_cost(X, Uo, dt=self.dt, t0=float(self.tt[-1]), terminal_cost=float(self.terminal_cost))
+        T = Ud.shape[0]
+        self._xd_prev, self._xd = x, X[0, T].contiguous()
+        Xh = X[0].detach().to("cpu", torch.float64).numpy()
+        self._hist.extend([Xh[k].T.copy() for k in range(1, T + 1)] if history else [Xh[T].T.copy()])
+        for _ in range(T):
+            self.tt.append(self.tt[-1] + self.dt)
+        return {"X": X[0], "xN": self._xd, "cost": c["cost"][0], "terminated": c["terminated"][0]}
+
+
 def _finish(env):
     env.oDim = int(env.xDim + np.sum(env.xIsAngle))
 

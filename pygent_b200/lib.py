@@ -47,6 +47,9 @@ SIGNATURES = {
                        _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "pg_ilqr_commit": [_i32, _i32, _i64, _i32, _i32, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _dp, _vp, _vp, _vp, _vp,
                        _vp],
+    "pg_ilqr_backward_ext": [_i32, _i64, _i32, _f64, _i32, _vp, _vp, _vp, _vp, _vp, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pg_traj_cost": [_i32, _i64, _i32, _f64, _f64, _i32, _vp, _vp, _f64, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pg_ilqr_commit_copy": [_i32, _i64, _i32, _i32, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "pg_observe": [_i32, _i64, _vp, _vp, _vp],
     "pg_eval": [_i32, _i64, _i32] + [_vp] * 16,
 }
@@ -289,6 +292,58 @@ class ProblemLibrary:
             _ptr(KK_acc, dtype, (T, m, n, B), "KK_acc"), _ptr(kk_acc, dtype, (T, m, B), "kk_acc"), *self._work(work, B),
             self._stream())
         self._check(rc, "pg_ilqr_commit")
+        self.launches += 1
+
+    # -- dynamics integrated / linearised outside the library (learned MLP) --------------------------
+    def ilqr_backward_ext(self, xbar, ubar, mu, A, Bm, dt=0.02, reg_type=2, ulim=None, out=None, work=None):
+        """Riccati sweep with caller-supplied continuous-time Jacobians A [T,n,n,B], Bm [T,n,m,B]."""
+        n, m = self.n, self.m
+        dtype, dev = xbar.dtype, xbar.device
+        T, B = ubar.shape[0], ubar.shape[2]
+        out = out or {}
+        g = lambda k, shape, dt_=dtype, zero=False: out[k] if out.get(k) is not None else (
+            torch.zeros(shape, dtype=dt_, device=dev) if zero else torch.empty(shape, dtype=dt_, device=dev))
+        KK, kk = g("KK", (T, m, n, B), zero=True), g("kk", (T, m, B), zero=True)
+        dV, gnorm, success = g("dV", (2, B)), g("gnorm", (B,)), g("success", (B,), torch.uint8)
+        rc = self.dll.pg_ilqr_backward_ext(
+            _dtype_code(dtype), B, T, dt, reg_type, _ptr(mu, dtype, (B,), "mu"), _ptr(xbar, dtype, (T + 1, n, B), "xbar"),
+            _ptr(ubar, dtype, (T, m, B), "ubar"), _ptr(A, dtype, (T, n, n, B), "A"), _ptr(Bm, dtype, (T, n, m, B), "Bm"),
+            _host_doubles(ulim), _ptr(KK, dtype, (T, m, n, B), "KK"), _ptr(kk, dtype, (T, m, B), "kk"),
+            _ptr(dV, dtype, (2, B), "dV"), _ptr(gnorm, dtype, (B,), "gnorm"), _ptr(success, torch.uint8, (B,), "success"),
+            *self._work(work, B), self._stream())
+        self._check(rc, "pg_ilqr_backward_ext")
+        self.launches += 1
+        return {"KK": KK, "kk": kk, "dV": dV, "gnorm": gnorm, "success": success}
+
+    def traj_cost(self, X, U, dt=0.02, t0=0.0, terminal_cost=0.0, out=None, work=None):
+        """X [n_alpha,T+1,n,B], U [n_alpha,T,m,B] -> dict(cost, diverged, terminated), each [n_alpha,B]."""
+        n, m = self.n, self.m
+        dtype, dev = X.dtype, X.device
+        A, T, B = X.shape[0], X.shape[1] - 1, X.shape[3]
+        out = out or {}
+        cost = out.get("cost") if out.get("cost") is not None else torch.empty((A, B), dtype=dtype, device=dev)
+        div = out.get("diverged") if out.get("diverged") is not None else torch.empty((A, B), dtype=torch.uint8, device=dev)
+        term = out.get("terminated") if out.get("terminated") is not None else torch.empty((A, B), dtype=torch.uint8, device=dev)
+        rc = self.dll.pg_traj_cost(_dtype_code(dtype), B, T, dt, t0, A, _ptr(X, dtype, (A, T + 1, n, B), "X"),
+                                   _ptr(U, dtype, (A, T, m, B), "U"), terminal_cost, _ptr(cost, dtype, (A, B), "cost_out"),
+                                   _ptr(div, torch.uint8, (A, B), "diverged_out"), _ptr(term, torch.uint8, (A, B), "terminated_out"),
+                                   *self._work(work, B), self._stream())
+        self._check(rc, "pg_traj_cost")
+        self.launches += 1
+        return {"cost": cost, "diverged": div, "terminated": term}
+
+    def ilqr_commit_copy(self, alphas, alpha_best, accept, X_cand, U_cand, xbar, ubar, KK, kk, KK_acc, kk_acc, work=None):
+        n, m = self.n, self.m
+        dtype = xbar.dtype
+        A, T, B = X_cand.shape[0], ubar.shape[0], ubar.shape[2]
+        rc = self.dll.pg_ilqr_commit_copy(
+            _dtype_code(dtype), B, T, A, _host_doubles(alphas), _ptr(alpha_best, dtype, (B,), "alpha_best"),
+            _ptr(accept, torch.uint8, (B,), "accept"), _ptr(X_cand, dtype, (A, T + 1, n, B), "X_cand"),
+            _ptr(U_cand, dtype, (A, T, m, B), "U_cand"), _ptr(xbar, dtype, (T + 1, n, B), "xbar"),
+            _ptr(ubar, dtype, (T, m, B), "ubar"), _ptr(KK, dtype, (T, m, n, B), "KK"), _ptr(kk, dtype, (T, m, B), "kk"),
+            _ptr(KK_acc, dtype, (T, m, n, B), "KK_acc"), _ptr(kk_acc, dtype, (T, m, B), "kk_acc"), *self._work(work, B),
+            self._stream())
+        self._check(rc, "pg_ilqr_commit_copy")
         self.launches += 1
 
     def observe(self, x):

@@ -59,6 +59,10 @@ SIGNATURES = {
     "pg_mlp_rollout": [_i32, _dims_p, _vp, _i64, _i32, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _f64,
                        ctypes.POINTER(ctypes.c_double), _vp, _vp, _vp],
 }
+SIGNATURES["pg_mlp_forward"] = [_i32, _dims_p, _vp, _i64, _i32, _f64, _i32, ctypes.POINTER(ctypes.c_double), _vp, _vp, _vp, _vp,
+                              _vp, _vp, ctypes.POINTER(ctypes.c_double), _vp, _vp, _vp, _vp, _vp]
+SIGNATURES["pg_mlp_linearize"] = [_i32, _i32, _dims_p, _vp, _i64, _i32, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+LIN_MODES = {"analytic": 0, "fd": 1}
 _dll = None
 
 
@@ -170,3 +174,36 @@ class MLPDynamics:
                                     _ptr(X), _ptr(Uo), self._stream()), "pg_mlp_rollout")
         self.launches += 1
         return (X, Uo) if want_u else X
+
+    def forward_device(self, x0, dt, alphas, gains, ulim=None, precision="bf16", out=None, work=None):
+        """iLQR.forward_pass for every alpha in one launch: gains = (KK, kk, xbar, ubar) in kernel layout.
+        Returns (X [A,T+1,n,B], U [A,T,m,B]); `work` = (index i32 [B], count i32 [1]) restricts the trajectories."""
+        B = x0.shape[1]
+        KK, kk, xbar, ubar = gains
+        T, A = ubar.shape[0], len(alphas)
+        out = out or {}
+        X = out.get("X") if out.get("X") is not None else torch.empty((A, T + 1, self.n, B), dtype=torch.float64, device=self.device)
+        Uo = out.get("U") if out.get("U") is not None else torch.empty((A, T, self.m, B), dtype=torch.float64, device=self.device)
+        al = (ctypes.c_double * A)(*[float(v) for v in alphas])
+        lim = None if ulim is None else (ctypes.c_double * len(ulim))(*[float(v) for v in ulim])
+        idx, cnt = (None, None) if work is None else (ctypes.c_void_p(work[0].data_ptr()), ctypes.c_void_p(work[1].data_ptr()))
+        _check(dll().pg_mlp_forward(PRECISIONS[precision], ctypes.byref(self.dims), ctypes.c_void_p(self.packed.data_ptr()), B, T,
+                                    dt, A, al, _ptr(x0), None, _ptr(KK), _ptr(kk), _ptr(xbar), _ptr(ubar), lim, _ptr(X), _ptr(Uo),
+                                    idx, cnt, self._stream()), "pg_mlp_forward")
+        self.launches += 1
+        return X, Uo
+
+    def linearize_device(self, xbar, ubar, dt, mode="analytic", precision="bf16", out=None, work=None):
+        """Continuous-time Jacobians of MBRL.ode along (xbar [T+1,n,B], ubar [T,m,B]): A [T,n,n,B], Bm [T,n,m,B].
+        mode "fd": the reference's central differences (eps = 1e-3, 2(n+m) network evaluations per point);
+        mode "analytic": chain rule on the tensor cores (precision "bf16" only)."""
+        T, B = ubar.shape[0], ubar.shape[2]
+        out = out or {}
+        A = out.get("A") if out.get("A") is not None else torch.empty((T, self.n, self.n, B), dtype=torch.float64, device=self.device)
+        Bm = out.get("B") if out.get("B") is not None else torch.empty((T, self.n, self.m, B), dtype=torch.float64, device=self.device)
+        idx, cnt = (None, None) if work is None else (ctypes.c_void_p(work[0].data_ptr()), ctypes.c_void_p(work[1].data_ptr()))
+        _check(dll().pg_mlp_linearize(PRECISIONS[precision], LIN_MODES[mode], ctypes.byref(self.dims),
+                                      ctypes.c_void_p(self.packed.data_ptr()), B, T, dt, _ptr(xbar), _ptr(ubar), _ptr(A), _ptr(Bm),
+                                      idx, cnt, self._stream()), "pg_mlp_linearize")
+        self.launches += 1
+        return A, Bm

@@ -86,3 +86,177 @@ def test_mlp_tensor_core_path_tracks_fp32_at_scale():
     b = dyn.ode_device(x, u, 0.02, "bf16").cpu().numpy()
     assert rel(b, a) < TOL["bf16"]
     assert np.sqrt(np.mean((a[2:] - b[2:]) ** 2)) / np.sqrt(np.mean(a[2:] ** 2)) < 5e-3
+
+
+# ---- iLQR over the learned dynamics (BASELINE.json config 5) --------------------------------------------------------
+def c_k(x, u, mod):
+    x1, x2, x3, x4 = x
+    u1, = u
+    return 10 * x1 ** 2 + 5 * x2 ** 2 + .01 * x3 ** 2 + .01 * x4 ** 2 + 0.1 * u1 ** 2
+
+
+def c_N(x, mod):
+    x1, x2, x3, x4 = x
+    return 100 * x1 ** 2 + 100 * x2 ** 2 + 10 * x3 ** 2 + 10 * x4 ** 2
+
+
+COST = mo.QuadCost([10, 5, .01, .01], [0.1], [100, 100, 10, 10])
+
+
+def learned_env(x0, precision, linearization=None, dt=0.02):
+    from pygent_b200.environments import LearnedStateSpaceModel
+    from pygent_b200.nn_models import NNDynamics
+    w, mom = mo.make_weights(6, 2), mo.make_moments(5, 1, 2)
+    net = NNDynamics(4, 1, dxDim=2, oDim=5, xIsAngle=IS_ANGLE[4])
+    with torch.no_grad():
+        for i, l in enumerate((net.layer1, net.layer2, net.layer3), 1):
+            l.weight.copy_(torch.from_numpy(w["W%d" % i]))
+            l.bias.copy_(torch.from_numpy(w["b%d" % i]))
+    for k, a in (("oMean", "o_mean"), ("oVar", "o_var"), ("uMean", "u_mean"), ("uVar", "u_var"), ("dxMean", "dx_mean"), ("dxVar", "dx_var")):
+        setattr(net, k, torch.from_numpy(mom[a])[None])
+    env = LearnedStateSpaceModel(net, c_k, x0, 1, dt, precision=precision, linearization=linearization)
+    env.uMax = np.array([8.0])
+    return env, w, mom
+
+
+def test_mlp_linearize_fd_matches_oracle():
+    """pg_mlp_linearize, PG_MLP_LIN_FD on the fp32 path = helpers.system_linearization on MBRL.ode; tolerance is the
+    noise of differencing an fp32 network at eps = 1e-3."""
+    dyn, w, mom, ia = model()
+    rng = np.random.default_rng(3)
+    T, B, dt = 7, 37, 0.02
+    xb = np.array([0, np.pi, 0, 0]) + rng.uniform(-1, 1, (B, T + 1, 4))
+    ub = rng.uniform(-6, 6, (B, T, 1))
+    d = lambda a: torch.as_tensor(np.ascontiguousarray(np.moveaxis(a, 0, -1)), device="cuda")
+    A, Bm = dyn.linearize_device(d(xb), d(ub), dt, mode="fd", precision="fp32")
+    Ao, Bo = mo.fd_linearize(w, mom, ia, xb[:, :-1].reshape(-1, 4), ub.reshape(-1, 1), dt)
+    A, Bm = np.moveaxis(A.cpu().numpy(), -1, 0).reshape(-1, 4, 4), np.moveaxis(Bm.cpu().numpy(), -1, 0).reshape(-1, 4, 1)
+    assert rel(A, Ao) < 2e-3 and rel(Bm, Bo) < 2e-3
+    assert np.max(np.abs(A[:, :2, :2])) < 1e-9 and np.max(np.abs(A[:, 0, 2] - 1)) < 1e-9  # position rows: [0 I]
+
+
+def test_mlp_linearize_analytic_on_tensor_cores_matches_exact_jacobian():
+    """PG_MLP_LIN_ANALYTIC (three tcgen05 GEMM passes) against the float64 chain rule.  The Jacobian of a ReLU network
+    is piecewise constant: with bf16 operands a few near-zero units switch side, and each switch moves an entry by
+    ~1/sqrt(active units) of its scale.  So the bulk of the entries agrees to bf16 rounding (median error 4e-4 of the
+    scale measured, bound 2e-3) while ~8% of them carry a switch (Frobenius error 5e-2 measured, bound 8e-2) -- the
+    reference's own central differences through the fp32 network sit at 2e-2 for the same reason (kinks within eps)."""
+    dyn, w, mom, ia = model()
+    rng = np.random.default_rng(4)
+    T, B, dt = 5, 203, 0.02  # 1015 rows: ragged last tile
+    xb = np.array([0, np.pi, 0, 0]) + rng.uniform(-1.5, 1.5, (B, T + 1, 4))
+    ub = rng.uniform(-8, 8, (B, T, 1))
+    d = lambda a: torch.as_tensor(np.ascontiguousarray(np.moveaxis(a, 0, -1)), device="cuda")
+    A, Bm = dyn.linearize_device(d(xb), d(ub), dt, mode="analytic", precision="bf16")
+    Ae, Be = mo.exact_jacobian(w, mom, ia, xb[:, :-1].reshape(-1, 4), ub.reshape(-1, 1), dt)
+    A, Bm = np.moveaxis(A.cpu().numpy(), -1, 0).reshape(-1, 4, 4), np.moveaxis(Bm.cpu().numpy(), -1, 0).reshape(-1, 4, 1)
+    for g, e in ((A[:, 2:], Ae[:, 2:]), (Bm[:, 2:], Be[:, 2:])):
+        err = np.abs(g - e) / np.abs(e).max()
+        assert np.median(err) < 2e-3 and err.max() < 0.5
+        assert np.linalg.norm(g - e) < 8e-2 * np.linalg.norm(e)
+    assert np.array_equal(A[:, :2], Ae[:, :2]) and np.array_equal(Bm[:, :2], Be[:, :2])
+    # same points through the reference's scheme on the fp32 path: the two approximations of the same derivative
+    Af, Bf = dyn.linearize_device(d(xb), d(ub), dt, mode="fd", precision="fp32")
+    Af = np.moveaxis(Af.cpu().numpy(), -1, 0).reshape(-1, 4, 4)
+    assert np.linalg.norm(Af[:, 2:] - Ae[:, 2:]) < 5e-2 * np.linalg.norm(Ae[:, 2:])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_mlp_forward_all_alphas_equals_single_rollouts(precision):
+    """pg_mlp_forward: every (alpha, trajectory) row equals the one-alpha rollout bit for bit; a compacted work list
+    touches exactly the listed trajectories."""
+    dyn, w, mom, ia = model()
+    rng = np.random.default_rng(5)
+    B, T, dt = 150, 9, 0.02
+    d = lambda a: torch.as_tensor(np.ascontiguousarray(np.moveaxis(a, 0, -1)), device="cuda")
+    x0 = d(rng.uniform(-1, 1, (B, 4)))
+    gains = (d(rng.uniform(-.5, .5, (B, T, 1, 4))), d(rng.uniform(-1, 1, (B, T, 1))), d(rng.uniform(-1, 1, (B, T + 1, 4))),
+             d(rng.uniform(-3, 3, (B, T, 1))))
+    alphas = [1.0, 0.5, 0.1]
+    X, U = dyn.forward_device(x0, dt, alphas, gains, ulim=[5.0], precision=precision)
+    for i, al in enumerate(alphas):
+        X1, U1 = dyn.rollout_device(x0, dt, gains=gains, alpha=al, ulim=[5.0], precision=precision, want_u=True)
+        assert torch.equal(X[i], X1) and torch.equal(U[i], U1)
+    idx = torch.tensor(sorted(rng.choice(B, 40, replace=False)) + [0] * (B - 40), dtype=torch.int32, device="cuda")
+    cnt = torch.tensor([40], dtype=torch.int32, device="cuda")
+    out = {"X": torch.full_like(X, -7.0), "U": torch.full_like(U, -7.0)}
+    dyn.forward_device(x0, dt, alphas, gains, ulim=[5.0], precision=precision, out=out, work=(idx, cnt))
+    sel = idx[:40].long()
+    mask = torch.zeros(B, dtype=torch.bool, device="cuda")
+    mask[sel] = True
+    assert torch.equal(out["X"][..., sel], X[..., sel]) and torch.equal(out["U"][..., sel], U[..., sel])
+    assert bool((out["X"][..., ~mask] == -7.0).all())
+
+
+def test_backward_ext_and_traj_cost_match_oracle():
+    """pg_ilqr_backward_ext on given Jacobians = ilqr.py:233-346 restated in numpy; pg_traj_cost = the summed
+    fast_step costs + final cost."""
+    env, w, mom = learned_env(np.zeros((3, 4)), "fp32")
+    from pygent_b200.algorithms.ilqr import iLQR
+    rng = np.random.default_rng(6)
+    B, T, dt = 3, 25, 0.02
+    x0 = np.array([0.2, np.pi - .3, .1, -.2]) + rng.uniform(-.1, .1, (B, 4))
+    env.reset(x0)
+    alg = iLQR(env, T * dt, dt, fastForward=True, fcost=c_N, printing=False)
+    U = rng.uniform(-3, 3, (B, T, 1))
+    X, _ = mo.rollout(w, mom, IS_ANGLE[4], x0, dt, U=U)
+    d = lambda a: torch.as_tensor(np.ascontiguousarray(np.moveaxis(a, 0, -1)), device="cuda")
+    c = alg.lib.traj_cost(d(X)[None], d(U)[None], dt=dt)
+    co = [mo.traj_cost(COST, X[b], U[b], dt) for b in range(B)]
+    assert rel(c["cost"][0].cpu().numpy(), co) < 1e-12
+    A = rng.uniform(-1, 1, (B, T, 4, 4))
+    Bm = rng.uniform(-1, 1, (B, T, 4, 1))
+    mu = torch.full((B,), 1e-6, dtype=torch.float64, device="cuda")
+    r = alg.lib.ilqr_backward_ext(d(X), d(U), mu, d(A), d(Bm), dt=dt)
+    for b in range(B):
+        V1, V2, ok, KK, kk = mo.ilqr_backward(COST, A[b], Bm[b], X[b], U[b], 1e-6, dt)
+        assert ok and bool(r["success"][b])
+        assert rel(r["KK"][..., b].cpu().numpy(), np.array(KK)) < 1e-8
+        assert rel(r["kk"][..., b].cpu().numpy(), np.array(kk).reshape(T, 1)) < 1e-8
+        assert rel(r["dV"][:, b].cpu().numpy(), [np.sum(V1), np.sum(V2)]) < 1e-8
+
+
+def test_learned_ilqr_matches_reference_planner(golden):
+    """The whole learned-dynamics planner on the reference precision path (fp32 network, central differences) against
+    the reference's iLQR on StateSpaceModel(MBRL.ode) -- tolerances: see test_mlp_ilqr_oracle_matches_reference."""
+    from pygent_b200.algorithms.ilqr import iLQR
+    g = golden("mlp_ilqr_cart_pole")
+    T, dt = int(g["T"]), float(g["dt"])
+    env, w, mom = learned_env(list(g["x0"]), "fp32", "fd")
+    alg = iLQR(env, T * dt, dt, fastForward=True, fcost=c_N, constrained=False, printing=False, maxIters=12)
+    assert rel(alg.cost, g["cost0"]) < 1e-6 and rel(alg.xx, g["xx0"]) < 1e-6
+    Ad, Bd, _ = alg.linearization(g["xx0"][:-1], np.zeros((T, 1)))
+    assert rel(Ad, g["Ad0"]) < 5e-5 and rel(Bd, g["Bd0"]) < 5e-5
+    V1, V2, ok, KK, kk = alg.backward_pass()
+    assert ok and rel(KK, g["KK1"]) < 2e-2 and rel(kk[..., 0], g["kk1"]) < 2e-2
+    assert rel(V1, g["sV1"]) < 1e-3 and rel(V2, g["sV2"]) < 1e-3
+    xx, uu, cost, _ = alg.forward_pass(1.0, KK, kk)
+    assert rel(cost, g["cost_alpha1"]) < 1e-5
+    xx, uu, cost = alg.run_optim()
+    assert rel(cost, g["cost"]) < 1e-4 and rel(xx, g["xx"]) < 5e-3
+    assert alg.iterations == 12
+
+
+def test_learned_ilqr_tensor_core_path_batched():
+    """bf16 rollouts + analytic tensor-core Jacobians, a ragged batch with work lists: costs fall monotonically, every
+    trajectory ends close to the fp32 / finite-difference planner, and a trajectory's result does not depend on its
+    neighbours in the batch."""
+    from pygent_b200.algorithms.ilqr import iLQR
+    rng = np.random.default_rng(8)
+    B, T, dt = 197, 40, 0.02
+    x0 = np.array([0.3, np.pi - 0.4, 0.2, -0.5]) + rng.uniform(-.2, .2, (B, 4))
+    res = {}
+    for prec, lin in (("bf16", "analytic"), ("fp32", "fd")):
+        env, _, _ = learned_env(x0, prec, lin)
+        alg = iLQR(env, T * dt, dt, fastForward=True, fcost=c_N, printing=False, maxIters=15)
+        c0 = alg.cost.copy()
+        alg.run_optim()
+        res[prec] = (c0, alg.cost.copy(), alg.iters.copy())
+        assert np.all(alg.cost <= c0 + 1e-12) and np.all(np.isfinite(alg.cost))
+    assert rel(res["bf16"][0], res["fp32"][0]) < 5e-3
+    assert np.max(np.abs(res["bf16"][1] - res["fp32"][1]) / res["fp32"][1]) < 1e-2
+    sub = [5, 77, 196]
+    env, _, _ = learned_env(x0[sub], "bf16", "analytic")
+    alg = iLQR(env, T * dt, dt, fastForward=True, fcost=c_N, printing=False, maxIters=15)
+    alg.run_optim()
+    assert np.array_equal(alg.cost, res["bf16"][1][sub]) and np.array_equal(alg.iters, res["bf16"][2][sub])

@@ -38,7 +38,19 @@ def test_header_declares_what_the_library_exports(built):
             assert hasattr(dll, name), (p, name)
     L = lib.ProblemLibrary(paths[0])
     assert (L.n, L.m, L.n_obs, L.has_ab) == (4, 1, 5, True) and L.name == "cart_pole_lin"
-    assert L.info.abi_version == 1
+    assert L.info.abi_version == 2
+
+
+def test_mlp_header_declares_what_the_library_exports():
+    """include/pygent_b200_mlp.h vs the learned-dynamics library and its ctypes signatures (no compute call)."""
+    from pygent_b200 import mlp
+    hdr = open(os.path.join(ROOT, "include", "pygent_b200_mlp.h")).read()
+    declared = set(re.findall(r"^int (pg_\w+)\(", hdr, flags=re.M))
+    assert declared == set(mlp.SIGNATURES), declared ^ set(mlp.SIGNATURES)
+    dll = ctypes.CDLL(mlp.build_library())
+    for name in declared | {"pg_mlp_packed_bytes"}:
+        assert hasattr(dll, name), name
+    assert ctypes.sizeof(mlp.Dims) == 24
 
 
 def test_select_params_layout_matches_header():

@@ -96,3 +96,40 @@ def test_ilqr_solve_matches_reference(golden, run):
         assert out["alpha"][0] == pytest.approx(float(g["alpha"]))
     # else: the reference left through "mu > mu_max" on its last iteration -- a rounding-level
     # knife edge at mu ~ 1e9 (dcost ~ 1e-12); costs and trajectories above still agree
+
+
+# ---- learned-MLP dynamics: the numpy restatement (oracle/mlp_oracle.py) against the reference's own classes ---------
+MLP_IS_ANGLE = [False, True, False, False]
+
+
+def _mlp_setup():
+    from oracle import mlp_oracle as mo
+    return mo, mo.make_weights(6, 2), mo.make_moments(5, 1, 2), mo.QuadCost([10, 5, .01, .01], [0.1], [100, 100, 10, 10])
+
+
+def test_mlp_oracle_matches_reference_ode_and_euler(golden):
+    mo, w, mom, _ = _mlp_setup()
+    g = golden("mlp_cart_pole")
+    assert rel(mo.mbrl_ode(w, mom, MLP_IS_ANGLE, g["xs"], g["us"], float(g["dt"])), g["rhs"]) < 2e-6
+    X, _ = mo.rollout(w, mom, MLP_IS_ANGLE, g["x0"][None], float(g["dt"]), U=g["U"][None])
+    assert rel(X[0], g["X"]) < 2e-6
+
+
+def test_mlp_ilqr_oracle_matches_reference(golden):
+    """iLQR(StateSpaceModel(MBRL.ode), fastForward=True) of the reference (oracle/make_golden_mlp.py).  The reference
+    linearises by central differences through its fp32 network: eps = 1e-3 against ~1e-7 rounding, so Jacobians carry
+    ~1e-4 relative noise that depends on the summation order of the GEMM -- gains agree to that noise, costs much
+    better."""
+    mo, w, mom, cost = _mlp_setup()
+    g = golden("mlp_ilqr_cart_pole")
+    T, dt = int(g["T"]), float(g["dt"])
+    r = mo.ilqr_solve(w, mom, MLP_IS_ANGLE, cost, g["x0"], T, dt, max_iters=12)
+    assert rel(r["cost0"], g["cost0"]) < 1e-7 and rel(r["xx0"], g["xx0"]) < 1e-6
+    assert rel(r["A0"] * dt + np.eye(4), g["Ad0"]) < 5e-5 and rel(r["B0"] * dt, g["Bd0"]) < 5e-5
+    assert rel(r["KK1"], g["KK1"]) < 2e-2 and rel(r["kk1"], g["kk1"]) < 2e-2
+    assert rel(r["sV1"], g["sV1"]) < 1e-3 and rel(r["sV2"], g["sV2"]) < 1e-3
+    assert rel(r["cost_alpha1"], g["cost_alpha1"]) < 1e-5
+    assert rel(r["cost"], g["cost"]) < 1e-4
+    # the exact derivative of the piecewise-linear network is what the differences approximate
+    Ae, Be = mo.exact_jacobian(w, mom, MLP_IS_ANGLE, g["xx0"][:-1], np.zeros((T, 1)), dt)
+    assert rel(Ae, r["A0"]) < 5e-2 and rel(Be, r["B0"]) < 5e-3
