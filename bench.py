@@ -14,6 +14,8 @@ nothing on the data path).  Prints ONE JSON line (rank 0):
              on this pool's B200 (profiles/fp_peak_b200.json), plus the HBM view of the same launch
   cpu_baseline  the CPU oracle (C port of the reference's step loop) on a bounded sample, all host threads
   ilqr       iLQR iterations/s on 16,384 cart-pole swing-ups per GPU (BASELINE.json config 3), to convergence
+  mlp_ilqr   iLQR iterations/s through the learned-MLP dynamics, 4,096 trajectories per GPU (config 5 = 32,768 over
+             8 GPUs), tensor-core rollouts and Jacobian chain, 10 iterations
 `--impl reference` times the reference's algorithm on the host cores (the C oracle port -- the reference
 itself is pure Python and does not travel to the GPU box) on the same config/metric.
 """
@@ -34,6 +36,10 @@ B_ENVS, T_STEPS, SUBSTEPS, DT, U_MAX = 65536, 500, 4, 0.02, 10.0
 FLOPS_PER_SUBSTEP = 228   # 4 f-evals (8 arith + 36 sincos) + 13n combine, n = 4, fp64
 FLOPS_COST = 14           # quadratic running cost per control interval
 ILQR_B, ILQR_T = 16384, 100
+MLP_B, MLP_ITERS = 4096, 10
+# dram__bytes_read.sum + dram__bytes_write.sum of one rollout_queue_kernel launch at the benchmark size, from the
+# `ncu --set full` capture summarised in profiles/r01_rollout_queue_ncu_summary.txt (264.5 MB + 4.0 MB)
+NCU_TRAFFIC_BYTES = 268.5e6
 CONFIG = {"workload": "batched cart-pole RK4 rollouts, 65,536 envs x 500 steps per GPU, random actions "
                       "(BASELINE.json configs[1])",
           "system": "CartPole(linearized=True)", "envs_per_gpu": B_ENVS, "horizon": T_STEPS, "substeps": SUBSTEPS,
@@ -152,6 +158,57 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def learned_ilqr_bench(dev, rank, world, barrier):
+    """BASELINE.json configs[4] per GPU: iLQR over NNDynamics(4, 1, oDim=5, dxDim=2) with default-initialised weights
+    (torch.manual_seed(0)), moments 0/1, Euler, horizon 100, costs of examples/mbrl/cart_pole_hpc.py:24-33."""
+    import torch
+    import torch.distributed as dist
+    from pygent_b200.algorithms.ilqr import iLQR
+    from pygent_b200.environments import LearnedStateSpaceModel
+    from pygent_b200.nn_models import NNDynamics
+
+    def c_k(x, u, mod):
+        x1, x2, x3, x4 = x
+        u1, = u
+        return 10 * x1 ** 2 + 5 * x2 ** 2 + .01 * x3 ** 2 + .01 * x4 ** 2 + 0.1 * u1 ** 2
+
+    def c_N(x, mod):
+        x1, x2, x3, x4 = x
+        return 100 * x1 ** 2 + 100 * x2 ** 2 + 10 * x3 ** 2 + 10 * x4 ** 2
+
+    torch.manual_seed(0)
+    net = NNDynamics(4, 1, dxDim=2, oDim=5, xIsAngle=[False, True, False, False])
+    rng = np.random.default_rng(2000 + rank)
+    x0 = np.array([0, np.pi, 0, 0]) + rng.uniform(-1, 1, (MLP_B, 4)) * np.array([.5, .3, .5, .5])
+    env = LearnedStateSpaceModel(net, c_k, x0, 1, DT, precision="bf16", linearization="analytic", device=dev)
+    env.uMax = np.array([U_MAX])
+    alg = iLQR(env, ILQR_T * DT, DT, fastForward=True, fcost=c_N, printing=False, maxIters=MLP_ITERS)
+    c0 = float(np.mean(alg.cost))
+    alg.run_optim()  # warm-up solve (same work)
+    env.reset(x0)
+    alg.reset()
+    barrier()
+    l0 = alg.lib.launches + env.dynamics.launches
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    alg.run_optim()
+    b.record()
+    barrier()
+    ms, total = a.elapsed_time(b), int(alg.iters.sum())
+    if world > 1:
+        t = torch.tensor([ms, -float(total)], dtype=torch.float64, device=dev)
+        tm, ts = t.clone(), t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        ms, total = float(tm[0]), int(-ts[1])
+    evals = total * ILQR_T * (11 + 3)  # 11 line-search rollouts + 3 GEMM passes of the Jacobian chain per point
+    return {"metric": "mlp_ilqr_iterations_per_s", "value": total / (ms * 1e-3), "unit": "iLQR iterations/s",
+            "trajectories_per_gpu": MLP_B, "horizon": ILQR_T, "iterations_total": total, "ms": ms,
+            "network": "6->500->500->2, bf16 tcgen05 layer 2, fp32 accumulate", "linearization": "analytic chain on tensor cores",
+            "tflops": evals * 2.0 * 512 * 512 / (ms * 1e-3) / 1e12, "gpu_launches": alg.lib.launches + env.dynamics.launches - l0,
+            "mean_cost_before": c0, "mean_cost_after": float(np.mean(alg.cost))}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -160,6 +217,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-ilqr", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-mlp", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -292,6 +350,11 @@ def main():
                 "converged_frac": float(np.mean((st == pglib.ST_CONV_FUN) | (st == pglib.ST_CONV_GRAD))),
                 "mean_final_cost": float(np.mean(solver.cost)), "line_search": "serial semantics, 11 alphas evaluated per launch"}
 
+    # ---- iLQR through the learned-MLP dynamics (config 5 sized per GPU) --------------------------------
+    mlp_ilqr = None
+    if not args.no_mlp:
+        mlp_ilqr = learned_ilqr_bench(dev, rank, world, barrier)
+
     clocks = sampler.stop()
     if rank == 0:
         peak_tf, peak_src = fp64_peak()
@@ -307,9 +370,12 @@ def main():
             "e2e": {"value": e2e_value, "unit": "env-steps/s",
                     "h2d_bytes_per_step": int(U_pin.numel() * 8 + x0_pin.numel() * 8),
                     "d2h_bytes_per_step": int(cost_pin.numel() * 8 + xN_pin.numel() * 8), "steps": e2e_steps},
-            "roofline": {"bound": "fp64", "kernel": "rollout_kernel<Problem,double,RK4>", "achieved": achieved,
+            "roofline": {"bound": "fp64", "kernel": "rollout_queue_kernel<Problem,double,RK4,1>", "achieved": achieved,
                          "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "peak_source": peak_src,
-                         "flops_per_launch": flops, "kernel_ms": kernel_ms, "traffic": None,
+                         "flops_per_launch": flops, "kernel_ms": kernel_ms, "traffic": NCU_TRAFFIC_BYTES,
+                         "note": "FP64 FMA pipe roofline (SURVEY 8d): algorithmic flops of the RK4 schedule (228 per substep) over "
+                                 "the measured DFMA peak; the kernel issues fewer FP64 instructions than that count (sin/cos of "
+                                 "the RK stages are rotations of one anchor per interval), pipe utilisation under ncu is 0.71",
                          "hbm": {"achieved": hbm_bytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_gbs, "unit": "GB/s",
                                  "frac": hbm_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_gbs, "bytes_per_launch": hbm_bytes,
                                  "peak_source": hbm_src}},
@@ -317,6 +383,8 @@ def main():
         }
         if ilqr is not None:
             res["ilqr"] = ilqr
+        if mlp_ilqr is not None:
+            res["mlp_ilqr"] = mlp_ilqr
         if not args.no_cpu:
             import oracle
             oracle.build()
