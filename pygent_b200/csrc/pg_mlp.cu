@@ -32,11 +32,12 @@ constexpr int H = PG_MLP_HPAD;      // 512
 constexpr int HID = PG_MLP_HIDDEN;  // 500
 constexpr int MAXIN = PG_MLP_MAX_IN;
 constexpr int MAXDX = PG_MLP_MAX_DX;
-constexpr int CHUNK_BYTES = 256 * 64 * 2;  // one W2 chunk image: 256 n-rows x 64 k bf16 = 32 KB
-constexpr int N_CHUNKS = 16;               // 8 k-blocks x 2 n-halves
+constexpr int CHUNK_N = 128;                   // n-rows (output columns) of one W2 chunk = N of one MMA
+constexpr int CHUNK_BYTES = CHUNK_N * 64 * 2;  // one W2 chunk image: 128 n-rows x 64 k bf16 = 16 KB
+constexpr int N_CHUNKS = 32;                   // 8 k-blocks x 4 n-quarters
 
 struct alignas(1024) MlpPacked {
-    uint16_t W2b[N_CHUNKS][CHUNK_BYTES / 2];  // bf16, 128B-swizzled K-major images, chunk = kb * 2 + half
+    uint16_t W2b[N_CHUNKS][CHUNK_BYTES / 2];  // bf16, 128B-swizzled K-major images, chunk = quarter * 8 + kb
     uint16_t W2bT[N_CHUNKS][CHUNK_BYTES / 2];  // the same for W2^T (contraction over layer 2's OUTPUT index)
     float W2t[H][H];                          // [k][n] fp32 (FFMA path)
     float W1[H][MAXIN];                       // [k][input]
@@ -44,6 +45,9 @@ struct alignas(1024) MlpPacked {
     float b2[H];
     float W3[H][MAXDX];                       // [k][output]
     float b3[MAXDX];
+    float W1b[H][MAXIN];                      // W1 row with b1 in slot n_in (the input vector carries a 1 there)
+    float4 ep[H];                             // epilogue constants of hidden unit k: {b2, W3[k][0], W3[k][1], W3[k][2]}
+    float W3T[MAXDX][H];                      // [output][k]
     float o_mean[MAXIN], o_var[MAXIN];
     float u_mean[2], u_var[2];
     float dx_mean[MAXDX], dx_var[MAXDX];
@@ -173,6 +177,7 @@ __device__ __forceinline__ void network_input(const MlpArgs& a, const pg::MathCt
         in[c] = ((float)u[j] - w->u_mean[j]) / w->u_var[j];
         c++;
     }
+    in[c++] = 1.0f;  // multiplies the bias column of W1b (zero in W1)
     for (; c < MAXIN; c++) in[c] = 0.0f;
 }
 
@@ -392,8 +397,8 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
-// D (fp32) = A (bf16, K-major) x B (bf16, K-major), M = 128, N = 256
-constexpr uint32_t UMMA_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+// D (fp32) = A (bf16, K-major) x B (bf16, K-major), M = 128, N = CHUNK_N
+constexpr uint32_t UMMA_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)CHUNK_N >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
     asm volatile(
@@ -420,28 +425,35 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-constexpr int T_ROWS = 128, T_STAGES = 2, T_THREADS = 512, T_SPLIT = T_THREADS / T_ROWS;
+constexpr int T_ROWS = 128, T_STAGES = 3, T_THREADS = 512, T_SPLIT = T_THREADS / T_ROWS;
 constexpr int T_A_BYTES = T_ROWS * H * 2;  // 128 KB: 8 k-blocks of [128 rows x 64 k] bf16
-constexpr int T_INS_BYTES = T_ROWS * MAXIN * 4;            // network inputs of the 128 rows
-constexpr int T_YP_BYTES = T_SPLIT * T_ROWS * MAXDX * 4;   // partial layer-3 sums
-constexpr int T_SMEM = T_A_BYTES + T_STAGES * CHUNK_BYTES + T_INS_BYTES + T_YP_BYTES + 256;
+constexpr int INS_STRIDE = MAXIN + 4;      // floats per row of the input tile (padded: conflict-free 128-bit reads)
+constexpr int T_INS_BYTES = T_ROWS * INS_STRIDE * 4;  // network inputs of the 128 rows; reused for the partial layer-3 sums
+constexpr int T_EP_BYTES = H * 16;                    // epilogue constants {b2, W3[.][0..2]} per hidden unit
+constexpr int W1S_FLOATS = 8;                         // layer-1 weight rows kept in smem when inputs + 1 <= 8 (else read from L2)
+constexpr int T_W1_BYTES = H * W1S_FLOATS * 4;
+constexpr int T_CONST_BYTES = T_EP_BYTES + T_W1_BYTES;
+constexpr int T_SMEM = T_A_BYTES + T_STAGES * CHUNK_BYTES + T_INS_BYTES + T_CONST_BYTES + 256;
+constexpr int PRODUCER_THREAD = 384, ISSUER_THREAD = 416;  // in the warps of accumulator quarter 3, which finishes last
 
-// One 128 x 512 x 512 GEMM of the CTA: D (TMEM, fp32) = A (smem image, bf16) x B (16 chunk images streamed from L2).
-// Thread 0 produces the chunk ring, thread 32 issues the 64 MMAs; everybody returns when the accumulators are
-// readable.  `img` selects the weight images (W2b: forward, W2bT: transposed).
+// One 128 x 512 x 512 GEMM of the CTA: D (TMEM, fp32) = A (smem image, bf16) x B (32 chunk images of 16 KB streamed
+// from L2 through a 3-stage ring).  Chunks come quarter-major -- all 8 k-blocks of output columns 0..127, then 128..255,
+// ... -- and each accumulator quarter has its own completion barrier, so the threads that own quarter q run their
+// epilogue while the tensor core works on q+1..3.  One thread produces the ring, one issues the 128 MMAs (M128 N128
+// K16); both sit in the warps of quarter 3.  `img` selects the weight images (W2b: forward, W2bT: transposed).
 struct GemmPipe {
     uint8_t* As;
     uint8_t* Bs;
     uint64_t* full;
     uint64_t* empty;
-    uint64_t* accum;
+    uint64_t* accum;  // [4]
     uint32_t tmem_base;
     uint32_t chunk_no;  // producer and issuer count chunks the same way
     uint32_t passes;
 };
 
-__device__ __forceinline__ void gemm_pass(GemmPipe& p, const uint16_t (*img)[CHUNK_BYTES / 2], int t) {
-    if (t == 0) {  // producer: weight chunks, L2 -> smem ring
+__device__ __forceinline__ void gemm_issue(GemmPipe& p, const uint16_t (*img)[CHUNK_BYTES / 2], int t) {
+    if (t == PRODUCER_THREAD) {  // weight chunks, L2 -> smem ring
         uint32_t c = p.chunk_no;
         for (int i = 0; i < N_CHUNKS; i++, c++) {
             const uint32_t s = c % T_STAGES, use = c / T_STAGES;
@@ -449,28 +461,122 @@ __device__ __forceinline__ void gemm_pass(GemmPipe& p, const uint16_t (*img)[CHU
             mbar_expect_tx(&p.full[s], CHUNK_BYTES);
             bulk_g2s(p.Bs + s * CHUNK_BYTES, &img[i][0], CHUNK_BYTES, &p.full[s]);
         }
-    } else if (t == 32) {  // MMA issuer: one thread drives the tensor core for the whole CTA
+    } else if (t == ISSUER_THREAD) {  // one thread drives the tensor core for the whole CTA
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t c = p.chunk_no;
         for (int i = 0; i < N_CHUNKS; i++, c++) {
             const uint32_t s = c % T_STAGES, use = c / T_STAGES;
             mbar_wait(&p.full[s], use & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int kb = i >> 1, half = i & 1;
+            const int quarter = i >> 3, kb = i & 7;
             const uint32_t a_addr = smem_u32(p.As + kb * (T_ROWS * 128));
             const uint32_t b_addr = smem_u32(p.Bs + s * CHUNK_BYTES);
 #pragma unroll
             for (int ks = 0; ks < 4; ks++)  // K = 16 per instruction = 32 bytes along the swizzled row
-                umma_bf16(p.tmem_base + half * 256, umma_desc_sw128(a_addr + ks * 32), umma_desc_sw128(b_addr + ks * 32),
+                umma_bf16(p.tmem_base + quarter * CHUNK_N, umma_desc_sw128(a_addr + ks * 32), umma_desc_sw128(b_addr + ks * 32),
                           (kb > 0 || ks > 0) ? 1u : 0u);
-            umma_commit(&p.empty[s]);  // frees the stage when these MMAs have read it
+            umma_commit(&p.empty[s]);                   // frees the stage when these MMAs have read it
+            if (kb == 7) umma_commit(&p.accum[quarter]);  // this quarter's accumulators are final
         }
-        umma_commit(p.accum);  // all 64 MMAs of this pass done -> accumulators readable
     }
     p.chunk_no += N_CHUNKS;
-    mbar_wait(p.accum, p.passes & 1);
-    p.passes++;
+}
+
+// wait until accumulator columns [128 q, 128 q + 128) of the current pass are readable
+__device__ __forceinline__ void gemm_wait(const GemmPipe& p, int q) {
+    mbar_wait(&p.accum[q], p.passes & 1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// per-CTA constants -> shared memory (after the smem carve-out only ~40 KB of L1 remain: left in global memory these
+// warp-uniform loads missed half of the time)
+__device__ __forceinline__ void stage_constants(const MlpPacked* w, float4* eps, float* w1s, int t) {
+    for (int i = t; i < H; i += T_THREADS) eps[i] = w->ep[i];
+    for (int i = t; i < H * (W1S_FLOATS / 4); i += T_THREADS) {
+        const int k = i / (W1S_FLOATS / 4), q = i % (W1S_FLOATS / 4);
+        reinterpret_cast<float4*>(w1s)[i] = reinterpret_cast<const float4*>(&w->W1b[k][0])[q];
+    }
+}
+
+// Layer 1 of the CTA's 128 rows, straight into the bf16 A image tcgen05.mma reads (and, with MASK, the ReLU mask words).
+// Element (row, kk) of k-block kb lives at
+//   kb * 16 KB + (row / 8) * 1024 + (row % 8) * 128 + (((kk / 8) ^ (row % 8)) * 16) + (kk % 8) * 2
+// Thread mapping: a warp owns 128 / R hidden units and 32 R rows, lane l the rows l + 32 i: the weight rows (NQ float4
+// each, bias folded in) are warp-uniform 128-bit loads reused for R rows -- 64 loads per thread instead of the ~900
+// scalar ones of a one-row-per-thread mapping, which kept this stage L1-wavefront bound.
+template <int NQ, int R, bool MASK>
+__device__ __forceinline__ void layer1_image(const float* w1, int w1_stride, const float* ins, uint8_t* As, uint32_t* m1, int t) {
+    constexpr int SETS = 4 / R;             // row sets of 32 R rows
+    constexpr int CHUNKS = (H / 8) / (4 * R);  // 16-byte chunks (8 hidden units) per thread
+    const int lane = t & 31, wi = t >> 5;
+    const int rs = wi % SETS, up = wi / SETS;
+    float in[R][NQ * 4];
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+        const float4* src = reinterpret_cast<const float4*>(ins + (rs * 32 * R + lane + 32 * i) * INS_STRIDE);
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            const float4 v = src[q];
+            in[i][q * 4 + 0] = v.x;
+            in[i][q * 4 + 1] = v.y;
+            in[i][q * 4 + 2] = v.z;
+            in[i][q * 4 + 3] = v.w;
+        }
+    }
+    uint32_t mw[R];
+#pragma unroll
+    for (int i = 0; i < R; i++) mw[i] = 0;
+    for (int c = 0; c < CHUNKS; c++) {
+        const int g = up * CHUNKS + c;  // 8 hidden units g*8 .. g*8+7
+        float acc[R][8];
+#pragma unroll
+        for (int i = 0; i < R; i++)
+#pragma unroll
+            for (int e = 0; e < 8; e++) acc[i][e] = 0.0f;
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const float4* wr = reinterpret_cast<const float4*>(w1 + (g * 8 + e) * w1_stride);
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+                const float4 ww = wr[q];
+#pragma unroll
+                for (int i = 0; i < R; i++) {
+                    acc[i][e] = fmaf(ww.x, in[i][q * 4 + 0], acc[i][e]);
+                    acc[i][e] = fmaf(ww.y, in[i][q * 4 + 1], acc[i][e]);
+                    acc[i][e] = fmaf(ww.z, in[i][q * 4 + 2], acc[i][e]);
+                    acc[i][e] = fmaf(ww.w, in[i][q * 4 + 3], acc[i][e]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < R; i++) {
+            const int row = rs * 32 * R + lane + 32 * i;
+            uint32_t packed[4];
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+                const bool plo = (g * 8 + e) < HID && acc[i][e] > 0.0f, phi = (g * 8 + e + 1) < HID && acc[i][e + 1] > 0.0f;
+                const float lo = plo ? acc[i][e] : 0.0f, hi = phi ? acc[i][e + 1] : 0.0f;
+                if (MASK) mw[i] |= ((plo ? 1u : 0u) << ((g & 3) * 8 + e)) | ((phi ? 1u : 0u) << ((g & 3) * 8 + e + 1));
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(packed[e >> 1]) : "f"(hi), "f"(lo));
+            }
+            uint8_t* rowp = As + (row >> 3) * 1024 + (row & 7) * 128;
+            const int kb = g >> 3, cidx = (g & 7) ^ (row & 7);
+            *reinterpret_cast<uint4*>(rowp + kb * (T_ROWS * 128) + cidx * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            if (MASK && (g & 3) == 3) {  // hidden units 32 (g / 4) .. + 31 complete
+                m1[row * (H / 32) + (g >> 2)] = mw[i];
+                mw[i] = 0;
+            }
+        }
+    }
+}
+
+template <bool MASK>
+__device__ __forceinline__ void layer1_dispatch(int nin, const MlpPacked* w, const float* w1s, const float* ins, uint8_t* As, uint32_t* m1, int t) {
+    const int nq = (nin + 1 + 3) >> 2;  // inputs + the constant 1, in float4 units
+    if (nq <= 1) layer1_image<1, 4, MASK>(w1s, W1S_FLOATS, ins, As, m1, t);
+    else if (nq == 2) layer1_image<2, 4, MASK>(w1s, W1S_FLOATS, ins, As, m1, t);
+    else if (nq == 3) layer1_image<3, 2, MASK>(&w->W1b[0][0], MAXIN, ins, As, m1, t);
+    else layer1_image<4, 2, MASK>(&w->W1b[0][0], MAXIN, ins, As, m1, t);
 }
 
 // 512 threads per CTA: thread t works on row (t & 127); the four threads of a row split the hidden units
@@ -481,11 +587,13 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_bf16_kernel(const MlpArgs a)
     uint8_t* As = tsm;
     uint8_t* Bs = tsm + T_A_BYTES;
     float* ins = reinterpret_cast<float*>(tsm + T_A_BYTES + T_STAGES * CHUNK_BYTES);
-    float* yp = ins + T_ROWS * MAXIN;
-    uint64_t* full = reinterpret_cast<uint64_t*>(yp + T_SPLIT * T_ROWS * MAXDX);
+    float* yp = ins;  // partial layer-3 sums [T_SPLIT][T_ROWS][MAXDX]: the input tile is dead once layer 1 has run
+    float4* eps = reinterpret_cast<float4*>(tsm + T_A_BYTES + T_STAGES * CHUNK_BYTES + T_INS_BYTES);
+    float* w1s = reinterpret_cast<float*>(eps + H);
+    uint64_t* full = reinterpret_cast<uint64_t*>(w1s + H * W1S_FLOATS);
     uint64_t* empty = full + T_STAGES;
     uint64_t* accum = empty + T_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 4);
     const MlpPacked* w = a.w;
     const int t = threadIdx.x, warp = t >> 5, row = t & (T_ROWS - 1), part = t >> 7;
     if ((int64_t)blockIdx.x * T_ROWS >= total_rows(a)) return;  // compacted work list: surplus CTAs
@@ -500,13 +608,14 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_bf16_kernel(const MlpArgs a)
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(accum, 1);
+        for (int q = 0; q < 4; q++) mbar_init(&accum[q], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {  // the whole accumulator file of the SM: 128 lanes x 512 fp32 columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    stage_constants(w, eps, w1s, t);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -522,42 +631,16 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_bf16_kernel(const MlpArgs a)
             float in[MAXIN];
             network_input(a, mc, xe, ue, in);
 #pragma unroll
-            for (int j = 0; j < MAXIN; j++) ins[row * MAXIN + j] = in[j];
+            for (int j = 0; j < MAXIN; j++) ins[row * INS_STRIDE + j] = in[j];
         }
         __syncthreads();
-        // layer 1 -> bf16 -> swizzled K-major A image: element (row, kk) of k-block kb lives at
-        //   kb * 16 KB + (row / 8) * 1024 + (row % 8) * 128 + (((kk / 8) ^ (row % 8)) * 16) + (kk % 8) * 2
-        {
-            float in[MAXIN];
-#pragma unroll
-            for (int j = 0; j < MAXIN; j++) in[j] = ins[row * MAXIN + j];
-            uint8_t* rowp = As + (row >> 3) * 1024 + (row & 7) * 128;
-            for (int g = part * (H / 8 / T_SPLIT); g < (part + 1) * (H / 8 / T_SPLIT); g++) {  // 8 hidden units = one 16-byte chunk
-                float acc[8];
-#pragma unroll
-                for (int e = 0; e < 8; e++) acc[e] = w->b1[g * 8 + e];
-#pragma unroll
-                for (int j = 0; j < MAXIN; j++) {
-                    if (j < nin) {
-#pragma unroll
-                        for (int e = 0; e < 8; e++) acc[e] = fmaf(w->W1[g * 8 + e][j], in[j], acc[e]);
-                    }
-                }
-                uint32_t packed[4];
-#pragma unroll
-                for (int e = 0; e < 8; e += 2) {
-                    const float lo = (g * 8 + e) < HID ? fmaxf(acc[e], 0.0f) : 0.0f;
-                    const float hi = (g * 8 + e + 1) < HID ? fmaxf(acc[e + 1], 0.0f) : 0.0f;
-                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(packed[e >> 1]) : "f"(hi), "f"(lo));
-                }
-                const int kb = g >> 3, cidx = (g & 7) ^ (row & 7);
-                *reinterpret_cast<uint4*>(rowp + kb * (T_ROWS * 128) + cidx * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            }
-        }
+        layer1_dispatch<false>(nin, w, w1s, ins, As, nullptr, t);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA unit
         __syncthreads();
-        gemm_pass(pipe, w->W2b, t);
-        // epilogue: TMEM lane = row; this thread's quarter of the 512 columns: +b2, ReLU, layer 3
+        gemm_issue(pipe, w->W2b, t);
+        // epilogue: TMEM lane = row; this thread's quarter of the 512 columns, as soon as that quarter is final:
+        // +b2, ReLU, layer 3
+        gemm_wait(pipe, part);
         {
             float y[MAXDX] = {0.0f, 0.0f, 0.0f, 0.0f};
             for (int cb = part * (H / 32 / T_SPLIT); cb < (part + 1) * (H / 32 / T_SPLIT); cb++) {
@@ -566,16 +649,17 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_bf16_kernel(const MlpArgs a)
 #pragma unroll
                 for (int c = 0; c < 32; c++) {
                     const int nn = cb * 32 + c;
-                    const float h2 = fmaxf(__uint_as_float(v[c]) + w->b2[nn], 0.0f);
-                    const float4 w3 = *reinterpret_cast<const float4*>(&w->W3[nn][0]);
-                    y[0] = fmaf(h2, w3.x, y[0]);
-                    y[1] = fmaf(h2, w3.y, y[1]);
-                    y[2] = fmaf(h2, w3.z, y[2]);
-                    y[3] = fmaf(h2, w3.w, y[3]);
+                    const float4 e4 = eps[nn];  // {b2, W3[nn][0..2]}: one 128-bit smem broadcast per column
+                    const float h2 = fmaxf(__uint_as_float(v[c]) + e4.x, 0.0f);
+                    y[0] = fmaf(h2, e4.y, y[0]);
+                    y[1] = fmaf(h2, e4.z, y[1]);
+                    y[2] = fmaf(h2, e4.w, y[2]);
+                    if (a.d.dx_dim > 3) y[3] = fmaf(h2, w->W3[nn][3], y[3]);
                 }
             }
             *reinterpret_cast<float4*>(&yp[(part * T_ROWS + row) * MAXDX]) = make_float4(y[0], y[1], y[2], y[3]);
         }
+        pipe.passes++;
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();  // every lane has read its accumulators before the next interval's MMAs overwrite them
         if (owner) {
@@ -602,19 +686,21 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_bf16_kernel(const MlpArgs a)
 // A image are reused between passes; after a pass has completed the A image doubles as scratch for the partial sums.
 constexpr int J_MASK_WORDS = H / 32;                          // 16 mask words per row and layer
 constexpr int J_MASK_BYTES = 2 * T_ROWS * J_MASK_WORDS * 4;   // both hidden layers
-constexpr int J_SMEM = T_A_BYTES + T_STAGES * CHUNK_BYTES + T_INS_BYTES + J_MASK_BYTES + 256;
+constexpr int J_SMEM = T_A_BYTES + T_STAGES * CHUNK_BYTES + T_INS_BYTES + T_CONST_BYTES + J_MASK_BYTES + 256;
 
 __global__ void __launch_bounds__(T_THREADS, 1) mlp_jac_kernel(const MlpArgs a) {
     extern __shared__ __align__(1024) uint8_t tsm[];
     uint8_t* As = tsm;
     uint8_t* Bs = tsm + T_A_BYTES;
     float* ins = reinterpret_cast<float*>(tsm + T_A_BYTES + T_STAGES * CHUNK_BYTES);
-    uint32_t* m1 = reinterpret_cast<uint32_t*>(ins + T_ROWS * MAXIN);
+    float4* eps = reinterpret_cast<float4*>(tsm + T_A_BYTES + T_STAGES * CHUNK_BYTES + T_INS_BYTES);
+    float* w1s = reinterpret_cast<float*>(eps + H);
+    uint32_t* m1 = reinterpret_cast<uint32_t*>(w1s + H * W1S_FLOATS);
     uint32_t* m2 = m1 + T_ROWS * J_MASK_WORDS;
     uint64_t* full = reinterpret_cast<uint64_t*>(m2 + T_ROWS * J_MASK_WORDS);
     uint64_t* empty = full + T_STAGES;
     uint64_t* accum = empty + T_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 4);
     const MlpPacked* w = a.w;
     const int t = threadIdx.x, warp = t >> 5, row = t & (T_ROWS - 1), part = t >> 7;
     if ((int64_t)blockIdx.x * T_ROWS >= total_rows(a)) return;
@@ -629,13 +715,14 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_jac_kernel(const MlpArgs a) 
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(accum, 1);
+        for (int q = 0; q < 4; q++) mbar_init(&accum[q], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    stage_constants(w, eps, w1s, t);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -648,48 +735,16 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_jac_kernel(const MlpArgs a) 
         float in[MAXIN];
         network_input(a, mc, x, u, in);
 #pragma unroll
-        for (int j = 0; j < MAXIN; j++) ins[row * MAXIN + j] = in[j];
+        for (int j = 0; j < MAXIN; j++) ins[row * INS_STRIDE + j] = in[j];
     }
     __syncthreads();
     uint8_t* rowp = As + (row >> 3) * 1024 + (row & 7) * 128;
-    constexpr int G0 = H / 8 / T_SPLIT;  // 16 groups of 8 hidden units per thread
-    {  // pass 0, A image: layer 1 (as in mlp_bf16_kernel) + its ReLU mask
-        float in[MAXIN];
-#pragma unroll
-        for (int j = 0; j < MAXIN; j++) in[j] = ins[row * MAXIN + j];
-        uint32_t mw = 0;
-        for (int gi = 0; gi < G0; gi++) {
-            const int g = part * G0 + gi;
-            float acc[8];
-#pragma unroll
-            for (int e = 0; e < 8; e++) acc[e] = w->b1[g * 8 + e];
-#pragma unroll
-            for (int j = 0; j < MAXIN; j++) {
-                if (j < nin) {
-#pragma unroll
-                    for (int e = 0; e < 8; e++) acc[e] = fmaf(w->W1[g * 8 + e][j], in[j], acc[e]);
-                }
-            }
-            uint32_t packed[4];
-#pragma unroll
-            for (int e = 0; e < 8; e += 2) {
-                const bool plo = (g * 8 + e) < HID && acc[e] > 0.0f, phi = (g * 8 + e + 1) < HID && acc[e + 1] > 0.0f;
-                const float lo = plo ? acc[e] : 0.0f, hi = phi ? acc[e + 1] : 0.0f;
-                mw |= (plo ? 1u : 0u) << ((gi & 3) * 8 + e);
-                mw |= (phi ? 1u : 0u) << ((gi & 3) * 8 + e + 1);
-                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(packed[e >> 1]) : "f"(hi), "f"(lo));
-            }
-            const int kb = g >> 3, cidx = (g & 7) ^ (row & 7);
-            *reinterpret_cast<uint4*>(rowp + kb * (T_ROWS * 128) + cidx * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            if ((gi & 3) == 3) {  // hidden units 32 w .. 32 w + 31 -> mask word w = g / 4
-                m1[row * J_MASK_WORDS + (g >> 2)] = mw;
-                mw = 0;
-            }
-        }
-    }
+    constexpr int G0 = H / 8 / T_SPLIT;  // 16 groups of 8 hidden units per thread (passes 1..: one row per thread)
+    layer1_dispatch<true>(nin, w, w1s, ins, As, m1, t);  // pass 0, A image: layer 1 + its ReLU mask
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    gemm_pass(pipe, w->W2b, t);
+    gemm_issue(pipe, w->W2b, t);
+    gemm_wait(pipe, part);
     // mask of layer 2: [acc + b2 > 0]
     for (int cb = part * (H / 32 / T_SPLIT); cb < (part + 1) * (H / 32 / T_SPLIT); cb++) {
         uint32_t v[32];
@@ -698,10 +753,11 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_jac_kernel(const MlpArgs a) 
 #pragma unroll
         for (int c = 0; c < 32; c++) {
             const int nn = cb * 32 + c;
-            mw |= ((nn < HID && __uint_as_float(v[c]) + w->b2[nn] > 0.0f) ? 1u : 0u) << c;
+            mw |= ((nn < HID && __uint_as_float(v[c]) + eps[nn].x > 0.0f) ? 1u : 0u) << c;
         }
         m2[row * J_MASK_WORDS + cb] = mw;
     }
+    pipe.passes++;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
 
@@ -719,11 +775,14 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_jac_kernel(const MlpArgs a) 
         for (int gi = 0; gi < G0; gi++) {
             const int g = part * G0 + gi;
             const uint32_t bits = (m2[row * J_MASK_WORDS + (g >> 2)] >> ((g & 3) * 8)) & 0xffu;
+            const float4 wa = *reinterpret_cast<const float4*>(&w->W3T[j][g * 8]);
+            const float4 wb = *reinterpret_cast<const float4*>(&w->W3T[j][g * 8 + 4]);
+            const float w3[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
             uint32_t packed[4];
 #pragma unroll
             for (int e = 0; e < 8; e += 2) {
-                const float lo = ((bits >> e) & 1u) ? w->W3[g * 8 + e][j] : 0.0f;
-                const float hi = ((bits >> (e + 1)) & 1u) ? w->W3[g * 8 + e + 1][j] : 0.0f;
+                const float lo = ((bits >> e) & 1u) ? w3[e] : 0.0f;
+                const float hi = ((bits >> (e + 1)) & 1u) ? w3[e + 1] : 0.0f;
                 asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(packed[e >> 1]) : "f"(hi), "f"(lo));
             }
             const int kb = g >> 3, cidx = (g & 7) ^ (row & 7);
@@ -731,7 +790,8 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_jac_kernel(const MlpArgs a) 
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-        gemm_pass(pipe, w->W2bT, t);
+        gemm_issue(pipe, w->W2bT, t);
+        gemm_wait(pipe, part);
         // epilogue: g1 = acc * m1, gin = g1 W1 (this thread's quarter of the hidden units)
         {
             float gin[MAXIN];
@@ -744,7 +804,8 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_jac_kernel(const MlpArgs a) 
 #pragma unroll
                 for (int c = 0; c < 32; c++) {
                     const float g1 = ((mw >> c) & 1u) ? __uint_as_float(v[c]) : 0.0f;
-                    const float4* w1 = reinterpret_cast<const float4*>(&w->W1[cb * 32 + c][0]);
+                    const float4* w1 = nin + 1 <= W1S_FLOATS ? reinterpret_cast<const float4*>(w1s + (cb * 32 + c) * W1S_FLOATS)
+                                                             : reinterpret_cast<const float4*>(&w->W1[cb * 32 + c][0]);
 #pragma unroll
                     for (int q = 0; q < MAXIN / 4; q++) {
                         if (q * 4 < nin) {
@@ -757,9 +818,11 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_jac_kernel(const MlpArgs a) 
                     }
                 }
             }
+            gemm_wait(pipe, 3);  // the partial sums alias the A image: every MMA of this pass must have read it
 #pragma unroll
             for (int c = 0; c < MAXIN; c++) partial[(part * T_ROWS + row) * MAXIN + c] = gin[c];
         }
+        pipe.passes++;
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         if (rw.valid) {
@@ -850,7 +913,7 @@ bool dims_ok(const pg_mlp_dims_t* d) {
     if (!d || d->n < 2 || d->n > 8 || (d->n & 1) || d->m < 1 || d->m > 2) return false;
     int no = 0;
     for (int i = 0; i < d->n; i++) no += d->is_angle[i] ? 2 : 1;
-    return no == d->n_obs && d->n_obs + d->m <= MAXIN && d->dx_dim == d->n / 2 && d->dx_dim <= MAXDX;
+    return no == d->n_obs && d->n_obs + d->m + 1 <= MAXIN && d->dx_dim == d->n / 2 && d->dx_dim <= MAXDX;
 }
 
 }  // namespace
@@ -873,6 +936,12 @@ int pg_mlp_pack(const pg_mlp_dims_t* d, const float* W1, const float* b1, const 
         for (int j = 0; j < d->dx_dim; j++) p->W3[k][j] = W3[j * HID + k];
         for (int n = 0; n < HID; n++) p->W2t[k][n] = W2[n * HID + k];  // W2 is [out n][in k]
     }
+    for (int k = 0; k < HID; k++) {
+        for (int j = 0; j < nin; j++) p->W1b[k][j] = W1[k * nin + j];
+        p->W1b[k][nin] = b1[k];
+        p->ep[k] = make_float4(b2[k], W3[k], d->dx_dim > 1 ? W3[HID + k] : 0.0f, d->dx_dim > 2 ? W3[2 * HID + k] : 0.0f);
+        for (int j = 0; j < d->dx_dim; j++) p->W3T[j][k] = W3[j * HID + k];
+    }
     for (int j = 0; j < d->dx_dim; j++) {
         p->b3[j] = b3[j];
         p->dx_mean[j] = dx_mean ? dx_mean[j] : 0.0f;
@@ -886,25 +955,18 @@ int pg_mlp_pack(const pg_mlp_dims_t* d, const float* W1, const float* b1, const 
         p->u_mean[j] = (u_mean && j < d->m) ? u_mean[j] : 0.0f;
         p->u_var[j] = (u_var && j < d->m) ? u_var[j] : 1.0f;
     }
-    // bf16 chunk images: chunk = kb * 2 + half holds W2[n = half*256 + nl][k = kb*64 + kk] at the swizzled offset
+    // bf16 chunk images: chunk = kb * 4 + quarter holds W2[n = quarter*128 + nl][k = kb*64 + kk] at the swizzled offset,
+    // and the transposed set W2[nn = kb*64 + kk][kcol = quarter*128 + nl] (contraction over layer 2's output index)
     for (int kb = 0; kb < 8; kb++)
-        for (int half = 0; half < 2; half++) {
-            uint16_t* img = p->W2b[kb * 2 + half];
-            for (int nl = 0; nl < 256; nl++)
+        for (int qt = 0; qt < 4; qt++) {
+            uint16_t* img = p->W2b[qt * 8 + kb];  // load order of the GEMM: quarter-major
+            uint16_t* imgT = p->W2bT[qt * 8 + kb];
+            for (int nl = 0; nl < CHUNK_N; nl++)
                 for (int kk = 0; kk < 64; kk++) {
-                    const int n = half * 256 + nl, k = kb * 64 + kk;
-                    const float v = (n < HID && k < HID) ? W2[n * HID + k] : 0.0f;
+                    const int n = qt * CHUNK_N + nl, k = kb * 64 + kk;
                     const int off = (nl >> 3) * 1024 + (nl & 7) * 128 + (((kk >> 3) ^ (nl & 7)) << 4) + (kk & 7) * 2;
-                    img[off >> 1] = f32_to_bf16(v);
-                }
-            // transposed: output column kcol = half*256 + nl, contraction index nn = kb*64 + kk -> W2[nn][kcol]
-            uint16_t* imgT = p->W2bT[kb * 2 + half];
-            for (int nl = 0; nl < 256; nl++)
-                for (int kk = 0; kk < 64; kk++) {
-                    const int kcol = half * 256 + nl, nn = kb * 64 + kk;
-                    const float v = (nn < HID && kcol < HID) ? W2[nn * HID + kcol] : 0.0f;
-                    const int off = (nl >> 3) * 1024 + (nl & 7) * 128 + (((kk >> 3) ^ (nl & 7)) << 4) + (kk & 7) * 2;
-                    imgT[off >> 1] = f32_to_bf16(v);
+                    img[off >> 1] = f32_to_bf16((n < HID && k < HID) ? W2[n * HID + k] : 0.0f);
+                    imgT[off >> 1] = f32_to_bf16((k < HID && n < HID) ? W2[k * HID + n] : 0.0f);
                 }
         }
     return 0;
