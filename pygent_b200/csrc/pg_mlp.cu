@@ -383,10 +383,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (!ok && spins > (1u << 26)) __trap();  // a lost arrival must not hang the GPU
     }
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
+// ---- thread-block cluster of CL CTAs sharing one weight stream ------------------------------------------------------
+constexpr int CL = 2;
+constexpr uint16_t CL_MASK = (1u << CL) - 1;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// bulk copy global -> the same smem offset of every CTA in the mask; each destination's mbarrier (same offset) gets the bytes
+__device__ __forceinline__ void bulk_g2s_multicast(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+        : "memory");
 }
 // K-major, 128-byte swizzle: 8-row groups 1024 B apart (SBO), LBO field 1 (unused for swizzled K-major), version 1
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
@@ -411,6 +425,12 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// completion of this thread's earlier MMAs arrives on the barrier at the same offset in every CTA of the mask
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -425,7 +445,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-constexpr int T_ROWS = 128, T_STAGES = 3, T_THREADS = 512, T_SPLIT = T_THREADS / T_ROWS;
+constexpr int T_ROWS = 128, T_THREADS = 512, T_SPLIT = T_THREADS / T_ROWS;
+constexpr int T_STAGES = 4;  // weight ring of the rollout kernel (231,680 B of smem in total)
+constexpr int J_STAGES = 3;  // ... of the Jacobian kernel, which also holds the ReLU masks
 constexpr int T_A_BYTES = T_ROWS * H * 2;  // 128 KB: 8 k-blocks of [128 rows x 64 k] bf16
 constexpr int INS_STRIDE = MAXIN + 4;      // floats per row of the input tile (padded: conflict-free 128-bit reads)
 constexpr int T_INS_BYTES = T_ROWS * INS_STRIDE * 4;  // network inputs of the 128 rows; reused for the partial layer-3 sums
@@ -437,7 +459,10 @@ constexpr int T_SMEM = T_A_BYTES + T_STAGES * CHUNK_BYTES + T_INS_BYTES + T_CONS
 constexpr int PRODUCER_THREAD = 384, ISSUER_THREAD = 416;  // in the warps of accumulator quarter 3, which finishes last
 
 // One 128 x 512 x 512 GEMM of the CTA: D (TMEM, fp32) = A (smem image, bf16) x B (32 chunk images of 16 KB streamed
-// from L2 through a 3-stage ring).  Chunks come quarter-major -- all 8 k-blocks of output columns 0..127, then 128..255,
+// from L2 through a 3-stage ring).  The two CTAs of a cluster share the stream: CTA r fetches the chunks with
+// i % 2 == r and multicasts each into BOTH rings (with every SM streaming all 512 KB per control interval the kernel was
+// L2-bandwidth bound: ~12 us per GEMM against 7.2 us of MMA time); a stage is released to the producers only when the
+// MMAs of both CTAs have read it (multicast tcgen05.commit on barriers initialised to CL arrivals).  Chunks come quarter-major -- all 8 k-blocks of output columns 0..127, then 128..255,
 // ... -- and each accumulator quarter has its own completion barrier, so the threads that own quarter q run their
 // epilogue while the tensor core works on q+1..3.  One thread produces the ring, one issues the 128 MMAs (M128 N128
 // K16); both sit in the warps of quarter 3.  `img` selects the weight images (W2b: forward, W2bT: transposed).
@@ -452,20 +477,29 @@ struct GemmPipe {
     uint32_t passes;
 };
 
+template <int STAGES>
 __device__ __forceinline__ void gemm_issue(GemmPipe& p, const uint16_t (*img)[CHUNK_BYTES / 2], int t) {
-    if (t == PRODUCER_THREAD) {  // weight chunks, L2 -> smem ring
+    // the control lanes' 31 warp siblings park at __syncwarp() instead of spinning on the completion barrier: as
+    // divergent paths of the same warp they would take every other issue slot from the lane that feeds the tensor core
+    const int cw = t >> 5;
+    if (cw != (PRODUCER_THREAD >> 5) && cw != (ISSUER_THREAD >> 5)) {
+        p.chunk_no += N_CHUNKS;
+        return;
+    }
+    if (t == PRODUCER_THREAD) {  // weight chunks, L2 -> smem rings of the cluster
+        const uint32_t rank = cluster_ctarank();
         uint32_t c = p.chunk_no;
         for (int i = 0; i < N_CHUNKS; i++, c++) {
-            const uint32_t s = c % T_STAGES, use = c / T_STAGES;
-            mbar_wait(&p.empty[s], (use & 1) ^ 1);
-            mbar_expect_tx(&p.full[s], CHUNK_BYTES);
-            bulk_g2s(p.Bs + s * CHUNK_BYTES, &img[i][0], CHUNK_BYTES, &p.full[s]);
+            const uint32_t s = c % STAGES, use = c / STAGES;
+            mbar_wait(&p.empty[s], (use & 1) ^ 1);        // both CTAs are done with the stage's previous chunk
+            mbar_expect_tx(&p.full[s], CHUNK_BYTES);      // whoever fetches it, this CTA's ring receives the bytes
+            if ((uint32_t)(i % CL) == rank) bulk_g2s_multicast(p.Bs + s * CHUNK_BYTES, &img[i][0], CHUNK_BYTES, &p.full[s], CL_MASK);
         }
     } else if (t == ISSUER_THREAD) {  // one thread drives the tensor core for the whole CTA
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t c = p.chunk_no;
         for (int i = 0; i < N_CHUNKS; i++, c++) {
-            const uint32_t s = c % T_STAGES, use = c / T_STAGES;
+            const uint32_t s = c % STAGES, use = c / STAGES;
             mbar_wait(&p.full[s], use & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int quarter = i >> 3, kb = i & 7;
@@ -475,10 +509,11 @@ __device__ __forceinline__ void gemm_issue(GemmPipe& p, const uint16_t (*img)[CH
             for (int ks = 0; ks < 4; ks++)  // K = 16 per instruction = 32 bytes along the swizzled row
                 umma_bf16(p.tmem_base + quarter * CHUNK_N, umma_desc_sw128(a_addr + ks * 32), umma_desc_sw128(b_addr + ks * 32),
                           (kb > 0 || ks > 0) ? 1u : 0u);
-            umma_commit(&p.empty[s]);                   // frees the stage when these MMAs have read it
+            umma_commit_multicast(&p.empty[s], CL_MASK);  // one of the CL arrivals that free the stage in every CTA
             if (kb == 7) umma_commit(&p.accum[quarter]);  // this quarter's accumulators are final
         }
     }
+    __syncwarp();
     p.chunk_no += N_CHUNKS;
 }
 
@@ -582,7 +617,7 @@ __device__ __forceinline__ void layer1_dispatch(int nin, const MlpPacked* w, con
 // 512 threads per CTA: thread t works on row (t & 127); the four threads of a row split the hidden units
 // (layer 1) and the accumulator columns (epilogue) four ways.  Warp w reads TMEM lanes 32 (w % 4) .. +31, which
 // is exactly the row quarter (t & 127) >> 5 of its threads.  Threads 0..127 own the fp64 state of their row.
-__global__ void __launch_bounds__(T_THREADS, 1) mlp_bf16_kernel(const MlpArgs a) {
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_bf16_kernel(const MlpArgs a) {
     extern __shared__ __align__(1024) uint8_t tsm[];
     uint8_t* As = tsm;
     uint8_t* Bs = tsm + T_A_BYTES;
@@ -596,7 +631,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_bf16_kernel(const MlpArgs a)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 4);
     const MlpPacked* w = a.w;
     const int t = threadIdx.x, warp = t >> 5, row = t & (T_ROWS - 1), part = t >> 7;
-    if ((int64_t)blockIdx.x * T_ROWS >= total_rows(a)) return;  // compacted work list: surplus CTAs
+    if ((int64_t)(blockIdx.x / CL) * CL * T_ROWS >= total_rows(a)) return;  // compacted work list: surplus clusters
     const bool owner = t < T_ROWS;
     Row rw = decode_row(a, (int64_t)blockIdx.x * T_ROWS + row);
     rw.valid = rw.valid && owner;
@@ -606,7 +641,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_bf16_kernel(const MlpArgs a)
     if (t == 0) {
         for (int s = 0; s < T_STAGES; s++) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], CL);
         }
         for (int q = 0; q < 4; q++) mbar_init(&accum[q], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -618,6 +653,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_bf16_kernel(const MlpArgs a)
     stage_constants(w, eps, w1s, t);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    cluster_sync();  // the peer's barriers are initialised before anything is multicast to them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
@@ -637,7 +673,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_bf16_kernel(const MlpArgs a)
         layer1_dispatch<false>(nin, w, w1s, ins, As, nullptr, t);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA unit
         __syncthreads();
-        gemm_issue(pipe, w->W2b, t);
+        gemm_issue<T_STAGES>(pipe, w->W2b, t);
         // epilogue: TMEM lane = row; this thread's quarter of the 512 columns, as soon as that quarter is final:
         // +b2, ReLU, layer 3
         gemm_wait(pipe, part);
@@ -675,6 +711,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_bf16_kernel(const MlpArgs a)
         }
     }
     __syncthreads();
+    cluster_sync();  // no CTA leaves while its peer may still signal its barriers
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
@@ -686,24 +723,24 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_bf16_kernel(const MlpArgs a)
 // A image are reused between passes; after a pass has completed the A image doubles as scratch for the partial sums.
 constexpr int J_MASK_WORDS = H / 32;                          // 16 mask words per row and layer
 constexpr int J_MASK_BYTES = 2 * T_ROWS * J_MASK_WORDS * 4;   // both hidden layers
-constexpr int J_SMEM = T_A_BYTES + T_STAGES * CHUNK_BYTES + T_INS_BYTES + T_CONST_BYTES + J_MASK_BYTES + 256;
+constexpr int J_SMEM = T_A_BYTES + J_STAGES * CHUNK_BYTES + T_INS_BYTES + T_CONST_BYTES + J_MASK_BYTES + 256;
 
-__global__ void __launch_bounds__(T_THREADS, 1) mlp_jac_kernel(const MlpArgs a) {
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_jac_kernel(const MlpArgs a) {
     extern __shared__ __align__(1024) uint8_t tsm[];
     uint8_t* As = tsm;
     uint8_t* Bs = tsm + T_A_BYTES;
-    float* ins = reinterpret_cast<float*>(tsm + T_A_BYTES + T_STAGES * CHUNK_BYTES);
-    float4* eps = reinterpret_cast<float4*>(tsm + T_A_BYTES + T_STAGES * CHUNK_BYTES + T_INS_BYTES);
+    float* ins = reinterpret_cast<float*>(tsm + T_A_BYTES + J_STAGES * CHUNK_BYTES);
+    float4* eps = reinterpret_cast<float4*>(tsm + T_A_BYTES + J_STAGES * CHUNK_BYTES + T_INS_BYTES);
     float* w1s = reinterpret_cast<float*>(eps + H);
     uint32_t* m1 = reinterpret_cast<uint32_t*>(w1s + H * W1S_FLOATS);
     uint32_t* m2 = m1 + T_ROWS * J_MASK_WORDS;
     uint64_t* full = reinterpret_cast<uint64_t*>(m2 + T_ROWS * J_MASK_WORDS);
-    uint64_t* empty = full + T_STAGES;
-    uint64_t* accum = empty + T_STAGES;
+    uint64_t* empty = full + J_STAGES;
+    uint64_t* accum = empty + J_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 4);
     const MlpPacked* w = a.w;
     const int t = threadIdx.x, warp = t >> 5, row = t & (T_ROWS - 1), part = t >> 7;
-    if ((int64_t)blockIdx.x * T_ROWS >= total_rows(a)) return;
+    if ((int64_t)(blockIdx.x / CL) * CL * T_ROWS >= total_rows(a)) return;  // surplus clusters
     const bool owner = t < T_ROWS;
     Row rw = decode_row(a, (int64_t)blockIdx.x * T_ROWS + row);
     rw.valid = rw.valid && owner;
@@ -711,9 +748,9 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_jac_kernel(const MlpArgs a) 
     const pg::MathCtx<double> mc;
 
     if (t == 0) {
-        for (int s = 0; s < T_STAGES; s++) {
+        for (int s = 0; s < J_STAGES; s++) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], CL);
         }
         for (int q = 0; q < 4; q++) mbar_init(&accum[q], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -725,6 +762,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_jac_kernel(const MlpArgs a) 
     stage_constants(w, eps, w1s, t);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    cluster_sync();  // the peer's barriers are initialised before anything is multicast to them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     GemmPipe pipe = {As, Bs, full, empty, accum, tmem_base, 0u, 0u};
@@ -743,7 +781,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_jac_kernel(const MlpArgs a) 
     layer1_dispatch<true>(nin, w, w1s, ins, As, m1, t);  // pass 0, A image: layer 1 + its ReLU mask
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    gemm_issue(pipe, w->W2b, t);
+    gemm_issue<J_STAGES>(pipe, w->W2b, t);
     gemm_wait(pipe, part);
     // mask of layer 2: [acc + b2 > 0]
     for (int cb = part * (H / 32 / T_SPLIT); cb < (part + 1) * (H / 32 / T_SPLIT); cb++) {
@@ -790,7 +828,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_jac_kernel(const MlpArgs a) 
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-        gemm_issue(pipe, w->W2bT, t);
+        gemm_issue<J_STAGES>(pipe, w->W2bT, t);
         gemm_wait(pipe, part);
         // epilogue: g1 = acc * m1, gin = g1 W1 (this thread's quarter of the hidden units)
         {
@@ -864,6 +902,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_jac_kernel(const MlpArgs a) 
         }
     }
     __syncthreads();
+    cluster_sync();  // no CTA leaves while its peer may still signal its barriers
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
@@ -884,7 +923,7 @@ int launch(int precision, const MlpArgs& a, cudaStream_t st) {
             if (e != cudaSuccess) return (int)e;
             set = true;
         }
-        mlp_jac_kernel<<<(unsigned)((rows + T_ROWS - 1) / T_ROWS), T_THREADS, J_SMEM, st>>>(a);
+        mlp_jac_kernel<<<(unsigned)((rows + CL * T_ROWS - 1) / (CL * T_ROWS)) * CL, T_THREADS, J_SMEM, st>>>(a);
     } else if (precision == PG_MLP_FP32) {
         const int smem = (F_ROWS * F_HSTR + F_ROWS * MAXIN + F_ROWS * MAXDX) * 4;
         static bool set = false;
@@ -901,7 +940,7 @@ int launch(int precision, const MlpArgs& a, cudaStream_t st) {
             if (e != cudaSuccess) return (int)e;
             set = true;
         }
-        mlp_bf16_kernel<<<(unsigned)((rows + T_ROWS - 1) / T_ROWS), T_THREADS, T_SMEM, st>>>(a);
+        mlp_bf16_kernel<<<(unsigned)((rows + CL * T_ROWS - 1) / (CL * T_ROWS)) * CL, T_THREADS, T_SMEM, st>>>(a);
     } else {
         return PG_E_BADARG;
     }
