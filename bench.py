@@ -14,6 +14,8 @@ nothing on the data path).  Prints ONE JSON line (rank 0):
              on this pool's B200 (profiles/fp_peak_b200.json), plus the HBM view of the same launch
   cpu_baseline  the CPU oracle (C port of the reference's step loop) on a bounded sample, all host threads
   ilqr       iLQR iterations/s on 16,384 cart-pole swing-ups per GPU (BASELINE.json config 3), to convergence
+  nmpc       closed-loop control steps/s of 4,096 cart-pole plants under receding-horizon iLQR (NMPC/MPCAgent: one
+             planner iteration + final backward pass + action + plan shift + plant step per control step, on the device)
   mlp_ilqr   iLQR iterations/s through the learned-MLP dynamics, 4,096 trajectories per GPU (config 5 = 32,768 over
              8 GPUs), tensor-core rollouts and Jacobian chain, 10 iterations
 `--impl reference` times the reference's algorithm on the host cores (the C oracle port -- the reference
@@ -158,6 +160,40 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def nmpc_bench(dev, rank, world, barrier, plants=4096, steps=50, horizon=1.0):
+    """examples/nmpc/cart_pole.py for a batch: every plant has its own MPCAgent state; the planner's terminal value is
+    solved once on the host (cache_terminal_value) so the control loop never leaves the device."""
+    import torch
+    import torch.distributed as dist
+    from pygent_b200.algorithms.nmpc import NMPC
+    from pygent_b200.examples import CASES, make_env
+    _, c_N, _ = CASES["cart_pole"][3]()
+    rng = np.random.default_rng(3000 + rank)
+    x0 = np.array([0, 0, 0, 0]) + rng.uniform(-1, 1, (plants, 4)) * np.array([.3, .4, .3, .3])
+    alg = NMPC(make_env("cart_pole", x0=x0, device=dev), make_env("cart_pole", x0=x0, device=dev), steps * DT, DT, horizon,
+               fcost=c_N, constrained=False, maxIters=100, step_iterations=1, cache_terminal_value=True)
+    opt = alg.agent.traj_optimizer
+    alg.run(steps=5, printing=False)  # warm-up
+    alg.agent.init_optim(x0)
+    barrier()
+    l0 = opt.lib.launches + alg.environment.library().launches
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    cost = alg.run(steps=steps, printing=False)
+    b.record()
+    barrier()
+    ms = a.elapsed_time(b)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    return {"metric": "nmpc_control_steps_per_s", "value": world * plants * steps / (ms * 1e-3), "unit": "plant control steps/s",
+            "plants_per_gpu": plants, "control_steps": steps, "horizon_steps": int(horizon / DT), "ms": ms,
+            "ms_per_control_step": ms / steps, "gpu_launches": opt.lib.launches + alg.environment.library().launches - l0,
+            "mean_closed_loop_cost": float(np.mean(np.sum(cost, axis=-1))),
+            "stabilised_frac": float(np.mean(np.abs(alg.environment.history[:, -1, 1]) < 0.2))}
+
+
 def learned_ilqr_bench(dev, rank, world, barrier):
     """BASELINE.json configs[4] per GPU: iLQR over NNDynamics(4, 1, oDim=5, dxDim=2) with default-initialised weights
     (torch.manual_seed(0)), moments 0/1, Euler, horizon 100, costs of examples/mbrl/cart_pole_hpc.py:24-33."""
@@ -182,7 +218,7 @@ def learned_ilqr_bench(dev, rank, world, barrier):
     x0 = np.array([0, np.pi, 0, 0]) + rng.uniform(-1, 1, (MLP_B, 4)) * np.array([.5, .3, .5, .5])
     env = LearnedStateSpaceModel(net, c_k, x0, 1, DT, precision="bf16", linearization="analytic", device=dev)
     env.uMax = np.array([U_MAX])
-    alg = iLQR(env, ILQR_T * DT, DT, fastForward=True, fcost=c_N, printing=False, maxIters=MLP_ITERS)
+    alg = iLQR(env, ILQR_T * DT, DT, fastForward=True, fcost=c_N, printing=False, maxIters=MLP_ITERS, final_backpass=False)
     c0 = float(np.mean(alg.cost))
     alg.run_optim()  # warm-up solve (same work)
     env.reset(x0)
@@ -218,6 +254,7 @@ def main():
     ap.add_argument("--no-ilqr", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-mlp", action="store_true")
+    ap.add_argument("--no-nmpc", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -350,6 +387,11 @@ def main():
                 "converged_frac": float(np.mean((st == pglib.ST_CONV_FUN) | (st == pglib.ST_CONV_GRAD))),
                 "mean_final_cost": float(np.mean(solver.cost)), "line_search": "serial semantics, 11 alphas evaluated per launch"}
 
+    # ---- receding-horizon control of a batch of plants ------------------------------
+    nmpc = None
+    if not args.no_nmpc:
+        nmpc = nmpc_bench(dev, rank, world, barrier)
+
     # ---- iLQR through the learned-MLP dynamics (config 5 sized per GPU) --------------------------------
     mlp_ilqr = None
     if not args.no_mlp:
@@ -385,6 +427,8 @@ def main():
             res["ilqr"] = ilqr
         if mlp_ilqr is not None:
             res["mlp_ilqr"] = mlp_ilqr
+        if nmpc is not None:
+            res["nmpc"] = nmpc
         if not args.no_cpu:
             import oracle
             oracle.build()

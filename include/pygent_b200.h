@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define PG_ABI_VERSION 2
+#define PG_ABI_VERSION 3
 
 #define PG_F64 0
 #define PG_F32 1
@@ -110,7 +110,9 @@ int pg_rollout_balanced(int dtype, int integrator, int64_t B, int32_t T, int32_t
  *   terminal_cost: the environment's terminal_cost (environments.py:275), 0 by default;
  *   X_out [n_alpha,T+1,n,B] / U_out [n_alpha,T,m,B] or NULL; cost_out [n_alpha,B];
  *   diverged_out [n_alpha,B] or NULL: any(x > 1e8) over the rollout (ilqr.py:435);
- *   terminated_out [n_alpha,B] or NULL; active [B] or NULL: trajectories with active==0 are skipped;
+ *   terminated_out [n_alpha,B] or NULL; xN_out [n_alpha,n,B] or NULL: terminal state of every candidate (the state
+ *   the reference's planner environment is left in after a forward pass; used by pg_mpc_shift);
+ *   active [B] or NULL: trajectories with active==0 are skipped;
  *   index [<=B] (i32) + count [1] (i32, device) or both NULL: compacted work list -- only trajectories
  *   index[0..*count) are processed (written by pg_ilqr_select; late iLQR iterations touch few trajectories). */
 int pg_ilqr_forward(int dtype, int integrator, int64_t B, int32_t T, int32_t S, double dt,
@@ -118,17 +120,20 @@ int pg_ilqr_forward(int dtype, int integrator, int64_t B, int32_t T, int32_t S, 
                     const void* x0, const void* xbar, const void* ubar,
                     const void* KK, const void* kk, int32_t Tk, const double* ulim, double terminal_cost,
                     void* X_out, void* U_out, void* cost_out, uint8_t* diverged_out,
-                    uint8_t* terminated_out, const uint8_t* active,
+                    uint8_t* terminated_out, void* xN_out, const uint8_t* active,
                     const int32_t* index, const int32_t* count, void* stream);
 
 /* Backward Riccati pass along (xbar, ubar).
  *   lin_mode 0: analytic A, B (requires has_ab); 1: central differences eps=1e-3 of f.
  *   mu [B] per-trajectory regularisation; reg_type 1 or 2 (ilqr.py:291-295);
  *   ulim host [m] or NULL: box-constrained gains (ilqr.py:304-327, exact-clip restatement);
+ *   Vxx_T [n,n,B] or NULL: the FINAL backward pass (ilqr.py:246-260, :487-494) -- terminal value Hessian P from the
+ *   discrete Riccati equation at the final-cost equilibrium (solved on the host like the reference does, scipy), terminal
+ *   gradient zero; the caller passes mu = 0 and ulim = NULL for it;
  *   outputs: KK [T,m,n,B], kk [T,m,B], dV [2,B] = (sum V1, sum V2), gnorm [B] (ilqr.py:418-420),
  *   success [B] (0 = Quu not positive definite at some step; KK/kk then incomplete). */
 int pg_ilqr_backward(int dtype, int64_t B, int32_t T, double dt, int32_t reg_type, int32_t lin_mode,
-                     const void* mu, const void* xbar, const void* ubar, const double* ulim,
+                     const void* mu, const void* xbar, const void* ubar, const double* ulim, const void* Vxx_T,
                      void* KK, void* kk, void* dV, void* gnorm, uint8_t* success,
                      const uint8_t* active, const int32_t* index, const int32_t* count, void* stream);
 
@@ -147,13 +152,16 @@ typedef struct {
  *   io : cost [B], mu [B], mu_d [B], dcost [B], success_gradient [B] (u8), status [B] (i32), iters [B] (i32)
  *   out: alpha_best [B], accept [B] (u8), active [B] (u8), n_active (device int32 counter: += trajectories still
  *        running), index_out [B] or NULL: their indices, compacted (the next iteration's work list);
- *   index_in / count_in: this iteration's work list or NULL (all B). */
+ *   index_in / count_in: this iteration's work list or NULL (all B);
+ *   last_tried [B] (i32) or NULL: index of the last alpha the (serial) search evaluated, -1 when the backward pass
+ *   failed and no forward pass ran. */
 int pg_ilqr_select(int dtype, int64_t B, const pg_select_params_t* params,
                    const void* cost_cand, const uint8_t* diverged, const void* dV, const void* gnorm,
                    const uint8_t* bw_success, void* cost, void* mu, void* mu_d, void* dcost,
                    uint8_t* success_gradient, int32_t* status, int32_t* iters,
                    void* alpha_best, uint8_t* accept, uint8_t* active, int32_t* n_active,
-                   const int32_t* index_in, const int32_t* count_in, int32_t* index_out, void* stream);
+                   const int32_t* index_in, const int32_t* count_in, int32_t* index_out, int32_t* last_tried,
+                   void* stream);
 
 /* For accepted trajectories: re-run the winning alpha and store it as the new nominal trajectory
  * (xbar, ubar updated in place) and copy the candidate gains into the accepted gains. */
@@ -171,7 +179,7 @@ int pg_ilqr_commit(int dtype, int integrator, int64_t B, int32_t T, int32_t S, d
  * (xbar, ubar); discretised like the reference, Ad = I + A dt, Bd = B dt (ilqr.py:530-531). */
 int pg_ilqr_backward_ext(int dtype, int64_t B, int32_t T, double dt, int32_t reg_type, const void* mu,
                          const void* xbar, const void* ubar, const void* A, const void* Bm, const double* ulim,
-                         void* KK, void* kk, void* dV, void* gnorm, uint8_t* success,
+                         const void* Vxx_T, void* KK, void* kk, void* dV, void* gnorm, uint8_t* success,
                          const int32_t* index, const int32_t* count, void* stream);
 
 /* Cost of candidate trajectories produced elsewhere: X [n_alpha,T+1,n,B], U [n_alpha,T,m,B] ->
@@ -188,6 +196,24 @@ int pg_ilqr_commit_copy(int dtype, int64_t B, int32_t T, int32_t n_alpha, const 
                         const void* alpha_best, const uint8_t* accept, const void* X_cand, const void* U_cand,
                         void* xbar, void* ubar, const void* KK, const void* kk, void* KK_acc, void* kk_acc,
                         const int32_t* index, const int32_t* count, void* stream);
+
+/* --- receding-horizon control: MPCAgent (pygent/algorithms/nmpc.py:126-299) --------------------------------------
+ * pg_mpc_action = take_action (:187-211) after the planner iteration: u = K_0 (x - xbar_0) + ubar_0 + alpha k_0
+ * (+ noise [m,B] or NULL), clipped to +-ulim (host [m]).  KK, kk, xbar, ubar: the planner's arrays (first interval is
+ * read), alpha [B] = alpha_best, x [n,B] the measured state, u_out [m,B]. */
+int pg_mpc_action(int dtype, int64_t B, const void* KK, const void* kk, const void* xbar, const void* ubar,
+                  const void* alpha, const void* x, const void* noise, const double* ulim, void* u_out, void* stream);
+
+/* pg_mpc_shift = shift_planner (:257-277), in place: cost -= c(x_0,u_0,x_1) dt + fcost(x_T) dt; xbar, ubar move one
+ * interval forward, ubar_{T-1} = 0; the LAST entries of the gains KK, kk are zeroed (they are not shifted -- reference
+ * behaviour); one interval with u = 0 is integrated from the planner-environment state and appended as xbar_T, and
+ * cost += its transition cost (at time t_env + dt) + fcost(xbar_T) dt.  The planner-environment state is
+ * xN_cand[last_tried[b]] (outputs of pg_ilqr_forward / pg_ilqr_select: end of the last line-search candidate
+ * evaluated) or, when last_tried[b] < 0 or the pointers are NULL, xe [n,B]; xe receives the appended state.
+ * x_new_ext [n,B] or NULL: the appended state when the caller integrates it (learned dynamics). */
+int pg_mpc_shift(int dtype, int integrator, int64_t B, int32_t T, int32_t S, double dt, double t_env,
+                 void* xbar, void* ubar, void* KK, void* kk, void* cost, void* xe, const void* xN_cand,
+                 int32_t n_alpha, const int32_t* last_tried, const void* x_new_ext, double terminal_cost, void* stream);
 
 /* o [n_obs,B] = observation(x [n,B]) : angle -> [cos, sin] (helpers.py:20-29). */
 int pg_observe(int dtype, int64_t B, const void* x, void* o, void* stream);

@@ -61,8 +61,9 @@ class iLQR(Algorithm):
                  reset_mu=True,
                  saving=True,
                  parallel=False,
-                 final_backpass=False,
-                 check_every=4):
+                 final_backpass=True,
+                 check_every=4,
+                 cache_terminal_value=False):
         self.uDim = environment.uDim
         self.xDim = environment.xDim
         self.saving = path is not None
@@ -77,11 +78,13 @@ class iLQR(Algorithm):
         if finite_diff:
             raise NotImplementedError("finite_diff=True (central-difference cost expansion, helpers.py:41-128) "
                                       "is not on the GPU path yet; the analytic expansion is generated from the cost")
-        if final_backpass:
-            raise NotImplementedError("final_backpass (equilibrium + DARE terminal gain, ilqr.py:246-260, :487-494) "
-                                      "is not implemented; pass final_backpass=False")
         self.finite_diff = finite_diff
         self.final_backpass = final_backpass
+        # final backward pass: the terminal value P depends on the final-cost equilibrium only; with this flag it is
+        # solved once (host: scipy minimise + discrete Riccati equation) and reused, which removes the host round trip
+        # from every later run_optim / MPC control step.  Off by default: the reference re-solves it every time.
+        self.cache_terminal_value = cache_terminal_value
+        self._P_cache = None
         # final cost expression: fcost(x) or fcost(x, mod) called on symbols (ilqr.py:119-125, :552)
         xs = list(environment.system.xs)
         if fcost is None:
@@ -152,7 +155,8 @@ class iLQR(Algorithm):
                     "accept": u8(B), "active": u8(B) + 1}
         A = len(self.alphas)
         self._bw = {"KK": self._KKc, "kk": self._kkc, "dV": z(2, B), "gnorm": z(B), "success": u8(B)}
-        self._fw = {"cost": z(A, B), "diverged": u8(A, B), "terminated": u8(A, B)}
+        self._fw = {"cost": z(A, B), "diverged": u8(A, B), "terminated": u8(A, B), "xN": z(A, n, B)}
+        self._last_tried = i32(B) - 1   # last alpha evaluated per trajectory (MPC plan shift)
         # compacted work lists (ping-pong): trajectories still running, written by the select kernel
         self._idx = [torch.arange(B, dtype=torch.int32, device=dev), i32(B)]
         self._cnt = [i32(1) + B, i32(1)]
@@ -281,22 +285,62 @@ class iLQR(Algorithm):
                                      integrator=self.integrator, ulim=self._ulim(),
                                      terminal_cost=float(env.terminal_cost), want_traj=True, out=out, work=work)
 
-    def _backward(self, work=None):
+    def _backward(self, work=None, Vxx_T=None):
+        """One Riccati sweep into the candidate gains.  Vxx_T: the final backward pass (mu = 0, unconstrained)."""
+        final = Vxx_T is not None
+        mu = torch.zeros_like(self._st["mu"]) if final else self._st["mu"]
+        ulim = None if final else self._ulim()
         if self.learned:
             env = self.environment
             env.dynamics.linearize_device(self._xbar, self._ubar, self.dt, mode=env.linearization, precision=env.precision,
                                           out=self._lin, work=work)
-            return self.lib.ilqr_backward_ext(self._xbar, self._ubar, self._st["mu"], self._lin["A"], self._lin["B"], dt=self.dt,
-                                              reg_type=self.regType, ulim=self._ulim(), out=self._bw, work=work)
-        return self.lib.ilqr_backward(self._xbar, self._ubar, self._st["mu"], dt=self.dt, reg_type=self.regType,
-                                      lin_mode=self.lin_mode, ulim=self._ulim(), out=self._bw, work=work)
+            return self.lib.ilqr_backward_ext(self._xbar, self._ubar, mu, self._lin["A"], self._lin["B"], dt=self.dt,
+                                              reg_type=self.regType, ulim=ulim, out=self._bw, work=work, Vxx_T=Vxx_T)
+        return self.lib.ilqr_backward(self._xbar, self._ubar, mu, dt=self.dt, reg_type=self.regType,
+                                      lin_mode=self.lin_mode, ulim=ulim, out=self._bw, work=work, Vxx_T=Vxx_T)
+
+    # -- final backward pass (ilqr.py:246-260, :487-494) ----------------------------------------------------------------
+    def _terminal_value(self):
+        """P [n, n, B]: solution of the discrete Riccati equation at the equilibrium of the final cost, computed on the
+        host exactly as the reference does: `scipy.optimize.minimize(fcost, x_N)`, linearisation and cost expansion at
+        (x*, u = 0, t = tt[-1]), `scipy.linalg.solve_discrete_are(Ad, Bd, Cxx, Cuu, s=Cxu)`.  Per trajectory for small
+        batches; for B > 32 the equilibrium search starts from trajectory 0's terminal state and the result is shared
+        (the final cost has one minimiser in every shipped example)."""
+        from scipy import linalg, optimize
+        xs = list(self.environment.system.xs)
+        f_l = sp.lambdify(xs, self._fcost_expr, modules="numpy")
+        f = lambda x: float(f_l(*x))
+        xN = np.atleast_2d(self._host(self._xbar[self.steps]))
+        reps = range(self.B) if self.B <= 32 else [0]
+        x_eq = np.array([optimize.minimize(f, xN[b]).x for b in reps])
+        u0 = np.zeros((len(x_eq), self.uDim))
+        Ad, Bd, _ = self.linearization(x_eq, u0)
+        Cxx, Cuu, Cxu, _, _ = self.cost_lin(x_eq, u0, float(self.tt[-1]))
+        Ad, Bd, Cxx, Cuu, Cxu = (np.asarray(a).reshape((len(x_eq),) + np.asarray(a).shape[-2:]) for a in (Ad, Bd, Cxx, Cuu, Cxu))
+        P = np.array([linalg.solve_discrete_are(Ad[i], Bd[i], Cxx[i], Cuu[i], s=Cxu[i]) for i in range(len(x_eq))])
+        if len(P) != self.B:
+            P = np.broadcast_to(P[0], (self.B,) + P.shape[1:])
+        return torch.as_tensor(np.ascontiguousarray(np.moveaxis(P, 0, -1)), dtype=self.dtype, device=self.environment.device)
+
+    def _final_backpass(self):
+        """`self.mu = 0; backward_pass(final=True); if success: self.KK, self.kk = KK, kk` for every trajectory."""
+        try:
+            P = self._P_cache if self._P_cache is not None else self._terminal_value()
+        except (np.linalg.LinAlgError, ValueError):  # no stabilising solution: the reference would raise here
+            return
+        if self.cache_terminal_value:
+            self._P_cache = P
+        r = self._backward(Vxx_T=P)
+        ok = r["success"].bool()
+        self._KK.copy_(torch.where(ok, self._KKc, self._KK))
+        self._kk.copy_(torch.where(ok, self._kkc, self._kk))
+        self._st["mu"].zero_()
+        self._have_gains = True
 
     def backward_pass(self, final=False):
         """Riccati sweep along (xx, uu) (ilqr.py:233-346).  Returns V1, V2, success, KK, kk where V1, V2
         are the SUMS of the reference's per-step lists (only their sums are ever used, ilqr.py:442)."""
-        if final:
-            raise NotImplementedError("final backward pass (DARE terminal value) is not implemented")
-        r = self._backward()
+        r = self._backward(Vxx_T=self._terminal_value() if final else None)
         dV = r["dV"].to("cpu", torch.float64).numpy()
         ok = r["success"].cpu().numpy().astype(bool)
         KK, kk = self._host(r["KK"]), self._host(r["kk"])[..., None]
@@ -368,7 +412,8 @@ class iLQR(Algorithm):
                            terminal_cost=float(self.environment.terminal_cost), out=self._fw, work=work)
         self._cnt[nxt].zero_()
         L.ilqr_select(self._sel, self._fw["cost"], self._fw["diverged"], self._bw["dV"], self._bw["gnorm"],
-                      self._bw["success"], st, self._cnt[nxt], work=work, index_out=self._idx[nxt])
+                      self._bw["success"], st, self._cnt[nxt], work=work, index_out=self._idx[nxt],
+                      last_tried=self._last_tried)
         if self.learned:
             L.ilqr_commit_copy(list(self.alphas), st["alpha_best"], st["accept"], self._cand["X"], self._cand["U"], self._xbar,
                                self._ubar, self._KKc, self._kkc, self._KK, self._kk, work=work)
@@ -378,6 +423,25 @@ class iLQR(Algorithm):
         self._cur = nxt
         self._n_active = self._cnt[nxt]
         self._have_gains = True
+
+    def run_iterations(self, n):
+        """`n` loop bodies of run_optim for every trajectory, device only: no host synchronisation, nothing copied
+        back (the receding-horizon agent calls this once per control step)."""
+        st = self._st
+        if self.reset_mu:
+            st["mu"].fill_(self.mu0)
+            st["mu_d"].fill_(1.0)
+        st["status"].zero_()
+        st["iters"].zero_()
+        st["active"].fill_(1)
+        st["success_gradient"].zero_()
+        self._rearm()
+        self._sel = self._select_params()
+        self._sel.max_iters = int(n)
+        for _ in range(int(n)):
+            self.iterate()
+        if self.final_backpass:
+            self._final_backpass()
 
     def run_optim(self):
         """Trajectory optimisation (ilqr.py:399-499).  Returns (xx, uu, cost)."""
@@ -400,6 +464,8 @@ class iLQR(Algorithm):
             if it % self.check_every == 0 or it == self.max_iters:
                 if int(self._n_active.item()) == 0:  # the only host<->device sync of the loop
                     break
+        if self.final_backpass:
+            self._final_backpass()
         self.iterations = int(st["iters"].max().item())
         xx, uu = self.xx, self.uu
         self.agent.set_history(uu)

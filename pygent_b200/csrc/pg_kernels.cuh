@@ -399,6 +399,7 @@ struct ForwardArgs {
     T* cost_out;
     uint8_t* diverged_out;
     uint8_t* terminated_out;
+    T* xN_out;  // [n_alpha, n, B] or NULL: terminal state of every candidate (what the planner's environment is left in)
     const uint8_t* active;
     const int32_t* index;  // optional work list: thread i handles trajectory index[i], i < *count
     const int32_t* count;
@@ -527,6 +528,10 @@ __global__ void __launch_bounds__(32 * MAX_ALPHAS) ilqr_forward_kernel(const For
         a.cost_out[o] = cost;
         if (a.diverged_out) a.diverged_out[o] = div ? 1 : 0;
         if (a.terminated_out) a.terminated_out[o] = term ? 1 : 0;
+        if (a.xN_out) {
+#pragma unroll
+            for (int i = 0; i < N; i++) a.xN_out[((int64_t)ia * N + i) * B + b] = x[i];
+        }
     }
 }
 
@@ -579,6 +584,8 @@ struct BackwardArgs {
     const int32_t* count;
     const T* A_ext;  // LIN == 2: continuous-time Jacobians supplied by the caller, [T, n, n, B] and [T, n, m, B]
     const T* B_ext;
+    const T* Vxx_T;  // [n, n, B] or NULL: terminal value Hessian of the final backward pass (DARE solution, ilqr.py:246-260;
+                     // the terminal gradient is zero there) instead of the final-cost expansion
 };
 
 template <typename T>
@@ -609,11 +616,18 @@ __global__ void __launch_bounds__(64) ilqr_backward_kernel(const BackwardArgs<T>
     for (int i = 0; i < N; i++) x[i] = a.xbar[((int64_t)Ts * N + i) * B + b];
     // vx = cfx(x_N)*dt, Vxx = Cfxx(x_N)*dt (ilqr.py:244-245)
     T vx[N], Vxx[N * N];
-    P::fcost_derivs(m, x, vx, Vxx);
+    if (a.Vxx_T) {  // vx = P x * 0, Vxx = P (ilqr.py:258-259)
 #pragma unroll
-    for (int i = 0; i < N; i++) vx[i] *= dt;
+        for (int i = 0; i < N; i++) vx[i] = T(0);
 #pragma unroll
-    for (int i = 0; i < N * N; i++) Vxx[i] = P::cfxx_nz(i) ? Vxx[i] * dt : T(0);
+        for (int i = 0; i < N * N; i++) Vxx[i] = a.Vxx_T[(int64_t)i * B + b];
+    } else {
+        P::fcost_derivs(m, x, vx, Vxx);
+#pragma unroll
+        for (int i = 0; i < N; i++) vx[i] *= dt;
+#pragma unroll
+        for (int i = 0; i < N * N; i++) Vxx[i] = P::cfxx_nz(i) ? Vxx[i] * dt : T(0);
+    }
     T sV1 = T(0), sV2 = T(0);
     T gmax[M];
 #pragma unroll
@@ -976,6 +990,7 @@ struct SelectArgs {
     const int32_t* index_in;  // optional work list of this iteration ...
     const int32_t* count_in;
     int32_t* index_out;       // ... and the compacted list of trajectories still running after it
+    int32_t* last_tried;      // [B] or NULL: index of the last alpha the serial search evaluated, -1 if no forward pass ran
 };
 
 template <typename T>
@@ -1000,6 +1015,7 @@ __device__ __forceinline__ int select_one(const SelectArgs<T>& a, const int64_t 
     int status = 0;
     const int it = a.iters[b] + 1;
     a.iters[b] = it;
+    if (a.last_tried) a.last_tried[b] = -1;
     if (!a.bw_success[b]) {
         increase_mu();  // ilqr.py:411-413
         increase_mu();  // ... and again on the "forward not successful" branch (ilqr.py:478-479)
@@ -1027,6 +1043,7 @@ __device__ __forceinline__ int select_one(const SelectArgs<T>& a, const int64_t 
                 if (!p.parallel) break;
             }
         }
+        if (a.last_tried) a.last_tried[b] = n_tried - 1;
         if (success_fw) {
             // best_idx = np.argmin(cost_list): first minimum, a NaN wins (ilqr.py:458)
             int best = 0;
@@ -1188,6 +1205,116 @@ __global__ void commit_copy_kernel(const CommitCopyArgs<T> a) {
     for (int64_t r = 0; r < (int64_t)Ts * M; r++) a.ubar[r * B + b] = U[r * B + b];
     for (int64_t r = 0; r < (int64_t)Ts * M * N; r++) a.KK_acc[r * B + b] = a.KK[r * B + b];
     for (int64_t r = 0; r < (int64_t)Ts * M; r++) a.kk_acc[r * B + b] = a.kk[r * B + b];
+}
+
+// ---- receding-horizon control (MPCAgent, pygent/algorithms/nmpc.py:187-277) -------------------------------------------
+// take_action (:187-211): u = K_0 (x - xbar_0) + ubar_0 + alpha k_0 (+ noise), clipped to +-uMax.
+template <typename T>
+struct MpcActionArgs {
+    int64_t B;
+    int N, M;
+    const T* KK;
+    const T* kk;
+    const T* xbar;
+    const T* ubar;
+    const T* alpha;
+    const T* x;
+    const T* noise;
+    T ulim[2];
+    T* u_out;
+};
+
+template <typename T>
+__global__ void mpc_action_kernel(const MpcActionArgs<T> a) {
+    const int64_t B = a.B;
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    for (int r = 0; r < a.M; r++) {
+        T acc = T(0);
+        for (int i = 0; i < a.N; i++) acc += a.KK[((int64_t)r * a.N + i) * B + b] * (a.x[(int64_t)i * B + b] - a.xbar[(int64_t)i * B + b]);
+        acc = acc + a.ubar[(int64_t)r * B + b];
+        acc = acc + a.alpha[b] * a.kk[(int64_t)r * B + b];
+        if (a.noise) acc = acc + a.noise[(int64_t)r * B + b];
+        a.u_out[(int64_t)r * B + b] = pg::clamp(acc, -a.ulim[r], a.ulim[r]);
+    }
+}
+
+// shift_planner (:257-277): drop the first interval of the plan, append one interval with u = 0 integrated from the
+// state the planner's environment was left in (the end of the last line-search candidate evaluated -- accepted or not),
+// keep the cost consistent; the gains are NOT shifted, only their last entry is zeroed (as the reference does).
+template <typename T>
+struct MpcShiftArgs {
+    int64_t B;
+    int T_steps, S, n_alpha;
+    T dt, t_env, terminal_cost;
+    T* xbar;
+    T* ubar;
+    T* KK;
+    T* kk;
+    T* cost;
+    T* xe;                      // [n, B] planner-environment state: in = fallback start, out = appended terminal state
+    const T* xN_cand;           // [n_alpha, n, B] or NULL
+    const int32_t* last_tried;  // [B] or NULL
+    const T* x_new_ext;         // [n, B] or NULL: appended state integrated by the caller (learned dynamics)
+};
+
+template <typename P, typename T, int INTEG>
+__global__ void mpc_shift_kernel(const MpcShiftArgs<T> a) {
+    const typename P::template Ctx<T> m;
+    constexpr int N = P::N, M = P::M;
+    const int64_t B = a.B;
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int Ts = a.T_steps;
+    T x0[N], x1[N], xN[N], u0[M], xs[N], u[M];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        x0[i] = a.xbar[(int64_t)i * B + b];
+        x1[i] = a.xbar[((int64_t)N + i) * B + b];
+        xN[i] = a.xbar[((int64_t)Ts * N + i) * B + b];
+    }
+#pragma unroll
+    for (int r = 0; r < M; r++) {
+        u0[r] = a.ubar[(int64_t)r * B + b];
+        u[r] = T(0);
+    }
+    // cost -= c(x0, u0, x1, t = None) dt + fcost(xN) dt   (the example costs do not use t: evaluated at 0)
+    T cost = a.cost[b] - (P::cost(m, x0, u0, x1, T(0)) * a.dt + P::fcost(m, xN) * a.dt);
+    for (int k = 0; k < Ts; k++) {  // np.roll(xx, -1), np.roll(uu, -1)
+#pragma unroll
+        for (int i = 0; i < N; i++) a.xbar[((int64_t)k * N + i) * B + b] = a.xbar[((int64_t)(k + 1) * N + i) * B + b];
+        if (k + 1 < Ts) {
+#pragma unroll
+            for (int r = 0; r < M; r++) a.ubar[((int64_t)k * M + r) * B + b] = a.ubar[((int64_t)(k + 1) * M + r) * B + b];
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < M; r++) {
+        a.ubar[((int64_t)(Ts - 1) * M + r) * B + b] = T(0);
+        a.kk[((int64_t)(Ts - 1) * M + r) * B + b] = T(0);
+#pragma unroll
+        for (int i = 0; i < N; i++) a.KK[(((int64_t)(Ts - 1) * M + r) * N + i) * B + b] = T(0);
+    }
+    const int lt = a.last_tried ? a.last_tried[b] : -1;
+#pragma unroll
+    for (int i = 0; i < N; i++)
+        xs[i] = (lt >= 0 && a.xN_cand) ? a.xN_cand[((int64_t)lt * N + i) * B + b] : a.xe[(int64_t)i * B + b];
+    T xn[N];
+    copy(xn, xs);
+    if (a.x_new_ext) {
+#pragma unroll
+        for (int i = 0; i < N; i++) xn[i] = a.x_new_ext[(int64_t)i * B + b];
+    } else {
+        env_step<P, T, INTEG>(m, xn, u, a.dt, a.dt / T(a.S), a.S);  // environment.step(u = 0)
+    }
+    const bool term = P::terminate(m, xn);
+    cost += (P::cost(m, xs, u, xn, a.t_env + a.dt) + (term ? a.terminal_cost : T(0))) * a.dt + P::fcost(m, xn) * a.dt;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        a.xbar[((int64_t)Ts * N + i) * B + b] = xn[i];
+        a.xe[(int64_t)i * B + b] = xn[i];
+    }
+    a.cost[b] = cost;
 }
 
 // ---- observation (helpers.observation, pygent/helpers.py:20-29) -----------------------------------

@@ -132,6 +132,7 @@ def make_ilqr(case, T, x0=None, env_kw=None, **kw):
     _, c_N, _ = CASES[case][3]()
     dt = CASES[case][5]
     kw.setdefault("printing", False)
+    kw.setdefault("final_backpass", False)  # the goldens of the plain solves were made without it (oracle/make_golden.py)
     return iLQR(env, T * dt, dt, fcost=c_N, **kw)
 
 

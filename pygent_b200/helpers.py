@@ -86,3 +86,22 @@ def fxu(f, xx, uu, eps=1e-3):
             ex, eu = _unit(n, i, eps), _unit(m, j, eps)
             H[i, j] = (f(xx + ex, uu + eu) - f(xx - ex, uu + eu) - f(xx + ex, uu - eu) + f(xx - ex, uu - eu)) / (4 * eps ** 2)
     return H
+
+
+class OUnoise(object):
+    """Ornstein-Uhlenbeck exploration noise, discrete Euler form (reference: pygent/helpers.py:170-203):
+    dx = theta (mu - x) dt + sigma sqrt(dt) N(0, 1).  `shape` may carry a batch axis."""
+
+    def __init__(self, uDim, dt, mu=0, theta=0.15, sigma=0.2, seed=0, batch=None):
+        self.uDim, self.mu, self.theta, self.sigma, self.dt = uDim, mu, theta, sigma, dt
+        self.shape = (uDim,) if batch is None else (batch, uDim)
+        self.rng = np.random.RandomState(seed)
+        self.reset()
+
+    def reset(self):
+        self.x = np.ones(self.shape) * self.mu
+
+    def sample(self):
+        dx = self.theta * (self.mu - self.x) * self.dt + self.sigma * np.sqrt(self.dt) * self.rng.normal(size=self.shape)
+        self.x = self.x + dx
+        return self.x

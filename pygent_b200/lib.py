@@ -40,14 +40,17 @@ SIGNATURES = {
     "pg_rollout": [_i32, _i32, _i64, _i32, _i32, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _i32, _vp],
     "pg_rollout_balanced": [_i32, _i32, _i64, _i32, _i32, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _i32, _vp, _i64, _vp],
     "pg_ilqr_forward": [_i32, _i32, _i64, _i32, _i32, _f64, _i32, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _dp, _f64,
-                        _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
-    "pg_ilqr_backward": [_i32, _i64, _i32, _f64, _i32, _i32, _vp, _vp, _vp, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                        _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pg_ilqr_backward": [_i32, _i64, _i32, _f64, _i32, _i32, _vp, _vp, _vp, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                          _vp],
     "pg_ilqr_select": [_i32, _i64, ctypes.POINTER(SelectParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                       _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+                       _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pg_mpc_action": [_i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _dp, _vp, _vp],
+    "pg_mpc_shift": [_i32, _i32, _i64, _i32, _i32, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _f64, _vp],
     "pg_ilqr_commit": [_i32, _i32, _i64, _i32, _i32, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _dp, _vp, _vp, _vp, _vp,
                        _vp],
-    "pg_ilqr_backward_ext": [_i32, _i64, _i32, _f64, _i32, _vp, _vp, _vp, _vp, _vp, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pg_ilqr_backward_ext": [_i32, _i64, _i32, _f64, _i32, _vp, _vp, _vp, _vp, _vp, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                             _vp],
     "pg_traj_cost": [_i32, _i64, _i32, _f64, _f64, _i32, _vp, _vp, _f64, _vp, _vp, _vp, _vp, _vp, _vp],
     "pg_ilqr_commit_copy": [_i32, _i64, _i32, _i32, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "pg_observe": [_i32, _i64, _vp, _vp, _vp],
@@ -206,6 +209,7 @@ class ProblemLibrary:
             term = torch.empty((n_alpha, B), dtype=torch.uint8, device=dev)
         X = out.get("X")
         Uo = out.get("U")
+        xN = out.get("xN")  # [n_alpha, n, B]: terminal states of the candidates (MPC plan shift)
         if want_traj and X is None:
             X = torch.empty((n_alpha, T + 1, n, B), dtype=dtype, device=dev)
             Uo = torch.empty((n_alpha, T, m, B), dtype=dtype, device=dev)
@@ -216,15 +220,15 @@ class ProblemLibrary:
             _ptr(KK, dtype, (Tk, m, n, B), "KK"), _ptr(kk, dtype, (Tk, m, B), "kk"), Tk, _host_doubles(ulim),
             terminal_cost, _ptr(X, dtype, (n_alpha, T + 1, n, B), "X_out"), _ptr(Uo, dtype, (n_alpha, T, m, B), "U_out"),
             _ptr(cost, dtype, (n_alpha, B), "cost_out"), _ptr(div, torch.uint8, (n_alpha, B), "diverged_out"),
-            _ptr(term, torch.uint8, (n_alpha, B), "terminated_out"), _ptr(active, torch.uint8, (B,), "active"),
-            *self._work(work, B), self._stream())
+            _ptr(term, torch.uint8, (n_alpha, B), "terminated_out"), _ptr(xN, dtype, (n_alpha, n, B), "xN_out"),
+            _ptr(active, torch.uint8, (B,), "active"), *self._work(work, B), self._stream())
         self._check(rc, "pg_ilqr_forward")
         self.launches += 1
-        return {"cost": cost, "diverged": div, "terminated": term, "X": X, "U": Uo}
+        return {"cost": cost, "diverged": div, "terminated": term, "X": X, "U": Uo, "xN": xN}
 
     # -- K3 ------------------------------------------------------------------------------------
     def ilqr_backward(self, xbar, ubar, mu, dt=0.02, reg_type=2, lin_mode=None, ulim=None, active=None, out=None,
-                      work=None):
+                      work=None, Vxx_T=None):
         n, m = self.n, self.m
         dtype, dev = xbar.dtype, xbar.device
         T, B = ubar.shape[0], ubar.shape[2]
@@ -249,6 +253,7 @@ class ProblemLibrary:
         rc = self.dll.pg_ilqr_backward(
             _dtype_code(dtype), B, T, dt, reg_type, lin_mode, _ptr(mu, dtype, (B,), "mu"),
             _ptr(xbar, dtype, (T + 1, n, B), "xbar"), _ptr(ubar, dtype, (T, m, B), "ubar"), _host_doubles(ulim),
+            _ptr(Vxx_T, dtype, (n, n, B), "Vxx_T"),
             _ptr(KK, dtype, (T, m, n, B), "KK"), _ptr(kk, dtype, (T, m, B), "kk"), _ptr(dV, dtype, (2, B), "dV"),
             _ptr(gnorm, dtype, (B,), "gnorm"), _ptr(success, torch.uint8, (B,), "success"),
             _ptr(active, torch.uint8, (B,), "active"), *self._work(work, B), self._stream())
@@ -258,7 +263,7 @@ class ProblemLibrary:
 
     # -- K4 ------------------------------------------------------------------------------------
     def ilqr_select(self, params, cost_cand, diverged, dV, gnorm, bw_success, state, n_active=None, work=None,
-                    index_out=None):
+                    index_out=None, last_tried=None):
         """state: dict of per-trajectory tensors cost, mu, mu_d, dcost, success_gradient, status, iters,
         alpha_best, accept, active (updated in place)."""
         dtype = cost_cand.dtype
@@ -274,7 +279,7 @@ class ProblemLibrary:
             _ptr(state["iters"], i32, (B,), "iters"), _ptr(state["alpha_best"], dtype, (B,), "alpha_best"),
             _ptr(state["accept"], u8, (B,), "accept"), _ptr(state["active"], u8, (B,), "active"),
             _ptr(n_active, i32, None, "n_active"), *self._work(work, B), _ptr(index_out, i32, (B,), "index_out"),
-            self._stream())
+            _ptr(last_tried, i32, (B,), "last_tried"), self._stream())
         self._check(rc, "pg_ilqr_select")
         self.launches += 1
 
@@ -295,7 +300,7 @@ class ProblemLibrary:
         self.launches += 1
 
     # -- dynamics integrated / linearised outside the library (learned MLP) --------------------------
-    def ilqr_backward_ext(self, xbar, ubar, mu, A, Bm, dt=0.02, reg_type=2, ulim=None, out=None, work=None):
+    def ilqr_backward_ext(self, xbar, ubar, mu, A, Bm, dt=0.02, reg_type=2, ulim=None, out=None, work=None, Vxx_T=None):
         """Riccati sweep with caller-supplied continuous-time Jacobians A [T,n,n,B], Bm [T,n,m,B]."""
         n, m = self.n, self.m
         dtype, dev = xbar.dtype, xbar.device
@@ -308,9 +313,9 @@ class ProblemLibrary:
         rc = self.dll.pg_ilqr_backward_ext(
             _dtype_code(dtype), B, T, dt, reg_type, _ptr(mu, dtype, (B,), "mu"), _ptr(xbar, dtype, (T + 1, n, B), "xbar"),
             _ptr(ubar, dtype, (T, m, B), "ubar"), _ptr(A, dtype, (T, n, n, B), "A"), _ptr(Bm, dtype, (T, n, m, B), "Bm"),
-            _host_doubles(ulim), _ptr(KK, dtype, (T, m, n, B), "KK"), _ptr(kk, dtype, (T, m, B), "kk"),
-            _ptr(dV, dtype, (2, B), "dV"), _ptr(gnorm, dtype, (B,), "gnorm"), _ptr(success, torch.uint8, (B,), "success"),
-            *self._work(work, B), self._stream())
+            _host_doubles(ulim), _ptr(Vxx_T, dtype, (n, n, B), "Vxx_T"), _ptr(KK, dtype, (T, m, n, B), "KK"),
+            _ptr(kk, dtype, (T, m, B), "kk"), _ptr(dV, dtype, (2, B), "dV"), _ptr(gnorm, dtype, (B,), "gnorm"),
+            _ptr(success, torch.uint8, (B,), "success"), *self._work(work, B), self._stream())
         self._check(rc, "pg_ilqr_backward_ext")
         self.launches += 1
         return {"KK": KK, "kk": kk, "dV": dV, "gnorm": gnorm, "success": success}
@@ -344,6 +349,37 @@ class ProblemLibrary:
             _ptr(KK_acc, dtype, (T, m, n, B), "KK_acc"), _ptr(kk_acc, dtype, (T, m, B), "kk_acc"), *self._work(work, B),
             self._stream())
         self._check(rc, "pg_ilqr_commit_copy")
+        self.launches += 1
+
+    # -- receding-horizon control ------------------------------------------------------------------
+    def mpc_action(self, KK, kk, xbar, ubar, alpha, x, ulim, noise=None, out=None):
+        """u [m,B] = clip(K_0 (x - xbar_0) + ubar_0 + alpha k_0 + noise, +-ulim) (nmpc.py:197-206)."""
+        n, m = self.n, self.m
+        dtype = x.dtype
+        B = x.shape[1]
+        u = out if out is not None else torch.empty((m, B), dtype=dtype, device=x.device)
+        rc = self.dll.pg_mpc_action(_dtype_code(dtype), B, _ptr(KK, dtype, None, "KK"), _ptr(kk, dtype, None, "kk"),
+                                    _ptr(xbar, dtype, None, "xbar"), _ptr(ubar, dtype, None, "ubar"),
+                                    _ptr(alpha, dtype, (B,), "alpha"), _ptr(x, dtype, (n, B), "x"),
+                                    _ptr(noise, dtype, (m, B), "noise"), _host_doubles(ulim), _ptr(u, dtype, (m, B), "u_out"),
+                                    self._stream())
+        self._check(rc, "pg_mpc_action")
+        self.launches += 1
+        return u
+
+    def mpc_shift(self, xbar, ubar, KK, kk, cost, xe, dt=0.02, S=4, integrator=INTEG_RK4, t_env=0.0, xN_cand=None,
+                  last_tried=None, x_new_ext=None, terminal_cost=0.0):
+        """shift_planner (nmpc.py:257-277) in place; see include/pygent_b200.h."""
+        n, m = self.n, self.m
+        dtype = xbar.dtype
+        T, B = ubar.shape[0], ubar.shape[2]
+        n_alpha = xN_cand.shape[0] if xN_cand is not None else 0
+        rc = self.dll.pg_mpc_shift(_dtype_code(dtype), integrator, B, T, S, dt, t_env, _ptr(xbar, dtype, (T + 1, n, B), "xbar"),
+                                   _ptr(ubar, dtype, (T, m, B), "ubar"), _ptr(KK, dtype, (T, m, n, B), "KK"),
+                                   _ptr(kk, dtype, (T, m, B), "kk"), _ptr(cost, dtype, (B,), "cost"), _ptr(xe, dtype, (n, B), "xe"),
+                                   _ptr(xN_cand, dtype, None, "xN_cand"), n_alpha, _ptr(last_tried, torch.int32, (B,), "last_tried"),
+                                   _ptr(x_new_ext, dtype, (n, B), "x_new_ext"), terminal_cost, self._stream())
+        self._check(rc, "pg_mpc_shift")
         self.launches += 1
 
     def observe(self, x):

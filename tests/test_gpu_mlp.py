@@ -197,7 +197,7 @@ def test_backward_ext_and_traj_cost_match_oracle():
     B, T, dt = 3, 25, 0.02
     x0 = np.array([0.2, np.pi - .3, .1, -.2]) + rng.uniform(-.1, .1, (B, 4))
     env.reset(x0)
-    alg = iLQR(env, T * dt, dt, fastForward=True, fcost=c_N, printing=False)
+    alg = iLQR(env, T * dt, dt, fastForward=True, fcost=c_N, printing=False, final_backpass=False)
     U = rng.uniform(-3, 3, (B, T, 1))
     X, _ = mo.rollout(w, mom, IS_ANGLE[4], x0, dt, U=U)
     d = lambda a: torch.as_tensor(np.ascontiguousarray(np.moveaxis(a, 0, -1)), device="cuda")
@@ -223,7 +223,7 @@ def test_learned_ilqr_matches_reference_planner(golden):
     g = golden("mlp_ilqr_cart_pole")
     T, dt = int(g["T"]), float(g["dt"])
     env, w, mom = learned_env(list(g["x0"]), "fp32", "fd")
-    alg = iLQR(env, T * dt, dt, fastForward=True, fcost=c_N, constrained=False, printing=False, maxIters=12)
+    alg = iLQR(env, T * dt, dt, fastForward=True, fcost=c_N, constrained=False, printing=False, maxIters=12, final_backpass=False)
     assert rel(alg.cost, g["cost0"]) < 1e-6 and rel(alg.xx, g["xx0"]) < 1e-6
     Ad, Bd, _ = alg.linearization(g["xx0"][:-1], np.zeros((T, 1)))
     assert rel(Ad, g["Ad0"]) < 5e-5 and rel(Bd, g["Bd0"]) < 5e-5
@@ -248,7 +248,7 @@ def test_learned_ilqr_tensor_core_path_batched():
     res = {}
     for prec, lin in (("bf16", "analytic"), ("fp32", "fd")):
         env, _, _ = learned_env(x0, prec, lin)
-        alg = iLQR(env, T * dt, dt, fastForward=True, fcost=c_N, printing=False, maxIters=15)
+        alg = iLQR(env, T * dt, dt, fastForward=True, fcost=c_N, printing=False, maxIters=15, final_backpass=False)
         c0 = alg.cost.copy()
         alg.run_optim()
         res[prec] = (c0, alg.cost.copy(), alg.iters.copy())
@@ -257,6 +257,6 @@ def test_learned_ilqr_tensor_core_path_batched():
     assert np.max(np.abs(res["bf16"][1] - res["fp32"][1]) / res["fp32"][1]) < 1e-2
     sub = [5, 77, 196]
     env, _, _ = learned_env(x0[sub], "bf16", "analytic")
-    alg = iLQR(env, T * dt, dt, fastForward=True, fcost=c_N, printing=False, maxIters=15)
+    alg = iLQR(env, T * dt, dt, fastForward=True, fcost=c_N, printing=False, maxIters=15, final_backpass=False)
     alg.run_optim()
     assert np.array_equal(alg.cost, res["bf16"][1][sub]) and np.array_equal(alg.iters, res["bf16"][2][sub])

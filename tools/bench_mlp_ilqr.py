@@ -61,7 +61,7 @@ def timed(fn, reps=3):
 rng = np.random.default_rng(0)
 x0 = np.array([0.3, np.pi - 0.4, 0.2, -0.5]) + rng.uniform(-.2, .2, (B, 4))
 env, w, mom = make(x0, "bf16", "analytic")
-alg = iLQR(env, T * dt, dt, fastForward=True, fcost=c_N, printing=False, maxIters=iters)
+alg = iLQR(env, T * dt, dt, fastForward=True, fcost=c_N, printing=False, maxIters=iters, final_backpass=False)
 dyn = env.dynamics
 EVAL = 2.0 * (6 * 500 + 500 * 500 + 500 * 2)  # flops of one network evaluation
 
@@ -102,7 +102,7 @@ print("candidate costs: %.3f ms" % t_c, flush=True)
 
 for prec, lin in (("bf16", "analytic"),) + ((("fp32", "fd"),) if B <= 4096 else ()):
     env, _, _ = make(x0, prec, lin)
-    alg = iLQR(env, T * dt, dt, fastForward=True, fcost=c_N, printing=False, maxIters=iters)
+    alg = iLQR(env, T * dt, dt, fastForward=True, fcost=c_N, printing=False, maxIters=iters, final_backpass=False)
     c0 = float(np.mean(alg.cost))
     alg.run_optim()
     env.reset(x0)
