@@ -487,6 +487,57 @@ class iLQR(Algorithm):
         self._ubar.copy_(r["U"][0])
         self._st["cost"].copy_(r["cost"][0])
 
+    def run_disk(self, x0):
+        """Load a controller written by `save()` -- this package's or the reference's (ilqr.py:646-656) -- and apply it
+        from x0 (ilqr.py:353-396).  Files under `path + 'data/'`: `K_.npy [T,m,n]`, `k.npy [T,m,1]`, `uu.npy [T,m]`,
+        `xx.npy [T+1,n]`, `alpha.npy`, `time_info.p` (pickled list of the T+1 time stamps); one plant, or the same
+        arrays with a leading batch axis.  A controller stored at another step size is re-sampled with a zero-order hold
+        (`interp1d(kind='previous')` in the reference; its own version of this branch raises when the stored final time
+        carries rounding, so the intended semantics are implemented: sample k of the new grid takes the stored entry
+        floor(k dt_new / dt_old))."""
+        d = (self.path or "") + 'data/'
+        if not (self.path and os.path.isfile(d + 'K_.npy') and os.path.isfile(d + 'time_info.p')):
+            self.environment.reset(x0)
+            print("iLQR controller couldn't be loaded. Running initial trajectory.")
+            self.init_trajectory()
+            return
+        with open(d + 'time_info.p', 'rb') as fh:
+            tt = pickle.load(fh)
+        dt_old = float(tt[1] - tt[0])
+        KK, kk, uu, xx = (np.load(d + f) for f in ('K_.npy', 'k.npy', 'uu.npy', 'xx.npy'))
+        alpha = np.load(d + 'alpha.npy')
+        lead = (self.B,) if self.batched else ()
+        T, n, m = self.steps, self.xDim, self.uDim
+        KK = KK.reshape(lead + (-1, m, n))
+        kk, uu, xx = kk.reshape(lead + (-1, m)), uu.reshape(lead + (-1, m)), xx.reshape(lead + (-1, n))
+        ax = len(lead)
+        T_old = KK.shape[ax]
+        if self.dt == dt_old:
+            src = np.minimum(np.arange(T), T_old - 1)        # forward_pass clamps j = min(len(KK) - 1, i) (ilqr.py:205)
+        else:
+            src = np.minimum(np.floor(np.arange(T) * self.dt / dt_old + 1e-9).astype(int), T_old - 1)
+        KK, kk, uu = np.take(KK, src, axis=ax), np.take(kk, src, axis=ax), np.take(uu, src, axis=ax)
+        xx = np.take(xx, np.append(src, min(src[-1] + 1, T_old)), axis=ax)
+        self.environment.reset(x0)
+        self._x0 = self.environment._to_dev(self.environment._x0_host, n)
+        dev = lambda a: torch.as_tensor(np.ascontiguousarray(np.moveaxis(a.reshape((self.B,) + a.shape[ax:]), 0, -1)),
+                                        dtype=self.dtype, device=self.environment.device)
+        self._xbar.copy_(dev(xx))
+        self._ubar.copy_(dev(uu))
+        self._KK.copy_(dev(KK))
+        self._kk.copy_(dev(kk))
+        self._st["alpha_best"].copy_(torch.as_tensor(np.broadcast_to(np.asarray(alpha, dtype=float), (self.B,)).copy(),
+                                                     dtype=self.dtype, device=self.environment.device))
+        self._have_gains = True
+        r = self.lib.ilqr_forward(self._x0, self._xbar, self._ubar, self._KK, self._kk, alpha_dev=self._st["alpha_best"],
+                                  S=self.substeps, dt=self.dt, integrator=self.integrator, ulim=self._ulim(),
+                                  terminal_cost=float(self.environment.terminal_cost), want_traj=True) \
+            if not self.learned else self._forward_candidates([float(np.asarray(alpha).ravel()[0])], self._KK, self._kk)
+        self._xbar.copy_(r["X"][0])
+        self._ubar.copy_(r["U"][0])
+        self._st["cost"].copy_(r["cost"][0])
+        self.agent.set_history(self.uu)
+
     def save(self):
         """Controller on disk in the reference's format (ilqr.py:646-656)."""
         d = self.path + 'data/'

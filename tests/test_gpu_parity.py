@@ -465,3 +465,44 @@ def test_environment_api_batched_and_user_ode():
     env2 = user_ode_env(x0)
     env2.rollout(U)
     assert rel(env2.history, ro["X"]) < 1e-10
+
+
+def test_run_disk_loads_a_reference_controller(golden, tmp_path):
+    """tests/golden/ilqr_disk/data/ holds a controller written by the UNMODIFIED reference's iLQR.save(); run_disk from
+    another initial state must reproduce the reference's run_disk (oracle/make_golden_disk.py).  Then the round trip:
+    this package's save() writes the same six files with the same shapes, and a batched solver reloads them."""
+    import os
+    import pickle
+    import shutil
+    from pygent_b200.algorithms.ilqr import iLQR
+    from pygent_b200.examples import CASES, make_env
+    g = golden("ilqr_disk")
+    _, c_N, _ = CASES["cart_pole"][3]()
+    src = os.path.join(os.path.dirname(__file__), "golden", "ilqr_disk", "data")
+    path = str(tmp_path) + "/"
+    shutil.copytree(src, path + "data")
+    alg = iLQR(make_env("cart_pole", x0=list(g["x0b"])), 1.0, 0.02, fcost=c_N, constrained=False, path=path, printing=False,
+               final_backpass=False, init=False)
+    alg.run_disk(list(g["x0b"]))
+    assert rel(alg.xx, g["same_xx"]) < 1e-9 and rel(alg.uu, g["same_uu"]) < 1e-9 and rel(alg.cost, g["same_cost"]) < 1e-9
+    assert rel(alg.KK, g["same_KK"]) < 1e-12
+    # zero-order-hold re-sampling to dt = 0.01: every stored gain is applied for two intervals
+    env2 = type(alg.environment)(alg.environment._user_cost, list(g["x0b"]), 0.01)
+    alg2 = iLQR(env2, 1.0, 0.01, fcost=c_N, constrained=False, path=path, printing=False, final_backpass=False, init=False)
+    alg2.run_disk(list(g["x0b"]))
+    assert alg2.KK.shape == (100, 1, 4) and np.array_equal(alg2.KK[0::2], g["same_KK"]) and np.array_equal(alg2.KK[1::2], g["same_KK"])
+    assert np.isfinite(alg2.cost) and rel(alg2.xx[-1], g["same_xx"][-1]) < 0.2
+    # round trip through this package's save(): same files, same shapes, loadable by a batch
+    out = str(tmp_path) + "/mine/"
+    alg3 = iLQR(make_env("cart_pole", x0=list(g["x0"])), 1.0, 0.02, fcost=c_N, constrained=False, path=out, printing=False,
+                final_backpass=False)
+    alg3.run_optim()
+    assert rel(alg3.cost, g["cost"]) < 1e-7
+    for f in ("K_.npy", "k.npy", "uu.npy", "xx.npy", "alpha.npy"):
+        assert np.load(out + "data/" + f).shape == np.load(os.path.join(src, f)).shape, f
+    with open(out + "data/time_info.p", "rb") as fh:
+        assert len(pickle.load(fh)) == 51
+    alg4 = iLQR(make_env("cart_pole", x0=list(g["x0b"])), 1.0, 0.02, fcost=c_N, constrained=False, path=out, printing=False,
+                final_backpass=False, init=False)
+    alg4.run_disk(list(g["x0b"]))
+    assert rel(alg4.xx, g["same_xx"]) < 1e-5 and rel(alg4.cost, g["same_cost"]) < 1e-6
