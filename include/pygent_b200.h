@@ -123,6 +123,20 @@ int pg_ilqr_forward(int dtype, int integrator, int64_t B, int32_t T, int32_t S, 
                     uint8_t* terminated_out, void* xN_out, const uint8_t* active,
                     const int32_t* index, const int32_t* count, void* stream);
 
+/* pg_ilqr_forward for large line searches, load-balanced like pg_rollout_balanced: persistent worker warps pull
+ * (32-entry group of the work list, alpha, 20-step time chunk) units from a ticket queue.  Costs and flags only (no
+ * X_out / U_out); cost_out, diverged_out and xN_out are required (they carry a candidate between chunks).  Bit-identical
+ * to pg_ilqr_forward.  workspace: device scratch of at least pg_ilqr_forward_workspace_bytes(B, T, n_alpha) bytes;
+ * workspace[8..12) holds an error flag afterwards (non-zero: a worker gave up waiting -- never expected). */
+int64_t pg_ilqr_forward_workspace_bytes(int64_t B, int32_t T, int32_t n_alpha);
+int pg_ilqr_forward_balanced(int dtype, int integrator, int64_t B, int32_t T, int32_t S, double dt,
+                             int32_t n_alpha, const double* alphas, const void* alpha_dev,
+                             const void* x0, const void* xbar, const void* ubar,
+                             const void* KK, const void* kk, int32_t Tk, const double* ulim, double terminal_cost,
+                             void* cost_out, uint8_t* diverged_out, uint8_t* terminated_out, void* xN_out,
+                             const int32_t* index, const int32_t* count,
+                             void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Backward Riccati pass along (xbar, ubar).
  *   lin_mode 0: analytic A, B (requires has_ab); 1: central differences eps=1e-3 of f.
  *   mu [B] per-trajectory regularisation; reg_type 1 or 2 (ilqr.py:291-295);

@@ -535,6 +535,133 @@ __global__ void __launch_bounds__(32 * MAX_ALPHAS) ilqr_forward_kernel(const For
     }
 }
 
+// ---- K2b: the candidate rollouts, load-balanced -----------------------------------------------------------------
+// 16,384 trajectories x 11 alphas are 5,632 warps: with ilqr_forward_kernel's 126 registers that is ONE 352-thread CTA
+// per SM (2.75 warps per scheduler) in 3.46 -> 4 waves.  Here the K1b scheme: 3 persistent worker warps per scheduler
+// pull (group of 32 work-list entries, alpha, time chunk) units from the ticket queue; between chunks a candidate lives
+// in its output slots (xN_out, cost_out, diverged_out) and its clock in tq.  Evaluates costs only (no X_out / U_out);
+// results are bit-identical to ilqr_forward_kernel.  The group count depends on the device-side work-list length, so
+// every worker derives it from *count.
+template <typename T>
+struct ForwardQueueArgs {
+    ForwardArgs<T> f;
+    int n_chunks;
+    int bounds[MAX_CHUNKS + 1];
+    int* counters;  // [0] next ticket, [1] next free queue slot, [2] error flag
+    int* queue;
+    int* progress;  // [n_alpha * ceil(B / 32)]
+    T* tq;
+};
+
+template <typename P, typename T, int INTEG>
+__global__ void __launch_bounds__(128, 3) ilqr_forward_queue_kernel(const ForwardQueueArgs<T> q) {
+    const typename P::template Ctx<T> m;
+    constexpr int N = P::N, M = P::M;
+    const ForwardArgs<T>& a = q.f;
+    const int64_t B = a.B;
+    const int lane = threadIdx.x & 31;
+    const int64_t cnt = a.index ? (int64_t)*a.count : B;
+    const int ng = (int)((cnt + 31) / 32);
+    const int G = ng * a.n_alpha, total = G * q.n_chunks;
+    const T h = a.dt / T(a.S);
+    for (;;) {
+        int g = -1;
+        if (lane == 0) {
+            const int s = atomicAdd(&q.counters[0], 1);
+            if (s < G) {
+                g = s;
+            } else if (s < total) {
+                volatile int* slot = q.queue + (s - G);
+                int v = 0, spins = 0;
+                while ((v = *slot) == 0) {
+                    __nanosleep(128);
+                    if (++spins > (1 << 24)) {
+                        atomicExch(&q.counters[2], 1);
+                        break;
+                    }
+                }
+                g = v - 1;
+                __threadfence();
+            }
+        }
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g < 0) return;
+        const int c = __ldcg(&q.progress[g]);
+        const int ia = g / ng, tg = g - ia * ng;
+        const int64_t w = (int64_t)tg * 32 + lane;
+        const bool valid = w < cnt;
+        const int64_t wv = valid ? w : cnt - 1;  // ragged last group: idle lanes shadow the last entry
+        const int64_t b = a.index ? (int64_t)a.index[wv] : wv;
+        const int64_t o = (int64_t)ia * B + b;
+        const int k0 = q.bounds[c], k1 = q.bounds[c + 1];
+        const T alpha = a.alpha_dev ? a.alpha_dev[b] : a.alphas[ia];
+        T x[N], u[M];
+        T cost, t;
+        bool div = false, term = false;
+        if (c == 0) {
+#pragma unroll
+            for (int i = 0; i < N; i++) x[i] = a.x0[i * B + b];
+#pragma unroll
+            for (int i = 0; i < N; i++) div |= (x[i] > T(1e8));
+            cost = T(0);
+            t = T(0);
+        } else {
+#pragma unroll
+            for (int i = 0; i < N; i++) x[i] = __ldcg(&a.xN_out[((int64_t)ia * N + i) * B + b]);
+            cost = __ldcg(&a.cost_out[o]);
+            div = __ldcg(&a.diverged_out[o]) != 0;
+            t = __ldcg(&q.tq[g]);
+        }
+        Nominal<P, T> cur, nxt;
+        if (k0 < k1) nxt.load(a.KK, a.kk, a.xbar, a.ubar, (k0 < a.Tk) ? k0 : (a.Tk - 1), B, b);
+        for (int k = k0; k < k1; k++) {
+            cur = nxt;
+            if (k + 1 < k1) {
+                const int j = (k + 1 < a.Tk) ? (k + 1) : (a.Tk - 1);
+                nxt.load(a.KK, a.kk, a.xbar, a.ubar, j, B, b);
+            }
+#pragma unroll
+            for (int r = 0; r < M; r++) {  // u = KK[j] @ (x - xx_[j]) + alpha*kk[j] + uu_[j]   (ilqr.py:206)
+                T acc = T(0);
+#pragma unroll
+                for (int i = 0; i < N; i++) acc += cur.K[r * N + i] * (x[i] - cur.xb[i]);
+                acc = acc + alpha * cur.k[r];
+                acc = acc + cur.ub[r];
+                if (a.clip) acc = pg::clamp(acc, -a.ulim[r], a.ulim[r]);
+                u[r] = acc;
+            }
+            T xp[N];
+            copy(xp, x);
+            env_step<P, T, INTEG>(m, x, u, a.dt, h, a.S);
+            t += a.dt;
+            term = P::terminate(m, x);
+            cost += (P::cost(m, xp, u, x, t) + (term ? a.terminal_cost : T(0))) * a.dt;
+#pragma unroll
+            for (int i = 0; i < N; i++) div |= (x[i] > T(1e8));
+        }
+        const bool last = k1 >= a.T_steps;
+        if (last) cost += P::fcost(m, x) * a.dt;
+        if (valid) {
+#pragma unroll
+            for (int i = 0; i < N; i++) a.xN_out[((int64_t)ia * N + i) * B + b] = x[i];
+            a.cost_out[o] = cost;
+            a.diverged_out[o] = div ? 1 : 0;
+            if (last && a.terminated_out) a.terminated_out[o] = term ? 1 : 0;
+        }
+        if (!last) {
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) {
+                q.tq[g] = t;
+                q.progress[g] = c + 1;
+                __threadfence();
+                const int p = atomicAdd(&q.counters[1], 1);
+                atomicExch(&q.queue[p], g + 1);
+            }
+        }
+    }
+}
+
 // ---- linearisation ------------------------------------------------------------------------------
 // lin_mode 1: helpers.system_linearization (pygent/helpers.py:130-148), central differences, eps=1e-3.
 template <typename P, typename T>

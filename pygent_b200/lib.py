@@ -41,6 +41,8 @@ SIGNATURES = {
     "pg_rollout_balanced": [_i32, _i32, _i64, _i32, _i32, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _i32, _vp, _i64, _vp],
     "pg_ilqr_forward": [_i32, _i32, _i64, _i32, _i32, _f64, _i32, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _dp, _f64,
                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pg_ilqr_forward_balanced": [_i32, _i32, _i64, _i32, _i32, _f64, _i32, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _dp, _f64,
+                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "pg_ilqr_backward": [_i32, _i64, _i32, _f64, _i32, _i32, _vp, _vp, _vp, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                          _vp],
     "pg_ilqr_select": [_i32, _i64, ctypes.POINTER(SelectParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
@@ -104,6 +106,8 @@ class ProblemLibrary:
             fn.restype = ctypes.c_int
         self.dll.pg_rollout_workspace_bytes.argtypes = [_i64, _i32]
         self.dll.pg_rollout_workspace_bytes.restype = _i64
+        self.dll.pg_ilqr_forward_workspace_bytes.argtypes = [_i64, _i32, _i32]
+        self.dll.pg_ilqr_forward_workspace_bytes.restype = _i64
         self._workspace = {}
         info = ProblemInfo()
         self._check(self.dll.pg_get_problem_info(ctypes.byref(info)), "pg_get_problem_info")
@@ -189,8 +193,10 @@ class ProblemLibrary:
     # -- K2 ------------------------------------------------------------------------------------
     def ilqr_forward(self, x0, xbar, ubar, KK, kk, alphas=None, alpha_dev=None, S=4, dt=0.02,
                      integrator=INTEG_RK4, ulim=None, terminal_cost=0.0, want_traj=False, active=None, out=None,
-                     work=None):
-        """work: (index i32 [B], count i32 [1]) compacted list of trajectories to process, or None (all)."""
+                     work=None, balanced=None):
+        """work: (index i32 [B], count i32 [1]) compacted list of trajectories to process, or None (all).
+        balanced: use the work-queue kernel (pg_ilqr_forward_balanced; costs only); default: when there are more
+        (32-trajectory group, alpha) pairs than the 3 x 4 x SM persistent workers."""
         n, m = self.n, self.m
         dtype, dev = x0.dtype, x0.device
         B = x0.shape[1]
@@ -213,6 +219,26 @@ class ProblemLibrary:
         if want_traj and X is None:
             X = torch.empty((n_alpha, T + 1, n, B), dtype=dtype, device=dev)
             Uo = torch.empty((n_alpha, T, m, B), dtype=dtype, device=dev)
+        if balanced is None:
+            balanced = use_balanced_forward(B, n_alpha, T, dev)
+        if balanced and not want_traj and X is None and active is None and T >= 1:
+            if xN is None:
+                xN = torch.empty((n_alpha, n, B), dtype=dtype, device=dev)
+            nbytes = int(self.dll.pg_ilqr_forward_workspace_bytes(B, T, n_alpha))
+            ws = self._workspace.get(("fw", dev))
+            if ws is None or ws.numel() < nbytes:
+                ws = self._workspace[("fw", dev)] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            rc = self.dll.pg_ilqr_forward_balanced(
+                _dtype_code(dtype), integrator, B, T, S, dt, n_alpha, _host_doubles(alphas),
+                _ptr(alpha_dev, dtype, (B,), "alpha_dev"), _ptr(x0, dtype, (n, B), "x0"),
+                _ptr(xbar, dtype, (T + 1, n, B), "xbar"), _ptr(ubar, dtype, (T, m, B), "ubar"),
+                _ptr(KK, dtype, (Tk, m, n, B), "KK"), _ptr(kk, dtype, (Tk, m, B), "kk"), Tk, _host_doubles(ulim),
+                terminal_cost, _ptr(cost, dtype, (n_alpha, B), "cost_out"), _ptr(div, torch.uint8, (n_alpha, B), "diverged_out"),
+                _ptr(term, torch.uint8, (n_alpha, B), "terminated_out"), _ptr(xN, dtype, (n_alpha, n, B), "xN_out"),
+                *self._work(work, B), _ptr(ws), nbytes, self._stream())
+            self._check(rc, "pg_ilqr_forward_balanced")
+            self.launches += 1
+            return {"cost": cost, "diverged": div, "terminated": term, "X": None, "U": None, "xN": xN}
         rc = self.dll.pg_ilqr_forward(
             _dtype_code(dtype), integrator, B, T, S, dt, n_alpha, _host_doubles(alphas),
             _ptr(alpha_dev, dtype, (B,), "alpha_dev"), _ptr(x0, dtype, (n, B), "x0"),
@@ -426,6 +452,15 @@ def use_balanced_rollout(B, T, dev):
         return False
     per = warps / sched
     return (-(-warps // sched)) / per > 1.04
+
+
+def use_balanced_forward(B, n_alpha, T, dev):
+    """Queue kernel for the line search when its (group, alpha) pairs outnumber the persistent workers (3 per warp
+    scheduler) and the horizon spans several 20-step chunks."""
+    if dev.type != "cuda" or T < 40:
+        return False
+    workers = 3 * 4 * _sm_count(dev.index if dev.index is not None else torch.cuda.current_device())
+    return ((B + 31) // 32) * n_alpha > workers
 
 
 def _cuda_error_name(rc):

@@ -506,3 +506,34 @@ def test_run_disk_loads_a_reference_controller(golden, tmp_path):
                 final_backpass=False, init=False)
     alg4.run_disk(list(g["x0b"]))
     assert rel(alg4.xx, g["same_xx"]) < 1e-5 and rel(alg4.cost, g["same_cost"]) < 1e-6
+
+
+@pytest.mark.parametrize("case,B,T", [("cart_pole", 6000, 100), ("double_parallel", 5500, 50), ("cart_pole", 333, 45)])
+def test_balanced_forward_is_bit_identical(case, B, T):
+    """pg_ilqr_forward_balanced (persistent workers + ticket queue over group x alpha x time chunk) must return exactly
+    the bits of pg_ilqr_forward: costs, flags, terminal states -- for the whole batch and for a compacted work list."""
+    alg = solver(case, T, x0=None)
+    n, m = alg.lib.n, alg.lib.m
+    rng = np.random.default_rng(B)
+    x0 = np.array(CASES[case][4]) + rng.uniform(-0.3, 0.3, (B, n))
+    alg = solver(case, T, x0=x0)
+    alg.backward_pass()                      # candidate gains along the u = 0 trajectory
+    L, al = alg.lib, list(alg.alphas)
+    args = (alg._x0, alg._xbar, alg._ubar, alg._KKc, alg._kkc)
+    kw = dict(alphas=al, S=alg.substeps, dt=alg.dt, ulim=[float(np.ravel(alg.environment.uMax)[0])])
+    a = L.ilqr_forward(*args, balanced=False, out={"xN": torch.zeros((len(al), n, B), dtype=torch.float64, device="cuda")}, **kw)
+    b = L.ilqr_forward(*args, balanced=True, **kw)
+    for k in ("cost", "diverged", "terminated", "xN"):
+        assert torch.equal(a[k], b[k]), k
+    assert int(L._workspace[("fw", alg._x0.device)][8:12].view(torch.int32).item()) == 0
+    # compacted work list: only the listed trajectories are touched
+    sel = torch.as_tensor(np.sort(rng.choice(B, B // 3, replace=False)), dtype=torch.int32, device="cuda")
+    idx = torch.zeros(B, dtype=torch.int32, device="cuda")
+    idx[: len(sel)] = sel
+    cnt = torch.tensor([len(sel)], dtype=torch.int32, device="cuda")
+    out = {"cost": torch.full_like(a["cost"], -1.0), "diverged": torch.full_like(a["diverged"], 7), "xN": torch.full_like(a["xN"], -1.0)}
+    c = L.ilqr_forward(*args, balanced=True, work=(idx, cnt), out=out, **kw)
+    mask = torch.zeros(B, dtype=torch.bool, device="cuda")
+    mask[sel.long()] = True
+    assert torch.equal(c["cost"][:, mask], a["cost"][:, mask]) and torch.equal(c["xN"][..., mask], a["xN"][..., mask])
+    assert bool((c["cost"][:, ~mask] == -1.0).all()) and bool((c["diverged"][:, ~mask] == 7).all())
