@@ -14,6 +14,8 @@ nothing on the data path).  Prints ONE JSON line (rank 0):
              on this pool's B200 (profiles/fp_peak_b200.json), plus the HBM view of the same launch
   cpu_baseline  the CPU oracle (C port of the reference's step loop) on a bounded sample, all host threads
   ilqr       iLQR iterations/s on 16,384 cart-pole swing-ups per GPU (BASELINE.json config 3), to convergence
+  ilqr_c4    BASELINE.json configs[3]: 8,192 double-pendulum-on-a-cart (n = 6) and acrobot trajectories, horizon 100,
+             parallel line search (`parallel=True`), 100 iterations at most
   nmpc       closed-loop control steps/s of 4,096 cart-pole plants under receding-horizon iLQR (NMPC/MPCAgent: one
              planner iteration + final backward pass + action + plan shift + plant step per control step, on the device)
   mlp_ilqr   iLQR iterations/s through the learned-MLP dynamics, 4,096 trajectories per GPU (config 5 = 32,768 over
@@ -387,6 +389,34 @@ def main():
                 "converged_frac": float(np.mean((st == pglib.ST_CONV_FUN) | (st == pglib.ST_CONV_GRAD))),
                 "mean_final_cost": float(np.mean(solver.cost)), "line_search": "serial semantics, 11 alphas evaluated per launch"}
 
+    # ---- config 4: n = 6 double pendulum / acrobot, parallel line search -------------------------------
+    ilqr_c4 = None
+    if not args.no_ilqr:
+        ilqr_c4 = {}
+        for case, nominal in (("double_parallel", [0, np.pi, np.pi, 0, 0, 0]), ("acrobot", [np.pi, 0, 0, 0])):
+            rng = np.random.default_rng(4000 + rank)
+            xi = np.array(nominal) + rng.uniform(-0.1, 0.1, (8192, len(nominal)))
+            solver = make_ilqr(case, ILQR_T, x0=xi, env_kw={"device": dev}, maxIters=100, parallel=True)
+            solver.run_optim()
+            solver.environment.reset(xi)
+            solver.reset()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            solver.run_optim()
+            b.record()
+            barrier()
+            ms, total_iters = a.elapsed_time(b), int(solver.iters.sum())
+            if world > 1:
+                t = torch.tensor([ms, -float(total_iters)], dtype=torch.float64, device=dev)
+                tm, ts = t.clone(), t.clone()
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+                ms, total_iters = float(tm[0]), int(-ts[1])
+            ilqr_c4[case] = {"value": total_iters / (ms * 1e-3), "unit": "iLQR iterations/s", "trajectories_per_gpu": 8192,
+                             "state_dim": len(nominal), "horizon": ILQR_T, "line_search": "parallel=True, 11 alphas", "ms": ms,
+                             "iterations_total": total_iters, "mean_final_cost": float(np.mean(solver.cost))}
+
     # ---- receding-horizon control of a batch of plants ------------------------------
     nmpc = None
     if not args.no_nmpc:
@@ -429,6 +459,8 @@ def main():
             res["mlp_ilqr"] = mlp_ilqr
         if nmpc is not None:
             res["nmpc"] = nmpc
+        if ilqr_c4:
+            res["ilqr_c4"] = ilqr_c4
         if not args.no_cpu:
             import oracle
             oracle.build()
