@@ -14,6 +14,8 @@ nothing on the data path).  Prints ONE JSON line (rank 0):
              on this pool's B200 (profiles/fp_peak_b200.json), plus the HBM view of the same launch
   cpu_baseline  the CPU oracle (C port of the reference's step loop) on a bounded sample, all host threads
   ilqr       iLQR iterations/s on 16,384 cart-pole swing-ups per GPU (BASELINE.json config 3), to convergence
+  fp32       the same rollout workload through the fp32 instantiation of the kernels (stated tolerance vs fp64: 5e-3
+             relative on states over 100 control intervals), against the measured FFMA peak
   ilqr_c4    BASELINE.json configs[3]: 8,192 double-pendulum-on-a-cart (n = 6) and acrobot trajectories, horizon 100,
              parallel line search (`parallel=True`), 100 iterations at most
   nmpc       closed-loop control steps/s of 4,096 cart-pole plants under receding-horizon iLQR (NMPC/MPCAgent: one
@@ -113,6 +115,14 @@ def fp64_peak():
         with open(p) as fh:
             return float(json.load(fh)["fp64_fma_tflops"]), "measured DFMA microbenchmark on this pool's B200 (profiles/fp_peak_b200.json, tools/fp_peak.cu)"
     return 37.2, "nominal 148 SM x 64 lanes x 2 x 1.965 GHz (no measurement committed)"
+
+
+def fp32_peak():
+    p = os.path.join(ROOT, "profiles", "fp_peak_b200.json")
+    if os.path.isfile(p):
+        with open(p) as fh:
+            return float(json.load(fh)["fp32_fma_tflops"])
+    return 74.4
 
 
 def hbm_peak():
@@ -323,6 +333,24 @@ def main():
         elapsed_ms = float(tmax.item())
     value = world * B_ENVS * T_STEPS * args.steps / (elapsed_ms * 1e-3)
 
+    # ---- the same workload in fp32 (FP32 FMA pipe view) ------------------------------------------------
+    x0_32, U_32 = x0.float(), U.float()
+    out32 = {"xN": torch.empty((4, B_ENVS), dtype=torch.float32, device=dev), "cost": torch.empty((B_ENVS,), dtype=torch.float32, device=dev),
+             "terminated": torch.empty((B_ENVS,), dtype=torch.uint8, device=dev)}
+    for _ in range(args.warmup):
+        L.rollout(x0_32, U_32, S=SUBSTEPS, dt=DT, out=out32)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n32 = max(10, min(args.steps, 100))
+    f0.record()
+    for _ in range(n32):
+        L.rollout(x0_32, U_32, S=SUBSTEPS, dt=DT, out=out32)
+    f1.record()
+    barrier()
+    ms32 = f0.elapsed_time(f1) / n32
+    err32 = float(((out32["xN"].double() - out["xN"]).abs() / (out["xN"].abs() + 1)).max())
+    del x0_32, U_32
+
     # ---- end to end through the public API, host buffers --------------------------------------------
     from pygent_b200.examples import make_env
     env = make_env("cart_pole", x0=np.ascontiguousarray(x0_h.numpy().T), device=dev)
@@ -452,6 +480,13 @@ def main():
                                  "frac": hbm_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_gbs, "bytes_per_launch": hbm_bytes,
                                  "peak_source": hbm_src}},
             "best": best,
+            "fp32": {"value": world * B_ENVS * T_STEPS / (ms32 * 1e-3), "unit": "env-steps/s", "ms_per_step": ms32,
+                     "roofline": {"bound": "fp32", "achieved": B_ENVS * T_STEPS * (SUBSTEPS * 188 + FLOPS_COST) / (ms32 * 1e-3) / 1e12,
+                                  "peak": fp32_peak(), "unit": "TFLOP/s",
+                                  "frac": B_ENVS * T_STEPS * (SUBSTEPS * 188 + FLOPS_COST) / (ms32 * 1e-3) / 1e12 / fp32_peak(),
+                                  "flops_per_substep": 188},
+                     "max_rel_state_error_vs_f64_after_500_intervals": err32,
+                     "stated_tolerance": "5e-3 relative on states over 100 control intervals (tests/test_gpu_parity.py)"},
         }
         if ilqr is not None:
             res["ilqr"] = ilqr

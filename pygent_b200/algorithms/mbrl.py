@@ -10,9 +10,16 @@ the CPU tests), and every rank applies the identical Adagrad update.  This is th
 dynamics path besides the final cost/argmin gather.  The dense algebra here is plain library GEMMs
 (cuBLAS through torch); the planner's hot path through the network is `pygent_b200.mlp`.
 """
+import copy
+import os
+import pickle
+import time
+
 import numpy as np
 import torch
 import torch.distributed as dist
+
+from .core import Algorithm
 
 
 class DynamicsTrainer(object):
@@ -112,3 +119,219 @@ class DynamicsTrainer(object):
                 print('NN dynamics training loss:', losses[-1])
         self.nn_dynamics.invalidate()  # the planner's packed device copy is rebuilt from the new weights
         return losses
+
+
+class MBRL(Algorithm):
+    """Model-based RL outer loop (reference: pygent/algorithms/mbrl.py:26-337): random warm-up episodes fill `D_rand`,
+    the learned model is (re)trained on `D_rand + D_RL`, episodes are planned on the learned model (iLQR / NMPC on
+    `LearnedStateSpaceModel`, tensor-core rollouts and Jacobians) and executed on the real environment, and transitions
+    the model predicts badly are added to `D_RL`.  Same constructor arguments and method names as the reference; plotting
+    and animation are out of scope.  `precision` selects the planner's network path ("bf16": tensor cores)."""
+
+    def __init__(self, environment, t, dt,
+                 test_t=0.,
+                 plotInterval=1,
+                 nData=int(1e6),
+                 path='../results/mbrl/',
+                 checkInterval=2,
+                 evalPolicyInterval=100,
+                 warm_up_episodes=10,
+                 dyn_lr=1e-3,
+                 batch_size=512,
+                 training_epochs=60,
+                 data_ratio=1,
+                 aggregation_interval=1,
+                 fcost=None,
+                 horizon=None,
+                 use_mpc=False,
+                 ilqr_print=False,
+                 ilqr_save=False,
+                 ilqr_save_interval=100,
+                 print_dyn_error=False,
+                 weight_decay=1e-3,
+                 data_noise=1e-3,
+                 prediction_error_bound=1e-3,
+                 ou_theta=1,
+                 ou_sigma=0.2,
+                 maxIters=500,
+                 sparse_dyn=True,
+                 precision="bf16",
+                 seed=0):
+        from ..data import DataSet
+        from ..environments import LearnedStateSpaceModel
+        from ..nn_models import NNDynamics
+        from .nmpc import NMPC
+        if not sparse_dyn:
+            raise NotImplementedError("the GPU network path implements the sparse_dyn model (velocity half, mbrl.py:54-57)")
+        if environment.batched:
+            raise NotImplementedError("MBRL learns from one plant; batched planning is available through NMPC / iLQR")
+        self.sparse_dyn = sparse_dyn
+        xDim, oDim, uDim = environment.xDim, environment.oDim, environment.uDim
+        if horizon is None or not use_mpc:
+            horizon = t
+        self.dt = dt
+        self.rng = np.random.RandomState(seed)
+        self.nn_dynamics = NNDynamics(xDim, uDim, oDim=oDim, dxDim=xDim // 2, xIsAngle=environment.xIsAngle)
+        self.trainer = DynamicsTrainer(self.nn_dynamics, dyn_lr=dyn_lr, weight_decay=weight_decay, batch_size=batch_size,
+                                       training_epochs=training_epochs, sparse_dyn=sparse_dyn, device=environment.device)
+        self.optim = self.trainer.optim
+        self.nn_environment = LearnedStateSpaceModel(self.nn_dynamics, environment._user_cost, environment.x0, uDim, dt,
+                                                     precision=precision, device=environment.device)
+        self.nn_environment.uMax = environment.uMax
+        self.path = path
+        for sub in ("", "plots/", "animations/", "data/"):
+            os.makedirs(path + sub, exist_ok=True)
+        self.nmpc_algorithm = NMPC(environment, self.nn_environment, t, dt, horizon,
+                                   init_optim=False, add_noise=True, path=path, fcost=fcost, fastForward=True,
+                                   maxIters=maxIters, step_iterations=1, ilqr_print=ilqr_print, ilqr_save=ilqr_save,
+                                   tolFun=1e-4, save_interval=ilqr_save_interval, noise_gain=0.005, ou_theta=ou_theta,
+                                   ou_sigma=ou_sigma, constrained=True)
+        super(MBRL, self).__init__(environment, self.nmpc_algorithm.agent, t, dt)
+        self.D_rand = DataSet(nData, seed=seed)
+        self.D_RL = DataSet(nData, seed=seed + 1)
+        self.test_t = test_t
+        self.plotInterval = plotInterval
+        self.evalPolicyInterval = evalPolicyInterval
+        self.checkInterval = checkInterval
+        self.warm_up = warm_up_episodes * int(t / dt)
+        self.batch_size = batch_size
+        self.training_epochs = training_epochs
+        self.data_ratio = data_ratio
+        self.aggregation_interval = aggregation_interval
+        self.use_mpc = use_mpc
+        self.dynamics_first_trained = False
+        self.print_dyn_error = print_dyn_error
+        self.data_noise = data_noise
+        self.prediction_error_bound = prediction_error_bound
+        self.training_time, self.optim_time = [], []
+        self.expCost, self.episode_steps = [], []
+
+    def ode(self, t, x, u):
+        """[x[n/2:], 1/dt * nn_dynamics.ode(x, u)] (mbrl.py:125-130), evaluated by the learned-dynamics library."""
+        return self.nn_environment.ode(t, x, u)
+
+    def _transition(self, c):
+        env, n = self.environment, self.rng.normal
+        return {'x_': env.x_ + n(0, self.data_noise, env.xDim), 'u': np.asarray(self.agent.u, dtype=float) + n(0, self.data_noise, env.uDim),
+                'x': env.x + n(0, self.data_noise, env.xDim), 'o_': env.o_ + n(0, self.data_noise, env.oDim),
+                'o': env.o + n(0, self.data_noise, env.oDim), 'c': [c], 't': [env.terminated]}
+
+    def _finish_episode(self, cost, i):
+        self.meanCost.append(np.mean(cost))
+        self.totalCost.append(np.sum(cost))
+        self.episode_steps.append(i)
+        self.episode += 1
+
+    def run_random_episode(self):
+        """Warm-up episode with uniformly random controls (mbrl.py:208-244)."""
+        env = self.environment
+        env.reset(env.x0)
+        self.agent.reset()
+        cost, i = [], 0
+        for i, _ in enumerate(np.arange(0, self.t, self.dt)):
+            u = self.agent.take_random_action(self.dt, ou_noise=False)
+            c = env.step(u, self.dt)
+            cost.append(c)
+            self.D_rand.force_add_sample(self._transition(c))
+            if env.terminated:
+                break
+        self._finish_episode(cost, i)
+
+    def pred_loss(self, transition):
+        return self.trainer.pred_loss(transition)
+
+    def run_episode(self, reinit=True):
+        """Plan on the learned model, act on the real environment, keep what the model predicts badly (mbrl.py:132-185)."""
+        env, agent = self.environment, self.agent
+        start = time.time()
+        agent.init_optim(env.x0, init=True)
+        self.optim_time.append(time.time() - start)
+        env.reset(env.x0)
+        agent.reset()
+        cost, i = [], 0
+        for i, _ in enumerate(np.arange(0, self.t + self.test_t, self.dt)):
+            u = agent.take_action(self.dt, env.x) if self.use_mpc else agent.take_action_plan_feedback(self.dt, env.x, i)
+            c = env.step(u, self.dt)
+            cost.append(c)
+            tr = self._transition(c)
+            if self.pred_loss(tr) > self.prediction_error_bound:
+                self.D_RL.force_add_sample(tr)
+            if env.terminated:
+                break
+        self._finish_episode(cost, i)
+
+    def run_controller(self, x0):
+        env, agent = self.environment, self.agent
+        env.reset(x0)
+        agent.reset()
+        for i, _ in enumerate(np.arange(0, self.t + self.test_t, self.dt)):
+            env.step(agent.take_action(self.dt, env.x), self.dt)
+            if env.terminated:
+                break
+
+    def train_dynamics(self):
+        """mbrl.py:439-448: train on D_rand + data_ratio x D_RL, then the planner sees the new model."""
+        start = time.time()
+        data = copy.copy(self.D_rand)
+        data.data = list(self.D_rand.data)
+        for _ in range(self.data_ratio):
+            data.data += self.D_RL.data
+        losses = self.trainer.training(data)
+        self.training_time.append(time.time() - start)
+        return losses
+
+    def training(self, dataSet):
+        return self.trainer.training(dataSet)
+
+    def run_learning(self, n):
+        """mbrl.py:283-310."""
+        for steps in range(1, int(n) + 1):
+            if len(self.D_rand.data) < max(self.batch_size, self.warm_up):
+                self.run_random_episode()
+            else:
+                if not self.dynamics_first_trained:
+                    self.train_dynamics()
+                    self.dynamics_first_trained = True
+                elif steps % self.aggregation_interval == 0:
+                    self.train_dynamics()
+                self.run_episode()
+                if not self.use_mpc and self.agent.traj_optimizer.saving:
+                    self.agent.traj_optimizer.save()
+            if self.episode % self.checkInterval == 0:
+                self.save()
+
+    def save(self):
+        """Checkpoint in the reference's files (mbrl.py:312-337)."""
+        d = self.path + 'data/'
+        cpu_state = {k: v.detach().cpu() for k, v in self.nn_dynamics.state_dict().items()}
+        for name in ('checkpoint' + str(self.episode - 1) + '.pth', 'checkpoint.pth'):
+            torch.save({'nn_dynamics': cpu_state}, d + name)
+        self.nn_dynamics.save_moments(str(self.episode - 1), self.path)
+        self.D_rand.save(d + 'dataSet_D_rand.p')
+        self.D_RL.save(d + 'dataSet_D_RL.p')
+        self.D_RL.save(d + 'dataSet_D_RL' + str(self.episode - 1) + '.p')
+        with open(d + 'learning_curve.p', 'wb') as fh:
+            pickle.dump({'totalCost': self.totalCost, 'meanCost': self.meanCost, 'expCost': self.expCost,
+                         'episode_steps': self.episode_steps}, fh)
+        for name, v in (('training_time.p', self.training_time), ('optim_time.p', self.optim_time)):
+            with open(d + name, 'wb') as fh:
+                pickle.dump(v, fh)
+
+    def load(self, episode=''):
+        """mbrl.py:339-388."""
+        d = self.path + 'data/'
+        if os.path.isfile(d + 'checkpoint' + episode + '.pth'):
+            self.nn_dynamics.load_state_dict(torch.load(d + 'checkpoint' + episode + '.pth')['nn_dynamics'])
+        if os.path.isfile(d + 'moments_dict' + episode + '.p'):
+            self.nn_dynamics.load_moments(self.path)
+        self.nn_dynamics.invalidate()
+        if os.path.isfile(d + 'dataSet_D_rand.p'):
+            self.D_rand.load(d + 'dataSet_D_rand.p')
+        if os.path.isfile(d + 'dataSet_D_RL' + episode + '.p'):
+            self.D_RL.load(d + 'dataSet_D_RL' + episode + '.p')
+        if os.path.isfile(d + 'learning_curve.p'):
+            with open(d + 'learning_curve.p', 'rb') as fh:
+                lc = pickle.load(fh)
+            self.meanCost, self.totalCost = lc['meanCost'], lc['totalCost']
+            self.expCost, self.episode_steps = lc['expCost'], lc['episode_steps']
+            self.episode = len(self.meanCost) + 1

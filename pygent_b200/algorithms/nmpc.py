@@ -164,15 +164,23 @@ class MPCAgent(Agent):
         self.u = self._host_u(self.take_action_device(self._x_dev(x)))
         return self.u
 
-    def _plan_action(self, i, x=None):
+    def _plan_host(self):
+        """host copy of the plan (one device read per plan, not per control step)"""
         opt = self.traj_optimizer
-        u = opt.uu[..., i, :] + np.reshape(opt.current_alpha, (-1, 1) if self.batch is not None else ()) * opt.kk[..., i, :, 0]
+        key = (opt.lib.launches, id(opt))
+        if getattr(self, "_plan_cache", (None,))[0] != key:
+            self._plan_cache = (key, opt.xx, opt.uu, opt.KK, opt.kk, np.asarray(opt.current_alpha, dtype=float))
+        return self._plan_cache[1:]
+
+    def _plan_action(self, i, x=None):
+        xx, uu, KK, kk, alpha = self._plan_host()
+        u = uu[..., i, :] + np.reshape(alpha, (-1, 1) if self.batch is not None else ()) * kk[..., i, :, 0]
         if x is not None:
-            K = opt.KK[..., i, :, :]
-            u = u + np.einsum("...mn,...n->...m", K, np.asarray(x, dtype=float) - opt.xx[..., i, :])
+            K = KK[..., i, :, :]
+            u = u + np.einsum("...mn,...n->...m", K, np.asarray(x, dtype=float) - xx[..., i, :])
         u = u + self.add_noise * self.noise()
         self.u = np.clip(u, -self.uMax, self.uMax)
-        self.control(opt.dt, self.u)
+        self.control(self.traj_optimizer.dt, self.u)
         return self.u
 
     def take_action_plan(self, dt, i):

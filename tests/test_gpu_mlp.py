@@ -260,3 +260,39 @@ def test_learned_ilqr_tensor_core_path_batched():
     alg = iLQR(env, T * dt, dt, fastForward=True, fcost=c_N, printing=False, maxIters=15, final_backpass=False)
     alg.run_optim()
     assert np.array_equal(alg.cost, res["bf16"][1][sub]) and np.array_equal(alg.iters, res["bf16"][2][sub])
+
+
+def test_mbrl_outer_loop_runs_end_to_end(tmp_path):
+    """MBRL.run_learning on the cart-pole with small settings (reference loop: mbrl.py:283-310): warm-up episodes fill
+    D_rand, the model is trained (loss falls), an episode is planned on the learned model with the tensor-core planner and
+    executed on the real environment, transitions are gated by the prediction error, and the checkpoint round-trips."""
+    from pygent_b200.algorithms.mbrl import MBRL
+    from pygent_b200.environments import CartPole
+
+    def cost(x, u, mod):
+        x1, x2, x3, x4 = x
+        u1, = u
+        return 10 * x1 ** 2 + 5 * x2 ** 2 + .01 * x3 ** 2 + .01 * x4 ** 2 + 0.1 * u1 ** 2
+    env = CartPole(cost, [0, np.pi, 0, 0], 0.02)
+    alg = MBRL(env, 1.0, 0.02, path=str(tmp_path) + "/", warm_up_episodes=12, batch_size=256, training_epochs=8, fcost=c_N,
+               maxIters=6, checkInterval=1000, dyn_lr=1e-3)
+    while len(alg.D_rand.data) < max(alg.batch_size, alg.warm_up):
+        alg.run_random_episode()
+    n_rand = len(alg.D_rand.data)
+    assert n_rand >= 600 and alg.episode >= 13
+    tr = alg.D_rand.data[5]
+    assert set(tr) == {"x_", "u", "x", "o_", "o", "c", "t"} and len(tr["o"]) == 5
+    losses = alg.train_dynamics()
+    assert losses[-1] < 0.5 * losses[0]
+    rhs = alg.ode(0.0, np.array([0.1, 3.0, 0.2, -0.1]), np.array([1.0]))
+    assert rhs.shape == (4,) and rhs[0] == pytest.approx(0.2) and np.all(np.isfinite(rhs))
+    alg.run_learning(1)                          # one planned episode on the real plant
+    assert len(alg.environment.history) > 5 and np.all(np.isfinite(alg.environment.history))
+    assert np.all(np.abs(alg.agent.history) <= 10.0 + 1e-9)
+    assert len(alg.D_RL.data) <= len(alg.environment.history) - 1 and len(alg.optim_time) == 1
+    alg.save()
+    w = alg.nn_dynamics.layer2.weight.detach().cpu().clone()
+    other = MBRL(CartPole(cost, [0, np.pi, 0, 0], 0.02), 1.0, 0.02, path=str(tmp_path) + "/", fcost=c_N, maxIters=6)
+    other.load()
+    assert torch.equal(other.nn_dynamics.layer2.weight.detach().cpu(), w) and len(other.D_rand.data) == n_rand
+    assert other.episode == alg.episode

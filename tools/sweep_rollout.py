@@ -11,10 +11,11 @@ from pygent_b200.examples import make_ilqr  # noqa: E402
 
 alg = make_ilqr("cart_pole", 10, x0=np.zeros((2, 4)))
 L = alg.lib
+DTYPE = torch.float32 if os.environ.get("PG_DTYPE") == "f32" else torch.float64
 for B in [int(b) for b in sys.argv[1:]]:
-    x0 = torch.zeros((4, B), dtype=torch.float64, device="cuda")
+    x0 = torch.zeros((4, B), dtype=DTYPE, device="cuda")
     x0[1] = np.pi
-    U = (torch.rand((500, 1, B), dtype=torch.float64, device="cuda") * 2 - 1) * 10
+    U = (torch.rand((500, 1, B), dtype=DTYPE, device="cuda") * 2 - 1) * 10
     for _ in range(3):
         L.rollout(x0, U, S=4, dt=0.02)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
