@@ -1312,10 +1312,15 @@ struct CommitCopyArgs {
     const int32_t* count;
 };
 
+// blockDim = (32 trajectories, COPY_ROWS row lanes): the ~(T+1) n + T m (n + 2) rows of a trajectory are spread over the
+// row lanes so that a launch with a few hundred live trajectories still has thousands of loads in flight (a one-thread-
+// per-trajectory loop is bound by ~1,000 dependent-issue memory round trips).
+constexpr int COPY_ROWS = 16;
+
 template <typename T>
 __global__ void commit_copy_kernel(const CommitCopyArgs<T> a) {
     const int64_t B = a.B;
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t tid = (int64_t)blockIdx.x * 32 + threadIdx.x;
     int64_t b = tid;
     if (a.index) {
         if (tid >= *a.count) return;
@@ -1331,10 +1336,17 @@ __global__ void commit_copy_kernel(const CommitCopyArgs<T> a) {
     const int N = a.N, M = a.M, Ts = a.T_steps;
     const T* X = a.X_cand + (int64_t)ia * (Ts + 1) * N * B;
     const T* U = a.U_cand + (int64_t)ia * Ts * M * B;
-    for (int64_t r = 0; r < (int64_t)(Ts + 1) * N; r++) a.xbar[r * B + b] = X[r * B + b];
-    for (int64_t r = 0; r < (int64_t)Ts * M; r++) a.ubar[r * B + b] = U[r * B + b];
-    for (int64_t r = 0; r < (int64_t)Ts * M * N; r++) a.KK_acc[r * B + b] = a.KK[r * B + b];
-    for (int64_t r = 0; r < (int64_t)Ts * M; r++) a.kk_acc[r * B + b] = a.kk[r * B + b];
+    const int64_t nx = (int64_t)(Ts + 1) * N, nu = (int64_t)Ts * M, nK = (int64_t)Ts * M * N;
+    const int ry = threadIdx.y;
+#pragma unroll 4
+    for (int64_t r = ry; r < nx; r += COPY_ROWS) a.xbar[r * B + b] = X[r * B + b];
+#pragma unroll 4
+    for (int64_t r = ry; r < nu; r += COPY_ROWS) {
+        a.ubar[r * B + b] = U[r * B + b];
+        a.kk_acc[r * B + b] = a.kk[r * B + b];
+    }
+#pragma unroll 4
+    for (int64_t r = ry; r < nK; r += COPY_ROWS) a.KK_acc[r * B + b] = a.KK[r * B + b];
 }
 
 // ---- receding-horizon control (MPCAgent, pygent/algorithms/nmpc.py:187-277) -------------------------------------------

@@ -537,3 +537,20 @@ def test_balanced_forward_is_bit_identical(case, B, T):
     mask[sel.long()] = True
     assert torch.equal(c["cost"][:, mask], a["cost"][:, mask]) and torch.equal(c["xN"][..., mask], a["xN"][..., mask])
     assert bool((c["cost"][:, ~mask] == -1.0).all()) and bool((c["diverged"][:, ~mask] == 7).all())
+
+
+def test_triple_pendulum_ilqr_matches_oracle():
+    """CartPoleTriple (n = 8, the largest state the register-resident kernels are instantiated for; environments.py:660-679):
+    five iLQR iterations on a small batch against the C oracle -- initial cost, costs after each iteration's bookkeeping,
+    trajectories and gains."""
+    case, T, B = "triple", 40, 6
+    rng = np.random.default_rng(11)
+    x0 = np.array(CASES[case][4]) + rng.uniform(-0.05, 0.05, (B, 8))
+    alg = solver(case, T, x0=x0, maxIters=5)
+    p = oracle_problem(case, S=4)
+    so = oracle.ilqr_solve(p, oracle.ilqr_params(max_iters=5), x0, T)
+    assert rel(alg.cost, so["cost0"]) < 1e-9
+    alg.run_optim()
+    assert np.array_equal(alg.iters, so["iters"]) and np.array_equal(alg.status, so["status"])
+    assert rel(alg.cost, so["cost"]) < 1e-7 and rel(alg.xx, so["xx"]) < 1e-6 and rel(alg.uu, so["uu"]) < 1e-5
+    assert rel(alg.KK, so["KK"]) < 1e-5
