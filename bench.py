@@ -172,9 +172,10 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
-def nmpc_bench(dev, rank, world, barrier, plants=4096, steps=50, horizon=1.0):
+def nmpc_bench(dev, rank, world, barrier, plants=4096, steps=100, horizon=1.0):
     """examples/nmpc/cart_pole.py for a batch: every plant has its own MPCAgent state; the planner's terminal value is
-    solved once on the host (cache_terminal_value) so the control loop never leaves the device."""
+    solved once on the host (cache_terminal_value) so the control loop never leaves the device (GPU-bound at this batch:
+    launched eagerly; small batches replay the step as a CUDA graph, see NMPC.run)."""
     import torch
     import torch.distributed as dist
     from pygent_b200.algorithms.nmpc import NMPC

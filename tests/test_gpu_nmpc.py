@@ -95,3 +95,24 @@ def test_nmpc_batch_is_independent_plants(golden):
     noisy.run(steps=3, printing=False)
     d = np.abs(noisy.agent.history[:, 1] - quiet.agent.history[:, 1])
     assert np.all(d > 0) and np.all(d < 10 * 0.01 * 6)  # uMax * N(0, noise_gain)
+
+
+def test_nmpc_cuda_graph_replay_equals_eager_loop():
+    """The control step captured into a CUDA graph (possible once the planner's terminal value is cached) replays to
+    exactly the eager loop's states, controls and costs."""
+    rng = np.random.default_rng(5)
+    x0 = np.array([0.1, 0.2, 0.0, 0.0]) + rng.uniform(-0.05, 0.05, (64, 4))
+    runs = []
+    for use_graph in (False, True):
+        _, c_N, _ = CASES["cart_pole"][3]()
+        alg = NMPC(make_env("cart_pole", x0=x0), make_env("cart_pole", x0=x0), 1.0, 0.02, 1.0, fcost=c_N, constrained=False,
+                   maxIters=50, step_iterations=1, cache_terminal_value=True)
+        assert alg._graph_ok()
+        cost = alg.run(steps=15, printing=False, use_graph=use_graph)
+        runs.append((alg.environment.history.copy(), alg.agent.history.copy(), cost.copy(), alg.agent.traj_optimizer.cost.copy()))
+    for a, b in zip(*runs):
+        assert np.array_equal(a, b)
+    plain = controller(x0[:2], 1.0, 0.02)
+    assert not plain._graph_ok()  # final backward pass re-solved on the host every step
+    with pytest.raises(ValueError):
+        plain.run(steps=6, printing=False, use_graph=True)
