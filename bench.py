@@ -172,7 +172,7 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
-def nmpc_bench(dev, rank, world, barrier, plants=4096, steps=100, horizon=1.0):
+def nmpc_bench(dev, rank, world, barrier, plants=4096, steps=50, horizon=1.0):
     """examples/nmpc/cart_pole.py for a batch: every plant has its own MPCAgent state; the planner's terminal value is
     solved once on the host (cache_terminal_value) so the control loop never leaves the device (GPU-bound at this batch:
     launched eagerly; small batches replay the step as a CUDA graph, see NMPC.run)."""
@@ -182,7 +182,7 @@ def nmpc_bench(dev, rank, world, barrier, plants=4096, steps=100, horizon=1.0):
     from pygent_b200.examples import CASES, make_env
     _, c_N, _ = CASES["cart_pole"][3]()
     rng = np.random.default_rng(3000 + rank)
-    x0 = np.array([0, 0, 0, 0]) + rng.uniform(-1, 1, (plants, 4)) * np.array([.3, .4, .3, .3])
+    x0 = np.array([0, 0, 0, 0]) + rng.uniform(-1, 1, (plants, 4)) * np.array([.2, .25, .2, .2])
     alg = NMPC(make_env("cart_pole", x0=x0, device=dev), make_env("cart_pole", x0=x0, device=dev), steps * DT, DT, horizon,
                fcost=c_N, constrained=False, maxIters=100, step_iterations=1, cache_terminal_value=True)
     opt = alg.agent.traj_optimizer

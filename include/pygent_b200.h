@@ -112,6 +112,8 @@ int pg_rollout_balanced(int dtype, int integrator, int64_t B, int32_t T, int32_t
  *   diverged_out [n_alpha,B] or NULL: any(x > 1e8) over the rollout (ilqr.py:435);
  *   terminated_out [n_alpha,B] or NULL; xN_out [n_alpha,n,B] or NULL: terminal state of every candidate (the state
  *   the reference's planner environment is left in after a forward pass; used by pg_mpc_shift);
+ *   xS [n_alpha, pg_ilqr_num_snapshots(T), n, B] or NULL: state of every candidate at the boundaries of the 20-step time
+ *   chunks (what pg_ilqr_commit_chunked restarts from);
  *   active [B] or NULL: trajectories with active==0 are skipped;
  *   index [<=B] (i32) + count [1] (i32, device) or both NULL: compacted work list -- only trajectories
  *   index[0..*count) are processed (written by pg_ilqr_select; late iLQR iterations touch few trajectories). */
@@ -120,7 +122,7 @@ int pg_ilqr_forward(int dtype, int integrator, int64_t B, int32_t T, int32_t S, 
                     const void* x0, const void* xbar, const void* ubar,
                     const void* KK, const void* kk, int32_t Tk, const double* ulim, double terminal_cost,
                     void* X_out, void* U_out, void* cost_out, uint8_t* diverged_out,
-                    uint8_t* terminated_out, void* xN_out, const uint8_t* active,
+                    uint8_t* terminated_out, void* xN_out, void* xS, const uint8_t* active,
                     const int32_t* index, const int32_t* count, void* stream);
 
 /* pg_ilqr_forward for large line searches, load-balanced like pg_rollout_balanced: persistent worker warps pull
@@ -133,7 +135,7 @@ int pg_ilqr_forward_balanced(int dtype, int integrator, int64_t B, int32_t T, in
                              int32_t n_alpha, const double* alphas, const void* alpha_dev,
                              const void* x0, const void* xbar, const void* ubar,
                              const void* KK, const void* kk, int32_t Tk, const double* ulim, double terminal_cost,
-                             void* cost_out, uint8_t* diverged_out, uint8_t* terminated_out, void* xN_out,
+                             void* cost_out, uint8_t* diverged_out, uint8_t* terminated_out, void* xN_out, void* xS,
                              const int32_t* index, const int32_t* count,
                              void* workspace, int64_t workspace_bytes, void* stream);
 
@@ -228,6 +230,17 @@ int pg_mpc_action(int dtype, int64_t B, const void* KK, const void* kk, const vo
 int pg_mpc_shift(int dtype, int integrator, int64_t B, int32_t T, int32_t S, double dt, double t_env,
                  void* xbar, void* ubar, void* KK, void* kk, void* cost, void* xe, const void* xN_cand,
                  int32_t n_alpha, const int32_t* last_tried, const void* x_new_ext, double terminal_cost, void* stream);
+
+/* pg_ilqr_commit with the winner's time chunks integrated in parallel: every (accepted trajectory, chunk) pair restarts
+ * from the snapshot xS of candidate alpha_best[b] (looked up in the host array alphas) and overwrites its piece of
+ * xbar / ubar in place (a chunk writes its own start state and leaves its end state to the next chunk's thread, so
+ * nothing is read after it was overwritten), copying the candidate gains of its intervals as it goes.  Same results as
+ * pg_ilqr_commit; n_chunks times shorter dependent chains. */
+int32_t pg_ilqr_num_snapshots(int32_t T);
+int pg_ilqr_commit_chunked(int dtype, int integrator, int64_t B, int32_t T, int32_t S, double dt, int32_t n_alpha,
+                           const double* alphas, const void* alpha_best, const uint8_t* accept, const void* x0,
+                           void* xbar, void* ubar, const void* KK, const void* kk, const double* ulim, const void* xS,
+                           void* KK_acc, void* kk_acc, const int32_t* index, const int32_t* count, void* stream);
 
 /* o [n_obs,B] = observation(x [n,B]) : angle -> [cos, sin] (helpers.py:20-29). */
 int pg_observe(int dtype, int64_t B, const void* x, void* o, void* stream);

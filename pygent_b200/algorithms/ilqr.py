@@ -156,6 +156,10 @@ class iLQR(Algorithm):
         A = len(self.alphas)
         self._bw = {"KK": self._KKc, "kk": self._kkc, "dV": z(2, B), "gnorm": z(B), "success": u8(B)}
         self._fw = {"cost": z(A, B), "diverged": u8(A, B), "terminated": u8(A, B), "xN": z(A, n, B)}
+        # chunk-parallel commit: the candidates' states at the 20-step chunk boundaries
+        self._n_snap = 0 if self.learned else self.lib.num_snapshots(T)
+        if self._n_snap > 0:
+            self._fw["xS"] = z(A, self._n_snap, n, B)
         self._last_tried = i32(B) - 1   # last alpha evaluated per trajectory (MPC plan shift)
         # compacted work lists (ping-pong): trajectories still running, written by the select kernel
         self._idx = [torch.arange(B, dtype=torch.int32, device=dev), i32(B)]
@@ -417,6 +421,10 @@ class iLQR(Algorithm):
         if self.learned:
             L.ilqr_commit_copy(list(self.alphas), st["alpha_best"], st["accept"], self._cand["X"], self._cand["U"], self._xbar,
                                self._ubar, self._KKc, self._kkc, self._KK, self._kk, work=work)
+        elif self._n_snap > 0:
+            L.ilqr_commit_chunked(list(self.alphas), self._x0, self._xbar, self._ubar, self._KKc, self._kkc, self._KK, self._kk,
+                                  st["alpha_best"], st["accept"], self._fw["xS"], S=self.substeps, dt=self.dt,
+                                  integrator=self.integrator, ulim=self._ulim(), work=work)
         else:
             L.ilqr_commit(self._x0, self._xbar, self._ubar, self._KKc, self._kkc, self._KK, self._kk, st["alpha_best"],
                           st["accept"], S=self.substeps, dt=self.dt, integrator=self.integrator, ulim=self._ulim(), work=work)

@@ -403,6 +403,9 @@ struct ForwardArgs {
     uint8_t* diverged_out;
     uint8_t* terminated_out;
     T* xN_out;  // [n_alpha, n, B] or NULL: terminal state of every candidate (what the planner's environment is left in)
+    T* xS;      // [n_alpha, n_snap, n, B] or NULL: state of every candidate at the chunk boundaries snap[1..n_snap]
+    int n_snap;
+    int snap[MAX_CHUNKS + 1];  // snap[c] = first control interval of chunk c (queue_schedule() of pg_abi.cu)
     const uint8_t* active;
     const int32_t* index;  // optional work list: thread i handles trajectory index[i], i < *count
     const int32_t* count;
@@ -481,6 +484,7 @@ __global__ void __launch_bounds__(32 * MAX_ALPHAS) ilqr_forward_kernel(const For
 #pragma unroll
         for (int i = 0; i < N; i++) Xo[i * B + b] = x[i];
     }
+    int sc = 0;  // next snapshot
     for (int k = 0; k < a.T_steps; k++) {
         cur = nxt;
         if (k + 1 < a.T_steps) {
@@ -511,6 +515,13 @@ __global__ void __launch_bounds__(32 * MAX_ALPHAS) ilqr_forward_kernel(const For
         if (Xo) {
 #pragma unroll
             for (int i = 0; i < N; i++) Xo[((int64_t)(k + 1) * N + i) * B + b] = x[i];
+        }
+        if constexpr (!COMMIT) {
+            if (a.xS && sc < a.n_snap && k + 1 == a.snap[sc + 1]) {  // end of chunk sc
+#pragma unroll
+                for (int i = 0; i < N; i++) a.xS[(((int64_t)ia * a.n_snap + sc) * N + i) * B + b] = x[i];
+                sc++;
+            }
         }
         if (Uo) {
 #pragma unroll
@@ -650,6 +661,10 @@ __global__ void __launch_bounds__(128, 3) ilqr_forward_queue_kernel(const Forwar
             a.cost_out[o] = cost;
             a.diverged_out[o] = div ? 1 : 0;
             if (last && a.terminated_out) a.terminated_out[o] = term ? 1 : 0;
+            if (a.xS && !last && c < a.n_snap) {
+#pragma unroll
+                for (int i = 0; i < N; i++) a.xS[(((int64_t)ia * a.n_snap + c) * N + i) * B + b] = x[i];
+            }
         }
         if (!last) {
             __threadfence();
@@ -661,6 +676,91 @@ __global__ void __launch_bounds__(128, 3) ilqr_forward_queue_kernel(const Forwar
                 const int p = atomicAdd(&q.counters[1], 1);
                 atomicExch(&q.queue[p], g + 1);
             }
+        }
+    }
+}
+
+// ---- K2'': chunk-parallel commit -------------------------------------------------------------------------------------
+// Re-integrating the accepted candidate as ONE rollout (ilqr_forward_kernel<..., COMMIT>) is a dependent chain of T
+// control intervals run by B / 32 warps: 95 us for the cart-pole, 240-360 us for the n = 6 systems.  With the candidates'
+// states at the chunk boundaries (xS, written by the line search) every chunk of the winner is integrated by its own
+// thread: n_chunks times more warps, chains n_chunks times shorter.  In place: thread (b, c) reads the nominal points
+// k0 .. k1-1 of its chunk and writes x_{k0} .. x_{k1-1} (its own start state included, AFTER loading the nominal there)
+// but not x_{k1}, which thread (b, c+1) owns -- so no thread writes what another one reads; the last chunk also writes
+// x_T.  Bit-identical to the single-rollout commit: the snapshots are the states that rollout passes through.
+template <typename T>
+struct CommitChunkArgs {
+    ForwardArgs<T> f;   // B, T_steps, S, Tk, n_alpha, dt, alphas, x0, KK, kk, clip, ulim, xS, n_snap, snap, index, count
+    const T* alpha_best;
+    const uint8_t* accept;
+    T* xbar_io;         // [T+1, n, B]
+    T* ubar_io;         // [T, m, B]
+    T* KK_acc;
+    T* kk_acc;
+};
+
+template <typename P, typename T, int INTEG>
+__global__ void __launch_bounds__(64) ilqr_commit_chunks_kernel(const CommitChunkArgs<T> q) {
+    const typename P::template Ctx<T> m;
+    constexpr int N = P::N, M = P::M;
+    const ForwardArgs<T>& a = q.f;
+    const int64_t B = a.B;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y;
+    int64_t b = tid;
+    if (a.index) {
+        if (tid >= *a.count) return;
+        b = a.index[tid];
+    } else if (b >= B) {
+        return;
+    }
+    if (!q.accept[b]) return;
+    const T alpha = q.alpha_best[b];
+    int ia = 0;
+    for (int i = 0; i < a.n_alpha; i++)
+        if (a.alphas[i] == alpha) ia = i;
+    const int k0 = a.snap[c], k1 = a.snap[c + 1];
+    T x[N], u[M];
+    if (c == 0) {
+#pragma unroll
+        for (int i = 0; i < N; i++) x[i] = a.x0[i * B + b];
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; i++) x[i] = a.xS[(((int64_t)ia * a.n_snap + (c - 1)) * N + i) * B + b];
+    }
+    const T h = a.dt / T(a.S);
+    Nominal<P, T> cur, nxt;
+    if (k0 < k1) nxt.load(a.KK, a.kk, q.xbar_io, q.ubar_io, (k0 < a.Tk) ? k0 : (a.Tk - 1), B, b);
+#pragma unroll
+    for (int i = 0; i < N; i++) q.xbar_io[((int64_t)k0 * N + i) * B + b] = x[i];  // own start state, nominal k0 is in registers
+    for (int k = k0; k < k1; k++) {
+        cur = nxt;
+        if (k + 1 < k1) {
+            const int j = (k + 1 < a.Tk) ? (k + 1) : (a.Tk - 1);
+            nxt.load(a.KK, a.kk, q.xbar_io, q.ubar_io, j, B, b);
+        }
+#pragma unroll
+        for (int r = 0; r < M; r++) {
+            T acc = T(0);
+#pragma unroll
+            for (int i = 0; i < N; i++) acc += cur.K[r * N + i] * (x[i] - cur.xb[i]);
+            acc = acc + alpha * cur.k[r];
+            acc = acc + cur.ub[r];
+            if (a.clip) acc = pg::clamp(acc, -a.ulim[r], a.ulim[r]);
+            u[r] = acc;
+        }
+        env_step<P, T, INTEG>(m, x, u, a.dt, h, a.S);
+        if (k + 1 < k1 || k1 >= a.T_steps) {  // x_{k1} belongs to the next chunk's thread, except at the very end
+#pragma unroll
+            for (int i = 0; i < N; i++) q.xbar_io[((int64_t)(k + 1) * N + i) * B + b] = x[i];
+        }
+#pragma unroll
+        for (int r = 0; r < M; r++) q.ubar_io[((int64_t)k * M + r) * B + b] = u[r];
+        if (k < a.Tk) {  // self.KK = KK; self.kk = kk (ilqr.py:463-464)
+#pragma unroll
+            for (int r = 0; r < M * N; r++) q.KK_acc[((int64_t)k * M * N + r) * B + b] = cur.K[r];
+#pragma unroll
+            for (int r = 0; r < M; r++) q.kk_acc[((int64_t)k * M + r) * B + b] = cur.k[r];
         }
     }
 }

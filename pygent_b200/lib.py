@@ -40,9 +40,11 @@ SIGNATURES = {
     "pg_rollout": [_i32, _i32, _i64, _i32, _i32, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _i32, _vp],
     "pg_rollout_balanced": [_i32, _i32, _i64, _i32, _i32, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _i32, _vp, _i64, _vp],
     "pg_ilqr_forward": [_i32, _i32, _i64, _i32, _i32, _f64, _i32, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _dp, _f64,
-                        _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+                        _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "pg_ilqr_forward_balanced": [_i32, _i32, _i64, _i32, _i32, _f64, _i32, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _dp, _f64,
-                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
+                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
+    "pg_ilqr_commit_chunked": [_i32, _i32, _i64, _i32, _i32, _f64, _i32, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _dp, _vp, _vp,
+                               _vp, _vp, _vp, _vp],
     "pg_ilqr_backward": [_i32, _i64, _i32, _f64, _i32, _i32, _vp, _vp, _vp, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                          _vp],
     "pg_ilqr_select": [_i32, _i64, ctypes.POINTER(SelectParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
@@ -108,6 +110,8 @@ class ProblemLibrary:
         self.dll.pg_rollout_workspace_bytes.restype = _i64
         self.dll.pg_ilqr_forward_workspace_bytes.argtypes = [_i64, _i32, _i32]
         self.dll.pg_ilqr_forward_workspace_bytes.restype = _i64
+        self.dll.pg_ilqr_num_snapshots.argtypes = [_i32]
+        self.dll.pg_ilqr_num_snapshots.restype = _i32
         self._workspace = {}
         info = ProblemInfo()
         self._check(self.dll.pg_get_problem_info(ctypes.byref(info)), "pg_get_problem_info")
@@ -216,6 +220,8 @@ class ProblemLibrary:
         X = out.get("X")
         Uo = out.get("U")
         xN = out.get("xN")  # [n_alpha, n, B]: terminal states of the candidates (MPC plan shift)
+        xS = out.get("xS")  # [n_alpha, num_snapshots(T), n, B]: candidates at the chunk boundaries (chunk-parallel commit)
+        xS_ptr = _ptr(xS, dtype, (n_alpha, self.num_snapshots(T), n, B), "xS") if xS is not None else None
         if want_traj and X is None:
             X = torch.empty((n_alpha, T + 1, n, B), dtype=dtype, device=dev)
             Uo = torch.empty((n_alpha, T, m, B), dtype=dtype, device=dev)
@@ -234,7 +240,7 @@ class ProblemLibrary:
                 _ptr(xbar, dtype, (T + 1, n, B), "xbar"), _ptr(ubar, dtype, (T, m, B), "ubar"),
                 _ptr(KK, dtype, (Tk, m, n, B), "KK"), _ptr(kk, dtype, (Tk, m, B), "kk"), Tk, _host_doubles(ulim),
                 terminal_cost, _ptr(cost, dtype, (n_alpha, B), "cost_out"), _ptr(div, torch.uint8, (n_alpha, B), "diverged_out"),
-                _ptr(term, torch.uint8, (n_alpha, B), "terminated_out"), _ptr(xN, dtype, (n_alpha, n, B), "xN_out"),
+                _ptr(term, torch.uint8, (n_alpha, B), "terminated_out"), _ptr(xN, dtype, (n_alpha, n, B), "xN_out"), xS_ptr,
                 *self._work(work, B), _ptr(ws), nbytes, self._stream())
             self._check(rc, "pg_ilqr_forward_balanced")
             self.launches += 1
@@ -246,7 +252,7 @@ class ProblemLibrary:
             _ptr(KK, dtype, (Tk, m, n, B), "KK"), _ptr(kk, dtype, (Tk, m, B), "kk"), Tk, _host_doubles(ulim),
             terminal_cost, _ptr(X, dtype, (n_alpha, T + 1, n, B), "X_out"), _ptr(Uo, dtype, (n_alpha, T, m, B), "U_out"),
             _ptr(cost, dtype, (n_alpha, B), "cost_out"), _ptr(div, torch.uint8, (n_alpha, B), "diverged_out"),
-            _ptr(term, torch.uint8, (n_alpha, B), "terminated_out"), _ptr(xN, dtype, (n_alpha, n, B), "xN_out"),
+            _ptr(term, torch.uint8, (n_alpha, B), "terminated_out"), _ptr(xN, dtype, (n_alpha, n, B), "xN_out"), xS_ptr,
             _ptr(active, torch.uint8, (B,), "active"), *self._work(work, B), self._stream())
         self._check(rc, "pg_ilqr_forward")
         self.launches += 1
@@ -406,6 +412,25 @@ class ProblemLibrary:
                                    _ptr(xN_cand, dtype, None, "xN_cand"), n_alpha, _ptr(last_tried, torch.int32, (B,), "last_tried"),
                                    _ptr(x_new_ext, dtype, (n, B), "x_new_ext"), terminal_cost, self._stream())
         self._check(rc, "pg_mpc_shift")
+        self.launches += 1
+
+    def num_snapshots(self, T):
+        return int(self.dll.pg_ilqr_num_snapshots(int(T)))
+
+    def ilqr_commit_chunked(self, alphas, x0, xbar, ubar, KK, kk, KK_acc, kk_acc, alpha_best, accept, xS,
+                            S=4, dt=0.02, integrator=INTEG_RK4, ulim=None, work=None):
+        """pg_ilqr_commit with the winner's time chunks integrated in parallel from the snapshots xS."""
+        n, m = self.n, self.m
+        dtype = x0.dtype
+        B, T, A = x0.shape[1], ubar.shape[0], len(alphas)
+        rc = self.dll.pg_ilqr_commit_chunked(
+            _dtype_code(dtype), integrator, B, T, S, dt, A, _host_doubles(alphas), _ptr(alpha_best, dtype, (B,), "alpha_best"),
+            _ptr(accept, torch.uint8, (B,), "accept"), _ptr(x0, dtype, (n, B), "x0"), _ptr(xbar, dtype, (T + 1, n, B), "xbar"),
+            _ptr(ubar, dtype, (T, m, B), "ubar"), _ptr(KK, dtype, (T, m, n, B), "KK"), _ptr(kk, dtype, (T, m, B), "kk"),
+            _host_doubles(ulim), _ptr(xS, dtype, (A, self.num_snapshots(T), n, B), "xS"),
+            _ptr(KK_acc, dtype, (T, m, n, B), "KK_acc"), _ptr(kk_acc, dtype, (T, m, B), "kk_acc"), *self._work(work, B),
+            self._stream())
+        self._check(rc, "pg_ilqr_commit_chunked")
         self.launches += 1
 
     def observe(self, x):
