@@ -554,3 +554,18 @@ def test_triple_pendulum_ilqr_matches_oracle():
     assert np.array_equal(alg.iters, so["iters"]) and np.array_equal(alg.status, so["status"])
     assert rel(alg.cost, so["cost"]) < 1e-7 and rel(alg.xx, so["xx"]) < 1e-6 and rel(alg.uu, so["uu"]) < 1e-5
     assert rel(alg.KK, so["KK"]) < 1e-5
+
+
+@pytest.mark.parametrize("T", [15, 20, 21, 45, 100])
+def test_ilqr_horizons_around_the_chunk_length_match_oracle(T):
+    """The chunk-parallel commit restarts from snapshots every 20 control intervals: horizons below, at, just above and
+    not a multiple of the chunk length (T <= 20 uses the single-rollout commit) against the C oracle, 8 iterations."""
+    case, B = "cart_pole", 40
+    rng = np.random.default_rng(T)
+    x0 = np.array(CASES[case][4]) + rng.uniform(-0.3, 0.3, (B, 4))
+    alg = solver(case, T, x0=x0, maxIters=8)
+    so = oracle.ilqr_solve(oracle_problem(case, S=4), oracle.ilqr_params(max_iters=8), x0, T)
+    alg.run_optim()
+    assert np.array_equal(alg.iters, so["iters"]) and np.array_equal(alg.status, so["status"])
+    assert rel(alg.cost, so["cost"]) < 1e-8 and rel(alg.xx, so["xx"]) < 1e-7 and rel(alg.uu, so["uu"]) < 1e-6
+    assert rel(alg.KK, so["KK"]) < 1e-6 and rel(alg.kk[..., 0], so["kk"]) < 1e-6
