@@ -402,6 +402,18 @@ __device__ __forceinline__ void bulk_g2s_multicast(void* dst, const void* src, u
         "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
         : "memory");
 }
+// plain bulk copy global -> own smem, completion on an own mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
 // K-major, 128-byte swizzle: 8-row groups 1024 B apart (SBO), LBO field 1 (unused for swizzled K-major), version 1
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
@@ -421,6 +433,23 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(UMMA_IDESC), "r"(accumulate)
         : "memory");
+}
+// The CTA pair as ONE MMA unit (cta_group::2): D [256 x 256] (fp32; rows 0-127 in the leader's TMEM, 128-255 in the
+// peer's) += A [256 x 16] (each CTA's own 128 rows, same smem offset) x B [256 x 16] (output columns 0-127 from the
+// leader's smem, 128-255 from the peer's).  Issued by the leader only.
+constexpr uint32_t UMMA_IDESC_2SM = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(UMMA_IDESC_2SM), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -466,12 +495,18 @@ constexpr int PRODUCER_THREAD = 384, ISSUER_THREAD = 416;  // in the warps of ac
 // ... -- and each accumulator quarter has its own completion barrier, so the threads that own quarter q run their
 // epilogue while the tensor core works on q+1..3.  One thread produces the ring, one issues the 128 MMAs (M128 N128
 // K16); both sit in the warps of quarter 3.  `img` selects the weight images (W2b: forward, W2bT: transposed).
+#define PG_TMEM_ALLOC_1SM "tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;"
+#define PG_TMEM_ALLOC_2SM "tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;"
+constexpr bool TWO_SM = true;  // pair the two CTAs of a cluster into one M = 256 MMA unit (false: one M = 128 unit per CTA)
+
 struct GemmPipe {
     uint8_t* As;
     uint8_t* Bs;
     uint64_t* full;
     uint64_t* empty;
-    uint64_t* accum;  // [4]
+    uint64_t* accum;   // [4]
+    uint64_t* pfull;   // leader: the peer's copy of stage s has landed (relayed by the peer)
+    uint64_t* a_ready; // leader: the peer's A image is written
     uint32_t tmem_base;
     uint32_t chunk_no;  // producer and issuer count chunks the same way
     uint32_t passes;
@@ -481,40 +516,92 @@ template <int STAGES>
 __device__ __forceinline__ void gemm_issue(GemmPipe& p, const uint16_t (*img)[CHUNK_BYTES / 2], int t) {
     // the control lanes' 31 warp siblings park at __syncwarp() instead of spinning on the completion barrier: as
     // divergent paths of the same warp they would take every other issue slot from the lane that feeds the tensor core
+    constexpr int PER_PASS = TWO_SM ? N_CHUNKS / 2 : N_CHUNKS;  // chunks this CTA loads per GEMM
     const int cw = t >> 5;
     if (cw != (PRODUCER_THREAD >> 5) && cw != (ISSUER_THREAD >> 5)) {
-        p.chunk_no += N_CHUNKS;
+        p.chunk_no += PER_PASS;
         return;
     }
-    if (t == PRODUCER_THREAD) {  // weight chunks, L2 -> smem rings of the cluster
-        const uint32_t rank = cluster_ctarank();
-        uint32_t c = p.chunk_no;
-        for (int i = 0; i < N_CHUNKS; i++, c++) {
-            const uint32_t s = c % STAGES, use = c / STAGES;
-            mbar_wait(&p.empty[s], (use & 1) ^ 1);        // both CTAs are done with the stage's previous chunk
-            mbar_expect_tx(&p.full[s], CHUNK_BYTES);      // whoever fetches it, this CTA's ring receives the bytes
-            if ((uint32_t)(i % CL) == rank) bulk_g2s_multicast(p.Bs + s * CHUNK_BYTES, &img[i][0], CHUNK_BYTES, &p.full[s], CL_MASK);
-        }
-    } else if (t == ISSUER_THREAD) {  // one thread drives the tensor core for the whole CTA
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        uint32_t c = p.chunk_no;
-        for (int i = 0; i < N_CHUNKS; i++, c++) {
-            const uint32_t s = c % STAGES, use = c / STAGES;
-            mbar_wait(&p.full[s], use & 1);
+    const uint32_t rank = cluster_ctarank();
+    if constexpr (TWO_SM) {
+        // Chunk i of a pass: output-column half q2 = i / 8 (256 columns), k-block kb = i % 8.  CTA r holds the 128
+        // columns [256 q2 + 128 r, +128) of it: weight image quarter 2 q2 + r.  Nothing is multicast: each CTA streams only
+        // the half of W2 its own tensor core multiplies.
+        if (t == PRODUCER_THREAD) {
+            uint32_t c = p.chunk_no;
+            for (int i = 0; i < PER_PASS; i++, c++) {
+                const uint32_t s = c % STAGES, use = c / STAGES;
+                mbar_wait(&p.empty[s], (use & 1) ^ 1);
+                mbar_expect_tx(&p.full[s], CHUNK_BYTES);
+                bulk_g2s(p.Bs + s * CHUNK_BYTES, &img[(2 * (i >> 3) + rank) * 8 + (i & 7)][0], CHUNK_BYTES, &p.full[s]);
+            }
+        } else if (t == ISSUER_THREAD && rank != 0) {  // peer: tell the leader when a stage of OUR ring is full
+            uint32_t c = p.chunk_no;
+            for (int i = 0; i < PER_PASS; i++, c++) {
+                const uint32_t s = c % STAGES, use = c / STAGES;
+                mbar_wait(&p.full[s], use & 1);
+                mbar_arrive_remote(&p.pfull[s], 0);
+            }
+        } else if (t == ISSUER_THREAD) {  // leader: one thread drives both tensor cores
+            mbar_wait(p.a_ready, p.passes & 1);  // the peer's A image (ours is ordered by the CTA barrier before this call)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int quarter = i >> 3, kb = i & 7;
-            const uint32_t a_addr = smem_u32(p.As + kb * (T_ROWS * 128));
-            const uint32_t b_addr = smem_u32(p.Bs + s * CHUNK_BYTES);
+            uint32_t c = p.chunk_no;
+            for (int i = 0; i < PER_PASS; i++, c++) {
+                const uint32_t s = c % STAGES, use = c / STAGES;
+                mbar_wait(&p.full[s], use & 1);
+                mbar_wait(&p.pfull[s], use & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const int q2 = i >> 3, kb = i & 7;
+                const uint32_t a_addr = smem_u32(p.As + kb * (T_ROWS * 128));
+                const uint32_t b_addr = smem_u32(p.Bs + s * CHUNK_BYTES);
 #pragma unroll
-            for (int ks = 0; ks < 4; ks++)  // K = 16 per instruction = 32 bytes along the swizzled row
-                umma_bf16(p.tmem_base + quarter * CHUNK_N, umma_desc_sw128(a_addr + ks * 32), umma_desc_sw128(b_addr + ks * 32),
-                          (kb > 0 || ks > 0) ? 1u : 0u);
-            umma_commit_multicast(&p.empty[s], CL_MASK);  // one of the CL arrivals that free the stage in every CTA
-            if (kb == 7) umma_commit(&p.accum[quarter]);  // this quarter's accumulators are final
+                for (int ks = 0; ks < 4; ks++)
+                    umma_bf16_2sm(p.tmem_base + q2 * 256, umma_desc_sw128(a_addr + ks * 32), umma_desc_sw128(b_addr + ks * 32),
+                                  (kb > 0 || ks > 0) ? 1u : 0u);
+                umma_commit_2sm(&p.empty[s], CL_MASK);  // frees the stage in both CTAs
+                if (kb == 7) {                            // 256 accumulator columns final in both CTAs
+                    umma_commit_2sm(&p.accum[2 * q2], CL_MASK);
+                    umma_commit_2sm(&p.accum[2 * q2 + 1], CL_MASK);
+                }
+            }
+        }
+    } else {
+        if (t == PRODUCER_THREAD) {  // weight chunks, L2 -> smem rings of the cluster
+            uint32_t c = p.chunk_no;
+            for (int i = 0; i < N_CHUNKS; i++, c++) {
+                const uint32_t s = c % STAGES, use = c / STAGES;
+                mbar_wait(&p.empty[s], (use & 1) ^ 1);        // both CTAs are done with the stage's previous chunk
+                mbar_expect_tx(&p.full[s], CHUNK_BYTES);      // whoever fetches it, this CTA's ring receives the bytes
+                if ((uint32_t)(i % CL) == rank) bulk_g2s_multicast(p.Bs + s * CHUNK_BYTES, &img[i][0], CHUNK_BYTES, &p.full[s], CL_MASK);
+            }
+        } else if (t == ISSUER_THREAD) {  // one thread drives the tensor core for the whole CTA
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t c = p.chunk_no;
+            for (int i = 0; i < N_CHUNKS; i++, c++) {
+                const uint32_t s = c % STAGES, use = c / STAGES;
+                mbar_wait(&p.full[s], use & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const int quarter = i >> 3, kb = i & 7;
+                const uint32_t a_addr = smem_u32(p.As + kb * (T_ROWS * 128));
+                const uint32_t b_addr = smem_u32(p.Bs + s * CHUNK_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < 4; ks++)  // K = 16 per instruction = 32 bytes along the swizzled row
+                    umma_bf16(p.tmem_base + quarter * CHUNK_N, umma_desc_sw128(a_addr + ks * 32), umma_desc_sw128(b_addr + ks * 32),
+                              (kb > 0 || ks > 0) ? 1u : 0u);
+                umma_commit_multicast(&p.empty[s], CL_MASK);  // one of the CL arrivals that free the stage in every CTA
+                if (kb == 7) umma_commit(&p.accum[quarter]);  // this quarter's accumulators are final
+            }
         }
     }
     __syncwarp();
-    p.chunk_no += N_CHUNKS;
+    p.chunk_no += PER_PASS;
+}
+
+// The A image of this CTA is complete (call after fence.proxy.async + the CTA barrier): the peer tells the leader.
+__device__ __forceinline__ void gemm_a_ready(GemmPipe& p, int t) {
+    if constexpr (TWO_SM) {
+        if (t == 0 && cluster_ctarank() != 0) mbar_arrive_remote(p.a_ready, 0);
+    }
 }
 
 // wait until accumulator columns [128 q, 128 q + 128) of the current pass are readable
@@ -628,7 +715,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_b
     uint64_t* full = reinterpret_cast<uint64_t*>(w1s + H * W1S_FLOATS);
     uint64_t* empty = full + T_STAGES;
     uint64_t* accum = empty + T_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 4);
+    uint64_t* pfull = accum + 4;
+    uint64_t* a_ready = pfull + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
     const MlpPacked* w = a.w;
     const int t = threadIdx.x, warp = t >> 5, row = t & (T_ROWS - 1), part = t >> 7;
     if ((int64_t)(blockIdx.x / CL) * CL * T_ROWS >= total_rows(a)) return;  // compacted work list: surplus clusters
@@ -641,14 +730,21 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_b
     if (t == 0) {
         for (int s = 0; s < T_STAGES; s++) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], CL);
+            mbar_init(&empty[s], TWO_SM ? 1 : CL);
+            mbar_init(&pfull[s], 1);
         }
         for (int q = 0; q < 4; q++) mbar_init(&accum[q], 1);
+        mbar_init(a_ready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {  // the whole accumulator file of the SM: 128 lanes x 512 fp32 columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (TWO_SM) {
+            asm volatile(PG_TMEM_ALLOC_2SM ::"r"(smem_u32(tmem_slot)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile(PG_TMEM_ALLOC_1SM ::"r"(smem_u32(tmem_slot)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     stage_constants(w, eps, w1s, t);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -659,7 +755,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_b
 
     double x[8], u[2], xe[8], ue[2], fplus[8];
     if (owner) load_row(a, rw, x, u);
-    GemmPipe pipe = {As, Bs, full, empty, accum, tmem_base, 0u, 0u};
+    GemmPipe pipe = {As, Bs, full, empty, accum, pfull, a_ready, tmem_base, 0u, 0u};
     const int steps = steps_of(a);
     for (int k = 0; k < steps; k++) {
         if (owner) {
@@ -673,6 +769,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_b
         layer1_dispatch<false>(nin, w, w1s, ins, As, nullptr, t);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA unit
         __syncthreads();
+        gemm_a_ready(pipe, t);
         gemm_issue<T_STAGES>(pipe, w->W2b, t);
         // epilogue: TMEM lane = row; this thread's quarter of the 512 columns, as soon as that quarter is final:
         // +b2, ReLU, layer 3
@@ -712,7 +809,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_b
     }
     __syncthreads();
     cluster_sync();  // no CTA leaves while its peer may still signal its barriers
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    if (warp == 0) {
+        if constexpr (TWO_SM) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
 }
 
 // ---- analytic Jacobian on the tensor cores ---------------------------------------------------------------------
@@ -737,7 +837,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_j
     uint64_t* full = reinterpret_cast<uint64_t*>(m2 + T_ROWS * J_MASK_WORDS);
     uint64_t* empty = full + J_STAGES;
     uint64_t* accum = empty + J_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 4);
+    uint64_t* pfull = accum + 4;
+    uint64_t* a_ready = pfull + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
     const MlpPacked* w = a.w;
     const int t = threadIdx.x, warp = t >> 5, row = t & (T_ROWS - 1), part = t >> 7;
     if ((int64_t)(blockIdx.x / CL) * CL * T_ROWS >= total_rows(a)) return;  // surplus clusters
@@ -750,14 +852,21 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_j
     if (t == 0) {
         for (int s = 0; s < J_STAGES; s++) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], CL);
+            mbar_init(&empty[s], TWO_SM ? 1 : CL);
+            mbar_init(&pfull[s], 1);
         }
         for (int q = 0; q < 4; q++) mbar_init(&accum[q], 1);
+        mbar_init(a_ready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (TWO_SM) {
+            asm volatile(PG_TMEM_ALLOC_2SM ::"r"(smem_u32(tmem_slot)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile(PG_TMEM_ALLOC_1SM ::"r"(smem_u32(tmem_slot)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     stage_constants(w, eps, w1s, t);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -765,7 +874,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_j
     cluster_sync();  // the peer's barriers are initialised before anything is multicast to them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    GemmPipe pipe = {As, Bs, full, empty, accum, tmem_base, 0u, 0u};
+    GemmPipe pipe = {As, Bs, full, empty, accum, pfull, a_ready, tmem_base, 0u, 0u};
 
     double x[8], u[2];
     if (owner) {
@@ -781,6 +890,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_j
     layer1_dispatch<true>(nin, w, w1s, ins, As, m1, t);  // pass 0, A image: layer 1 + its ReLU mask
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
+    gemm_a_ready(pipe, t);
     gemm_issue<J_STAGES>(pipe, w->W2b, t);
     gemm_wait(pipe, part);
     // mask of layer 2: [acc + b2 > 0]
@@ -828,6 +938,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_j
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
+        gemm_a_ready(pipe, t);
         gemm_issue<J_STAGES>(pipe, w->W2bT, t);
         gemm_wait(pipe, part);
         // epilogue: g1 = acc * m1, gin = g1 W1 (this thread's quarter of the hidden units)
@@ -903,7 +1014,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_j
     }
     __syncthreads();
     cluster_sync();  // no CTA leaves while its peer may still signal its barriers
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    if (warp == 0) {
+        if constexpr (TWO_SM) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
 }
 
 int64_t max_rows(const MlpArgs& a) {  // upper bound of total_rows() known on the host (the work list may be shorter)
