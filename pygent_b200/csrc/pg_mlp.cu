@@ -510,10 +510,15 @@ struct GemmPipe {
     uint32_t tmem_base;
     uint32_t chunk_no;  // producer and issuer count chunks the same way
     uint32_t passes;
+    uint32_t prefetched;  // producer thread: chunks of THIS pass already requested at the end of the previous one
 };
 
+// `next_img`: the weight images of the following pass (nullptr after the last one).  When its own chunks are out the
+// producer requests the first STAGES chunks of the next pass right away: the stages free up as this pass's MMAs retire,
+// so the next GEMM starts with a full ring instead of paying the L2 latency again while the tensor core idles.
 template <int STAGES>
-__device__ __forceinline__ void gemm_issue(GemmPipe& p, const uint16_t (*img)[CHUNK_BYTES / 2], int t) {
+__device__ __forceinline__ void gemm_issue(GemmPipe& p, const uint16_t (*img)[CHUNK_BYTES / 2], int t,
+                                           const uint16_t (*next_img)[CHUNK_BYTES / 2] = nullptr) {
     // the control lanes' 31 warp siblings park at __syncwarp() instead of spinning on the completion barrier: as
     // divergent paths of the same warp they would take every other issue slot from the lane that feeds the tensor core
     constexpr int PER_PASS = TWO_SM ? N_CHUNKS / 2 : N_CHUNKS;  // chunks this CTA loads per GEMM
@@ -528,12 +533,22 @@ __device__ __forceinline__ void gemm_issue(GemmPipe& p, const uint16_t (*img)[CH
         // columns [256 q2 + 128 r, +128) of it: weight image quarter 2 q2 + r.  Nothing is multicast: each CTA streams only
         // the half of W2 its own tensor core multiplies.
         if (t == PRODUCER_THREAD) {
-            uint32_t c = p.chunk_no;
-            for (int i = 0; i < PER_PASS; i++, c++) {
+            uint32_t c = p.chunk_no + p.prefetched;
+            for (int i = (int)p.prefetched; i < PER_PASS; i++, c++) {
                 const uint32_t s = c % STAGES, use = c / STAGES;
                 mbar_wait(&p.empty[s], (use & 1) ^ 1);
                 mbar_expect_tx(&p.full[s], CHUNK_BYTES);
                 bulk_g2s(p.Bs + s * CHUNK_BYTES, &img[(2 * (i >> 3) + rank) * 8 + (i & 7)][0], CHUNK_BYTES, &p.full[s]);
+            }
+            p.prefetched = 0;
+            if (next_img) {
+                for (int i = 0; i < STAGES; i++, c++) {
+                    const uint32_t s = c % STAGES, use = c / STAGES;
+                    mbar_wait(&p.empty[s], (use & 1) ^ 1);
+                    mbar_expect_tx(&p.full[s], CHUNK_BYTES);
+                    bulk_g2s(p.Bs + s * CHUNK_BYTES, &next_img[(2 * (i >> 3) + rank) * 8 + (i & 7)][0], CHUNK_BYTES, &p.full[s]);
+                }
+                p.prefetched = STAGES;
             }
         } else if (t == ISSUER_THREAD && rank != 0) {  // peer: tell the leader when a stage of OUR ring is full
             uint32_t c = p.chunk_no;
@@ -755,7 +770,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_b
 
     double x[8], u[2], xe[8], ue[2], fplus[8];
     if (owner) load_row(a, rw, x, u);
-    GemmPipe pipe = {As, Bs, full, empty, accum, pfull, a_ready, tmem_base, 0u, 0u};
+    GemmPipe pipe = {As, Bs, full, empty, accum, pfull, a_ready, tmem_base, 0u, 0u, 0u};
     const int steps = steps_of(a);
     for (int k = 0; k < steps; k++) {
         if (owner) {
@@ -770,7 +785,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_b
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA unit
         __syncthreads();
         gemm_a_ready(pipe, t);
-        gemm_issue<T_STAGES>(pipe, w->W2b, t);
+        gemm_issue<T_STAGES>(pipe, w->W2b, t, (k + 1 < steps) ? w->W2b : nullptr);
         // epilogue: TMEM lane = row; this thread's quarter of the 512 columns, as soon as that quarter is final:
         // +b2, ReLU, layer 3
         gemm_wait(pipe, part);
@@ -874,7 +889,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_j
     cluster_sync();  // the peer's barriers are initialised before anything is multicast to them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    GemmPipe pipe = {As, Bs, full, empty, accum, pfull, a_ready, tmem_base, 0u, 0u};
+    GemmPipe pipe = {As, Bs, full, empty, accum, pfull, a_ready, tmem_base, 0u, 0u, 0u};
 
     double x[8], u[2];
     if (owner) {
@@ -891,7 +906,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_j
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     gemm_a_ready(pipe, t);
-    gemm_issue<J_STAGES>(pipe, w->W2b, t);
+    gemm_issue<J_STAGES>(pipe, w->W2b, t, w->W2bT);
     gemm_wait(pipe, part);
     // mask of layer 2: [acc + b2 > 0]
     for (int cb = part * (H / 32 / T_SPLIT); cb < (part + 1) * (H / 32 / T_SPLIT); cb++) {
@@ -939,7 +954,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_j
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         gemm_a_ready(pipe, t);
-        gemm_issue<J_STAGES>(pipe, w->W2bT, t);
+        gemm_issue<J_STAGES>(pipe, w->W2bT, t, (j + 1 < nh) ? w->W2bT : nullptr);
         gemm_wait(pipe, part);
         // epilogue: g1 = acc * m1, gin = g1 W1 (this thread's quarter of the hidden units)
         {
