@@ -416,7 +416,8 @@ def main():
                 "iterations_total": total_iters, "iterations_max": int(solver.iters.max()),
                 "gpu_launches": solver.lib.launches - l0,
                 "converged_frac": float(np.mean((st == pglib.ST_CONV_FUN) | (st == pglib.ST_CONV_GRAD))),
-                "mean_final_cost": float(np.mean(solver.cost)), "line_search": "serial semantics, 11 alphas evaluated per launch"}
+                "mean_final_cost": float(np.mean(solver.cost)), "line_search": "serial semantics; first 4 of 11 alphas for all live trajectories, the other 7 only where none has passed yet "
+                              "(one launch of all 11 once fewer than 64 x SMs trajectories are live)"}
 
     # ---- config 4: n = 6 double pendulum / acrobot, parallel line search -------------------------------
     ilqr_c4 = None

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define PG_ABI_VERSION 3
+#define PG_ABI_VERSION 4
 
 #define PG_F64 0
 #define PG_F32 1
@@ -103,6 +103,21 @@ int pg_rollout_balanced(int dtype, int integrator, int64_t B, int32_t T, int32_t
                         const void* x0, const void* U, void* X, void* xN, void* cost, uint8_t* terminated,
                         double terminal_cost, int32_t flags, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Alpha window of a SERIAL line search split over two launches (the reference stops at the first alpha that passes its
+ * z-test, ilqr.py:453-454 -- about 4.8 of its 11 alphas on average -- so the later alphas are evaluated only for the
+ * trajectories pg_ilqr_linesearch_filter keeps).  Both launches get the full alphas / output arrays:
+ *   phase 1 evaluates alphas [0, n_first), phase 2 alphas [n_first, n_alpha) --
+ *   unless *live_count <= small_count (device int32, read at kernel start): then phase 1 evaluates ALL alphas and phase 2
+ *   none, because a second dependent chain of T control intervals costs more than it saves on a GPU that is not full.
+ * NULL or phase 0: the whole search in one launch. */
+typedef struct pg_alpha_window {
+    int32_t phase;
+    int32_t n_first;
+    int32_t small_count;
+    int32_t reserved;
+    const int32_t* live_count;
+} pg_alpha_window;
+
 /* Closed-loop line-search rollouts u_k = K_j (x_k - xbar_j) + alpha k_j + ubar_j, j = min(Tk-1, k).
  *   alphas: host array of n_alpha values (<= PG_MAX_ALPHAS), all evaluated in one launch;
  *   alpha_dev [B] or NULL: when given, n_alpha must be 1 and each trajectory uses its own alpha;
@@ -123,7 +138,7 @@ int pg_ilqr_forward(int dtype, int integrator, int64_t B, int32_t T, int32_t S, 
                     const void* KK, const void* kk, int32_t Tk, const double* ulim, double terminal_cost,
                     void* X_out, void* U_out, void* cost_out, uint8_t* diverged_out,
                     uint8_t* terminated_out, void* xN_out, void* xS, const uint8_t* active,
-                    const int32_t* index, const int32_t* count, void* stream);
+                    const int32_t* index, const int32_t* count, const pg_alpha_window* window, void* stream);
 
 /* pg_ilqr_forward for large line searches, load-balanced like pg_rollout_balanced: persistent worker warps pull
  * (32-entry group of the work list, alpha, 20-step time chunk) units from a ticket queue.  Costs and flags only (no
@@ -137,7 +152,19 @@ int pg_ilqr_forward_balanced(int dtype, int integrator, int64_t B, int32_t T, in
                              const void* KK, const void* kk, int32_t Tk, const double* ulim, double terminal_cost,
                              void* cost_out, uint8_t* diverged_out, uint8_t* terminated_out, void* xN_out, void* xS,
                              const int32_t* index, const int32_t* count,
-                             void* workspace, int64_t workspace_bytes, void* stream);
+                             void* workspace, int64_t workspace_bytes, const pg_alpha_window* window, void* stream);
+
+/* Work lists of a SERIAL line search evaluated in two launches of pg_ilqr_forward(_balanced) (see pg_alpha_window):
+ *   phase 0: index_out / count_out = the entries of index_in whose backward pass succeeded (bw_success [B]);
+ *   phase 1: ... = the entries that, after the first n_first alphas (host array alphas; cost_cand, diverged [>= n_first, B];
+ *            cost [B] the current costs, dV [2,B]), have neither passed the z-test of pg_ilqr_select nor diverged.
+ *            Empty when *count_in <= small_count (launch 1 evaluated every alpha then).
+ * count_out must be zero on entry (device int32); order within a warp is kept.  pg_ilqr_select reads only the alphas the
+ * serial search tries, so evaluating the remaining alphas for the phase-1 list alone changes none of its decisions. */
+int pg_ilqr_linesearch_filter(int dtype, int64_t B, int32_t phase, int32_t n_first, const double* alphas, double zmin,
+                              const void* cost, const void* dV, const uint8_t* bw_success, const void* cost_cand,
+                              const uint8_t* diverged, const int32_t* index_in, const int32_t* count_in,
+                              int32_t* index_out, int32_t* count_out, int32_t small_count, void* stream);
 
 /* Backward Riccati pass along (xbar, ubar).
  *   lin_mode 0: analytic A, B (requires has_ab); 1: central differences eps=1e-3 of f.

@@ -167,6 +167,11 @@ class iLQR(Algorithm):
         self._cur = 0
         self._n_active = self._cnt[1]
         self._have_gains = False
+        # serial line search in two launches: work lists "backward pass succeeded" and "no success among the first alphas"
+        self.first_alphas = 4
+        self._ls_small = lib.split_search_threshold(self._x0.device)
+        self._ls_idx = [i32(B), i32(B)]
+        self._ls_cnt = i32(2)
         if self.learned:  # Jacobians along the nominal trajectory and the candidate trajectories of the line search
             self._lin = {"A": z(T, n, n, B), "B": z(T, n, m, B)}
             self._cand = {"X": z(A, T + 1, n, B), "U": z(A, T, m, B)}
@@ -410,6 +415,24 @@ class iLQR(Algorithm):
         self._backward(work=work)
         if self.learned:
             self._forward_candidates(list(self.alphas), self._KKc, self._kkc, out=self._fw, cand=self._cand, work=work)
+        elif (not self.parallel) and 0 < self.first_alphas < len(self.alphas) and self.B > self._ls_small:
+            # serial search in two launches: the first alphas for everybody whose backward pass succeeded, the others only
+            # where nothing has succeeded yet -- as long as more than _ls_small trajectories are live (decided on the device)
+            nf, al = self.first_alphas, [float(v) for v in self.alphas]
+            self._ls_cnt.zero_()
+            w0 = (self._ls_idx[0], self._ls_cnt[0:1])
+            w1 = (self._ls_idx[1], self._ls_cnt[1:2])
+            L.linesearch_filter(0, self._bw["success"], w0[0], w0[1], work=work)
+            fw = dict(alphas=al, S=self.substeps, dt=self.dt, integrator=self.integrator, ulim=self._ulim(),
+                      terminal_cost=float(self.environment.terminal_cost), out=self._fw,
+                      balanced=lib.use_balanced_forward(self.B, len(al), self._ubar.shape[0], self._x0.device))
+            L.ilqr_forward(self._x0, self._xbar, self._ubar, self._KKc, self._kkc, work=w0,
+                           window=(1, nf, self._ls_small, w0[1]), **fw)
+            L.linesearch_filter(1, self._bw["success"], w1[0], w1[1], work=w0, n_first=nf, alphas=al[:nf], zmin=self.zmin,
+                                cost=st["cost"], dV=self._bw["dV"], cost_cand=self._fw["cost"], diverged=self._fw["diverged"],
+                                small_count=self._ls_small)
+            L.ilqr_forward(self._x0, self._xbar, self._ubar, self._KKc, self._kkc, work=w1,
+                           window=(2, nf, self._ls_small, w0[1]), **fw)
         else:
             L.ilqr_forward(self._x0, self._xbar, self._ubar, self._KKc, self._kkc, alphas=self.alphas, S=self.substeps,
                            dt=self.dt, integrator=self.integrator, ulim=self._ulim(),

@@ -409,6 +409,9 @@ struct ForwardArgs {
     const uint8_t* active;
     const int32_t* index;  // optional work list: thread i handles trajectory index[i], i < *count
     const int32_t* count;
+    // alpha window of a line search split over two launches (pg_alpha_window): decided on the device from *win_count
+    int win_phase, win_first, win_small;
+    const int32_t* win_count;
     // commit mode
     const uint8_t* accept;
     T* xbar_io;
@@ -416,6 +419,20 @@ struct ForwardArgs {
     T* KK_acc;
     T* kk_acc;
 };
+
+// Alphas [lo, hi) this launch evaluates.  Launch 1 of a split search takes the first win_first alphas, launch 2 the
+// others -- unless at most win_small trajectories are live: then launch 1 takes them all and launch 2 none (a second
+// dependent chain of T intervals would cost more than it saves when the GPU is not full).
+template <typename T>
+__device__ __forceinline__ void alpha_window(const ForwardArgs<T>& a, int& lo, int& hi) {
+    lo = 0;
+    hi = a.n_alpha;
+    if (a.win_phase) {
+        const int split = (*a.win_count <= a.win_small) ? a.n_alpha : a.win_first;
+        if (a.win_phase == 1) hi = split;
+        else lo = split;
+    }
+}
 
 template <typename P, typename T>
 struct Nominal {  // gains and nominal point of one control interval
@@ -456,6 +473,9 @@ __global__ void __launch_bounds__(32 * MAX_ALPHAS) ilqr_forward_kernel(const For
         if (!a.accept[b]) return;
     } else {
         if (a.active && !a.active[b]) return;
+        int lo, hi;
+        alpha_window(a, lo, hi);
+        if (ia < lo || ia >= hi) return;
     }
     const T alpha = a.alpha_dev ? a.alpha_dev[b] : a.alphas[ia];
     const T* xbar = COMMIT ? a.xbar_io : a.xbar;
@@ -576,7 +596,9 @@ __global__ void __launch_bounds__(128, 3) ilqr_forward_queue_kernel(const Forwar
     const int lane = threadIdx.x & 31;
     const int64_t cnt = a.index ? (int64_t)*a.count : B;
     const int ng = (int)((cnt + 31) / 32);
-    const int G = ng * a.n_alpha, total = G * q.n_chunks;
+    int a_lo, a_hi;
+    alpha_window(a, a_lo, a_hi);
+    const int G = ng * (a_hi - a_lo), total = G * q.n_chunks;
     const T h = a.dt / T(a.S);
     for (;;) {
         int g = -1;
@@ -601,7 +623,7 @@ __global__ void __launch_bounds__(128, 3) ilqr_forward_queue_kernel(const Forwar
         g = __shfl_sync(0xffffffffu, g, 0);
         if (g < 0) return;
         const int c = __ldcg(&q.progress[g]);
-        const int ia = g / ng, tg = g - ia * ng;
+        const int tg = g % ng, ia = a_lo + g / ng;
         const int64_t w = (int64_t)tg * 32 + lane;
         const bool valid = w < cnt;
         const int64_t wv = valid ? w : cnt - 1;  // ragged last group: idle lanes shadow the last entry
@@ -1557,6 +1579,77 @@ __global__ void mpc_shift_kernel(const MpcShiftArgs<T> a) {
         a.xe[(int64_t)i * B + b] = xn[i];
     }
     a.cost[b] = cost;
+}
+
+// ---- line-search work lists (serial search in two phases) ---------------------------------------------------------
+// The serial line search stops at the first alpha with z > zmin (ilqr.py:453-454; ~4.8 of 11 alphas on average), so the
+// candidates are evaluated in two launches: the first `n_first` alphas for every trajectory whose backward pass succeeded
+// (phase 0 builds that list), the remaining ones only for trajectories that have neither succeeded nor diverged yet
+// (phase 1 builds that list from the first costs, with the z-test of ilqr_select_kernel).  K4 reads only the alphas the
+// serial search tries, so its decisions are unchanged.
+template <typename T>
+struct FilterArgs {
+    int64_t B;
+    int phase, n_first;
+    double alphas[MAX_ALPHAS];
+    double zmin;
+    const T* cost;
+    const T* dV;
+    const uint8_t* bw_success;
+    const T* cost_cand;
+    const uint8_t* diverged;
+    const int32_t* index_in;
+    const int32_t* count_in;
+    int32_t* index_out;
+    int32_t* count_out;
+    int small_count;  // phase 1: nothing to do when *count_in <= small_count (launch 1 took every alpha)
+};
+
+template <typename T>
+__global__ void ilqr_linesearch_filter_kernel(const FilterArgs<T> a) {
+    const int64_t B = a.B;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t b = tid;
+    bool valid = true;
+    if (a.index_in) {
+        valid = tid < *a.count_in;
+        b = valid ? a.index_in[tid] : 0;
+    } else {
+        valid = b < B;
+    }
+    bool keep = false;
+    if (valid) {
+        if (a.phase == 0) {
+            keep = a.bw_success[b] != 0;
+        } else if (a.count_in && *a.count_in <= a.small_count) {
+            keep = false;
+        } else {
+            keep = true;
+            const T cost_old = a.cost[b], sV1 = a.dV[b], sV2 = a.dV[B + b];
+            for (int i = 0; i < a.n_first; i++) {
+                if (a.diverged[(int64_t)i * B + b]) {  // 'forward diverged.': the search ends here
+                    keep = false;
+                    break;
+                }
+                const T alpha = T(a.alphas[i]);
+                const T dcost = cost_old - a.cost_cand[(int64_t)i * B + b];
+                const T expected = -alpha * (sV1 + alpha * sV2);
+                const T z = expected > T(0) ? dcost / expected : pg::sign(dcost);
+                if (z > T(a.zmin)) {
+                    keep = false;
+                    break;
+                }
+            }
+        }
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+    if (ballot) {
+        const int lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == __ffs(ballot) - 1) base = atomicAdd(a.count_out, __popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
+        if (keep) a.index_out[base + __popc(ballot & ((1u << lane) - 1))] = (int32_t)b;
+    }
 }
 
 // ---- observation (helpers.observation, pygent/helpers.py:20-29) -----------------------------------

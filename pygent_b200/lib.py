@@ -6,6 +6,7 @@ raises on a non-zero return code -- there is no fallback path.
 """
 import ctypes
 import functools
+import os
 
 import torch
 
@@ -35,16 +36,22 @@ class SelectParams(ctypes.Structure):
 
 
 # name -> argtypes (restype is always int); mirrors include/pygent_b200.h
+class AlphaWindow(ctypes.Structure):
+    """pg_alpha_window (include/pygent_b200.h): which alphas one launch of a split serial line search evaluates."""
+    _fields_ = [("phase", _i32), ("n_first", _i32), ("small_count", _i32), ("reserved", _i32), ("live_count", ctypes.c_void_p)]
+
+
 SIGNATURES = {
     "pg_get_problem_info": [ctypes.POINTER(ProblemInfo)],
     "pg_rollout": [_i32, _i32, _i64, _i32, _i32, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _i32, _vp],
     "pg_rollout_balanced": [_i32, _i32, _i64, _i32, _i32, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _i32, _vp, _i64, _vp],
     "pg_ilqr_forward": [_i32, _i32, _i64, _i32, _i32, _f64, _i32, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _dp, _f64,
-                        _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+                        _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "pg_ilqr_forward_balanced": [_i32, _i32, _i64, _i32, _i32, _f64, _i32, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _dp, _f64,
-                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
+                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
     "pg_ilqr_commit_chunked": [_i32, _i32, _i64, _i32, _i32, _f64, _i32, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _dp, _vp, _vp,
                                _vp, _vp, _vp, _vp],
+    "pg_ilqr_linesearch_filter": [_i32, _i64, _i32, _i32, _dp, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
     "pg_ilqr_backward": [_i32, _i64, _i32, _f64, _i32, _i32, _vp, _vp, _vp, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                          _vp],
     "pg_ilqr_select": [_i32, _i64, ctypes.POINTER(SelectParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
@@ -197,8 +204,9 @@ class ProblemLibrary:
     # -- K2 ------------------------------------------------------------------------------------
     def ilqr_forward(self, x0, xbar, ubar, KK, kk, alphas=None, alpha_dev=None, S=4, dt=0.02,
                      integrator=INTEG_RK4, ulim=None, terminal_cost=0.0, want_traj=False, active=None, out=None,
-                     work=None, balanced=None):
+                     work=None, balanced=None, window=None):
         """work: (index i32 [B], count i32 [1]) compacted list of trajectories to process, or None (all).
+        window: (phase, n_first, small_count, live_count i32 [1] device) of a split serial line search, or None.
         balanced: use the work-queue kernel (pg_ilqr_forward_balanced; costs only); default: when there are more
         (32-trajectory group, alpha) pairs than the 3 x 4 x SM persistent workers."""
         n, m = self.n, self.m
@@ -222,6 +230,10 @@ class ProblemLibrary:
         xN = out.get("xN")  # [n_alpha, n, B]: terminal states of the candidates (MPC plan shift)
         xS = out.get("xS")  # [n_alpha, num_snapshots(T), n, B]: candidates at the chunk boundaries (chunk-parallel commit)
         xS_ptr = _ptr(xS, dtype, (n_alpha, self.num_snapshots(T), n, B), "xS") if xS is not None else None
+        win = None
+        if window is not None:
+            win_struct = AlphaWindow(int(window[0]), int(window[1]), int(window[2]), 0, _ptr(window[3], torch.int32, (1,), "live_count"))
+            win = ctypes.addressof(win_struct)  # read on the host during the call; win_struct lives until we return
         if want_traj and X is None:
             X = torch.empty((n_alpha, T + 1, n, B), dtype=dtype, device=dev)
             Uo = torch.empty((n_alpha, T, m, B), dtype=dtype, device=dev)
@@ -241,7 +253,7 @@ class ProblemLibrary:
                 _ptr(KK, dtype, (Tk, m, n, B), "KK"), _ptr(kk, dtype, (Tk, m, B), "kk"), Tk, _host_doubles(ulim),
                 terminal_cost, _ptr(cost, dtype, (n_alpha, B), "cost_out"), _ptr(div, torch.uint8, (n_alpha, B), "diverged_out"),
                 _ptr(term, torch.uint8, (n_alpha, B), "terminated_out"), _ptr(xN, dtype, (n_alpha, n, B), "xN_out"), xS_ptr,
-                *self._work(work, B), _ptr(ws), nbytes, self._stream())
+                *self._work(work, B), _ptr(ws), nbytes, win, self._stream())
             self._check(rc, "pg_ilqr_forward_balanced")
             self.launches += 1
             return {"cost": cost, "diverged": div, "terminated": term, "X": None, "U": None, "xN": xN}
@@ -253,7 +265,7 @@ class ProblemLibrary:
             terminal_cost, _ptr(X, dtype, (n_alpha, T + 1, n, B), "X_out"), _ptr(Uo, dtype, (n_alpha, T, m, B), "U_out"),
             _ptr(cost, dtype, (n_alpha, B), "cost_out"), _ptr(div, torch.uint8, (n_alpha, B), "diverged_out"),
             _ptr(term, torch.uint8, (n_alpha, B), "terminated_out"), _ptr(xN, dtype, (n_alpha, n, B), "xN_out"), xS_ptr,
-            _ptr(active, torch.uint8, (B,), "active"), *self._work(work, B), self._stream())
+            _ptr(active, torch.uint8, (B,), "active"), *self._work(work, B), win, self._stream())
         self._check(rc, "pg_ilqr_forward")
         self.launches += 1
         return {"cost": cost, "diverged": div, "terminated": term, "X": X, "U": Uo, "xN": xN}
@@ -414,6 +426,19 @@ class ProblemLibrary:
         self._check(rc, "pg_mpc_shift")
         self.launches += 1
 
+    def linesearch_filter(self, phase, bw_success, index_out, count_out, work=None, n_first=0, alphas=None, zmin=0.0,
+                          cost=None, dV=None, cost_cand=None, diverged=None, small_count=0):
+        """Compacted work list of one phase of the two-launch serial line search (see include/pygent_b200.h)."""
+        B = bw_success.shape[0]
+        dtype = cost.dtype if cost is not None else torch.float64
+        rc = self.dll.pg_ilqr_linesearch_filter(
+            _dtype_code(dtype), B, phase, n_first, _host_doubles(alphas), zmin, _ptr(cost, dtype, (B,), "cost"),
+            _ptr(dV, dtype, (2, B), "dV"), _ptr(bw_success, torch.uint8, (B,), "bw_success"), _ptr(cost_cand, dtype, None, "cost_cand"),
+            _ptr(diverged, torch.uint8, None, "diverged"), *self._work(work, B), _ptr(index_out, torch.int32, (B,), "index_out"),
+            _ptr(count_out, torch.int32, (1,), "count_out"), int(small_count), self._stream())
+        self._check(rc, "pg_ilqr_linesearch_filter")
+        self.launches += 1
+
     def num_snapshots(self, T):
         return int(self.dll.pg_ilqr_num_snapshots(int(T)))
 
@@ -486,6 +511,17 @@ def use_balanced_forward(B, n_alpha, T, dev):
         return False
     workers = 3 * 4 * _sm_count(dev.index if dev.index is not None else torch.cuda.current_device())
     return ((B + 31) // 32) * n_alpha > workers
+
+
+def split_search_threshold(dev):
+    """Live trajectories below which a serial line search is evaluated in one launch (pg_alpha_window.small_count):
+    two dependent rollout chains only pay when the first one fills the GPU -- about 64 trajectories per SM."""
+    v = os.environ.get("PG_LS_SMALL")
+    if v is not None:
+        return int(v)
+    if dev.type != "cuda":
+        return 1 << 30
+    return 64 * _sm_count(dev.index if dev.index is not None else torch.cuda.current_device())
 
 
 def _cuda_error_name(rc):

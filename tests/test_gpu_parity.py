@@ -569,3 +569,23 @@ def test_ilqr_horizons_around_the_chunk_length_match_oracle(T):
     assert np.array_equal(alg.iters, so["iters"]) and np.array_equal(alg.status, so["status"])
     assert rel(alg.cost, so["cost"]) < 1e-8 and rel(alg.xx, so["xx"]) < 1e-7 and rel(alg.uu, so["uu"]) < 1e-6
     assert rel(alg.KK, so["KK"]) < 1e-6 and rel(alg.kk[..., 0], so["kk"]) < 1e-6
+
+
+@pytest.mark.parametrize("B,T", [(700, 60), (20000, 100)])
+def test_two_phase_line_search_changes_nothing(B, T):
+    """Serial line search evaluated in two launches (first 4 alphas for all, the other 7 only where nothing has succeeded
+    yet): iterations, statuses, costs, trajectories and gains must be exactly those of evaluating all 11 for everybody."""
+    rng = np.random.default_rng(B)
+    x0 = np.array(CASES["cart_pole"][4]) + rng.uniform(-0.4, 0.4, (B, 4))
+    res = []
+    for nf in (0, 4):
+        alg = solver("cart_pole", T, x0=x0, maxIters=12)
+        alg.first_alphas = nf
+        if B < 1000:
+            alg._ls_small = 64   # two launches while more than 64 trajectories are live, one afterwards
+        assert alg.B > alg._ls_small
+        alg.run_optim()
+        res.append((alg.iters.copy(), alg.status.copy(), np.array(alg.cost), np.array(alg.xx), np.array(alg.uu), np.array(alg.KK),
+                    alg.current_alpha.copy() if hasattr(alg.current_alpha, "copy") else alg.current_alpha))
+    for p, q in zip(*res):
+        assert np.array_equal(p, q)
