@@ -166,8 +166,14 @@ def golden_steps(rng, T=40):
             env.reset(list(x0))
             costs = []
             if S is None or S == 0:
-                for k in range(T):
-                    costs.append(env.fast_step(U[k], dt) if S == 0 else env.step(U[k], dt))
+                try:
+                    for k in range(T):
+                        costs.append(env.fast_step(U[k], dt) if S == 0 else env.step(U[k], dt))
+                except TypeError:
+                    # MarBot.ode returns a list: the reference's own fast_step fails on `dt*list` (environments.py:314);
+                    # there is no Euler golden for such a system
+                    assert S == 0
+                    continue
             else:
                 with rh.fixed_step(S):
                     for k in range(T):

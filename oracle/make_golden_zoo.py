@@ -1,0 +1,71 @@
+"""Goldens of the two hand-written systems of the reference that the example set does not cover:
+Car (m = 2 inputs; environments.py:730-761, cost of examples/ilqr/car.py:7-17) and MarBot (environments.py:826-868).
+
+    python -m oracle.make_golden_zoo        (only works where /root/reference exists)
+
+Same recipe as oracle/make_golden.py (whose helpers are used): control intervals with random actions through the
+reference's StateSpaceModel.step (native RK45, RK4 x 1, RK4 x 4, Euler) -> tests/golden/steps_zoo.npz, and one
+instrumented iLQR solve of the Car -> tests/golden/ilqr_car_rk4x4.npz.  The class has no analytic Jacobians, so the
+reference linearises it with helpers.system_linearization (central differences, eps = 1e-3).  TEST TOOLING ONLY.
+"""
+import os
+import time
+
+import numpy as np
+
+from . import make_golden as mg
+
+
+def _car():  # examples/ilqr/car.py:7-17
+    def c_k(x, u):
+        x1, x2, x3, x4 = x
+        u1, u2 = u
+        return x1 ** 2 + x2 ** 2 + 10 * u1 ** 2 + 0.1 * u2 ** 2
+
+    def c_N(x):
+        x1, x2, x3, x4 = x
+        return 100 * x1 ** 2 + 100 * x2 ** 2 + 1000 * x3 ** 2 + 300 * x4 ** 2
+    return c_k, c_N, dict(qx=[1, 1, 0, 0], ru=[10, 0.1], qf=[100, 100, 1000, 300])
+
+
+def _marbot():  # weights of examples/ddpg/marbot.py:6-10 (there on the next state; here the iLQR convention c(x, u))
+    def c_k(x, u):
+        x1, x2, x3, x4 = x
+        u1, = u
+        return 8.7 * x1 ** 2 + 8.7 * x2 ** 2 + 10e-5 * x3 ** 2 + 10e-5 * x4 ** 2 + 4.7 * u1 ** 2
+
+    def c_N(x):
+        x1, x2, x3, x4 = x
+        return 100 * x1 ** 2 + 100 * x2 ** 2 + 10 * x3 ** 2 + 10 * x4 ** 2
+    return c_k, c_N, dict(qx=[8.7, 8.7, 10e-5, 10e-5], ru=[4.7], qf=[100, 100, 10, 10])
+
+
+ZOO = {
+    "car": ("Car", {}, "car", _car, [1., 1., 1.5 * np.pi, 0.], 0.03),
+    "marbot": ("MarBot", {}, "marbot", _marbot, [0., 0.3, 0., 0.], 0.02),
+}
+
+
+def main():
+    saved = dict(mg.CASES)
+    mg.CASES.clear()
+    mg.CASES.update(ZOO)
+    try:
+        rng = np.random.default_rng(20261020)
+        t0 = time.time()
+        np.savez_compressed(os.path.join(mg.GOLDEN, "steps_zoo.npz"), **mg.golden_steps(rng))
+        print("steps_zoo.npz %.1fs" % (time.time() - t0))
+        # MarBot.ode returns a list: the reference's FD linearisation (helpers.py:144) and fast_step (environments.py:314)
+        # fail on it, so the reference itself can only STEP a MarBot (as its DDPG example does) -- no iLQR golden exists
+        for name, case, T in (("ilqr_car_rk4x4", "car", 100),):
+            t0 = time.time()
+            g = mg.golden_ilqr(case, T, 4, max_iters=60)
+            np.savez_compressed(os.path.join(mg.GOLDEN, name + ".npz"), **g)
+            print("%-24s iters=%-4d cost=%.12f  %.1fs" % (name, g["iters"], g["cost"], time.time() - t0))
+    finally:
+        mg.CASES.clear()
+        mg.CASES.update(saved)
+
+
+if __name__ == "__main__":
+    main()

@@ -236,7 +236,7 @@ class StateSpaceModel(Environment):
             U = np.asarray(U, dtype=float)
             if U.ndim == 2:
                 U = np.broadcast_to(U[None], (self.batch,) + U.shape)
-            Ud = torch.as_tensor(np.ascontiguousarray(U.transpose(1, 2, 0)), dtype=self.dtype, device=self.device)
+            Ud = torch.as_tensor(np.array(U.transpose(1, 2, 0), order="C"), dtype=self.dtype, device=self.device)
         T = Ud.shape[0]
         r = L.rollout(x, Ud, S=self.substeps, dt=self.dt, t0=float(self.tt[-1]),
                       integrator=lib.INTEG_EULER if fast else lib.INTEG_RK4, history=history,

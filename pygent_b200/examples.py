@@ -78,6 +78,30 @@ def triple():
     return c_k, c_N, dict(qx=[0.5 * (i + 1) for i in range(8)], ru=[0.01], qf=[10] * 8)
 
 
+def car():  # examples/ilqr/car.py:7-17 (m = 2)
+    def c_k(x, u):
+        x1, x2, x3, x4 = x
+        u1, u2 = u
+        return x1 ** 2 + x2 ** 2 + 10 * u1 ** 2 + 0.1 * u2 ** 2
+
+    def c_N(x):
+        x1, x2, x3, x4 = x
+        return 100 * x1 ** 2 + 100 * x2 ** 2 + 1000 * x3 ** 2 + 300 * x4 ** 2
+    return c_k, c_N, dict(qx=[1, 1, 0, 0], ru=[10, 0.1], qf=[100, 100, 1000, 300])
+
+
+def marbot():  # weights of examples/ddpg/marbot.py:6-10, in the iLQR convention c(x, u)
+    def c_k(x, u):
+        x1, x2, x3, x4 = x
+        u1, = u
+        return 8.7 * x1 ** 2 + 8.7 * x2 ** 2 + 10e-5 * x3 ** 2 + 10e-5 * x4 ** 2 + 4.7 * u1 ** 2
+
+    def c_N(x):
+        x1, x2, x3, x4 = x
+        return 100 * x1 ** 2 + 100 * x2 ** 2 + 10 * x3 ** 2 + 10 * x4 ** 2
+    return c_k, c_N, dict(qx=[8.7, 8.7, 10e-5, 10e-5], ru=[4.7], qf=[100, 100, 10, 10])
+
+
 # golden case -> (env class name, env kwargs, system name, cost factory, nominal x0, dt, terminate box)
 CASES = {
     "cart_pole": ("CartPole", {}, "cart_pole_lin", cart_pole_nmpc, [0, np.pi, 0, 0], 0.02, {0: 1.2, 2: 4.0}),
@@ -95,6 +119,8 @@ CASES = {
                             [0, np.pi, np.pi, 0, 0, 0], 0.01, {0: 1.5, 4: 25., 5: 25.}),
     "triple": ("CartPoleTriple", {}, "cart_pole_triple_lin", triple, [0, np.pi, np.pi, np.pi, 0, 0, 0, 0], 0.005, {0: 1.5}),
     "pendulum": ("Pendulum", {}, "pendulum", pendulum, [np.pi, 0], 0.05, {1: 10., 0: 8 * np.pi}),
+    "car": ("Car", {}, "car", car, [1., 1., 1.5 * np.pi, 0.], 0.03, {0: 5.0, 1: 5.0}),
+    "marbot": ("MarBot", {}, "marbot", marbot, [0., 0.3, 0., 0.], 0.02, {0: 1.0}),
 }
 
 # golden iLQR run -> (case, T, S, integrator (0 RK4, 1 Euler), iLQR kwargs)
@@ -110,6 +136,7 @@ ILQR_RUNS = {
     "ilqr_double_serial_rk4x4": ("double_serial", 100, 4, 0, {}),
     "ilqr_pendulum_fd_rk4x4": ("pendulum", 60, 4, 0, {}),
     "ilqr_cart_pole_euler": ("cart_pole", 100, 4, 1, {"fastForward": True}),
+    "ilqr_car_rk4x4": ("car", 100, 4, 0, {}),   # oracle/make_golden_zoo.py
 }
 
 

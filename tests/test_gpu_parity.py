@@ -5,7 +5,7 @@ import pytest
 import torch
 
 import oracle
-from cases import CASES, ILQR_RUNS, oracle_problem
+from cases import CASES, ILQR_RUNS, oracle_problem, rk45_tol
 from pygent_b200 import lib as pglib
 from pygent_b200.examples import make_env, make_ilqr
 
@@ -101,10 +101,12 @@ def test_rollout_matches_reference_golden(golden, case):
     x0 = dev(g[case + "/x0"][None])
     U = torch.as_tensor(np.ascontiguousarray(g[case + "/U"][:, :, None]), device="cuda")
     for tag, S, integ, tol in (("rk4x4", 4, 0, 1e-10), ("rk4x1", 1, 0, 1e-10), ("euler", 1, 1, 1e-10), ("rk45", 4, 0, None)):
+        if "%s/%s/X" % (case, tag) not in g.files:
+            continue   # MarBot: the reference's own fast_step fails on its list-valued ode, no Euler golden
         r = L.rollout(x0, U, S=S, dt=dt, integrator=integ, history=True)
         X = r["X"].cpu().numpy()[:, :, 0]
         if tol is None:
-            tol = 1e-6 if case in ("cart_pole", "cart_pole_tv", "pendulum", "acrobot", "double_parallel", "cart_pole_force") else 1e-5
+            tol = rk45_tol(case)
         assert rel(X, g["%s/%s/X" % (case, tag)]) < tol, tag
         if tag != "rk45":
             c = g["%s/%s/c" % (case, tag)].sum()
@@ -266,7 +268,8 @@ def reference_select(alphas, parallel, tol_fun, tol_grad, st, bw_ok, gnorm, sV1,
 @pytest.mark.parametrize("case,T,parallel,constrained,reg", [
     ("cart_pole", 100, False, False, 2), ("cart_pole", 100, True, False, 2), ("cart_pole", 60, False, True, 2),
     ("cart_pole", 60, False, False, 1), ("acrobot", 80, True, False, 2), ("double_parallel", 100, True, False, 2),
-    ("double_serial", 60, False, False, 2), ("pendulum", 60, False, True, 2), ("cart_pole_tv", 100, False, False, 2)])
+    ("double_serial", 60, False, False, 2), ("pendulum", 60, False, True, 2), ("cart_pole_tv", 100, False, False, 2),
+    ("car", 60, False, False, 2), ("car", 60, True, True, 2), ("marbot", 60, False, True, 2)])   # m = 2 (2-D box QP), FD Jacobians
 def test_ilqr_iterations_in_lockstep_with_oracle(case, T, parallel, constrained, reg):
     """25 iterations of a batch, checked one iteration at a time: from the GPU's own nominal trajectory the
     oracle recomputes the backward pass (K, k, sum V1/V2, gradient norm) and all 11 line-search costs, and

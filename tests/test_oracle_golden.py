@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import oracle
-from cases import CASES, ILQR_RUNS, oracle_problem
+from cases import CASES, ILQR_RUNS, oracle_problem, rk45_tol
 
 
 def rel(a, b):
@@ -34,6 +34,8 @@ def test_fixed_step_rollout_matches_reference(golden, case, tag, S, integ):
     g = golden("steps")
     p = oracle_problem(case, S=S, integrator=integ)
     r = oracle.rollout(p, g[case + "/x0"][None], U=g[case + "/U"][None])
+    if "%s/%s/X" % (case, tag) not in g.files:
+        pytest.skip("the reference's own fast_step fails on MarBot's list-valued ode (environments.py:314): no Euler golden")
     Xref, cref = g["%s/%s/X" % (case, tag)], g["%s/%s/c" % (case, tag)]
     assert rel(r["X"][0], Xref) < 1e-10
     assert abs(r["cost"][0] - cref.sum()) <= 1e-10 * (abs(cref.sum()) + 1)
@@ -48,7 +50,7 @@ def test_rk4x4_tracks_native_rk45(golden, case):
     g = golden("steps")
     p = oracle_problem(case, S=4)
     r = oracle.rollout(p, g[case + "/x0"][None], U=g[case + "/U"][None])
-    tol = 1e-6 if case in ("cart_pole", "cart_pole_tv", "pendulum", "acrobot", "double_parallel", "cart_pole_force") else 1e-5
+    tol = rk45_tol(case)
     assert rel(r["X"][0], g[case + "/rk45/X"]) < tol
 
 
