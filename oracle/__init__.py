@@ -26,7 +26,8 @@ _dp = ctypes.POINTER(ctypes.c_double)
 class Problem(ctypes.Structure):
     _fields_ = [("sys", _i32), ("n", _i32), ("m", _i32), ("S", _i32), ("integrator", _i32), ("lin_mode", _i32),
                 ("dt", _f64), ("qx", _f64 * NMAX), ("ru", _f64 * MMAX), ("re", _f64 * MMAX), ("rd", _f64),
-                ("qf", _f64 * NMAX), ("term_lim", _f64 * NMAX), ("terminal_cost", _f64)]
+                ("qf", _f64 * NMAX), ("term_lim", _f64 * NMAX), ("terminal_cost", _f64),
+                ("lx", _f64 * NMAX), ("c0", _f64), ("lf", _f64 * NMAX), ("cf0", _f64)]
 
 
 class ILQRParams(ctypes.Structure):
@@ -87,15 +88,15 @@ def system_dims(name):
 
 
 def make_problem(system, dt, S=4, integrator=0, lin_mode=None, qx=(), ru=(), re=(), rd=0.0, qf=(), term_lim=(),
-                 terminal_cost=0.0):
+                 terminal_cost=0.0, lx=(), c0=0.0, lf=(), cf0=0.0):
     """Cost family of the reference's examples:
-    c = sum qx_i x_i^2 + sum (ru_j + re_j exp(-rd t)) u_j^2 ; cf = sum qf_i x_i^2."""
+    c = c0 + sum (lx_i x_i + qx_i x_i^2) + sum (ru_j + re_j exp(-rd t)) u_j^2 ; cf = cf0 + sum (lf_i x_i + qf_i x_i^2)."""
     n, m, has_ab = system_dims(system)
     p = Problem()
     p.sys, p.n, p.m, p.S, p.integrator = system_id(system), n, m, S, integrator
     p.lin_mode = (0 if has_ab else 1) if lin_mode is None else lin_mode
-    p.dt, p.rd, p.terminal_cost = dt, rd, terminal_cost
-    for dst, src in ((p.qx, qx), (p.ru, ru), (p.re, re), (p.qf, qf), (p.term_lim, term_lim)):
+    p.dt, p.rd, p.terminal_cost, p.c0, p.cf0 = dt, rd, terminal_cost, c0, cf0
+    for dst, src in ((p.qx, qx), (p.ru, ru), (p.re, re), (p.qf, qf), (p.term_lim, term_lim), (p.lx, lx), (p.lf, lf)):
         for i, v in enumerate(src):
             dst[i] = v
     return p

@@ -102,6 +102,18 @@ def marbot():  # weights of examples/ddpg/marbot.py:6-10, in the iLQR convention
     return c_k, c_N, dict(qx=[8.7, 8.7, 10e-5, 10e-5], ru=[4.7], qf=[100, 100, 10, 10])
 
 
+def angular_pendulum():  # examples/ilqr/angular_pendulum.py:7-16 (affine in x1)
+    def c_k(x, u):
+        x1, x2, x3 = x
+        u1, = u
+        return (1 - x1) + 0.1 * x3 ** 2 + 0.01 * u1 ** 2
+
+    def c_N(x):
+        x1, x2, x3 = x
+        return 100 * (1 - x1) + 0.1 * x3 ** 2
+    return c_k, c_N, dict(qx=[0, 0, 0.1], ru=[0.01], qf=[0, 0, 0.1], lx=[-1, 0, 0], c0=1.0, lf=[-100, 0, 0], cf0=100.0)
+
+
 # golden case -> (env class name, env kwargs, system name, cost factory, nominal x0, dt, terminate box)
 CASES = {
     "cart_pole": ("CartPole", {}, "cart_pole_lin", cart_pole_nmpc, [0, np.pi, 0, 0], 0.02, {0: 1.2, 2: 4.0}),
@@ -121,6 +133,7 @@ CASES = {
     "pendulum": ("Pendulum", {}, "pendulum", pendulum, [np.pi, 0], 0.05, {1: 10., 0: 8 * np.pi}),
     "car": ("Car", {}, "car", car, [1., 1., 1.5 * np.pi, 0.], 0.03, {0: 5.0, 1: 5.0}),
     "marbot": ("MarBot", {}, "marbot", marbot, [0., 0.3, 0., 0.], 0.02, {0: 1.0}),
+    "angular_pendulum": ("AngularPendulum", {}, "angular_pendulum", angular_pendulum, [-np.cos(0.3), np.sin(0.3), 0.], 0.05, {2: 10.0}),
 }
 
 # golden iLQR run -> (case, T, S, integrator (0 RK4, 1 Euler), iLQR kwargs)
@@ -137,6 +150,7 @@ ILQR_RUNS = {
     "ilqr_pendulum_fd_rk4x4": ("pendulum", 60, 4, 0, {}),
     "ilqr_cart_pole_euler": ("cart_pole", 100, 4, 1, {"fastForward": True}),
     "ilqr_car_rk4x4": ("car", 100, 4, 0, {}),   # oracle/make_golden_zoo.py
+    "ilqr_angular_pendulum_rk4x4": ("angular_pendulum", 100, 4, 0, {}),
 }
 
 

@@ -57,15 +57,16 @@ def test_generated_functions_match_oracle(case):
     assert rel(host(r["B"]), np.array([b for _, b in AB])) < 1e-9
     cp = CASES[case][3]()[2]
     qx, qf = np.array(cp["qx"]), np.array(cp["qf"])
+    lx, lf = np.array(cp.get("lx", [0.0] * n)), np.array(cp.get("lf", [0.0] * n))   # affine part (angular pendulum)
     ru = np.array(cp["ru"])[None] + np.array(cp.get("re", [0.0] * m))[None] * np.exp(-cp.get("rd", 0.0) * ts)[:, None]
-    assert rel(host(r["c"]), (qx * xs ** 2).sum(1) + (ru * us ** 2).sum(1)) < 1e-12
-    assert rel(host(r["cx"]), 2 * qx * xs) < 1e-12
+    assert rel(host(r["c"]), cp.get("c0", 0.0) + (qx * xs ** 2 + lx * xs).sum(1) + (ru * us ** 2).sum(1)) < 1e-12
+    assert rel(host(r["cx"]), 2 * qx * xs + lx) < 1e-12
     assert rel(host(r["cu"]), 2 * ru * us) < 1e-12
     assert rel(host(r["Cxx"]), np.broadcast_to(np.diag(2 * qx), (P, n, n))) < 1e-12
     assert rel(host(r["Cuu"])[:, 0, 0], 2 * ru[:, 0]) < 1e-12
     assert rel(host(r["Cxu"]), 0) == 0
-    assert rel(host(r["cf"]), (qf * xs ** 2).sum(1)) < 1e-12
-    assert rel(host(r["cfx"]), 2 * qf * xs) < 1e-12
+    assert rel(host(r["cf"]), cp.get("cf0", 0.0) + (qf * xs ** 2 + lf * xs).sum(1)) < 1e-12
+    assert rel(host(r["cfx"]), 2 * qf * xs + lf) < 1e-12
     assert rel(host(r["Cfxx"]), np.broadcast_to(np.diag(2 * qf), (P, n, n))) < 1e-12
 
 
@@ -269,7 +270,8 @@ def reference_select(alphas, parallel, tol_fun, tol_grad, st, bw_ok, gnorm, sV1,
     ("cart_pole", 100, False, False, 2), ("cart_pole", 100, True, False, 2), ("cart_pole", 60, False, True, 2),
     ("cart_pole", 60, False, False, 1), ("acrobot", 80, True, False, 2), ("double_parallel", 100, True, False, 2),
     ("double_serial", 60, False, False, 2), ("pendulum", 60, False, True, 2), ("cart_pole_tv", 100, False, False, 2),
-    ("car", 60, False, False, 2), ("car", 60, True, True, 2), ("marbot", 60, False, True, 2)])   # m = 2 (2-D box QP), FD Jacobians
+    ("car", 60, False, False, 2), ("car", 60, True, True, 2), ("marbot", 60, False, True, 2),
+    ("angular_pendulum", 60, False, True, 2)])   # m = 2 (2-D box QP), FD Jacobians, affine cost
 def test_ilqr_iterations_in_lockstep_with_oracle(case, T, parallel, constrained, reg):
     """25 iterations of a batch, checked one iteration at a time: from the GPU's own nominal trajectory the
     oracle recomputes the backward pass (K, k, sum V1/V2, gradient norm) and all 11 line-search costs, and
