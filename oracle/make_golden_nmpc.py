@@ -22,20 +22,39 @@ def c_N(x):
     return 100 * x1 ** 2 + 100 * x2 ** 2 + 10 * x3 ** 2 + 10 * x4 ** 2
 
 
+def c_k_double(x, u):  # examples/nmpc/double.py:7-11 (regulation around the hanging configuration x2 = x3 = pi)
+    x1, x2, x3, x4, x5, x6 = x
+    u1, = u
+    return .5 * (20. * x1 ** 2 + 20 * (x2 - np.pi) ** 2 + .01 * x4 ** 2 + .01 * x5 ** 2) + 0.01 * u1 ** 2
+
+
+def c_N_double(x):  # the example passes no final cost (fcost=None does not run under sympy 1.14)
+    x1, x2, x3, x4, x5, x6 = x
+    return 100 * x1 ** 2 + 100 * (x2 - np.pi) ** 2 + 100 * (x3 - np.pi) ** 2 + 10 * x4 ** 2 + 10 * x5 ** 2 + 10 * x6 ** 2
+
+
 def main():
-    run("nmpc_cart_pole", [0, np.pi, 0, 0])                                    # swing-up, inputs saturated throughout
-    run("nmpc_cart_pole_stab", [0.2, 0.3, 0.1, -0.2], n_steps=40, horizon=1.0)  # stabilisation around the upright
+    import sys
+    only = sys.argv[1:]
+    if not only or "nmpc_cart_pole" in only:
+        run("nmpc_cart_pole", [0, np.pi, 0, 0])                                    # swing-up, inputs saturated throughout
+    if not only or "nmpc_cart_pole_stab" in only:
+        run("nmpc_cart_pole_stab", [0.2, 0.3, 0.1, -0.2], n_steps=40, horizon=1.0)  # stabilisation around the upright
+    if not only or "nmpc_double_serial" in only:   # examples/nmpc/double.py: n = 6, cart displaced by 0.5 m
+        run("nmpc_double_serial", [0.5, np.pi, np.pi, 0, 0, 0], n_steps=30, horizon=1.0, dt=0.01, cls="CartPoleDoubleSerial",
+            costs=(c_k_double, c_N_double))
 
 
-def run(name, x0, n_steps=50, horizon=2.0, dt=0.02, init_iterations=500):
+def run(name, x0, n_steps=50, horizon=2.0, dt=0.02, init_iterations=500, cls="CartPole", costs=None):
+    c_k, c_N = costs or (globals()["c_k"], globals()["c_N"])
     pg = rh.load_reference()
     import pygent.algorithms.ilqr as ref_ilqr
     import pygent.algorithms.nmpc as nmpc
     ref_ilqr.copyfile = lambda *a, **k: None  # the reference copies the executing script next to its results (ilqr.py:110)
     out = {"x0": np.array(x0), "dt": dt, "horizon": horizon, "n_steps": n_steps, "init_iterations": init_iterations}
     with rh.fixed_step(4), rh.quiet(), tempfile.TemporaryDirectory() as tmp:
-        env = pg.environments.CartPole(c_k, x0, dt)
-        mpc_env = pg.environments.CartPole(c_k, x0, dt)
+        env = getattr(pg.environments, cls)(c_k, x0, dt)
+        mpc_env = getattr(pg.environments, cls)(c_k, x0, dt)
         agent = nmpc.MPCAgent(mpc_env, horizon, dt, tmp + "/", init_iterations=init_iterations, step_iterations=1, fcost=c_N,
                               constrained=False, fastForward=False, printing=False, saving=False, init_optim=True,
                               finite_diff=False, add_noise=False)

@@ -156,6 +156,28 @@ ILQR_RUNS = {
 
 
 
+def double_nmpc():  # examples/nmpc/double.py:7-11: regulation around the hanging configuration x2 = x3 = pi
+    def c_k(x, u):
+        x1, x2, x3, x4, x5, x6 = x
+        u1, = u
+        return .5 * (20. * x1 ** 2 + 20 * (x2 - np.pi) ** 2 + .01 * x4 ** 2 + .01 * x5 ** 2) + 0.01 * u1 ** 2
+
+    def c_N(x):  # the example passes none (fcost=None does not run under sympy 1.14); oracle/make_golden_nmpc.py uses this one
+        x1, x2, x3, x4, x5, x6 = x
+        return 100 * x1 ** 2 + 100 * (x2 - np.pi) ** 2 + 100 * (x3 - np.pi) ** 2 + 10 * x4 ** 2 + 10 * x5 ** 2 + 10 * x6 ** 2
+    return c_k, c_N
+
+
+def make_nmpc_double(x0, dt=0.01, horizon=1.0, **kw):
+    """NMPC of examples/nmpc/double.py: CartPoleDoubleSerial, plants x0 [B, 6] or [6]."""
+    from . import environments
+    from .algorithms.nmpc import NMPC
+    c_k, c_N = double_nmpc()
+    env, mpc_env = environments.CartPoleDoubleSerial(c_k, x0, dt), environments.CartPoleDoubleSerial(c_k, x0, dt)
+    kw.setdefault("ilqr_print", False)
+    return NMPC(env, mpc_env, 1.0, dt, horizon, fcost=c_N, constrained=False, step_iterations=1, **kw)
+
+
 def make_env(case, x0=None, **kw):
     """Environment of a named case; x0 defaults to the case's nominal start (single plant)."""
     from . import environments

@@ -1,4 +1,4 @@
-"""Batched receding-horizon control (pygent_b200/algorithms/nmpc.py) against a closed-loop run of the unmodified
+"""Batched receding-horizon control (pygent_b200/algorithms/nmpc.py) against closed-loop runs of the unmodified
 reference's NMPC/MPCAgent (tests/golden/nmpc_cart_pole.npz, made by oracle/make_golden_nmpc.py: cart-pole of
 examples/nmpc/cart_pole.py, horizon 2 s, converged initial plan, 50 control steps, RK4 x 4, constrained=False)."""
 import numpy as np
@@ -116,3 +116,22 @@ def test_nmpc_cuda_graph_replay_equals_eager_loop():
     assert not plain._graph_ok()  # final backward pass re-solved on the host every step
     with pytest.raises(ValueError):
         plain.run(steps=6, printing=False, use_graph=True)
+
+
+def test_nmpc_double_pendulum_matches_reference(golden):
+    """examples/nmpc/double.py (CartPoleDoubleSerial, n = 6, the cost regulating around the hanging configuration x2 = x3 =
+    pi, cart displaced by 0.5 m): converged initial plan with the final backward pass at the final cost's equilibrium, then
+    30 control steps (27 accepted plans, 3 rejected line searches) against the unmodified reference's closed loop."""
+    from pygent_b200.examples import make_nmpc_double
+    g = golden("nmpc_double_serial")
+    dt, horizon, n_steps = float(g["dt"]), float(g["horizon"]), int(g["n_steps"])
+    alg = make_nmpc_double(list(g["x0"]), dt=dt, horizon=horizon, maxIters=int(g["init_iterations"]))
+    opt = alg.agent.traj_optimizer
+    assert rel(opt.cost, g["init_cost"]) < 1e-7 and rel(opt.xx, g["init_xx"]) < 1e-6 and rel(opt.uu, g["init_uu"]) < 1e-5
+    assert rel(opt.KK, g["init_KK"]) < 1e-5 and rel(opt.kk[..., 0], g["init_kk"]) < 1e-5
+    load_reference_plan(alg, g)
+    cost = alg.run(steps=n_steps, printing=False)
+    X, U = alg.environment.history, alg.agent.history[1:]
+    assert X.shape == g["X"].shape and U.shape == g["U"].shape
+    assert rel(X, g["X"]) < 1e-6 and rel(U, g["U"]) < 1e-5 and rel(cost, g["costs"]) < 1e-6
+    assert rel(opt.cost, g["plan_costs"][-1]) < 1e-6 and rel(opt.xx[-1], g["plan_xN"][-1]) < 1e-6
