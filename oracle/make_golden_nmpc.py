@@ -33,6 +33,18 @@ def c_N_double(x):  # the example passes no final cost (fcost=None does not run 
     return 100 * x1 ** 2 + 100 * (x2 - np.pi) ** 2 + 100 * (x3 - np.pi) ** 2 + 10 * x4 ** 2 + 10 * x5 ** 2 + 10 * x6 ** 2
 
 
+def c_k_triple(x, u):  # examples/nmpc/triple.py:7-11
+    x1, x2, x3, x4, x5, x6, x7, x8 = x
+    u1, = u
+    return .5 * (20. * x1 ** 2 + 20 * (x2 - np.pi) ** 2 + .01 * x5 ** 2 + .01 * x6 ** 2) + 0.01 * u1 ** 2
+
+
+def c_N_triple(x):
+    x1, x2, x3, x4, x5, x6, x7, x8 = x
+    return (100 * x1 ** 2 + 100 * (x2 - np.pi) ** 2 + 100 * (x3 - np.pi) ** 2 + 100 * (x4 - np.pi) ** 2 + 10 * x5 ** 2 + 10 * x6 ** 2
+            + 10 * x7 ** 2 + 10 * x8 ** 2)
+
+
 def main():
     import sys
     only = sys.argv[1:]
@@ -43,6 +55,9 @@ def main():
     if not only or "nmpc_double_serial" in only:   # examples/nmpc/double.py: n = 6, cart displaced by 0.5 m
         run("nmpc_double_serial", [0.5, np.pi, np.pi, 0, 0, 0], n_steps=30, horizon=1.0, dt=0.01, cls="CartPoleDoubleSerial",
             costs=(c_k_double, c_N_double))
+    if not only or "nmpc_triple" in only:          # examples/nmpc/triple.py: n = 8
+        run("nmpc_triple", [0.5, np.pi, np.pi, np.pi, 0, 0, 0, 0], n_steps=20, horizon=1.0, dt=0.01, cls="CartPoleTriple",
+            costs=(c_k_triple, c_N_triple))
 
 
 def run(name, x0, n_steps=50, horizon=2.0, dt=0.02, init_iterations=500, cls="CartPole", costs=None):

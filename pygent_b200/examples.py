@@ -168,12 +168,34 @@ def double_nmpc():  # examples/nmpc/double.py:7-11: regulation around the hangin
     return c_k, c_N
 
 
-def make_nmpc_double(x0, dt=0.01, horizon=1.0, **kw):
-    """NMPC of examples/nmpc/double.py: CartPoleDoubleSerial, plants x0 [B, 6] or [6]."""
+def triple_nmpc():  # examples/nmpc/triple.py:7-11
+    def c_k(x, u):
+        x1, x2, x3, x4, x5, x6, x7, x8 = x
+        u1, = u
+        return .5 * (20. * x1 ** 2 + 20 * (x2 - np.pi) ** 2 + .01 * x5 ** 2 + .01 * x6 ** 2) + 0.01 * u1 ** 2
+
+    def c_N(x):
+        x1, x2, x3, x4, x5, x6, x7, x8 = x
+        return (100 * x1 ** 2 + 100 * (x2 - np.pi) ** 2 + 100 * (x3 - np.pi) ** 2 + 100 * (x4 - np.pi) ** 2 + 10 * x5 ** 2
+                + 10 * x6 ** 2 + 10 * x7 ** 2 + 10 * x8 ** 2)
+    return c_k, c_N
+
+
+# the reference's receding-horizon examples beyond the cart-pole: name -> (env class, cost factory, x0, dt)
+NMPC_EXAMPLES = {
+    "double": ("CartPoleDoubleSerial", double_nmpc, [0.5, np.pi, np.pi, 0, 0, 0], 0.01),
+    "triple": ("CartPoleTriple", triple_nmpc, [0.5, np.pi, np.pi, np.pi, 0, 0, 0, 0], 0.01),
+}
+
+
+def make_nmpc_example(name, x0=None, horizon=1.0, **kw):
+    """NMPC of examples/nmpc/double.py / triple.py: plants x0 [B, n] or [n] (default: the example's start)."""
     from . import environments
     from .algorithms.nmpc import NMPC
-    c_k, c_N = double_nmpc()
-    env, mpc_env = environments.CartPoleDoubleSerial(c_k, x0, dt), environments.CartPoleDoubleSerial(c_k, x0, dt)
+    cls, costf, x0_default, dt = NMPC_EXAMPLES[name]
+    c_k, c_N = costf()
+    x0 = x0_default if x0 is None else x0
+    env, mpc_env = getattr(environments, cls)(c_k, x0, dt), getattr(environments, cls)(c_k, x0, dt)
     kw.setdefault("ilqr_print", False)
     return NMPC(env, mpc_env, 1.0, dt, horizon, fcost=c_N, constrained=False, step_iterations=1, **kw)
 

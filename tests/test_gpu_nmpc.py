@@ -118,14 +118,17 @@ def test_nmpc_cuda_graph_replay_equals_eager_loop():
         plain.run(steps=6, printing=False, use_graph=True)
 
 
-def test_nmpc_double_pendulum_matches_reference(golden):
-    """examples/nmpc/double.py (CartPoleDoubleSerial, n = 6, the cost regulating around the hanging configuration x2 = x3 =
-    pi, cart displaced by 0.5 m): converged initial plan with the final backward pass at the final cost's equilibrium, then
-    30 control steps (27 accepted plans, 3 rejected line searches) against the unmodified reference's closed loop."""
-    from pygent_b200.examples import make_nmpc_double
-    g = golden("nmpc_double_serial")
+@pytest.mark.parametrize("name,fixture", [("double", "nmpc_double_serial"), ("triple", "nmpc_triple")])
+def test_nmpc_pendulum_chains_match_reference(golden, name, fixture):
+    """examples/nmpc/double.py (CartPoleDoubleSerial, n = 6) and triple.py (CartPoleTriple, n = 8): the cost regulating
+    around the hanging configuration, cart displaced by 0.5 m -- converged initial plan with the final backward pass at the
+    final cost's equilibrium, then the closed loop (accepted plans and rejected line searches) against the unmodified
+    reference's."""
+    from pygent_b200.examples import make_nmpc_example
+    g = golden(fixture)
     dt, horizon, n_steps = float(g["dt"]), float(g["horizon"]), int(g["n_steps"])
-    alg = make_nmpc_double(list(g["x0"]), dt=dt, horizon=horizon, maxIters=int(g["init_iterations"]))
+    alg = make_nmpc_example(name, list(g["x0"]), horizon=horizon, maxIters=int(g["init_iterations"]))
+    assert alg.dt == dt
     opt = alg.agent.traj_optimizer
     assert rel(opt.cost, g["init_cost"]) < 1e-7 and rel(opt.xx, g["init_xx"]) < 1e-6 and rel(opt.uu, g["init_uu"]) < 1e-5
     assert rel(opt.KK, g["init_KK"]) < 1e-5 and rel(opt.kk[..., 0], g["init_kk"]) < 1e-5
