@@ -9,7 +9,8 @@ from pygent_b200 import mlp
 
 pytestmark = pytest.mark.gpu
 
-IS_ANGLE = {4: [False, True, False, False], 6: [False, True, True, False, False, False], 2: [True, False]}
+IS_ANGLE = {4: [False, True, False, False], 6: [False, True, True, False, False, False], 2: [True, False],
+            8: [False, True, True, True, False, False, False, False]}   # pendulum, cart-pole/acrobot, double, triple (examples/mbrl)
 
 
 def rel(a, b):
@@ -50,9 +51,9 @@ def test_mlp_euler_rollout_matches_reference(golden, precision):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-@pytest.mark.parametrize("n,B,T", [(4, 200, 25), (6, 129, 12), (2, 64, 10), (4, 1, 5)])
+@pytest.mark.parametrize("n,B,T", [(4, 200, 25), (6, 129, 12), (2, 64, 10), (4, 1, 5), (8, 70, 8)])
 def test_mlp_rollouts_match_oracle(precision, n, B, T):
-    """Open-loop and closed-loop (iLQR forward-pass law) rollouts, ragged batches, three state dimensions."""
+    """Open-loop and closed-loop (iLQR forward-pass law) rollouts, ragged batches, the four state dimensions of examples/mbrl/*.py."""
     dyn, w, mom, ia = model(n=n, seed=n)
     rng = np.random.default_rng(n)
     x0 = rng.uniform(-1, 1, (B, n))
