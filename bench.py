@@ -174,8 +174,8 @@ def run_reference(args, rank):
 
 def nmpc_bench(dev, rank, world, barrier, plants=4096, steps=50, horizon=1.0):
     """examples/nmpc/cart_pole.py for a batch: every plant has its own MPCAgent state; the planner's terminal value is
-    solved once on the host (cache_terminal_value) so the control loop never leaves the device (GPU-bound at this batch:
-    launched eagerly; small batches replay the step as a CUDA graph, see NMPC.run)."""
+    solved once on the host (cache_terminal_value) so the control loop never leaves the device: after two eager control
+    steps the step is captured into a CUDA graph and replayed (NMPC.run), which keeps the host out of the timed loop."""
     import torch
     import torch.distributed as dist
     from pygent_b200.algorithms.nmpc import NMPC

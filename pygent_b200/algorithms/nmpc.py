@@ -305,7 +305,9 @@ class NMPC(Algorithm):
         if use_graph is None:
             # pays where the step is launch-bound on the host: measured at 4,096 plants the ~25 kernels of a step take
             # 0.45 ms of GPU time and eager launching keeps up (0.49 ms per step), the capture itself costs ~15 ms
-            use_graph = self._graph_ok() and n_steps >= 50 and B <= 1024
+            # replaying costs the GPU nothing and takes the host out of the loop: at 4,096 plants the eager loop is
+            # GPU-bound on a quiet host (0.44 ms per step) but 0.57-1.09 ms when the host is busy; the replay stays at 0.45
+            use_graph = self._graph_ok() and n_steps >= 50 and os.environ.get("PG_NMPC_GRAPH", "1") != "0"
         elif use_graph and not self._graph_ok():
             raise ValueError("this controller needs the host inside a control step (noise, time-dependent cost, or an uncached "
                              "final backward pass): it cannot be captured into a CUDA graph")
@@ -319,15 +321,27 @@ class NMPC(Algorithm):
             x_in, x_out = X[eager].clone(), torch.empty_like(X[0])
             c_out = torch.empty_like(C[0])
             n_before = len(agent._u_dev)
-            torch.cuda.synchronize()
+            libs = {id(l): l for l in (L, agent.traj_optimizer.lib)}.values()
+            launched = [l.launches for l in libs]
+            # capture on a side stream with the raw API: `with torch.cuda.graph(...)` would first empty the caching
+            # allocator (hundreds of ms of cudaFree when another solver has just released its buffers)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                u_g = agent.take_action_device(x_in)
-                L.rollout(x_in, u_g[None], S=env.substeps, dt=self.dt, t0=0.0, terminal_cost=float(env.terminal_cost),
-                          out={"xN": x_out, "cost": c_out, "terminated": term})
-                x_in.copy_(x_out)
+            side = torch.cuda.Stream(device=env.device)
+            side.wait_stream(torch.cuda.current_stream(env.device))
+            with torch.cuda.stream(side):
+                graph.capture_begin()
+                try:
+                    u_g = agent.take_action_device(x_in)
+                    L.rollout(x_in, u_g[None], S=env.substeps, dt=self.dt, t0=0.0, terminal_cost=float(env.terminal_cost),
+                              out={"xN": x_out, "cost": c_out, "terminated": term})
+                    x_in.copy_(x_out)
+                finally:
+                    graph.capture_end()
+            torch.cuda.current_stream(env.device).wait_stream(side)
             del agent._u_dev[n_before:]  # capture recorded (did not run) one step: undo its host-side bookkeeping
             del agent.tt[-1:]
+            for l, n0 in zip(libs, launched):  # the capture launched nothing; every replay launches the captured kernels
+                l.launches = n0 + (l.launches - n0) * (n_steps - eager)
             # the capture did not execute: restore nothing, the planner state is untouched; replay from step `eager`
             Uh = torch.empty((n_steps - eager,) + tuple(u_g.shape), dtype=u_g.dtype, device=u_g.device)
             for i in range(eager, n_steps):
