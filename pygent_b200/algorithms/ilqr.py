@@ -62,7 +62,7 @@ class iLQR(Algorithm):
                  saving=True,
                  parallel=False,
                  final_backpass=True,
-                 check_every=4,
+                 check_every=4, use_graph=None,
                  cache_terminal_value=False):
         self.uDim = environment.uDim
         self.xDim = environment.xDim
@@ -113,6 +113,7 @@ class iLQR(Algorithm):
         self.printing = printing
         self.file_prefix = file_prefix
         self.check_every = max(1, int(check_every))
+        self.use_graph = use_graph  # None: replay iterations from a CUDA graph when possible (see _iterate_until_done)
 
         # algorithm parameters (ilqr.py:141-162)
         self.success_fw = False
@@ -474,6 +475,75 @@ class iLQR(Algorithm):
         if self.final_backpass:
             self._final_backpass()
 
+    def _iterate_until_done(self):
+        """Loop bodies of run_optim in blocks of `check_every` until no trajectory is running or max_iters is reached.
+        The number of running trajectories comes back through pinned memory one block LATE (the next block is already
+        enqueued when the host looks at it), so the device never waits for the host; the price is at most one block of
+        iterations over an empty work list.  After the first block the iterations are replayed from a CUDA graph of two
+        consecutive ones (the work lists ping-pong between two buffers), which takes the ~9 ctypes / torch calls per
+        iteration off the host: late iterations run a few stragglers and last ~270 us, about what the host needs to
+        launch them."""
+        dev = self.environment.device
+        cuda = dev.type == "cuda"
+        graph, use_graph = None, self.use_graph
+        if use_graph is None:
+            use_graph = cuda and not self.learned and self.check_every % 2 == 0 and self.max_iters >= 8 * self.check_every \
+                and os.environ.get("PG_ILQR_GRAPH", "1") != "0"
+        flags = torch.zeros(2, dtype=torch.int32, pin_memory=True) if cuda else None
+        it, k, pending = 0, 0, None
+        while it < self.max_iters:
+            n = min(self.check_every, self.max_iters - it)
+            if use_graph and it > 0 and n % 2 == 0:
+                if graph is None:
+                    graph = self._capture_two_iterations()
+                for _ in range(n // 2):
+                    graph.replay()
+                for l, per in self._graph_launches:
+                    l.launches += per * (n // 2)
+            else:
+                for _ in range(n):
+                    self.iterate()
+            it += n
+            if not cuda:
+                if int(self._n_active.item()) == 0:
+                    break
+                continue
+            slot = k % 2
+            k += 1
+            flags[slot:slot + 1].copy_(self._n_active.reshape(1), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            if pending is not None:
+                pending[0].synchronize()
+                if int(flags[pending[1]]) == 0:
+                    break
+            pending = (ev, slot)
+        self._graph = graph  # keep it alive until the results have been read
+
+    def _capture_two_iterations(self):
+        """CUDA graph of iterate(); iterate() -- raw capture on a side stream (`with torch.cuda.graph` would first empty
+        the caching allocator).  Everything iterate() touches is preallocated, its launch arguments are constants."""
+        dev = self.environment.device
+        libs = [self.lib]
+        before = [l.launches for l in libs]
+        cur = self._cur
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            graph.capture_begin()
+            try:
+                self.iterate()
+                self.iterate()
+            finally:
+                graph.capture_end()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        assert self._cur == cur
+        self._graph_launches = [(l, l.launches - b) for l, b in zip(libs, before)]
+        for l, b in zip(libs, before):  # the capture launched nothing
+            l.launches = b
+        return graph
+
     def run_optim(self):
         """Trajectory optimisation (ilqr.py:399-499).  Returns (xx, uu, cost)."""
         start_time = time.time()
@@ -488,13 +558,7 @@ class iLQR(Algorithm):
         st["success_gradient"].zero_()
         self._rearm()
         self._sel = self._select_params()
-        it = 0
-        while it < self.max_iters:
-            self.iterate()
-            it += 1
-            if it % self.check_every == 0 or it == self.max_iters:
-                if int(self._n_active.item()) == 0:  # the only host<->device sync of the loop
-                    break
+        self._iterate_until_done()
         if self.final_backpass:
             self._final_backpass()
         self.iterations = int(st["iters"].max().item())
