@@ -531,7 +531,7 @@ class iLQR(Algorithm):
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            graph.capture_begin()
+            graph.capture_begin(capture_error_mode="thread_local")  # other threads (NCCL watchdog, samplers) may call CUDA
             try:
                 self.iterate()
                 self.iterate()

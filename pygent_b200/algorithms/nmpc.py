@@ -329,7 +329,7 @@ class NMPC(Algorithm):
             side = torch.cuda.Stream(device=env.device)
             side.wait_stream(torch.cuda.current_stream(env.device))
             with torch.cuda.stream(side):
-                graph.capture_begin()
+                graph.capture_begin(capture_error_mode="thread_local")  # other threads (NCCL watchdog, samplers) may call CUDA
                 try:
                     u_g = agent.take_action_device(x_in)
                     L.rollout(x_in, u_g[None], S=env.substeps, dt=self.dt, t0=0.0, terminal_cost=float(env.terminal_cost),
