@@ -39,6 +39,8 @@ constexpr int N_CHUNKS = 32;                   // 8 k-blocks x 4 n-quarters
 struct alignas(1024) MlpPacked {
     uint16_t W2b[N_CHUNKS][CHUNK_BYTES / 2];  // bf16, 128B-swizzled K-major images, chunk = quarter * 8 + kb
     uint16_t W2bT[N_CHUNKS][CHUNK_BYTES / 2];  // the same for W2^T (contraction over layer 2's OUTPUT index)
+    uint16_t W1img[4][CHUNK_BYTES / 2];        // layer 1 as ONE k-block for the tensor core: per output quarter [128 n x 64 k],
+                                               // k = 16 seg + j: seg 0 hi(W1b[n][j]), 1 lo(...), 2 hi(...), 3 zero (see layer1_operand)
     float W2t[H][H];                          // [k][n] fp32 (FFMA path)
     float W1[H][MAXIN];                       // [k][input]
     float b1[H];
@@ -59,6 +61,13 @@ inline uint16_t f32_to_bf16(float f) {  // round to nearest even
     if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
     u += 0x7fffu + ((u >> 16) & 1u);
     return (uint16_t)(u >> 16);
+}
+
+inline float bf16_to_f32(uint16_t h) {
+    const uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
 }
 
 constexpr int MODE_ODE = 0, MODE_ROLLOUT = 1, MODE_LIN_FD = 2, MODE_LIN_AN = 3;
@@ -516,12 +525,17 @@ struct GemmPipe {
 // `next_img`: the weight images of the following pass (nullptr after the last one).  When its own chunks are out the
 // producer requests the first STAGES chunks of the next pass right away: the stages free up as this pass's MMAs retire,
 // so the next GEMM starts with a full ring instead of paying the L2 latency again while the tensor core idles.
-template <int STAGES>
+// KB: k-blocks of 64 this pass contracts over (8: a hidden layer of 512; 1: layer 1, whose operand is `a_img`);
+// NEXT_KB: the same for the pass that follows.
+template <int STAGES, int KB = 8, int NEXT_KB = 8>
 __device__ __forceinline__ void gemm_issue(GemmPipe& p, const uint16_t (*img)[CHUNK_BYTES / 2], int t,
-                                           const uint16_t (*next_img)[CHUNK_BYTES / 2] = nullptr) {
+                                           const uint16_t (*next_img)[CHUNK_BYTES / 2] = nullptr, const uint8_t* a_img = nullptr) {
     // the control lanes' 31 warp siblings park at __syncwarp() instead of spinning on the completion barrier: as
     // divergent paths of the same warp they would take every other issue slot from the lane that feeds the tensor core
-    constexpr int PER_PASS = TWO_SM ? N_CHUNKS / 2 : N_CHUNKS;  // chunks this CTA loads per GEMM
+    constexpr int PER_PASS = TWO_SM ? 4 * KB / 2 : 4 * KB;  // chunks this CTA loads per GEMM
+    constexpr int NEXT_PER_PASS = TWO_SM ? 4 * NEXT_KB / 2 : 4 * NEXT_KB;
+    constexpr int N_PREFETCH = NEXT_PER_PASS < STAGES ? NEXT_PER_PASS : STAGES;
+    const uint8_t* A = a_img ? a_img : p.As;
     const int cw = t >> 5;
     if (cw != (PRODUCER_THREAD >> 5) && cw != (ISSUER_THREAD >> 5)) {
         p.chunk_no += PER_PASS;
@@ -538,17 +552,18 @@ __device__ __forceinline__ void gemm_issue(GemmPipe& p, const uint16_t (*img)[CH
                 const uint32_t s = c % STAGES, use = c / STAGES;
                 mbar_wait(&p.empty[s], (use & 1) ^ 1);
                 mbar_expect_tx(&p.full[s], CHUNK_BYTES);
-                bulk_g2s(p.Bs + s * CHUNK_BYTES, &img[(2 * (i >> 3) + rank) * 8 + (i & 7)][0], CHUNK_BYTES, &p.full[s]);
+                bulk_g2s(p.Bs + s * CHUNK_BYTES, &img[(2 * (i / KB) + rank) * KB + (i % KB)][0], CHUNK_BYTES, &p.full[s]);
             }
             p.prefetched = 0;
             if (next_img) {
-                for (int i = 0; i < STAGES; i++, c++) {
+                for (int i = 0; i < N_PREFETCH; i++, c++) {
                     const uint32_t s = c % STAGES, use = c / STAGES;
                     mbar_wait(&p.empty[s], (use & 1) ^ 1);
                     mbar_expect_tx(&p.full[s], CHUNK_BYTES);
-                    bulk_g2s(p.Bs + s * CHUNK_BYTES, &next_img[(2 * (i >> 3) + rank) * 8 + (i & 7)][0], CHUNK_BYTES, &p.full[s]);
+                    bulk_g2s(p.Bs + s * CHUNK_BYTES, &next_img[(2 * (i / NEXT_KB) + rank) * NEXT_KB + (i % NEXT_KB)][0], CHUNK_BYTES,
+                             &p.full[s]);
                 }
-                p.prefetched = STAGES;
+                p.prefetched = N_PREFETCH;
             }
         } else if (t == ISSUER_THREAD && rank != 0) {  // peer: tell the leader when a stage of OUR ring is full
             uint32_t c = p.chunk_no;
@@ -566,15 +581,15 @@ __device__ __forceinline__ void gemm_issue(GemmPipe& p, const uint16_t (*img)[CH
                 mbar_wait(&p.full[s], use & 1);
                 mbar_wait(&p.pfull[s], use & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const int q2 = i >> 3, kb = i & 7;
-                const uint32_t a_addr = smem_u32(p.As + kb * (T_ROWS * 128));
+                const int q2 = i / KB, kb = i % KB;
+                const uint32_t a_addr = smem_u32(A + kb * (T_ROWS * 128));
                 const uint32_t b_addr = smem_u32(p.Bs + s * CHUNK_BYTES);
 #pragma unroll
                 for (int ks = 0; ks < 4; ks++)
                     umma_bf16_2sm(p.tmem_base + q2 * 256, umma_desc_sw128(a_addr + ks * 32), umma_desc_sw128(b_addr + ks * 32),
                                   (kb > 0 || ks > 0) ? 1u : 0u);
                 umma_commit_2sm(&p.empty[s], CL_MASK);  // frees the stage in both CTAs
-                if (kb == 7) {                            // 256 accumulator columns final in both CTAs
+                if (kb == KB - 1) {                       // 256 accumulator columns final in both CTAs
                     umma_commit_2sm(&p.accum[2 * q2], CL_MASK);
                     umma_commit_2sm(&p.accum[2 * q2 + 1], CL_MASK);
                 }
@@ -583,7 +598,7 @@ __device__ __forceinline__ void gemm_issue(GemmPipe& p, const uint16_t (*img)[CH
     } else {
         if (t == PRODUCER_THREAD) {  // weight chunks, L2 -> smem rings of the cluster
             uint32_t c = p.chunk_no;
-            for (int i = 0; i < N_CHUNKS; i++, c++) {
+            for (int i = 0; i < PER_PASS; i++, c++) {
                 const uint32_t s = c % STAGES, use = c / STAGES;
                 mbar_wait(&p.empty[s], (use & 1) ^ 1);        // both CTAs are done with the stage's previous chunk
                 mbar_expect_tx(&p.full[s], CHUNK_BYTES);      // whoever fetches it, this CTA's ring receives the bytes
@@ -592,19 +607,19 @@ __device__ __forceinline__ void gemm_issue(GemmPipe& p, const uint16_t (*img)[CH
         } else if (t == ISSUER_THREAD) {  // one thread drives the tensor core for the whole CTA
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t c = p.chunk_no;
-            for (int i = 0; i < N_CHUNKS; i++, c++) {
+            for (int i = 0; i < PER_PASS; i++, c++) {
                 const uint32_t s = c % STAGES, use = c / STAGES;
                 mbar_wait(&p.full[s], use & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const int quarter = i >> 3, kb = i & 7;
-                const uint32_t a_addr = smem_u32(p.As + kb * (T_ROWS * 128));
+                const int quarter = i / KB, kb = i % KB;
+                const uint32_t a_addr = smem_u32(A + kb * (T_ROWS * 128));
                 const uint32_t b_addr = smem_u32(p.Bs + s * CHUNK_BYTES);
 #pragma unroll
                 for (int ks = 0; ks < 4; ks++)  // K = 16 per instruction = 32 bytes along the swizzled row
                     umma_bf16(p.tmem_base + quarter * CHUNK_N, umma_desc_sw128(a_addr + ks * 32), umma_desc_sw128(b_addr + ks * 32),
                               (kb > 0 || ks > 0) ? 1u : 0u);
                 umma_commit_multicast(&p.empty[s], CL_MASK);  // one of the CL arrivals that free the stage in every CTA
-                if (kb == 7) umma_commit(&p.accum[quarter]);  // this quarter's accumulators are final
+                if (kb == KB - 1) umma_commit(&p.accum[quarter]);  // this quarter's accumulators are final
             }
         }
     }
@@ -629,6 +644,7 @@ __device__ __forceinline__ void gemm_wait(const GemmPipe& p, int q) {
 // warp-uniform loads missed half of the time)
 __device__ __forceinline__ void stage_constants(const MlpPacked* w, float4* eps, float* w1s, int t) {
     for (int i = t; i < H; i += T_THREADS) eps[i] = w->ep[i];
+    if (!w1s) return;
     for (int i = t; i < H * (W1S_FLOATS / 4); i += T_THREADS) {
         const int k = i / (W1S_FLOATS / 4), q = i % (W1S_FLOATS / 4);
         reinterpret_cast<float4*>(w1s)[i] = reinterpret_cast<const float4*>(&w->W1b[k][0])[q];
@@ -716,6 +732,55 @@ __device__ __forceinline__ void layer1_dispatch(int nin, const MlpPacked* w, con
     else layer1_image<4, 2, MASK>(&w->W1b[0][0], MAXIN, ins, As, m1, t);
 }
 
+
+// ---- layer 1 on the tensor core -------------------------------------------------------------------------------------
+// K = inputs + 1 <= 16 is far too short for an MMA in bf16 ALONE (the network inputs would lose 16 mantissa bits), but as
+// a split product it fits ONE 64-wide k-block:  x w ~ xh wh + xh wl + xl wh  with  x = xh + xl, w = wh + wl  in bf16 --
+// relative error ~2^-16, below the bf16 rounding of h1 that layer 2 applies anyway.  A row of the operand image is
+//   [xh_0..15 | xh_0..15 | xl_0..15 | 0]  against W1img's  [wh | wl | wh | 0]   (bias: the constant-1 input slot),
+// in the same 128-byte-swizzled K-major format as a k-block of the A image, so the pass reuses the layer-2 descriptors.
+// This replaces 1,024 FFMA per thread and interval (4.5 us of the 14.5 us interval) by 8 MMAs and one TMEM read-out.
+__device__ __forceinline__ void layer1_operand(const float (&in)[MAXIN], uint8_t* A1, int row) {
+    uint32_t hp[MAXIN / 2], lp[MAXIN / 2];
+#pragma unroll
+    for (int j = 0; j < MAXIN / 2; j++) {
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hp[j]) : "f"(in[2 * j + 1]), "f"(in[2 * j]));
+        const float h0 = __uint_as_float(hp[j] << 16), h1 = __uint_as_float(hp[j] & 0xffff0000u);
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lp[j]) : "f"(in[2 * j + 1] - h1), "f"(in[2 * j] - h0));
+    }
+    uint8_t* rowp = A1 + (row >> 3) * 1024 + (row & 7) * 128;
+    const int x = row & 7;
+    const uint4 h_lo = make_uint4(hp[0], hp[1], hp[2], hp[3]), h_hi = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+    *reinterpret_cast<uint4*>(rowp + ((0 ^ x) << 4)) = h_lo;
+    *reinterpret_cast<uint4*>(rowp + ((1 ^ x) << 4)) = h_hi;
+    *reinterpret_cast<uint4*>(rowp + ((2 ^ x) << 4)) = h_lo;
+    *reinterpret_cast<uint4*>(rowp + ((3 ^ x) << 4)) = h_hi;
+    *reinterpret_cast<uint4*>(rowp + ((4 ^ x) << 4)) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+    *reinterpret_cast<uint4*>(rowp + ((5 ^ x) << 4)) = make_uint4(lp[4], lp[5], lp[6], lp[7]);
+    *reinterpret_cast<uint4*>(rowp + ((6 ^ x) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(rowp + ((7 ^ x) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// h1 = relu(layer-1 accumulators) of this thread's row and column quarter: TMEM -> bf16 -> the A image of layer 2
+__device__ __forceinline__ void hidden_from_tmem(uint32_t tmem_base, int warp, int part, int row, uint8_t* As) {
+    uint8_t* rowp = As + (row >> 3) * 1024 + (row & 7) * 128;
+    for (int cb = part * (H / 32 / T_SPLIT); cb < (part + 1) * (H / 32 / T_SPLIT); cb++) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + cb * 32, v);
+#pragma unroll
+        for (int c8 = 0; c8 < 4; c8++) {
+            uint32_t packed[4];
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+                const float lo = fmaxf(__uint_as_float(v[c8 * 8 + e]), 0.0f), hi = fmaxf(__uint_as_float(v[c8 * 8 + e + 1]), 0.0f);
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(packed[e >> 1]) : "f"(hi), "f"(lo));
+            }
+            const int nn0 = cb * 32 + c8 * 8, kb = nn0 >> 6, cidx = ((nn0 & 63) >> 3) ^ (row & 7);
+            *reinterpret_cast<uint4*>(rowp + kb * (T_ROWS * 128) + cidx * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+    }
+}
+
 // 512 threads per CTA: thread t works on row (t & 127); the four threads of a row split the hidden units
 // (layer 1) and the accumulator columns (epilogue) four ways.  Warp w reads TMEM lanes 32 (w % 4) .. +31, which
 // is exactly the row quarter (t & 127) >> 5 of its threads.  Threads 0..127 own the fp64 state of their row.
@@ -726,8 +791,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_b
     float* ins = reinterpret_cast<float*>(tsm + T_A_BYTES + T_STAGES * CHUNK_BYTES);
     float* yp = ins;  // partial layer-3 sums [T_SPLIT][T_ROWS][MAXDX]: the input tile is dead once layer 1 has run
     float4* eps = reinterpret_cast<float4*>(tsm + T_A_BYTES + T_STAGES * CHUNK_BYTES + T_INS_BYTES);
-    float* w1s = reinterpret_cast<float*>(eps + H);
-    uint64_t* full = reinterpret_cast<uint64_t*>(w1s + H * W1S_FLOATS);
+    uint8_t* A1 = reinterpret_cast<uint8_t*>(eps + H);  // layer-1 operand image, one k-block (16 KB, 1024-byte aligned)
+    static_assert((T_A_BYTES + T_STAGES * CHUNK_BYTES + T_INS_BYTES + T_EP_BYTES) % 1024 == 0 && T_W1_BYTES >= CHUNK_BYTES, "A1 placement");
+    uint64_t* full = reinterpret_cast<uint64_t*>(A1 + T_W1_BYTES);
     uint64_t* empty = full + T_STAGES;
     uint64_t* accum = empty + T_STAGES;
     uint64_t* pfull = accum + 4;
@@ -761,7 +827,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_b
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         }
     }
-    stage_constants(w, eps, w1s, t);
+    stage_constants(w, eps, nullptr, t);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     cluster_sync();  // the peer's barriers are initialised before anything is multicast to them
@@ -772,20 +838,28 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_b
     if (owner) load_row(a, rw, x, u);
     GemmPipe pipe = {As, Bs, full, empty, accum, pfull, a_ready, tmem_base, 0u, 0u, 0u};
     const int steps = steps_of(a);
+    (void)nin;
     for (int k = 0; k < steps; k++) {
         if (owner) {
             pre_step(a, rw, k, x, u, xe, ue);
             float in[MAXIN];
             network_input(a, mc, xe, ue, in);
-#pragma unroll
-            for (int j = 0; j < MAXIN; j++) ins[row * INS_STRIDE + j] = in[j];
+            layer1_operand(in, A1, row);
         }
-        __syncthreads();
-        layer1_dispatch<false>(nin, w, w1s, ins, As, nullptr, t);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA unit
         __syncthreads();
+        // layer 1: one k-block against W1img, accumulators = pre-activations of all 512 hidden units
         gemm_a_ready(pipe, t);
-        gemm_issue<T_STAGES>(pipe, w->W2b, t, (k + 1 < steps) ? w->W2b : nullptr);
+        gemm_issue<T_STAGES, 1, 8>(pipe, w->W1img, t, w->W2b, A1);
+        gemm_wait(pipe, part);
+        hidden_from_tmem(tmem_base, warp, part, row, As);
+        pipe.passes++;
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();  // A image complete, every lane has read its layer-1 accumulators
+        gemm_a_ready(pipe, t);
+        if (k + 1 < steps) gemm_issue<T_STAGES, 8, 1>(pipe, w->W2b, t, w->W1img);
+        else gemm_issue<T_STAGES, 8, 1>(pipe, w->W2b, t, nullptr);
         // epilogue: TMEM lane = row; this thread's quarter of the 512 columns, as soon as that quarter is final:
         // +b2, ReLU, layer 3
         gemm_wait(pipe, part);
@@ -1137,6 +1211,16 @@ int pg_mlp_pack(const pg_mlp_dims_t* d, const float* W1, const float* b1, const 
                     imgT[off >> 1] = f32_to_bf16((k < HID && n < HID) ? W2[k * HID + n] : 0.0f);
                 }
         }
+    // layer 1 for the tensor core: W1b split into bf16 hi + lo parts (x w ~ xh wh + xh wl + xl wh, error ~2^-16)
+    for (int qt = 0; qt < 4; qt++)
+        for (int nl = 0; nl < CHUNK_N; nl++)
+            for (int kk = 0; kk < 64; kk++) {
+                const int n = qt * CHUNK_N + nl, seg = kk >> 4, j = kk & 15;
+                const float wv = (n < HID && j <= nin) ? p->W1b[n][j] : 0.0f;
+                const uint16_t hi = f32_to_bf16(wv), lo = f32_to_bf16(wv - bf16_to_f32(hi));
+                const int off = (nl >> 3) * 1024 + (nl & 7) * 128 + (((kk >> 3) ^ (nl & 7)) << 4) + (kk & 7) * 2;
+                p->W1img[qt][off >> 1] = seg == 1 ? lo : (seg == 3 ? (uint16_t)0 : hi);
+            }
     return 0;
 }
 
