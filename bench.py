@@ -172,6 +172,40 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+
+def ilqr_full_batch_roofline(xi, dev, n_iter=8):
+    """FP64-pipe roofline of iLQR while the whole batch is live: the first n_iter iterations of a fresh solve, timed with
+    CUDA events.  Algorithmic flops per iteration and trajectory: 570 per backward step + per alpha the serial
+    line search of the reference TRIES (last alpha index + 1) a closed-loop rollout of T x (S x 228 + 30)."""
+    solver = make_ilqr("cart_pole", ILQR_T, x0=xi, env_kw={"device": dev}, maxIters=500)
+    tried_flops = ILQR_T * (SUBSTEPS * FLOPS_PER_SUBSTEP + 30)
+    res = None
+    for rep in range(2):  # the first repetition warms up
+        solver.environment.reset(xi)
+        solver.reset()
+        solver._sel = solver._select_params()
+        solver._rearm()
+        tried, live = [], []
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(n_iter):
+            live.append(solver._st["active"].clone())
+            solver.iterate()
+            tried.append(solver._last_tried.clone())
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        n_live = sum(int(l.sum()) for l in live)
+        n_tried = sum(int(((t + 1) * l.to(torch.int32)).sum()) for t, l in zip(tried, live))
+        flops = n_live * ILQR_T * 570 + n_tried * tried_flops
+        res = {"iterations": n_live, "us_per_iteration": ms * 1e3 / n_iter, "value": n_live / (ms * 1e-3),
+               "unit": "iLQR iterations/s", "alphas_tried_mean": n_tried / max(n_live, 1),
+               "alphas_evaluated": "first 4 of 11 for all, the other 7 where none of those passed",
+               "achieved": flops / (ms * 1e-3) / 1e12, "unit_roofline": "TFLOP/s", "bound": "fp64"}
+    return res
+
+
 def nmpc_bench(dev, rank, world, barrier, plants=4096, steps=50, horizon=1.0):
     """examples/nmpc/cart_pole.py for a batch: every plant has its own MPCAgent state; the planner's terminal value is
     solved once on the host (cache_terminal_value) so the control loop never leaves the device: after two eager control
@@ -418,6 +452,7 @@ def main():
                 "converged_frac": float(np.mean((st == pglib.ST_CONV_FUN) | (st == pglib.ST_CONV_GRAD))),
                 "mean_final_cost": float(np.mean(solver.cost)), "line_search": "serial semantics; first 4 of 11 alphas for all live trajectories, the other 7 only where none has passed yet "
                               "(one launch of all 11 once fewer than 64 x SMs trajectories are live)"}
+        ilqr["full_batch"] = ilqr_full_batch_roofline(xi, dev)
 
     # ---- config 4: n = 6 double pendulum / acrobot, parallel line search -------------------------------
     ilqr_c4 = None
@@ -464,6 +499,9 @@ def main():
         flops = algorithmic_flops_per_launch()
         achieved = flops / (kernel_ms * 1e-3) / 1e12
         hbm_bytes = U.numel() * 8 + x0.numel() * 8 + B_ENVS * (8 * 4 + 8 + 1)
+        if ilqr and ilqr.get("full_batch"):
+            fb = ilqr["full_batch"]
+            fb["peak"], fb["frac"] = peak_tf, fb["achieved"] / peak_tf
         res = {
             "metric": "rk4_env_steps_per_s", "value": value, "unit": "env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,

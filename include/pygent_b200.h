@@ -43,13 +43,16 @@
 extern "C" {
 #endif
 
-#define PG_ABI_VERSION 4
+#define PG_ABI_VERSION 5
 
 #define PG_F64 0
 #define PG_F32 1
 
 #define PG_INTEG_RK4 0   /* classical RK4, S substeps per control interval (parity schedule S=4) */
 #define PG_INTEG_EULER 1 /* forward Euler, StateSpaceModel.fast_step (environments.py:291-322)  */
+
+#define PG_LIN_COST_FD 4 /* OR-ed into lin_mode: iLQR(finite_diff=True), the cost expansion by central differences of c*dt with
+                            eps = 1e-3 (helpers.py:41-128 via ilqr.py:240-242, :598-603); fp64 only */
 
 #define PG_ROLLOUT_FINAL_COST 1 /* add fcost(x_T)*dt to the cost (ilqr.py:513) */
 #define PG_ROLLOUT_ACCUMULATE 2 /* cost[b] holds the sum of earlier time segments of the same rollout */
@@ -167,7 +170,8 @@ int pg_ilqr_linesearch_filter(int dtype, int64_t B, int32_t phase, int32_t n_fir
                               int32_t* index_out, int32_t* count_out, int32_t small_count, void* stream);
 
 /* Backward Riccati pass along (xbar, ubar).
- *   lin_mode 0: analytic A, B (requires has_ab); 1: central differences eps=1e-3 of f.
+ *   lin_mode 0: analytic A, B (requires has_ab); 1: central differences eps=1e-3 of f; | PG_LIN_COST_FD: the cost
+ *   expansion (running and final) by central differences as well (finite_diff=True; PG_E_UNSUPPORTED in fp32).
  *   mu [B] per-trajectory regularisation; reg_type 1 or 2 (ilqr.py:291-295);
  *   ulim host [m] or NULL: box-constrained gains (ilqr.py:304-327, exact-clip restatement);
  *   Vxx_T [n,n,B] or NULL: the FINAL backward pass (ilqr.py:246-260, :487-494) -- terminal value Hessian P from the

@@ -32,7 +32,7 @@ class Problem(ctypes.Structure):
 
 class ILQRParams(ctypes.Structure):
     _fields_ = [("max_iters", _i32), ("reg_type", _i32), ("parallel", _i32), ("constrained", _i32), ("n_alpha", _i32),
-                ("reserved", _i32), ("tol_grad", _f64), ("tol_fun", _f64), ("zmin", _f64), ("mu_min", _f64),
+                ("finite_diff", _i32), ("tol_grad", _f64), ("tol_fun", _f64), ("zmin", _f64), ("mu_min", _f64),
                 ("mu_max", _f64), ("mu_d0", _f64), ("mu0", _f64), ("alphas", _f64 * 16), ("lims", _f64 * MMAX)]
 
 
@@ -133,9 +133,10 @@ def rollout(p, x0, U=None, T=None, t0=0.0, history=True, add_final_cost=False, n
 
 
 def ilqr_params(max_iters=500, tol_grad=1e-4, tol_fun=1e-7, reg_type=2, parallel=False, constrained=False,
-                lims=(), alphas=None):
+                lims=(), alphas=None, finite_diff=False):
     q = ILQRParams()
     q.max_iters, q.reg_type, q.parallel, q.constrained = max_iters, reg_type, int(parallel), int(constrained)
+    q.finite_diff = int(finite_diff)  # cost expansion by central differences (helpers.py:41-128)
     q.tol_grad, q.tol_fun, q.zmin = tol_grad, tol_fun, 0.0
     q.mu_min, q.mu_max, q.mu_d0, q.mu0 = 1e-6, 1e10, 1.6, 1e-6  # ilqr.py:143-148
     alphas = 10 ** np.linspace(0, -3, 11) if alphas is None else np.asarray(alphas, dtype=float)  # ilqr.py:149

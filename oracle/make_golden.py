@@ -249,6 +249,10 @@ def main():
         ("ilqr_double_serial_rk4x4", "double_serial", 100, 4, {}),
         ("ilqr_pendulum_fd_rk4x4", "pendulum", 60, 4, {}),
         ("ilqr_cart_pole_euler", "cart_pole", 100, 0, {"fastForward": True}),
+        # finite_diff=True: cost expansion by central differences (helpers.py:41-128, ilqr.py:240-242, :598-603)
+        ("ilqr_cart_pole_costfd_rk4x4", "cart_pole", 100, 4, {"finite_diff": True}),
+        ("ilqr_cart_pole_tv_costfd_rk4x4", "cart_pole_tv", 100, 4, {"finite_diff": True}),
+        ("ilqr_pendulum_fd_costfd_rk4x4", "pendulum", 60, 4, {"finite_diff": True}),
     ]
     only = sys.argv[1:]
     for name, case, T, S, kw in runs:

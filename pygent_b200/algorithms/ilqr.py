@@ -75,9 +75,6 @@ class iLQR(Algorithm):
         batch = environment.batch if environment.batched else None
         super(iLQR, self).__init__(environment, FeedBack(None, self.uDim, batch), t, dt)
         self.xIsAngle = self.environment.xIsAngle
-        if finite_diff:
-            raise NotImplementedError("finite_diff=True (central-difference cost expansion, helpers.py:41-128) "
-                                      "is not on the GPU path yet; the analytic expansion is generated from the cost")
         self.finite_diff = finite_diff
         self.final_backpass = final_backpass
         # final backward pass: the terminal value P depends on the final-cost equilibrium only; with this flag it is
@@ -105,6 +102,15 @@ class iLQR(Algorithm):
         self.integrator = lib.INTEG_EULER if fastForward else lib.INTEG_RK4
         self.substeps = environment.substeps
         self.lin_mode = 2 if self.learned else (0 if self.lib.has_ab else 1)
+        if finite_diff:
+            # the cost expansion by central differences (helpers.py:41-128 via ilqr.py:240-242, :598-603): same kernels,
+            # PG_LIN_COST_FD or-ed into the linearisation mode
+            if self.learned:
+                raise NotImplementedError("finite_diff=True with learned dynamics: MBRL plans with the analytic cost "
+                                          "expansion (NMPC's default, nmpc.py:29)")
+            if environment.dtype != torch.float64:
+                raise ValueError("finite_diff=True needs fp64: second differences with eps = 1e-3 are noise in fp32")
+            self.lin_mode |= lib.LIN_COST_FD
         self.dtype = environment.dtype
         self.B = environment.batch
         self.batched = environment.batched
@@ -370,7 +376,7 @@ class iLQR(Algorithm):
                                                      precision=env.precision)
             r = {"A": Ad_[0], "B": Bd_[0]}
         else:
-            r = self.lib.eval(xd, ud, lin_mode=self.lin_mode, what=("A", "B"))
+            r = self.lib.eval(xd, ud, lin_mode=self.lin_mode & 3, what=("A", "B"))
         A = np.moveaxis(r["A"].to("cpu", torch.float64).numpy(), -1, 0)
         Bm = np.moveaxis(r["B"].to("cpu", torch.float64).numpy(), -1, 0)
         Ad = A * self.dt + np.eye(self.xDim)
@@ -385,7 +391,8 @@ class iLQR(Algorithm):
         xd = torch.as_tensor(x.T.copy(), dtype=self.dtype, device=dev)
         ud = torch.as_tensor(u.T.copy(), dtype=self.dtype, device=dev)
         td = torch.as_tensor(np.broadcast_to(np.asarray(t, dtype=float), (len(x),)).copy(), dtype=self.dtype, device=dev)
-        r = self.lib.eval(xd, ud, td, what=("cx", "cu", "Cxx", "Cuu", "Cxu"))
+        r = self.lib.eval(xd, ud, td, lin_mode=self.lin_mode & ~3 if self.finite_diff else None,
+                          what=("cx", "cu", "Cxx", "Cuu", "Cxu"))
         g = lambda k: np.moveaxis(r[k].to("cpu", torch.float64).numpy(), -1, 0) * self.dt
         out = (g("Cxx"), g("Cuu"), g("Cxu"), g("cx")[..., None], g("cu")[..., None])
         return tuple(o[0] for o in out) if len(x) == 1 else out

@@ -11,7 +11,8 @@ without a host synchronisation,
 Reference behaviour that is kept on purpose: the gains are not shifted with the plan (only their last entry is
 zeroed); the appended terminal state is integrated from wherever the planner's environment was left, i.e. the end of
 the last line-search candidate evaluated, accepted or not; the transition cost of the shift uses t = None (0 here).
-Differences: `finite_diff` must be False (analytic cost expansion), `constrained=True` uses the exact-clip box QP
+`finite_diff` follows the reference's defaults (True for a bare MPCAgent, nmpc.py:139; False through NMPC, nmpc.py:29).
+Differences: `constrained=True` uses the exact-clip box QP
 (DESIGN.md section 4), the noise generator is a seeded numpy RandomState owned by the agent.
 """
 import os
@@ -40,7 +41,7 @@ class MPCAgent(Agent):
                  printing=True,
                  saving=True,
                  init_optim=True,
-                 finite_diff=False,
+                 finite_diff=True,
                  noise_gain=0.05,
                  add_noise=False,
                  ou_theta=0.15,

@@ -19,7 +19,7 @@ import hashlib
 import sympy as sp
 from sympy.printing.c import C99CodePrinter
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 CODEGEN_VERSION = 5  # bump to invalidate cached libraries when the emitted code changes
 
 _FUNCS = {"sin": "pg::sin", "cos": "pg::cos", "tan": "pg::tan", "exp": "pg::exp", "log": "pg::log",

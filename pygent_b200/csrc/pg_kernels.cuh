@@ -816,6 +816,105 @@ __device__ __forceinline__ void fd_AB(const typename P::template Ctx<T>& m, cons
     }
 }
 
+// products that must not be contracted into the following subtraction (a*b - c*d as fma(a, b, -(c*d)) rounds one product
+// and not the other: a one-sided error that the 1/(4 eps^2) of a second difference turns into 1e-10)
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+
+// finite_diff=True: the cost expansion by central differences, eps = 1e-3 (pygent/helpers.py:41-128 as called from
+// iLQR.cost_lin, ilqr.py:598-603, on cost_fnc = c(x, u, t) * dt, and from backward_pass, ilqr.py:240-242, on the raw final
+// cost).  Every entry of the Hessians is formed on its own like the reference does -- H[i][j] and H[j][i] see the two middle
+// evaluations in opposite order -- and the diagonal steps twice, (x + eps) + eps.  Returns the derivatives of c*dt.
+template <typename P, typename T>
+__device__ __forceinline__ void fd_cost_derivs(const typename P::template Ctx<T>& m, const T (&x)[P::N], const T (&u)[P::M], const T t, const T dt,
+                                               T (&cx)[P::N], T (&cu)[P::M], T (&Cxx)[P::N * P::N], T (&Cuu)[P::M * P::M], T (&Cxu)[P::N * P::M]) {
+    constexpr int N = P::N, M = P::M;
+    const T eps = T(1e-3);
+    const T d2 = T(2) * eps, d4 = T(4) * (eps * eps);
+    T xa[N], xb[N], ua[M], ub[M];
+    auto c = [&](const T (&xx)[N], const T (&uu)[M]) { return mul_rn(P::cost(m, xx, uu, xx, t), dt); };
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        copy(xa, x);
+        copy(xb, x);
+        xa[i] = x[i] + eps;
+        xb[i] = x[i] - eps;
+        cx[i] = (c(xa, u) - c(xb, u)) / d2;
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            T xpp[N], xmp[N], xpm[N], xmm[N];
+            copy(xpp, xa);
+            copy(xmp, xb);
+            copy(xpm, xa);
+            copy(xmm, xb);
+            xpp[j] = xa[j] + eps;
+            xmp[j] = xb[j] + eps;
+            xpm[j] = xa[j] - eps;
+            xmm[j] = xb[j] - eps;
+            Cxx[i * N + j] = (((c(xpp, u) - c(xmp, u)) - c(xpm, u)) + c(xmm, u)) / d4;
+        }
+#pragma unroll
+        for (int r = 0; r < M; r++) {
+            copy(ua, u);
+            copy(ub, u);
+            ua[r] = u[r] + eps;
+            ub[r] = u[r] - eps;
+            Cxu[i * M + r] = (((c(xa, ua) - c(xb, ua)) - c(xa, ub)) + c(xb, ub)) / d4;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < M; r++) {
+        copy(ua, u);
+        copy(ub, u);
+        ua[r] = u[r] + eps;
+        ub[r] = u[r] - eps;
+        cu[r] = (c(x, ua) - c(x, ub)) / d2;
+#pragma unroll
+        for (int s = 0; s < M; s++) {
+            T upp[M], ump[M], upm[M], umm[M];
+            copy(upp, ua);
+            copy(ump, ub);
+            copy(upm, ua);
+            copy(umm, ub);
+            upp[s] = ua[s] + eps;
+            ump[s] = ub[s] + eps;
+            upm[s] = ua[s] - eps;
+            umm[s] = ub[s] - eps;
+            Cuu[r * M + s] = (((c(x, upp) - c(x, ump)) - c(x, upm)) + c(x, umm)) / d4;
+        }
+    }
+}
+
+// helpers.fxN / fxxN on the final cost (ilqr.py:240-242); the caller scales by dt afterwards, like the reference.
+template <typename P, typename T>
+__device__ __forceinline__ void fd_fcost_derivs(const typename P::template Ctx<T>& m, const T (&x)[P::N], T (&cfx)[P::N], T (&Cfxx)[P::N * P::N]) {
+    constexpr int N = P::N;
+    const T eps = T(1e-3);
+    const T d2 = T(2) * eps, d4 = T(4) * (eps * eps);
+    T xa[N], xb[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        copy(xa, x);
+        copy(xb, x);
+        xa[i] = x[i] + eps;
+        xb[i] = x[i] - eps;
+        cfx[i] = (P::fcost(m, xa) - P::fcost(m, xb)) / d2;
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            T xpp[N], xmp[N], xpm[N], xmm[N];
+            copy(xpp, xa);
+            copy(xmp, xb);
+            copy(xpm, xa);
+            copy(xmm, xb);
+            xpp[j] = xa[j] + eps;
+            xmp[j] = xb[j] + eps;
+            xpm[j] = xa[j] - eps;
+            xmm[j] = xb[j] - eps;
+            Cfxx[i * N + j] = (((P::fcost(m, xpp) - P::fcost(m, xmp)) - P::fcost(m, xpm)) + P::fcost(m, xmm)) / d4;
+        }
+    }
+}
+
 // ---- K3: backward Riccati pass (iLQR.backward_pass, ilqr.py:233-346) --------------------------------
 template <typename T>
 struct BackwardArgs {
@@ -845,7 +944,7 @@ __device__ __forceinline__ bool np_isclose(T a, T b, T atol) {  // np.isclose(a,
     return fabs(a - b) <= atol + T(1e-5) * fabs(b);
 }
 
-template <typename P, typename T, int LIN>
+template <typename P, typename T, int LIN, bool CFD = false>
 __global__ void __launch_bounds__(64) ilqr_backward_kernel(const BackwardArgs<T> a) {
     const typename P::template Ctx<T> m;
     constexpr int N = P::N, M = P::M;
@@ -874,11 +973,12 @@ __global__ void __launch_bounds__(64) ilqr_backward_kernel(const BackwardArgs<T>
 #pragma unroll
         for (int i = 0; i < N * N; i++) Vxx[i] = a.Vxx_T[(int64_t)i * B + b];
     } else {
-        P::fcost_derivs(m, x, vx, Vxx);
+        if constexpr (CFD) fd_fcost_derivs<P, T>(m, x, vx, Vxx);
+        else P::fcost_derivs(m, x, vx, Vxx);
 #pragma unroll
         for (int i = 0; i < N; i++) vx[i] *= dt;
 #pragma unroll
-        for (int i = 0; i < N * N; i++) Vxx[i] = P::cfxx_nz(i) ? Vxx[i] * dt : T(0);
+        for (int i = 0; i < N * N; i++) Vxx[i] = (CFD || P::cfxx_nz(i)) ? Vxx[i] * dt : T(0);
     }
     T sV1 = T(0), sV2 = T(0);
     T gmax[M];
@@ -926,13 +1026,16 @@ __global__ void __launch_bounds__(64) ilqr_backward_kernel(const BackwardArgs<T>
 
         // cost expansion of c*dt at t_k = k*dt (ilqr.py:162, :236, :597-610)
         T cx[N], cu[M], Cxx[N * N], Cuu[M * M], Cxu[N * M];
-        P::cost_derivs(m, x, u, T(k) * dt, cx, cu, Cxx, Cuu, Cxu);
+        // (finite differences are taken of c*dt itself: cdt = 1 there, and no entry is structurally zero)
+        const T cdt = CFD ? T(1) : dt;
+        if constexpr (CFD) fd_cost_derivs<P, T>(m, x, u, T(k) * dt, dt, cx, cu, Cxx, Cuu, Cxu);
+        else P::cost_derivs(m, x, u, T(k) * dt, cx, cu, Cxx, Cuu, Cxu);
 #pragma unroll
-        for (int i = 0; i < N; i++) cx[i] *= dt;
+        for (int i = 0; i < N; i++) cx[i] *= cdt;
 #pragma unroll
-        for (int r = 0; r < M; r++) cu[r] *= dt;
+        for (int r = 0; r < M; r++) cu[r] *= cdt;
 #pragma unroll
-        for (int i = 0; i < M * M; i++) Cuu[i] *= dt;
+        for (int i = 0; i < M * M; i++) Cuu[i] *= cdt;
 
         // W = Vxx Ad, g = Vxx Bd
         T W[N * N], g[N * M];
@@ -991,7 +1094,7 @@ __global__ void __launch_bounds__(64) ilqr_backward_kernel(const BackwardArgs<T>
 #pragma unroll
                 for (int l = 0; l < N; l++)
                     if (bdnz(l, r)) acc += Bd[l * M + r] * W[l * N + j];
-                Qux[r * N + j] = (P::cxu_nz(j * M + r) ? Cxu[j * M + r] * dt : T(0)) + acc;
+                Qux[r * N + j] = ((CFD || P::cxu_nz(j * M + r)) ? Cxu[j * M + r] * cdt : T(0)) + acc;
             }
         }
         // regularisation (ilqr.py:291-295)
@@ -1013,7 +1116,7 @@ __global__ void __launch_bounds__(64) ilqr_backward_kernel(const BackwardArgs<T>
 #pragma unroll
                     for (int l = 0; l < N; l++)
                         if (bdnz(l, r)) acc += Bd[l * M + r] * (W[l * N + j] + mu * Ad[l * N + j]);
-                    QuxR[r * N + j] = (P::cxu_nz(j * M + r) ? Cxu[j * M + r] * dt : T(0)) + acc;
+                    QuxR[r * N + j] = ((CFD || P::cxu_nz(j * M + r)) ? Cxu[j * M + r] * cdt : T(0)) + acc;
                 }
             }
         } else {
@@ -1180,7 +1283,7 @@ __global__ void __launch_bounds__(64) ilqr_backward_kernel(const BackwardArgs<T>
 #pragma unroll
                 for (int l = 0; l < N; l++)
                     if (adnz(l, i)) acc += Ad[l * N + i] * W[l * N + j];
-                T q = (P::cxx_nz(i * N + j) ? Cxx[i * N + j] * dt : T(0)) + acc;
+                T q = ((CFD || P::cxx_nz(i * N + j)) ? Cxx[i * N + j] * cdt : T(0)) + acc;
                 T t1 = T(0), t2 = T(0), t3 = T(0);
 #pragma unroll
                 for (int r = 0; r < M; r++) {
@@ -1704,7 +1807,7 @@ __global__ void eval_kernel(const EvalArgs<T> a) {
     }
     if (a.A || a.Bm) {
         T A[N * N], Bm[N * M];
-        if (a.lin_mode == 0) P::AB(m, x, u, A, Bm);
+        if ((a.lin_mode & 3) == 0) P::AB(m, x, u, A, Bm);
         else fd_AB<P, T>(m, x, u, A, Bm);
         if (a.A) {
 #pragma unroll
@@ -1718,7 +1821,8 @@ __global__ void eval_kernel(const EvalArgs<T> a) {
     if (a.c) a.c[b] = P::cost(m, x, u, x, t);
     if (a.cx || a.cu || a.Cxx || a.Cuu || a.Cxu) {
         T cx[N], cu[M], Cxx[N * N], Cuu[M * M], Cxu[N * M];
-        P::cost_derivs(m, x, u, t, cx, cu, Cxx, Cuu, Cxu);
+        if (a.lin_mode & 4) fd_cost_derivs<P, T>(m, x, u, t, T(1), cx, cu, Cxx, Cuu, Cxu);  // finite_diff=True
+        else P::cost_derivs(m, x, u, t, cx, cu, Cxx, Cuu, Cxu);
         if (a.cx) {
 #pragma unroll
             for (int i = 0; i < N; i++) a.cx[i * B + b] = cx[i];
@@ -1743,7 +1847,8 @@ __global__ void eval_kernel(const EvalArgs<T> a) {
     if (a.cf) a.cf[b] = P::fcost(m, x);
     if (a.cfx || a.Cfxx) {
         T cfx[N], Cfxx[N * N];
-        P::fcost_derivs(m, x, cfx, Cfxx);
+        if (a.lin_mode & 4) fd_fcost_derivs<P, T>(m, x, cfx, Cfxx);
+        else P::fcost_derivs(m, x, cfx, Cfxx);
         if (a.cfx) {
 #pragma unroll
             for (int i = 0; i < N; i++) a.cfx[i * B + b] = cfx[i];

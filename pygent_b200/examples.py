@@ -151,6 +151,10 @@ ILQR_RUNS = {
     "ilqr_cart_pole_euler": ("cart_pole", 100, 4, 1, {"fastForward": True}),
     "ilqr_car_rk4x4": ("car", 100, 4, 0, {}),   # oracle/make_golden_zoo.py
     "ilqr_angular_pendulum_rk4x4": ("angular_pendulum", 100, 4, 0, {}),
+    # finite_diff=True: the cost expansion by central differences (helpers.py:41-128)
+    "ilqr_cart_pole_costfd_rk4x4": ("cart_pole", 100, 4, 0, {"finite_diff": True}),
+    "ilqr_cart_pole_tv_costfd_rk4x4": ("cart_pole_tv", 100, 4, 0, {"finite_diff": True}),
+    "ilqr_pendulum_fd_costfd_rk4x4": ("pendulum", 60, 4, 0, {"finite_diff": True}),
 }
 
 

@@ -14,6 +14,7 @@ from . import build
 
 PG_F64, PG_F32 = 0, 1
 INTEG_RK4, INTEG_EULER = 0, 1
+LIN_COST_FD = 4  # or-ed into lin_mode: cost expansion by central differences (iLQR(finite_diff=True))
 MAX_ALPHAS = 16
 ST_RUNNING, ST_CONV_FUN, ST_CONV_GRAD, ST_MU_MAX, ST_MAX_ITERS = range(5)
 STATUS_NAMES = {0: "running", 1: "converged: small improvement", 2: "converged: small gradient",

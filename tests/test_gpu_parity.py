@@ -183,14 +183,18 @@ def test_ilqr_backward_and_forward_match_golden(golden, run):
     """First backward pass (K, k, sum V1, sum V2) and the alpha = 1 forward pass of the reference."""
     case, T, S, integ, kw = ILQR_RUNS[run]
     g = golden(run)
-    alg = solver(case, T, x0=g["x0"], env_kw={"substeps": S}, fastForward=bool(integ), regType=kw.get("regType", 2))
+    alg = solver(case, T, x0=g["x0"], env_kw={"substeps": S}, fastForward=bool(integ), regType=kw.get("regType", 2),
+                 finite_diff=kw.get("finite_diff", False))
     assert rel(alg.xx, g["xx0"]) < 1e-10
     assert alg.cost == pytest.approx(float(g["cost0"]), rel=1e-11)
     V1, V2, ok, KK, kk = alg.backward_pass()
     assert ok
-    assert rel(KK, g["bw_KK"]) < 1e-8
-    assert rel(kk[..., 0], g["bw_kk"]) < 1e-8
-    assert rel([V1, V2], g["bw_sumV"]) < 1e-9
+    # finite_diff: second differences with eps = 1e-3 amplify the last-bit differences between two evaluations of the
+    # same cost expression (numpy there, CUDA with FMA here) by 1/(4 eps^2) -- 1e-10 absolute on the Hessians
+    tol = 1e-6 if kw.get("finite_diff") else 1e-8
+    assert rel(KK, g["bw_KK"]) < tol
+    assert rel(kk[..., 0], g["bw_kk"]) < tol
+    assert rel([V1, V2], g["bw_sumV"]) < tol / 10
     xx, uu, cost, term = alg.forward_pass(1.0, g["bw_KK"], g["bw_kk"])
     assert rel(xx, g["fw1_xx"]) < 1e-9
     assert rel(uu, g["fw1_uu"]) < 1e-9
@@ -203,14 +207,15 @@ def test_ilqr_solve_matches_reference(golden, run):
     case, T, S, integ, kw = ILQR_RUNS[run]
     g = golden(run)
     alg = solver(case, T, x0=g["x0"], env_kw={"substeps": S}, fastForward=bool(integ), regType=kw.get("regType", 2),
-                 parallel=kw.get("parallel", False))
+                 parallel=kw.get("parallel", False), finite_diff=kw.get("finite_diff", False))
     xx, uu, cost = alg.run_optim()
     assert alg.iters == int(g["iters"])
-    assert cost == pytest.approx(float(g["cost"]), rel=1e-7)
-    assert rel(xx, g["xx"]) < 1e-5
-    assert rel(uu, g["uu"]) < 1e-5
+    w = 100 if kw.get("finite_diff") else 1  # finite-difference noise of the cost Hessians, see the first-iteration test
+    assert cost == pytest.approx(float(g["cost"]), rel=1e-7 * w)
+    assert rel(xx, g["xx"]) < 1e-5 * w
+    assert rel(uu, g["uu"]) < 1e-5 * w
     if float(g["mu"]) <= 1e10:
-        assert rel(alg.KK, g["KK"]) < 1e-4
+        assert rel(alg.KK, g["KK"]) < 1e-4 * w
         assert alg.current_alpha == pytest.approx(float(g["alpha"]))
         assert alg.mu == pytest.approx(float(g["mu"]), rel=1e-9)
 

@@ -59,15 +59,19 @@ def test_ilqr_first_iteration_matches_reference(golden, run):
     case, T, S, integ, kw = ILQR_RUNS[run]
     g = golden(run)
     p = oracle_problem(case, S=S, integrator=integ)
-    q = oracle.ilqr_params(parallel=kw.get("parallel", False), reg_type=kw.get("regType", 2))
+    q = oracle.ilqr_params(parallel=kw.get("parallel", False), reg_type=kw.get("regType", 2),
+                           finite_diff=kw.get("finite_diff", False))
     r0 = oracle.rollout(p, g["x0"][None], T=T, add_final_cost=True)
     assert rel(r0["X"][0], g["xx0"]) < 1e-10
     assert abs(r0["cost"][0] - g["cost0"]) < 1e-10 * abs(g["cost0"])
     KK, kk, s1, s2, gn, ok = oracle.ilqr_backward(p, q, g["xx0"], g["uu0"], 1e-6)
     assert ok
-    assert rel(KK, g["bw_KK"]) < 1e-8
-    assert rel(kk, g["bw_kk"]) < 1e-8
-    assert rel([s1, s2], g["bw_sumV"]) < 1e-9
+    # finite_diff: second differences with eps = 1e-3 amplify the last-bit differences between two evaluations of the
+    # same cost expression (numpy there, C/CUDA here) by 1/(4 eps^2) -- 1e-10 absolute on the Hessians, 1e-7 on gains
+    tol = 1e-6 if kw.get("finite_diff") else 1e-8
+    assert rel(KK, g["bw_KK"]) < tol
+    assert rel(kk, g["bw_kk"]) < tol
+    assert rel([s1, s2], g["bw_sumV"]) < tol / 10
     xo, uo, c, div, term = oracle.ilqr_forward(p, q, 1.0, g["x0"], g["xx0"], g["uu0"], g["bw_KK"], g["bw_kk"])
     assert rel(xo, g["fw1_xx"]) < 1e-9
     assert rel(uo, g["fw1_uu"]) < 1e-9
@@ -80,21 +84,23 @@ def test_ilqr_solve_matches_reference(golden, run):
     case, T, S, integ, kw = ILQR_RUNS[run]
     g = golden(run)
     p = oracle_problem(case, S=S, integrator=integ)
-    q = oracle.ilqr_params(parallel=kw.get("parallel", False), reg_type=kw.get("regType", 2))
+    q = oracle.ilqr_params(parallel=kw.get("parallel", False), reg_type=kw.get("regType", 2),
+                           finite_diff=kw.get("finite_diff", False))
     out = oracle.ilqr_solve(p, q, g["x0"][None], T, trace=True)
     iters = int(g["iters"])
     assert out["iters"][0] == iters
     tr = out["trace"][0]
     # golden trace rows: (cost, mu, alpha) at the START of each iteration; ours: after each iteration
     ours_cost = np.concatenate([[out["cost0"][0]], tr[: iters - 1, 0]])
-    assert rel(ours_cost, g["trace"][:, 0]) < 1e-7
+    w = 100 if kw.get("finite_diff") else 1  # finite-difference noise of the cost Hessians, see the first-iteration test
+    assert rel(ours_cost, g["trace"][:, 0]) < 1e-7 * w
     ours_mu = np.concatenate([[1e-6], tr[: iters - 1, 2]])
     assert rel(ours_mu, g["trace"][:, 1]) < 1e-12
-    assert abs(out["cost"][0] - g["cost"]) < 1e-7 * abs(g["cost"])
-    assert rel(out["xx"][0], g["xx"]) < 1e-5
-    assert rel(out["uu"][0], g["uu"]) < 1e-5
+    assert abs(out["cost"][0] - g["cost"]) < 1e-7 * w * abs(g["cost"])
+    assert rel(out["xx"][0], g["xx"]) < 1e-5 * w
+    assert rel(out["uu"][0], g["uu"]) < 1e-5 * w
     if float(g["mu"]) <= 1e10:
-        assert rel(out["KK"][0], g["KK"]) < 1e-4
+        assert rel(out["KK"][0], g["KK"]) < 1e-4 * w
         assert out["alpha"][0] == pytest.approx(float(g["alpha"]))
     # else: the reference left through "mu > mu_max" on its last iteration -- a rounding-level
     # knife edge at mu ~ 1e9 (dcost ~ 1e-12); costs and trajectories above still agree
