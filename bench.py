@@ -177,6 +177,8 @@ def ilqr_full_batch_roofline(xi, dev, n_iter=8):
     """FP64-pipe roofline of iLQR while the whole batch is live: the first n_iter iterations of a fresh solve, timed with
     CUDA events.  Algorithmic flops per iteration and trajectory: 570 per backward step + per alpha the serial
     line search of the reference TRIES (last alpha index + 1) a closed-loop rollout of T x (S x 228 + 30)."""
+    import torch
+    from pygent_b200.examples import make_ilqr
     solver = make_ilqr("cart_pole", ILQR_T, x0=xi, env_kw={"device": dev}, maxIters=500)
     tried_flops = ILQR_T * (SUBSTEPS * FLOPS_PER_SUBSTEP + 30)
     res = None

@@ -75,6 +75,19 @@ int pg_mlp_forward(int precision, const pg_mlp_dims_t* dims, const void* packed,
                    const double* kk, const double* xbar, const double* ubar, const double* ulim, double* X, double* U_out,
                    const int32_t* index, const int32_t* count, void* stream);
 
+/* pg_mlp_forward on the tensor-core kernel (PG_MLP_BF16 only) with a load-balanced schedule: one cluster per pair of SMs,
+ * each taking an equal share of the (128-row tile, control interval) sequence instead of whole tiles, so that a launch
+ * whose tiles do not fill a whole number of waves (45,056 rows = 2.38 waves) loses nothing to the partial wave.  A tile
+ * that is split between two clusters is handed over through X itself plus one progress word per tile in `workspace`
+ * (device memory, pg_mlp_forward_workspace_bytes(B, n_alpha) bytes, cleared by the call; it must not be shared by calls
+ * that may run concurrently).  Results are bit-identical to pg_mlp_forward. */
+int64_t pg_mlp_forward_workspace_bytes(int64_t B, int32_t n_alpha);
+int pg_mlp_forward_balanced(int precision, const pg_mlp_dims_t* dims, const void* packed, int64_t B, int32_t T, double dt,
+                            int32_t n_alpha, const double* alphas, const double* x0, const double* U, const double* KK,
+                            const double* kk, const double* xbar, const double* ubar, const double* ulim, double* X,
+                            double* U_out, const int32_t* index, const int32_t* count, void* workspace,
+                            int64_t workspace_bytes, void* stream);
+
 /* Continuous-time Jacobians of MBRL.ode along a trajectory, for iLQR.linearization (ilqr.py:518-533):
  *   A [T, n, n, B], Bm [T, n, m, B] at (xbar_k, ubar_k), k < T;  xbar [T+1, n, B], ubar [T, m, B].
  *   PG_MLP_LIN_FD       central differences with eps = 1e-3 through 2(n+m) network evaluations -- what the reference does

@@ -25,6 +25,7 @@
 #include "pg_math.cuh"
 
 #define PG_E_BADARG (-1)
+#define PG_E_UNSUPPORTED (-2)
 
 namespace {
 
@@ -98,6 +99,7 @@ struct MlpArgs {
     double* rhs;
     double* A;
     double* Bm;
+    int32_t* progress;  // balanced rollouts: per 128-row tile, the number of control intervals whose states are in X
 };
 
 // Row r of the launch -> what it computes.  ROLLOUT: r = ia * cnt + w (line-search candidate ia of work item w);
@@ -784,6 +786,35 @@ __device__ __forceinline__ void hidden_from_tmem(uint32_t tmem_base, int warp, i
 // 512 threads per CTA: thread t works on row (t & 127); the four threads of a row split the hidden units
 // (layer 1) and the accumulator columns (epilogue) four ways.  Warp w reads TMEM lanes 32 (w % 4) .. +31, which
 // is exactly the row quarter (t & 127) >> 5 of its threads.  Threads 0..127 own the fp64 state of their row.
+// ---- hand-over of a tile between two clusters of a balanced rollout --------------------------------------------
+__device__ __forceinline__ void publish_progress(int32_t* p, int k) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(k) : "memory");
+}
+__device__ __forceinline__ void wait_progress(const int32_t* p, int k) {
+    unsigned long long t0 = 0;
+    for (int spins = 0;; spins++) {
+        int v;
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+        if (v >= k) return;
+        __nanosleep(256);
+        if ((spins & 1023) == 1023) {  // the producer runs its piece first, so this never waits long: trap rather than hang
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) __trap();
+        }
+    }
+}
+// states of interval k of a rollout row, as post_step of interval k - 1 wrote them (by another SM: read through L2)
+__device__ __forceinline__ void reload_row(const MlpArgs& a, const Row& row, int k, double (&x)[8], double (&u)[2]) {
+    for (int i = 0; i < 8; i++) x[i] = 0.0;
+    u[0] = u[1] = 0.0;
+    if (!row.valid) return;
+    const int n = a.d.n;
+    const int64_t B = a.Bs, b = row.b;
+    for (int i = 0; i < n; i++) x[i] = __ldcg(&a.X[(((int64_t)row.ia * (a.T + 1) + k) * n + i) * B + b]);
+}
+
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_bf16_kernel(const MlpArgs a) {
     extern __shared__ __align__(1024) uint8_t tsm[];
     uint8_t* As = tsm;
@@ -801,10 +832,26 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_b
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
     const MlpPacked* w = a.w;
     const int t = threadIdx.x, warp = t >> 5, row = t & (T_ROWS - 1), part = t >> 7;
-    if ((int64_t)(blockIdx.x / CL) * CL * T_ROWS >= total_rows(a)) return;  // compacted work list: surplus clusters
+    // The work of a launch is the sequence (tile pair p, control interval k), p-major.  Plain launches give every cluster
+    // one whole pair.  Balanced rollouts (a.progress) run one cluster per pair of SMs and cut the sequence into equal
+    // ranges, so that no SM idles through a partial last wave: a range covers the tail of one pair, whole pairs, and the
+    // head of another.  A cluster walks its range BACKWARDS -- the head [0, k) of its last pair first, the tail [k, T)
+    // of its first pair last -- so the cluster that continues a pair finds the states of interval k in X long before it
+    // gets there (it has a range of at least T intervals to walk first); `progress` carries the hand-over.
+    const int steps = steps_of(a);
+    const int64_t pairs = (total_rows(a) + CL * T_ROWS - 1) / (CL * T_ROWS), slot = blockIdx.x / CL;
+    int64_t lo, hi;
+    if (a.progress) {
+        const int64_t slots = min((int64_t)(gridDim.x / CL), pairs);
+        if (slot >= slots) return;
+        lo = slot * (pairs * steps) / slots;
+        hi = (slot + 1) * (pairs * steps) / slots;
+    } else {
+        if (slot >= pairs) return;  // compacted work list: surplus clusters
+        lo = slot * steps;
+        hi = lo + steps;
+    }
     const bool owner = t < T_ROWS;
-    Row rw = decode_row(a, (int64_t)blockIdx.x * T_ROWS + row);
-    rw.valid = rw.valid && owner;
     const int nin = a.d.n_obs + a.d.m;
     const pg::MathCtx<double> mc;
 
@@ -835,11 +882,29 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_b
     const uint32_t tmem_base = *tmem_slot;
 
     double x[8], u[2], xe[8], ue[2], fplus[8];
-    if (owner) load_row(a, rw, x, u);
     GemmPipe pipe = {As, Bs, full, empty, accum, pfull, a_ready, tmem_base, 0u, 0u, 0u};
-    const int steps = steps_of(a);
     (void)nin;
-    for (int k = 0; k < steps; k++) {
+    if (steps == 0 && owner) {  // T = 0: only the initial states
+        Row r0 = decode_row(a, (int64_t)blockIdx.x * T_ROWS + row);
+        load_row(a, r0, x, u);
+    }
+    for (int64_t pos = hi; pos > lo;) {
+    const int64_t pair = (pos - 1) / steps, base = pair * steps;
+    const int k_begin = (int)(max(lo, base) - base), k_end = (int)(pos - base);
+    pos = base + k_begin;
+    const bool last_piece = pos <= lo;
+    const int64_t tile = pair * CL + (blockIdx.x % CL);
+    Row rw = decode_row(a, tile * T_ROWS + row);
+    rw.valid = rw.valid && owner;
+    if (k_begin > 0) {  // continue where another cluster left this tile
+        if (t == 0) wait_progress(&a.progress[tile], k_begin);
+        __syncthreads();
+    }
+    if (owner) {
+        if (k_begin == 0) load_row(a, rw, x, u);
+        else reload_row(a, rw, k_begin, x, u);
+    }
+    for (int k = k_begin; k < k_end; k++) {
         if (owner) {
             pre_step(a, rw, k, x, u, xe, ue);
             float in[MAXIN];
@@ -858,7 +923,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_b
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();  // A image complete, every lane has read its layer-1 accumulators
         gemm_a_ready(pipe, t);
-        if (k + 1 < steps) gemm_issue<T_STAGES, 8, 1>(pipe, w->W2b, t, w->W1img);
+        if (k + 1 < k_end || !last_piece) gemm_issue<T_STAGES, 8, 1>(pipe, w->W2b, t, w->W1img);
         else gemm_issue<T_STAGES, 8, 1>(pipe, w->W2b, t, nullptr);
         // epilogue: TMEM lane = row; this thread's quarter of the 512 columns, as soon as that quarter is final:
         // +b2, ReLU, layer 3
@@ -895,6 +960,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_b
             }
             post_step(a, rw, k, y, x, u, xe, fplus);
         }
+    }
+    if (a.progress && k_end < steps) {  // the head of a pair: publish that X holds the states up to interval k_end
+        __threadfence();
+        __syncthreads();
+        if (t == 0) publish_progress(&a.progress[tile], k_end);
+    }
     }
     __syncthreads();
     cluster_sync();  // no CTA leaves while its peer may still signal its barriers
@@ -1143,7 +1214,32 @@ int launch(int precision, const MlpArgs& a, cudaStream_t st) {
             if (e != cudaSuccess) return (int)e;
             set = true;
         }
-        mlp_bf16_kernel<<<(unsigned)((rows + CL * T_ROWS - 1) / (CL * T_ROWS)) * CL, T_THREADS, T_SMEM, st>>>(a);
+        int64_t clusters = (rows + CL * T_ROWS - 1) / (CL * T_ROWS);
+        if (a.progress) {  // balanced rollout: at most one cluster per pair of SMs, all of them resident at once
+            static int resident = 0;
+            if (!resident) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(CL * 1024);
+                cfg.blockDim = dim3(T_THREADS);
+                cfg.dynamicSmemBytes = T_SMEM;
+                cudaLaunchAttribute at;
+                at.id = cudaLaunchAttributeClusterDimension;
+                at.val.clusterDim.x = CL;
+                at.val.clusterDim.y = at.val.clusterDim.z = 1;
+                cfg.attrs = &at;
+                cfg.numAttrs = 1;
+                int n = 0;
+                if (cudaOccupancyMaxActiveClusters(&n, mlp_bf16_kernel, &cfg) != cudaSuccess || n < 1) {
+                    (void)cudaGetLastError();
+                    return PG_E_UNSUPPORTED;
+                }
+                resident = n;
+            }
+            cudaError_t e = cudaMemsetAsync(a.progress, 0, sizeof(int32_t) * (size_t)(clusters * CL), st);
+            if (e != cudaSuccess) return (int)e;
+            if (clusters > resident) clusters = resident;
+        }
+        mlp_bf16_kernel<<<(unsigned)(clusters * CL), T_THREADS, T_SMEM, st>>>(a);
     } else {
         return PG_E_BADARG;
     }
@@ -1224,6 +1320,11 @@ int pg_mlp_pack(const pg_mlp_dims_t* d, const float* W1, const float* b1, const 
     return 0;
 }
 
+static int forward_impl(int precision, const pg_mlp_dims_t* dims, const void* packed, int64_t B, int32_t T, double dt,
+                        int32_t n_alpha, const double* alphas, const double* x0, const double* U, const double* KK,
+                        const double* kk, const double* xbar, const double* ubar, const double* ulim, double* X,
+                        double* U_out, const int32_t* index, const int32_t* count, int32_t* progress, void* stream);
+
 int pg_mlp_ode(int precision, const pg_mlp_dims_t* dims, const void* packed, int64_t R, double dt, const double* x,
                const double* u, double* rhs, void* stream) {
     if (R == 0) return 0;
@@ -1254,6 +1355,14 @@ int pg_mlp_forward(int precision, const pg_mlp_dims_t* dims, const void* packed,
                    int32_t n_alpha, const double* alphas, const double* x0, const double* U, const double* KK,
                    const double* kk, const double* xbar, const double* ubar, const double* ulim, double* X, double* U_out,
                    const int32_t* index, const int32_t* count, void* stream) {
+    return forward_impl(precision, dims, packed, B, T, dt, n_alpha, alphas, x0, U, KK, kk, xbar, ubar, ulim, X, U_out, index,
+                        count, nullptr, stream);
+}
+
+static int forward_impl(int precision, const pg_mlp_dims_t* dims, const void* packed, int64_t B, int32_t T, double dt,
+                        int32_t n_alpha, const double* alphas, const double* x0, const double* U, const double* KK,
+                        const double* kk, const double* xbar, const double* ubar, const double* ulim, double* X,
+                        double* U_out, const int32_t* index, const int32_t* count, int32_t* progress, void* stream) {
     if (B == 0) return 0;
     if (!dims_ok(dims) || !packed || B < 0 || T < 0 || !x0 || !X || !(dt > 0)) return PG_E_BADARG;
     if (n_alpha < 1 || n_alpha > MAX_ALPHAS || !alphas) return PG_E_BADARG;
@@ -1281,7 +1390,26 @@ int pg_mlp_forward(int precision, const pg_mlp_dims_t* dims, const void* packed,
     for (int j = 0; j < dims->m && ulim; j++) a.ulim[j] = ulim[j];
     a.X = X;
     a.U_out = U_out;
+    a.progress = T > 0 ? progress : nullptr;
     return launch(precision, a, (cudaStream_t)stream);
+}
+
+int64_t pg_mlp_forward_workspace_bytes(int64_t B, int32_t n_alpha) {
+    if (B < 0 || n_alpha < 1) return 0;
+    const int64_t clusters = (B * n_alpha + CL * T_ROWS - 1) / (CL * T_ROWS);
+    return (int64_t)sizeof(int32_t) * clusters * CL;
+}
+
+int pg_mlp_forward_balanced(int precision, const pg_mlp_dims_t* dims, const void* packed, int64_t B, int32_t T, double dt,
+                            int32_t n_alpha, const double* alphas, const double* x0, const double* U, const double* KK,
+                            const double* kk, const double* xbar, const double* ubar, const double* ulim, double* X,
+                            double* U_out, const int32_t* index, const int32_t* count, void* workspace,
+                            int64_t workspace_bytes, void* stream) {
+    if (B == 0) return 0;
+    if (precision != PG_MLP_BF16) return PG_E_UNSUPPORTED;  // the schedule exists in the tensor-core kernel only
+    if (!workspace || n_alpha < 1 || workspace_bytes < pg_mlp_forward_workspace_bytes(B, n_alpha)) return PG_E_BADARG;
+    return forward_impl(precision, dims, packed, B, T, dt, n_alpha, alphas, x0, U, KK, kk, xbar, ubar, ulim, X, U_out, index,
+                        count, (int32_t*)workspace, stream);
 }
 
 int pg_mlp_linearize(int precision, int lin_mode, const pg_mlp_dims_t* dims, const void* packed, int64_t B, int32_t T,

@@ -61,6 +61,7 @@ SIGNATURES = {
 }
 SIGNATURES["pg_mlp_forward"] = [_i32, _dims_p, _vp, _i64, _i32, _f64, _i32, ctypes.POINTER(ctypes.c_double), _vp, _vp, _vp, _vp,
                               _vp, _vp, ctypes.POINTER(ctypes.c_double), _vp, _vp, _vp, _vp, _vp]
+SIGNATURES["pg_mlp_forward_balanced"] = SIGNATURES["pg_mlp_forward"][:-1] + [_vp, _i64, _vp]
 SIGNATURES["pg_mlp_linearize"] = [_i32, _i32, _dims_p, _vp, _i64, _i32, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
 LIN_MODES = {"analytic": 0, "fd": 1}
 _dll = None
@@ -74,6 +75,7 @@ def dll():
             fn = getattr(_dll, name)
             fn.argtypes, fn.restype = argtypes, ctypes.c_int
         _dll.pg_mlp_packed_bytes.restype = ctypes.c_int64
+        _dll.pg_mlp_forward_workspace_bytes.argtypes, _dll.pg_mlp_forward_workspace_bytes.restype = [_i64, _i32], ctypes.c_int64
     return _dll
 
 
@@ -102,6 +104,18 @@ class MLPDynamics:
         self.dims, self.packed, self.device = dims, packed, device
         self.n, self.m = dims.n, dims.m
         self.launches = 0
+        # tensor-core rollouts on the load-balanced schedule (pg_mlp_forward_balanced; bit-identical to the plain one)
+        self.balanced = os.environ.get("PG_MLP_BALANCED", "1") != "0"
+        self._ws = {}
+
+    def _workspace(self, B, n_alpha):
+        """Progress words of a balanced rollout: one buffer per stream (calls on one stream are ordered)."""
+        nb = int(dll().pg_mlp_forward_workspace_bytes(B, n_alpha))
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() * 4 < nb:
+            ws = self._ws[key] = torch.zeros((max(nb // 4, 1024),), dtype=torch.int32, device=self.device)
+        return ws, ws.numel() * 4
 
     @classmethod
     def from_arrays(cls, n, m, is_angle, W1, b1, W2, b2, W3, b3, o_mean=None, o_var=None, u_mean=None, u_var=None,
@@ -169,9 +183,17 @@ class MLPDynamics:
         Uo = torch.empty((T, self.m, B), dtype=torch.float64, device=self.device) if want_u else None
         KK, kk, xbar, ubar = gains if gains is not None else (None, None, None, None)
         lim = None if ulim is None else (ctypes.c_double * len(ulim))(*[float(v) for v in ulim])
-        _check(dll().pg_mlp_rollout(PRECISIONS[precision], ctypes.byref(self.dims), ctypes.c_void_p(self.packed.data_ptr()),
-                                    B, T, dt, _ptr(x0), _ptr(U), _ptr(KK), _ptr(kk), _ptr(xbar), _ptr(ubar), alpha, lim,
-                                    _ptr(X), _ptr(Uo), self._stream()), "pg_mlp_rollout")
+        if precision == "bf16" and self.balanced:
+            ws, nb = self._workspace(B, 1)
+            al = (ctypes.c_double * 1)(float(alpha))
+            _check(dll().pg_mlp_forward_balanced(PRECISIONS[precision], ctypes.byref(self.dims), ctypes.c_void_p(self.packed.data_ptr()),
+                                                 B, T, dt, 1, al, _ptr(x0), _ptr(U), _ptr(KK), _ptr(kk), _ptr(xbar), _ptr(ubar),
+                                                 lim, _ptr(X), _ptr(Uo), None, None, ctypes.c_void_p(ws.data_ptr()), nb, self._stream()),
+                   "pg_mlp_forward_balanced")
+        else:
+            _check(dll().pg_mlp_rollout(PRECISIONS[precision], ctypes.byref(self.dims), ctypes.c_void_p(self.packed.data_ptr()),
+                                        B, T, dt, _ptr(x0), _ptr(U), _ptr(KK), _ptr(kk), _ptr(xbar), _ptr(ubar), alpha, lim,
+                                        _ptr(X), _ptr(Uo), self._stream()), "pg_mlp_rollout")
         self.launches += 1
         return (X, Uo) if want_u else X
 
@@ -187,9 +209,16 @@ class MLPDynamics:
         al = (ctypes.c_double * A)(*[float(v) for v in alphas])
         lim = None if ulim is None else (ctypes.c_double * len(ulim))(*[float(v) for v in ulim])
         idx, cnt = (None, None) if work is None else (ctypes.c_void_p(work[0].data_ptr()), ctypes.c_void_p(work[1].data_ptr()))
-        _check(dll().pg_mlp_forward(PRECISIONS[precision], ctypes.byref(self.dims), ctypes.c_void_p(self.packed.data_ptr()), B, T,
-                                    dt, A, al, _ptr(x0), None, _ptr(KK), _ptr(kk), _ptr(xbar), _ptr(ubar), lim, _ptr(X), _ptr(Uo),
-                                    idx, cnt, self._stream()), "pg_mlp_forward")
+        if precision == "bf16" and self.balanced:
+            ws, nb = self._workspace(B, A)
+            _check(dll().pg_mlp_forward_balanced(PRECISIONS[precision], ctypes.byref(self.dims), ctypes.c_void_p(self.packed.data_ptr()),
+                                                 B, T, dt, A, al, _ptr(x0), None, _ptr(KK), _ptr(kk), _ptr(xbar), _ptr(ubar), lim,
+                                                 _ptr(X), _ptr(Uo), idx, cnt, ctypes.c_void_p(ws.data_ptr()), nb, self._stream()),
+                   "pg_mlp_forward_balanced")
+        else:
+            _check(dll().pg_mlp_forward(PRECISIONS[precision], ctypes.byref(self.dims), ctypes.c_void_p(self.packed.data_ptr()), B, T,
+                                        dt, A, al, _ptr(x0), None, _ptr(KK), _ptr(kk), _ptr(xbar), _ptr(ubar), lim, _ptr(X), _ptr(Uo),
+                                        idx, cnt, self._stream()), "pg_mlp_forward")
         self.launches += 1
         return X, Uo
 

@@ -189,6 +189,43 @@ def test_mlp_forward_all_alphas_equals_single_rollouts(precision):
     assert bool((out["X"][..., ~mask] == -7.0).all())
 
 
+@pytest.mark.parametrize("B,T,n_alpha", [(150, 9, 3), (2048, 13, 11), (1900, 100, 11), (9600, 7, 2), (19000, 3, 1)])
+def test_mlp_balanced_schedule_is_bit_identical(B, T, n_alpha):
+    """pg_mlp_forward_balanced (one cluster per SM pair, equal shares of the (tile, interval) sequence, tiles handed
+    over between clusters through X) against pg_mlp_forward (one cluster per tile pair): same bits, with fewer tile
+    pairs than SM pairs, with more (every cluster's range then starts and ends inside a tile), and with a work list."""
+    dyn, w, mom, ia = model()
+    rng = np.random.default_rng(11)
+    dt = 0.02
+    d = lambda a: torch.as_tensor(np.ascontiguousarray(np.moveaxis(a, 0, -1)), device="cuda")
+    x0 = d(rng.uniform(-1, 1, (B, 4)))
+    gains = (d(rng.uniform(-.5, .5, (B, T, 1, 4))), d(rng.uniform(-1, 1, (B, T, 1))), d(rng.uniform(-1, 1, (B, T + 1, 4))),
+             d(rng.uniform(-3, 3, (B, T, 1))))
+    alphas = list(10 ** np.linspace(0, -3, 11))[:n_alpha]
+    assert dyn.balanced
+    Xb, Ub = dyn.forward_device(x0, dt, alphas, gains, ulim=[5.0], precision="bf16")
+    dyn.balanced = False
+    Xp, Up = dyn.forward_device(x0, dt, alphas, gains, ulim=[5.0], precision="bf16")
+    dyn.balanced = True
+    assert torch.equal(Xb, Xp) and torch.equal(Ub, Up)
+    # open loop through rollout_device, and a compacted work list
+    U = d(rng.uniform(-3, 3, (B, T, 1)))
+    Xo = dyn.rollout_device(x0, dt, U=U, precision="bf16")
+    dyn.balanced = False
+    assert torch.equal(Xo, dyn.rollout_device(x0, dt, U=U, precision="bf16"))
+    dyn.balanced = True
+    k = max(1, (B * 2) // 3)
+    idx = torch.tensor(sorted(rng.choice(B, k, replace=False)) + [0] * (B - k), dtype=torch.int32, device="cuda")
+    cnt = torch.tensor([k], dtype=torch.int32, device="cuda")
+    out = {"X": torch.full_like(Xb, -7.0), "U": torch.full_like(Ub, -7.0)}
+    dyn.forward_device(x0, dt, alphas, gains, ulim=[5.0], precision="bf16", out=out, work=(idx, cnt))
+    sel = idx[:k].long()
+    mask = torch.zeros(B, dtype=torch.bool, device="cuda")
+    mask[sel] = True
+    assert torch.equal(out["X"][..., sel], Xb[..., sel]) and torch.equal(out["U"][..., sel], Ub[..., sel])
+    assert bool((out["X"][..., ~mask] == -7.0).all())
+
+
 def test_backward_ext_and_traj_cost_match_oracle():
     """pg_ilqr_backward_ext on given Jacobians = ilqr.py:233-346 restated in numpy; pg_traj_cost = the summed
     fast_step costs + final cost."""
