@@ -455,13 +455,18 @@ struct Nominal {  // gains and nominal point of one control interval
 //                 nominal point of interval k+1 is always loaded BEFORE x_{k+1} is stored, so the
 //                 in-place update never reads its own output (the pointers are deliberately not
 //                 __restrict__).
+// Alphas per CTA: all of them while the state fits 128 registers; systems with n >= 8 (triple pendulum) get 8 warps per
+// CTA and the full register file per thread instead (the alphas then span gridDim.y CTAs).
+template <typename P>
+constexpr int forward_alphas_per_cta() { return P::N >= 8 ? 8 : MAX_ALPHAS; }
+
 template <typename P, typename T, int INTEG, bool COMMIT>
-__global__ void __launch_bounds__(32 * MAX_ALPHAS) ilqr_forward_kernel(const ForwardArgs<T> a) {
+__global__ void __launch_bounds__(32 * forward_alphas_per_cta<P>()) ilqr_forward_kernel(const ForwardArgs<T> a) {
     const typename P::template Ctx<T> m;
     constexpr int N = P::N, M = P::M;
     const int64_t B = a.B;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int ia = threadIdx.y;
+    const int ia = blockIdx.y * blockDim.y + threadIdx.y;
     int64_t b = tid;
     if (a.index) {  // compacted list of running trajectories (written by ilqr_select_kernel)
         if (tid >= *a.count) return;
