@@ -53,6 +53,26 @@ CONFIG = {"workload": "batched cart-pole RK4 rollouts, 65,536 envs x 500 steps p
           "l2_policy": "inputs larger than L2: U is 262 MB per GPU and is re-read from HBM every step"}
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: everything else that writes to file descriptor 1 (NCCL's version banner,
+    library chatter) is sent to stderr; emit() writes the line to the real stdout, unbuffered."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    fd = _REAL_STDOUT if _REAL_STDOUT is not None else 1
+    sys.stdout.flush()
+    os.write(fd, line)
+
+
 def algorithmic_flops_per_launch():
     return B_ENVS * T_STEPS * (SUBSTEPS * FLOPS_PER_SUBSTEP + FLOPS_COST)
 
@@ -163,13 +183,13 @@ def run_reference(args, rank):
         el += cpu_rollout_baseline(n, threads)[1]
     value = n * T_STEPS * args.steps / el
     sample = "%d of the 65,536 envs x 500 steps per step (RK4 x 4), OpenMP over all host threads" % n
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "rk4_env_steps_per_s", "value": value, "unit": "env-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": CONFIG,
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
 
 
@@ -296,6 +316,7 @@ def learned_ilqr_bench(dev, rank, world, barrier):
 
 def main():
     ap = argparse.ArgumentParser()
+    claim_stdout()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
@@ -387,6 +408,31 @@ def main():
     ms32 = f0.elapsed_time(f1) / n32
     err32 = float(((out32["xN"].double() - out["xN"]).abs() / (out["xN"].abs() + 1)).max())
     del x0_32, U_32
+
+    # ---- SURVEY 8(d) variants of the resident workload: S = 1, and S = 4 with the full state history written ----------
+    def time_variant(n, **kw):
+        for _ in range(args.warmup):
+            L.rollout(x0, U, dt=DT, **kw)
+        barrier()
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        v0.record()
+        for _ in range(n):
+            L.rollout(x0, U, dt=DT, **kw)
+        v1.record()
+        barrier()
+        ms = v0.elapsed_time(v1) / n
+        if world > 1:
+            tm = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ms = float(tm.item())
+        return ms
+    nv = max(10, min(args.steps, 50))
+    ms_s1 = time_variant(nv, S=1, out=out)
+    out_h = dict(out)
+    out_h["X"] = torch.empty((T_STEPS + 1, 4, B_ENVS), dtype=torch.float64, device=dev)  # 1.05 GB
+    ms_hist = time_variant(nv, S=SUBSTEPS, history=True, out=out_h)
+    del out_h
+    L.rollout(x0, U, S=SUBSTEPS, dt=DT, out=out)  # `out` holds the S = 4 results again (fp32 error, best-of-batch below)
 
     # ---- end to end through the public API, host buffers --------------------------------------------
     from pygent_b200.examples import make_env
@@ -522,6 +568,15 @@ def main():
                                  "frac": hbm_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_gbs, "bytes_per_launch": hbm_bytes,
                                  "peak_source": hbm_src}},
             "best": best,
+            "s1": {"value": world * B_ENVS * T_STEPS / (ms_s1 * 1e-3), "unit": "env-steps/s", "substeps": 1, "ms_per_step": ms_s1,
+                   "roofline": {"bound": "fp64", "achieved": B_ENVS * T_STEPS * (FLOPS_PER_SUBSTEP + FLOPS_COST) / (ms_s1 * 1e-3) / 1e12,
+                                "peak": peak_tf, "unit": "TFLOP/s",
+                                "frac": B_ENVS * T_STEPS * (FLOPS_PER_SUBSTEP + FLOPS_COST) / (ms_s1 * 1e-3) / 1e12 / peak_tf},
+                   "hbm_gbs": hbm_bytes / (ms_s1 * 1e-3) / 1e9},
+            "history": {"value": world * B_ENVS * T_STEPS / (ms_hist * 1e-3), "unit": "env-steps/s", "substeps": SUBSTEPS,
+                        "ms_per_step": ms_hist, "bytes_per_env_step": 40,
+                        "hbm_gbs": (hbm_bytes + 8.0 * 4 * B_ENVS * (T_STEPS + 1)) / (ms_hist * 1e-3) / 1e9,
+                        "note": "X [T+1, n, B] fp64 (1.05 GB per GPU) written as well"},
             "fp32": {"value": world * B_ENVS * T_STEPS / (ms32 * 1e-3), "unit": "env-steps/s", "ms_per_step": ms32,
                      "roofline": {"bound": "fp32", "achieved": B_ENVS * T_STEPS * (SUBSTEPS * 188 + FLOPS_COST) / (ms32 * 1e-3) / 1e12,
                                   "peak": fp32_peak(), "unit": "TFLOP/s",
@@ -548,7 +603,7 @@ def main():
             res["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port",
                                    "sample": "first %d of the 65,536 envs x 500 steps (RK4 x 4), C oracle, OpenMP; %.1f s" % (n, secs),
                                    "single_core": v1}
-        print(json.dumps(res))
+        emit(res)
     if world > 1:
         dist.destroy_process_group()
 
