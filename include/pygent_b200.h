@@ -223,8 +223,9 @@ int pg_ilqr_commit(int dtype, int integrator, int64_t B, int32_t T, int32_t S, d
  * problem library still owns the cost (sympy -> CUDA), the Riccati recursion and the line-search logic. */
 
 /* pg_ilqr_backward with caller-supplied CONTINUOUS-time Jacobians A [T,n,n,B], Bm [T,n,m,B] of the dynamics along
- * (xbar, ubar); discretised like the reference, Ad = I + A dt, Bd = B dt (ilqr.py:530-531). */
-int pg_ilqr_backward_ext(int dtype, int64_t B, int32_t T, double dt, int32_t reg_type, const void* mu,
+ * (xbar, ubar); discretised like the reference, Ad = I + A dt, Bd = B dt (ilqr.py:530-531).
+ * lin_flags: 0, or PG_LIN_COST_FD for the central-difference cost expansion (finite_diff=True; fp64 only). */
+int pg_ilqr_backward_ext(int dtype, int64_t B, int32_t T, double dt, int32_t reg_type, int32_t lin_flags, const void* mu,
                          const void* xbar, const void* ubar, const void* A, const void* Bm, const double* ulim,
                          const void* Vxx_T, void* KK, void* kk, void* dV, void* gnorm, uint8_t* success,
                          const int32_t* index, const int32_t* count, void* stream);

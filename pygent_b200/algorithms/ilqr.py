@@ -105,9 +105,6 @@ class iLQR(Algorithm):
         if finite_diff:
             # the cost expansion by central differences (helpers.py:41-128 via ilqr.py:240-242, :598-603): same kernels,
             # PG_LIN_COST_FD or-ed into the linearisation mode
-            if self.learned:
-                raise NotImplementedError("finite_diff=True with learned dynamics: MBRL plans with the analytic cost "
-                                          "expansion (NMPC's default, nmpc.py:29)")
             if environment.dtype != torch.float64:
                 raise ValueError("finite_diff=True needs fp64: second differences with eps = 1e-3 are noise in fp32")
             self.lin_mode |= lib.LIN_COST_FD
@@ -311,7 +308,8 @@ class iLQR(Algorithm):
             env.dynamics.linearize_device(self._xbar, self._ubar, self.dt, mode=env.linearization, precision=env.precision,
                                           out=self._lin, work=work)
             return self.lib.ilqr_backward_ext(self._xbar, self._ubar, mu, self._lin["A"], self._lin["B"], dt=self.dt,
-                                              reg_type=self.regType, ulim=ulim, out=self._bw, work=work, Vxx_T=Vxx_T)
+                                              reg_type=self.regType, ulim=ulim, out=self._bw, work=work, Vxx_T=Vxx_T,
+                                              cost_fd=self.finite_diff)
         return self.lib.ilqr_backward(self._xbar, self._ubar, mu, dt=self.dt, reg_type=self.regType,
                                       lin_mode=self.lin_mode, ulim=ulim, out=self._bw, work=work, Vxx_T=Vxx_T)
 

@@ -61,7 +61,7 @@ SIGNATURES = {
     "pg_mpc_shift": [_i32, _i32, _i64, _i32, _i32, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _f64, _vp],
     "pg_ilqr_commit": [_i32, _i32, _i64, _i32, _i32, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _dp, _vp, _vp, _vp, _vp,
                        _vp],
-    "pg_ilqr_backward_ext": [_i32, _i64, _i32, _f64, _i32, _vp, _vp, _vp, _vp, _vp, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+    "pg_ilqr_backward_ext": [_i32, _i64, _i32, _f64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                              _vp],
     "pg_traj_cost": [_i32, _i64, _i32, _f64, _f64, _i32, _vp, _vp, _f64, _vp, _vp, _vp, _vp, _vp, _vp],
     "pg_ilqr_commit_copy": [_i32, _i64, _i32, _i32, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
@@ -345,7 +345,8 @@ class ProblemLibrary:
         self.launches += 1
 
     # -- dynamics integrated / linearised outside the library (learned MLP) --------------------------
-    def ilqr_backward_ext(self, xbar, ubar, mu, A, Bm, dt=0.02, reg_type=2, ulim=None, out=None, work=None, Vxx_T=None):
+    def ilqr_backward_ext(self, xbar, ubar, mu, A, Bm, dt=0.02, reg_type=2, ulim=None, out=None, work=None, Vxx_T=None,
+                          cost_fd=False):
         """Riccati sweep with caller-supplied continuous-time Jacobians A [T,n,n,B], Bm [T,n,m,B]."""
         n, m = self.n, self.m
         dtype, dev = xbar.dtype, xbar.device
@@ -356,7 +357,8 @@ class ProblemLibrary:
         KK, kk = g("KK", (T, m, n, B), zero=True), g("kk", (T, m, B), zero=True)
         dV, gnorm, success = g("dV", (2, B)), g("gnorm", (B,)), g("success", (B,), torch.uint8)
         rc = self.dll.pg_ilqr_backward_ext(
-            _dtype_code(dtype), B, T, dt, reg_type, _ptr(mu, dtype, (B,), "mu"), _ptr(xbar, dtype, (T + 1, n, B), "xbar"),
+            _dtype_code(dtype), B, T, dt, reg_type, LIN_COST_FD if cost_fd else 0, _ptr(mu, dtype, (B,), "mu"),
+            _ptr(xbar, dtype, (T + 1, n, B), "xbar"),
             _ptr(ubar, dtype, (T, m, B), "ubar"), _ptr(A, dtype, (T, n, n, B), "A"), _ptr(Bm, dtype, (T, n, m, B), "Bm"),
             _host_doubles(ulim), _ptr(Vxx_T, dtype, (n, n, B), "Vxx_T"), _ptr(KK, dtype, (T, m, n, B), "KK"),
             _ptr(kk, dtype, (T, m, B), "kk"), _ptr(dV, dtype, (2, B), "dV"), _ptr(gnorm, dtype, (B,), "gnorm"),

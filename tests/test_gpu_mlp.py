@@ -252,6 +252,19 @@ def test_backward_ext_and_traj_cost_match_oracle():
         assert rel(r["KK"][..., b].cpu().numpy(), np.array(KK)) < 1e-8
         assert rel(r["kk"][..., b].cpu().numpy(), np.array(kk).reshape(T, 1)) < 1e-8
         assert rel(r["dV"][:, b].cpu().numpy(), [np.sum(V1), np.sum(V2)]) < 1e-8
+    # finite_diff=True (a bare MPCAgent's default, nmpc.py:139): the same sweep with the cost expansion by central
+    # differences; this cost is quadratic, so the differences are exact up to their rounding noise (1e-10 / 4 eps^2)
+    rf = alg.lib.ilqr_backward_ext(d(X), d(U), mu, d(A), d(Bm), dt=dt, cost_fd=True)
+    assert bool(rf["success"].all())
+    assert rel(rf["KK"].cpu().numpy(), r["KK"].cpu().numpy()) < 1e-6
+    assert rel(rf["kk"].cpu().numpy(), r["kk"].cpu().numpy()) < 1e-6
+    assert not torch.equal(rf["KK"], r["KK"])  # it did take the other path
+    alg_fd = iLQR(env, T * dt, dt, fastForward=True, fcost=c_N, printing=False, final_backpass=False, finite_diff=True,
+                  maxIters=3)
+    alg2 = iLQR(env, T * dt, dt, fastForward=True, fcost=c_N, printing=False, final_backpass=False, maxIters=3)
+    _, _, c_fd = alg_fd.run_optim()
+    _, _, c_an = alg2.run_optim()
+    assert rel(c_fd, c_an) < 1e-5
 
 
 def test_learned_ilqr_matches_reference_planner(golden):
