@@ -198,3 +198,19 @@ def test_oracle_threads_agree():
     q = oracle.ilqr_params(max_iters=5)
     sa, sb = oracle.ilqr_solve(p, q, x0[:4], 30, nthreads=1), oracle.ilqr_solve(p, q, x0[:4], 30, nthreads=4)
     assert np.array_equal(sa["xx"], sb["xx"]) and np.array_equal(sa["cost"], sb["cost"])
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py's stdout contract: ONE JSON line, whatever else writes to file descriptor 1 (the reference arm runs on the
+    host cores, so this is checkable without a GPU)."""
+    import json
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "rk4_env_steps_per_s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
