@@ -173,6 +173,8 @@ class iLQR(Algorithm):
         self._have_gains = False
         # serial line search in two launches: work lists "backward pass succeeded" and "no success among the first alphas"
         self.first_alphas = 4
+        self.tail_threshold = int(os.environ.get("PG_ILQR_TAIL", "2048"))  # live trajectories below which iterate() runs its tail variant
+        self._tail = False
         self._ls_small = lib.split_search_threshold(self._x0.device)
         self._ls_idx = [i32(B), i32(B)]
         self._ls_cnt = i32(2)
@@ -407,6 +409,7 @@ class iLQR(Algorithm):
     def _rearm(self):
         """Every trajectory back on the work list (start of run_optim)."""
         self._cur = 0
+        self._tail = False
         self._idx[0].copy_(torch.arange(self.B, dtype=torch.int32, device=self._idx[0].device))
         self._cnt[0].fill_(self.B)
         self._n_active = self._cnt[0]
@@ -421,6 +424,12 @@ class iLQR(Algorithm):
         self._backward(work=work)
         if self.learned:
             self._forward_candidates(list(self.alphas), self._KKc, self._kkc, out=self._fw, cand=self._cand, work=work)
+        elif self._tail:
+            # few trajectories left (the host has seen the count, one block late): every rollout is a latency-bound chain,
+            # so ONE launch of the plain kernel for all alphas -- no queue hand-offs between time chunks, no second launch
+            L.ilqr_forward(self._x0, self._xbar, self._ubar, self._KKc, self._kkc, alphas=self.alphas, S=self.substeps,
+                           dt=self.dt, integrator=self.integrator, ulim=self._ulim(),
+                           terminal_cost=float(self.environment.terminal_cost), out=self._fw, work=work, balanced=False)
         elif (not self.parallel) and 0 < self.first_alphas < len(self.alphas) and self.B > self._ls_small:
             # serial search in two launches: the first alphas for everybody whose backward pass succeeded, the others only
             # where nothing has succeeded yet -- as long as more than _ls_small trajectories are live (decided on the device)
@@ -520,8 +529,11 @@ class iLQR(Algorithm):
             ev.record()
             if pending is not None:
                 pending[0].synchronize()
-                if int(flags[pending[1]]) == 0:
+                live = int(flags[pending[1]])
+                if live == 0:
                     break
+                if not self._tail and not self.learned and live <= self.tail_threshold:
+                    self._tail, graph = True, None  # the count only falls: switch the line search for good (new graph)
             pending = (ev, slot)
         self._graph = graph  # keep it alive until the results have been read
 
