@@ -727,7 +727,7 @@ struct CommitChunkArgs {
 };
 
 template <typename P, typename T, int INTEG>
-__global__ void __launch_bounds__(64) ilqr_commit_chunks_kernel(const CommitChunkArgs<T> q) {
+__global__ void __launch_bounds__(128) ilqr_commit_chunks_kernel(const CommitChunkArgs<T> q) {
     const typename P::template Ctx<T> m;
     constexpr int N = P::N, M = P::M;
     const ForwardArgs<T>& a = q.f;
@@ -950,7 +950,7 @@ __device__ __forceinline__ bool np_isclose(T a, T b, T atol) {  // np.isclose(a,
 }
 
 template <typename P, typename T, int LIN, bool CFD = false>
-__global__ void __launch_bounds__(64) ilqr_backward_kernel(const BackwardArgs<T> a) {
+__global__ void __launch_bounds__(128) ilqr_backward_kernel(const BackwardArgs<T> a) {
     const typename P::template Ctx<T> m;
     constexpr int N = P::N, M = P::M;
     static_assert(M <= 2, "control dimension > 2 not supported by the closed-form Quu solve");
