@@ -599,3 +599,23 @@ def test_two_phase_line_search_changes_nothing(B, T):
                     alg.current_alpha.copy() if hasattr(alg.current_alpha, "copy") else alg.current_alpha))
     for p, q in zip(*res):
         assert np.array_equal(p, q)
+
+
+def test_tail_variant_changes_nothing():
+    """Once the host has seen few live trajectories, iterate() runs the line search as one launch of the plain kernel
+    (iLQR.tail_threshold): iterations, statuses, costs, trajectories and gains must be exactly those of never switching."""
+    B, T = 700, 60
+    rng = np.random.default_rng(77)
+    x0 = np.array(CASES["cart_pole"][4]) + rng.uniform(-0.4, 0.4, (B, 4))
+    res = []
+    for thr in (0, 10 ** 9, 300):   # never / from the first count the host sees / when most have converged
+        alg = solver("cart_pole", T, x0=x0, maxIters=80)
+        alg.tail_threshold = thr
+        alg._ls_small = 64
+        alg.run_optim()
+        assert alg._tail == (thr > 0) or thr == 300   # (300: only if the host saw the count while it was that low)
+        res.append((alg.iters.copy(), alg.status.copy(), np.array(alg.cost), np.array(alg.xx), np.array(alg.uu), np.array(alg.KK),
+                    np.array(alg.current_alpha)))
+    for other in res[1:]:
+        for p, q in zip(res[0], other):
+            assert np.array_equal(p, q)
