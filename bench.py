@@ -22,6 +22,8 @@ nothing on the data path).  Prints ONE JSON line (rank 0):
              planner iteration + final backward pass + action + plan shift + plant step per control step, on the device)
   mlp_ilqr   iLQR iterations/s through the learned-MLP dynamics, 4,096 trajectories per GPU (config 5 = 32,768 over
              8 GPUs), tensor-core rollouts and Jacobian chain, 10 iterations
+  train      optimiser steps/s of the dynamics training step (6 -> 500 -> 500 -> 2, batch 512 per GPU, Adagrad): hand-written
+             tcgen05 forward / input-gradient / weight-gradient GEMMs + ONE NCCL all-reduce of the 255,003-float bucket per step
 `--impl reference` times the reference's algorithm on the host cores (the C oracle port -- the reference
 itself is pure Python and does not travel to the GPU box) on the same config/metric.
 """
@@ -314,6 +316,120 @@ def learned_ilqr_bench(dev, rank, world, barrier):
             "mean_cost_before": c0, "mean_cost_after": float(np.mean(alg.cost))}
 
 
+TRAIN_ROWS = 512   # the reference's batch size (mbrl.py:50): per GPU here (weak scaling of the data-parallel step)
+
+
+def synthetic_transitions_np(n, seed):
+    """Cart-pole-like transitions with the column layout MBRL stores (mbrl.py:160-167): float32 arrays."""
+    rng = np.random.RandomState(seed)
+    x_ = np.array([0, np.pi, 0, 0]) + rng.uniform(-1, 1, (n, 4)) * np.array([.5, 1.5, 2., 4.])
+    u = rng.uniform(-8, 8, (n, 1))
+    f = np.stack([x_[:, 2], x_[:, 3], u[:, 0], 1.5 * u[:, 0] * np.cos(x_[:, 1]) + 14.5 * np.sin(x_[:, 1])], axis=1)
+    x = x_ + 0.02 * f + rng.normal(0, 1e-3, (n, 4))
+    o_ = np.stack([x_[:, 0], np.cos(x_[:, 1]), np.sin(x_[:, 1]), x_[:, 2], x_[:, 3]], axis=1)
+    return {k: v.astype(np.float32) for k, v in (("x_", x_), ("u", u), ("x", x), ("o_", o_))}
+
+
+def train_bench(dev, rank, world, barrier, steps=300, with_cpu=True):
+    """The dynamics training step: NNDynamics(4, 1, oDim=5, dxDim=2), batch 512 rows per GPU (global batch
+    512 x N, every rank back-propagates its strided slice), Adagrad(lr 1e-3, weight decay 1e-3), one all-reduce of the flat
+    gradient bucket per step (NCCL, on the compute stream).  Device-timed with CUDA events, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from pygent_b200.algorithms.mbrl import DynamicsTrainer
+    from pygent_b200.nn_models import NNDynamics
+    torch.manual_seed(0)
+    net = NNDynamics(4, 1, dxDim=2, oDim=5, xIsAngle=[False, True, False, False])
+    gb = TRAIN_ROWS * world
+    tr = DynamicsTrainer(net, dyn_lr=1e-3, weight_decay=1e-3, batch_size=gb, device=dev)
+    col = synthetic_transitions_np(8 * gb, seed=11)
+
+    class _D:  # the two DataSet methods the trainer uses
+        def columns(self):
+            return col
+    tr.set_moments(_D())
+    tr.set_data(col)
+    batches = [np.arange(i * gb, (i + 1) * gb) for i in range(8)]
+    k = tr.backend.k
+    idx_dev = [torch.as_tensor(b[rank::world].astype(np.int32), device=dev) for b in batches]
+
+    def step(i):  # DynamicsTrainer.train_step with the index upload hoisted out of the loop
+        k.grad(idx_dev[i % 8], gb)
+        if world > 1:
+            dist.all_reduce(k.bucket, op=dist.ReduceOp.SUM)
+        k.update(1e-3, 1e-3)
+    loss0 = None
+    for i in range(10):
+        step(i)
+        if loss0 is None:
+            loss0 = float(k.bucket[-1])
+    barrier()
+    l0 = k.launches
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        step(i)
+    b.record()
+    barrier()
+    ms = a.elapsed_time(b)
+    launches = k.launches - l0
+    loss1 = float(k.bucket[-1])
+    # the collective alone, back to back on the compute stream
+    ar_us = None
+    if world > 1:
+        for _ in range(5):
+            dist.all_reduce(k.bucket, op=dist.ReduceOp.SUM)
+        barrier()
+        a.record()
+        for _ in range(100):
+            dist.all_reduce(k.bucket, op=dist.ReduceOp.SUM)
+        b.record()
+        barrier()
+        ar_us = a.elapsed_time(b) * 10.0
+        t = torch.tensor([ms, ar_us], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ar_us = float(t[0]), float(t[1])
+    # the step without the collective (grad + update only), same loop
+    barrier()
+    a.record()
+    for i in range(steps):
+        k.grad(idx_dev[i % 8], gb)
+        k.update(1e-3, 1e-3)
+    b.record()
+    barrier()
+    ms_local = a.elapsed_time(b)
+    flops = 3 * 2.0 * TRAIN_ROWS * 500 * 500 + 2 * 2.0 * TRAIN_ROWS * 500 * (6 + 2) * 1.5  # layer-2 fwd/dgrad/wgrad + the thin layers
+    res = {"metric": "dynamics_train_steps_per_s", "value": steps / (ms * 1e-3), "unit": "optimiser steps/s",
+           "samples_per_s": world * TRAIN_ROWS * steps / (ms * 1e-3), "us_per_step": ms * 1e3 / steps,
+           "us_per_step_without_collective": ms_local * 1e3 / steps, "allreduce_us": ar_us,
+           "rows_per_gpu": TRAIN_ROWS, "global_batch": gb, "scaling": "weak (global batch grows with N)",
+           "network": "6->500->500->2 fp32 master weights; layer-2 GEMMs tcgen05 kind::f16 with fp16 hi/lo split operands (3 MMAs per product), fp32 accumulate",
+           "bucket_floats": int(k.count + 1), "collective": "one NCCL all-reduce(sum) of the flat gradient bucket + loss per step" if world > 1 else None,
+           "gpu_launches": launches, "launches_per_step": launches / steps, "loss_first": loss0, "loss_last": loss1,
+           "tflops_per_gpu": flops / (ms * 1e-3 / steps) / 1e12}
+    if with_cpu and rank == 0:
+        # the reference's own path for this step: torch autograd + torch.optim.Adagrad on the host cores (oracle/train_oracle.py)
+        from oracle.train_oracle import TorchBackend
+        net_c = NNDynamics(4, 1, dxDim=2, oDim=5, xIsAngle=[False, True, False, False])
+        cb = TorchBackend(net_c)
+        g = lambda t: t.detach().cpu().numpy().ravel()
+        cb.set_moments(g(net.oMean), g(net.oVar), g(net.uMean), g(net.uVar), g(net.dxMean), g(net.dxVar))
+        cb.set_data(col)
+        for i in range(3):
+            cb.grad(batches[i][:TRAIN_ROWS], TRAIN_ROWS)
+            cb.update(1e-3, 1e-3)
+        n_cpu = 40
+        t0 = time.perf_counter()
+        for i in range(n_cpu):
+            cb.grad(batches[i % 8][:TRAIN_ROWS], TRAIN_ROWS)
+            cb.update(1e-3, 1e-3)
+        secs = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": n_cpu / secs, "unit": "optimiser steps/s", "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": "%d steps of batch %d through torch autograd + torch.optim.Adagrad on the host (the reference's own "
+                                         "training path, mbrl.py:450-469)" % (n_cpu, TRAIN_ROWS)}
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     claim_stdout()
@@ -325,6 +441,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-mlp", action="store_true")
     ap.add_argument("--no-nmpc", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -540,6 +657,11 @@ def main():
     if not args.no_mlp:
         mlp_ilqr = learned_ilqr_bench(dev, rank, world, barrier)
 
+    # ---- dynamics training step + its gradient all-reduce --------------------------
+    train = None
+    if not args.no_train:
+        train = train_bench(dev, rank, world, barrier, with_cpu=not args.no_cpu)
+
     clocks = sampler.stop()
     if rank == 0:
         peak_tf, peak_src = fp64_peak()
@@ -593,6 +715,8 @@ def main():
             res["nmpc"] = nmpc
         if ilqr_c4:
             res["ilqr_c4"] = ilqr_c4
+        if train is not None:
+            res["train"] = train
         if not args.no_cpu:
             import oracle
             oracle.build()

@@ -100,6 +100,42 @@ int pg_mlp_linearize(int precision, int lin_mode, const pg_mlp_dims_t* dims, con
                      double dt, const double* xbar, const double* ubar, double* A, double* Bm, const int32_t* index,
                      const int32_t* count, void* stream);
 
+/* ---- dynamics training (K6): one optimiser step of `MBRL.training` on the device ------------------------------------------
+ * Reference: pygent/algorithms/mbrl.py:450-469 (loop over shuffled batches of 512: `training_data`, nn.MSELoss, zero_grad,
+ * backward, step), :471-485 (`training_data`: o_, u and dx = x - x_ standardised with the data-set moments; with sparse_dyn
+ * only the velocity half of dx), :71-73 (torch.optim.Adagrad(lr = dyn_lr, weight_decay)).
+ *
+ * Flat fp32 buffers in torch's parameter order of NNDynamics -- W1 [500, n_obs+m], b1 [500], W2 [500, 500], b2 [500],
+ * W3 [dx_dim, 500], b3 [dx_dim]: pg_mlp_train_param_count() floats (255,002 for the cart-pole):
+ *     params, state_sum (Adagrad's accumulator), bucket [count + 1] (the gradient and, in the last slot, the loss).
+ * Data set on the device, row-major fp32: x_ [N, n], x [N, n], o_ [N, n_obs], u [N, m]; idx [R] (i32) selects the rows of the
+ * batch (NULL: rows 0..R-1).  moments [48] fp32: o_mean at 0, o_var at 16, u_mean at 32, u_var at 34, dx_mean at 36, dx_var at 40.
+ * workspace: pg_mlp_train_workspace_bytes(max_rows) bytes, 1024-byte aligned, set up by pg_mlp_train_init (which also splits
+ * W2 into the fp16 hi/lo operand images of the tensor-core GEMMs; pg_mlp_train_update keeps them current) -- call it again
+ * whenever params are changed from outside.
+ *
+ * pg_mlp_train_grad   : forward + backward of R <= max_rows rows.  bucket <- sum over these rows of d(SSE)/d(theta) * 2 / (n_total *
+ *                       dx_dim), bucket[count] <- SSE / (n_total * dx_dim): with n_total = R the gradient and value of nn.MSELoss;
+ *                       data parallel, every rank passes its slice of the batch and the global n_total, and ONE sum-all-reduce of
+ *                       the bucket (count + 1 floats) yields the full-batch gradient and loss on every rank.
+ *                       Layer 2 forward, its input gradient and its weight gradient are 128 x 128-tile tcgen05.mma GEMMs with
+ *                       fp16 hi/lo split operands (22 mantissa bits, fp32 accumulation); everything else is fp32 on CUDA cores.
+ * pg_mlp_train_update : Adagrad  g += wd p;  s += g^2;  p -= lr g / (sqrt(s) + eps)  on the flat buffers.
+ * pg_mlp_train_step   : grad (n_total = R) + update, the single-GPU optimiser step. */
+#define PG_MLP_TRAIN_MOMENTS 48
+int64_t pg_mlp_train_param_count(const pg_mlp_dims_t* dims);
+int64_t pg_mlp_train_workspace_bytes(int32_t max_rows);
+int pg_mlp_train_init(const pg_mlp_dims_t* dims, const float* params, void* workspace, int64_t workspace_bytes, int32_t max_rows,
+                      void* stream);
+int pg_mlp_train_grad(const pg_mlp_dims_t* dims, const float* params, const float* moments, const float* x_, const float* x,
+                      const float* o_, const float* u, const int32_t* idx, int32_t R, int64_t n_total, void* workspace,
+                      int64_t workspace_bytes, int32_t max_rows, float* bucket, void* stream);
+int pg_mlp_train_update(const pg_mlp_dims_t* dims, float* params, float* state_sum, const float* bucket, float lr, float weight_decay,
+                        float eps, void* workspace, int64_t workspace_bytes, int32_t max_rows, void* stream);
+int pg_mlp_train_step(const pg_mlp_dims_t* dims, float* params, float* state_sum, const float* moments, const float* x_,
+                      const float* x, const float* o_, const float* u, const int32_t* idx, int32_t R, float lr, float weight_decay,
+                      float eps, void* workspace, int64_t workspace_bytes, int32_t max_rows, float* bucket, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,12 +3,13 @@
 :187-206; optimiser `torch.optim.Adagrad(lr=dyn_lr, weight_decay=weight_decay)` :71-73, MSE on standardised velocity
 increments, batch 512).
 
+The optimiser step runs as hand-written sm_100a kernels (csrc/pg_train.cu through `pygent_b200.mlp.TrainKernels`: layer 2's
+forward, input-gradient and weight-gradient GEMMs on the tcgen05 tensor cores with fp16 hi/lo split operands, fused Adagrad).
 Data parallel: every rank holds the same data set and the same network; a batch is cut into `world_size` strided
 slices, each rank back-propagates its slice of the SUM of squared errors divided by the full batch size, the gradients
-live in ONE flat fp32 bucket (255,002 elements) that is all-reduced once per step on the compute stream (NCCL; gloo in
-the CPU tests), and every rank applies the identical Adagrad update.  This is the only collective of the learned-
-dynamics path besides the final cost/argmin gather.  The dense algebra here is plain library GEMMs
-(cuBLAS through torch); the planner's hot path through the network is `pygent_b200.mlp`.
+live in ONE flat fp32 bucket (255,002 elements + the loss) that is all-reduced once per step on the compute stream (NCCL;
+gloo in the CPU tests), and every rank applies the identical Adagrad update.  This is the only collective of the learned-
+dynamics path besides the final cost/argmin gather.
 """
 import copy
 import os
@@ -22,27 +23,68 @@ import torch.distributed as dist
 from .core import Algorithm
 
 
+class _KernelBackend(object):
+    """The CUDA backend of `DynamicsTrainer`: `pygent_b200.mlp.TrainKernels` (csrc/pg_train.cu) on the module's parameters,
+    which are re-pointed at ONE flat fp32 device buffer in torch's parameter order so that the kernels update them in place."""
+
+    def __init__(self, net, device, max_rows):
+        from .. import mlp
+        from ..lib import PygentB200Error
+        device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device()) \
+            if torch.cuda.is_available() else None
+        if device is None or device.type != "cuda" or not torch.cuda.is_available():
+            raise PygentB200Error("DynamicsTrainer needs a CUDA device (B200): the training step is hand-written sm_100a "
+                                  "kernels and there is no CPU fallback")
+        self.net, self.device = net, device
+        net.to(device)
+        plist = list(net.parameters())
+        flat = torch.cat([p.detach().reshape(-1).float() for p in plist]).contiguous()
+        off = 0
+        for p in plist:
+            p.data = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.k = mlp.TrainKernels(mlp.make_dims(net.xDim, net.uDim, net.xIsAngle), flat, max_rows=max_rows, device=device)
+        self.bucket, self.count = self.k.bucket, self.k.count
+
+    launches = property(lambda self: self.k.launches)
+
+    def set_moments(self, *a):
+        self.k.set_moments(*a)
+
+    def set_data(self, col):
+        self.k.set_data(col)
+
+    def grad(self, idx, n_total):
+        self.k.grad(torch.as_tensor(np.ascontiguousarray(idx, dtype=np.int32), device=self.device), n_total)
+
+    def grad_device(self, idx, n_total):
+        self.k.grad(idx, n_total)
+
+    def update(self, lr, weight_decay, eps=1e-10):
+        self.k.update(lr, weight_decay, eps)
+
+
 class DynamicsTrainer(object):
+    """`MBRL.set_moments / training_data / training / pred_loss` (mbrl.py:450-509, :187-206) with the optimiser step on the
+    device.  `backend` is for tests only (a CPU stand-in that speaks the same protocol drives the host logic on gloo)."""
+
     def __init__(self, nn_dynamics, dyn_lr=1e-3, weight_decay=1e-3, batch_size=512, training_epochs=60, sparse_dyn=True,
-                 device=None, process_group=None):
+                 device=None, process_group=None, backend=None):
+        if not sparse_dyn:
+            raise NotImplementedError("the GPU network path implements the sparse_dyn model (velocity half, mbrl.py:54-57)")
         self.nn_dynamics = nn_dynamics
         self.sparse_dyn = sparse_dyn
         self.batch_size = batch_size
         self.training_epochs = training_epochs
-        self.device = torch.device(device) if device is not None else torch.device("cpu")
+        self.dyn_lr, self.weight_decay = float(dyn_lr), float(weight_decay)
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank(process_group) if self.world > 1 else 0
-        self.nn_dynamics.to(self.device)
-        params = list(self.nn_dynamics.parameters())
-        # one flat gradient bucket; every parameter's .grad is a view into it
-        self._flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=self.device)
-        off = 0
-        for p in params:
-            p.grad = self._flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
-        self.optim = torch.optim.Adagrad(params, lr=dyn_lr, weight_decay=weight_decay)
+        # a rank's slice of a batch never exceeds ceil(batch_size / world) rows (a data set smaller than one batch is ONE batch)
+        self.backend = backend if backend is not None else _KernelBackend(nn_dynamics, device, max_rows=batch_size)
+        self.device = getattr(self.backend, "device", torch.device("cpu"))
         self.collectives = 0
+        self.steps = 0
 
     # -- moments (mbrl.py:487-509): mean / unbiased std over the data set --------------------------------------------
     def set_moments(self, dataSet):
@@ -57,10 +99,23 @@ class DynamicsTrainer(object):
         net.oMean, net.oVar = o_.mean(dim=0, keepdim=True), o_.std(dim=0, keepdim=True)
         net.uMean, net.uVar = u.mean(dim=0, keepdim=True), u.std(dim=0, keepdim=True)
         net.invalidate()
+        self._push_moments()
 
-    def _standardised(self, col):
-        """(target dx_norm, network output) for column arrays of transitions (mbrl.py:471-485)."""
+    def _push_moments(self):
+        net = self.nn_dynamics
+        g = lambda t: t.detach().cpu().numpy().ravel()
+        self.backend.set_moments(g(net.oMean), g(net.oVar), g(net.uMean), g(net.uVar), g(net.dxMean), g(net.dxVar))
+
+    def set_data(self, dataSet_or_col):
+        col = dataSet_or_col if isinstance(dataSet_or_col, dict) else dataSet_or_col.columns()
+        self.backend.set_data(col)
+        self._push_moments()
+
+    def training_data(self, batch):
+        """batch: list of transition dicts -> (dx_norm, fOutputs_norm), as the reference returns them (mbrl.py:471-485)."""
         net, dev = self.nn_dynamics, self.device
+        keys = ("x_", "u", "x", "o_")
+        col = {k: np.asarray([np.asarray(s[k], dtype=np.float64).ravel() for s in batch]).astype(np.float32) for k in keys}
         t = lambda a: torch.as_tensor(a, dtype=torch.float32, device=dev)
         x_, x, o_, u = t(col["x_"]), t(col["x"]), t(col["o_"]), t(col["u"])
         o_n = (o_ - net.oMean.to(dev)) / net.oVar.to(dev)
@@ -68,53 +123,45 @@ class DynamicsTrainer(object):
         dx = x - x_
         if self.sparse_dyn:
             dx = dx[:, dx.shape[1] // 2:]
-        dx_n = (dx - net.dxMean.to(dev)) / net.dxVar.to(dev)
-        return dx_n, net(o_n, u_n)
-
-    def training_data(self, batch):
-        """batch: list of transition dicts -> (dx_norm, fOutputs_norm), as the reference returns them."""
-        keys = ("x_", "u", "x", "o_")
-        col = {k: np.asarray([np.asarray(s[k], dtype=np.float64).ravel() for s in batch]).astype(np.float32) for k in keys}
-        return self._standardised(col)
+        return (dx - net.dxMean.to(dev)) / net.dxVar.to(dev), net(o_n, u_n)
 
     def pred_loss(self, transition):
-        dx_n, f = self.training_data([transition])
-        return float(torch.linalg.vector_norm((f - dx_n).detach()).cpu())
+        """|| f(o_, u) - dx_norm ||_2 of one transition (mbrl.py:187-206), through the training kernels' forward pass:
+        the loss slot of the bucket holds SSE / dx_dim."""
+        keys = ("x_", "u", "x", "o_")
+        self.backend.set_data({k: np.asarray(transition[k], dtype=np.float64).reshape(1, -1).astype(np.float32) for k in keys})
+        self._push_moments()
+        self.backend.grad(np.zeros(1, dtype=np.int32), 1)
+        return float(np.sqrt(float(self.backend.bucket[-1]) * self.nn_dynamics.dxDim))
 
     # -- one optimiser step on one batch -------------------------------------------------------------------------------
-    def train_step(self, col):
-        """col: column arrays of ONE full batch (identical on every rank).  Returns the batch's MSE loss."""
-        n_total = len(col["x_"])
-        local = {k: v[self.rank::self.world] for k, v in col.items()}
-        self._flat.zero_()
-        if len(local["x_"]):
-            dx_n, f = self._standardised(local)
-            # nn.MSELoss over the whole batch = sum of squared errors / (rows * outputs); this rank's share of the sum
-            loss = ((f - dx_n) ** 2).sum() / float(n_total * dx_n.shape[1])
-            loss.backward()
-            loss = loss.detach()
-        else:
-            loss = torch.zeros((), device=self.device)
+    def train_step(self, idx):
+        """idx: rows of ONE full batch in the uploaded data set (identical on every rank).  Data parallel: every rank
+        back-propagates the strided slice idx[rank::world] of the batch with the full batch size in the MSE denominator,
+        ONE sum-all-reduce of the flat bucket (255,002 gradient floats + the loss) follows, and every rank applies the
+        identical Adagrad update.  Returns the batch's MSE loss (a view of the bucket's last slot: read it before the next step)."""
+        idx = np.asarray(idx)
+        self.backend.grad(idx[self.rank::self.world], len(idx))
         if self.world > 1:
-            buf = torch.cat([self._flat, loss.reshape(1)])  # gradient bucket + loss: ONE collective per step
-            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
-            self._flat.copy_(buf[:-1])
-            loss = buf[-1]
+            dist.all_reduce(self.backend.bucket, op=dist.ReduceOp.SUM, group=self.group)  # NCCL, on the compute stream
             self.collectives += 1
-        self.optim.step()
-        return loss
+        self.backend.update(self.dyn_lr, self.weight_decay)
+        self.steps += 1
+        return self.backend.bucket[-1]
 
     def training(self, dataSet, printing=False):
         """`MBRL.training`: moments from the data, then `training_epochs` passes over shuffled batches."""
         self.nn_dynamics.eval()
         self.set_moments(dataSet)
-        col = dataSet.columns()
+        self.set_data(dataSet)
         losses = []
         for epoch in range(self.training_epochs):
-            running, it = 0.0, 0
-            for it, idx in enumerate(dataSet.batch_indices(self.batch_size, shuffle=True)):
-                running += float(self.train_step({k: v[idx] for k, v in col.items()}))
-            losses.append(running / max(1, it))
+            batches = dataSet.batch_indices(self.batch_size, shuffle=True)
+            run = torch.zeros(len(batches), dtype=torch.float32, device=self.device)
+            it = 0
+            for it, idx in enumerate(batches):
+                run[it] = self.train_step(idx)  # stays on the device: one host read per epoch
+            losses.append(float(run.sum()) / max(1, it))
             if printing:
                 print('NN dynamics training loss:', losses[-1])
         self.nn_dynamics.invalidate()  # the planner's packed device copy is rebuilt from the new weights
@@ -174,7 +221,6 @@ class MBRL(Algorithm):
         self.nn_dynamics = NNDynamics(xDim, uDim, oDim=oDim, dxDim=xDim // 2, xIsAngle=environment.xIsAngle)
         self.trainer = DynamicsTrainer(self.nn_dynamics, dyn_lr=dyn_lr, weight_decay=weight_decay, batch_size=batch_size,
                                        training_epochs=training_epochs, sparse_dyn=sparse_dyn, device=environment.device)
-        self.optim = self.trainer.optim
         self.nn_environment = LearnedStateSpaceModel(self.nn_dynamics, environment._user_cost, environment.x0, uDim, dt,
                                                      precision=precision, device=environment.device)
         self.nn_environment.uMax = environment.uMax

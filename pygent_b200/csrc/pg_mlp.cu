@@ -23,11 +23,14 @@
 
 #include "../../include/pygent_b200_mlp.h"
 #include "pg_math.cuh"
+#include "pg_tc.cuh"
 
 #define PG_E_BADARG (-1)
 #define PG_E_UNSUPPORTED (-2)
 
 namespace {
+
+using namespace pgtc;
 
 constexpr int H = PG_MLP_HPAD;      // 512
 constexpr int HID = PG_MLP_HIDDEN;  // 500
@@ -371,29 +374,7 @@ __global__ void __launch_bounds__(256) mlp_fp32_kernel(const MlpArgs a) {
     }
 }
 
-// ---- tcgen05 helpers ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t ok = 0;
-    for (uint32_t spins = 0; !ok; spins++) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (!ok && spins > (1u << 26)) __trap();  // a lost arrival must not hang the GPU
-    }
-}
+// ---- tcgen05 helpers: the generic ones (mbarriers, bulk copies, descriptors, tcgen05.ld) live in pg_tc.cuh ----
 // ---- thread-block cluster of CL CTAs sharing one weight stream ------------------------------------------------------
 constexpr int CL = 2;
 constexpr uint16_t CL_MASK = (1u << CL) - 1;
@@ -413,26 +394,11 @@ __device__ __forceinline__ void bulk_g2s_multicast(void* dst, const void* src, u
         "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
         : "memory");
 }
-// plain bulk copy global -> own smem, completion on an own mbarrier
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
 // arrive on the barrier at the same smem offset in CTA `cta` of the cluster
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
     uint32_t remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
-}
-// K-major, 128-byte swizzle: 8-row groups 1024 B apart (SBO), LBO field 1 (unused for swizzled K-major), version 1
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
 }
 // D (fp32) = A (bf16, K-major) x B (bf16, K-major), M = 128, N = CHUNK_N
 constexpr uint32_t UMMA_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)CHUNK_N >> 3) << 17) | ((128u >> 4) << 24);
@@ -471,20 +437,6 @@ __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t ma
                  "h"(mask)
                  : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
 constexpr int T_ROWS = 128, T_THREADS = 512, T_SPLIT = T_THREADS / T_ROWS;
 constexpr int T_STAGES = 4;  // weight ring of the rollout kernel (231,680 B of smem in total)
 constexpr int J_STAGES = 3;  // ... of the Jacobian kernel, which also holds the ReLU masks

@@ -16,8 +16,9 @@ from . import build as pgbuild
 from .lib import PygentB200Error
 
 PRECISIONS = {"fp32": 0, "bf16": 1}
-_SRC = [os.path.join(pgbuild.CSRC, "pg_mlp.cu"), os.path.join(pgbuild.CSRC, "pg_math.cuh"),
-        os.path.join(pgbuild.INCLUDE, "pygent_b200_mlp.h")]
+_CU = [os.path.join(pgbuild.CSRC, "pg_mlp.cu"), os.path.join(pgbuild.CSRC, "pg_train.cu")]
+_SRC = _CU + [os.path.join(pgbuild.CSRC, "pg_math.cuh"), os.path.join(pgbuild.CSRC, "pg_tc.cuh"),
+              os.path.join(pgbuild.INCLUDE, "pygent_b200_mlp.h")]
 
 
 class Dims(ctypes.Structure):
@@ -43,9 +44,9 @@ def build_library(force=False):
         raise RuntimeError("pygent_b200: %s is missing and nvcc was not found; there is no CPU fallback" % so)
     os.makedirs(pgbuild.CACHE, exist_ok=True)
     tmp = so + ".tmp%d" % os.getpid()
-    res = subprocess.run([nvcc] + pgbuild.NVCC_FLAGS + [_SRC[0], "-o", tmp], capture_output=True, text=True)
+    res = subprocess.run([nvcc] + pgbuild.NVCC_FLAGS + _CU + ["-o", tmp], capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed for pg_mlp.cu:\n" + res.stderr[-4000:])
+        raise RuntimeError("nvcc failed for pg_mlp.cu / pg_train.cu:\n" + res.stderr[-4000:])
     os.replace(tmp, so)
     return so
 
@@ -63,6 +64,11 @@ SIGNATURES["pg_mlp_forward"] = [_i32, _dims_p, _vp, _i64, _i32, _f64, _i32, ctyp
                               _vp, _vp, ctypes.POINTER(ctypes.c_double), _vp, _vp, _vp, _vp, _vp]
 SIGNATURES["pg_mlp_forward_balanced"] = SIGNATURES["pg_mlp_forward"][:-1] + [_vp, _i64, _vp]
 SIGNATURES["pg_mlp_linearize"] = [_i32, _i32, _dims_p, _vp, _i64, _i32, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+_f32 = ctypes.c_float
+SIGNATURES["pg_mlp_train_init"] = [_dims_p, _vp, _vp, _i64, _i32, _vp]
+SIGNATURES["pg_mlp_train_grad"] = [_dims_p, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _i64, _i32, _vp, _vp]
+SIGNATURES["pg_mlp_train_update"] = [_dims_p, _vp, _vp, _vp, _f32, _f32, _f32, _vp, _i64, _i32, _vp]
+SIGNATURES["pg_mlp_train_step"] = [_dims_p, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _vp, _i64, _i32, _vp, _vp]
 LIN_MODES = {"analytic": 0, "fd": 1}
 _dll = None
 
@@ -76,6 +82,8 @@ def dll():
             fn.argtypes, fn.restype = argtypes, ctypes.c_int
         _dll.pg_mlp_packed_bytes.restype = ctypes.c_int64
         _dll.pg_mlp_forward_workspace_bytes.argtypes, _dll.pg_mlp_forward_workspace_bytes.restype = [_i64, _i32], ctypes.c_int64
+        _dll.pg_mlp_train_param_count.argtypes, _dll.pg_mlp_train_param_count.restype = [_dims_p], ctypes.c_int64
+        _dll.pg_mlp_train_workspace_bytes.argtypes, _dll.pg_mlp_train_workspace_bytes.restype = [_i32], ctypes.c_int64
     return _dll
 
 
@@ -236,3 +244,96 @@ class MLPDynamics:
                                       idx, cnt, self._stream()), "pg_mlp_linearize")
         self.launches += 1
         return A, Bm
+
+
+def make_dims(n, m, is_angle):
+    d = Dims()
+    d.n, d.m = n, m
+    d.n_obs = int(n + np.sum(np.asarray(is_angle, dtype=bool)))
+    d.dx_dim = n // 2
+    for i, a in enumerate(is_angle):
+        d.is_angle[i] = 1 if a else 0
+    return d
+
+
+class TrainKernels:
+    """Device state and launches of the dynamics training step (include/pygent_b200_mlp.h, "dynamics training"; reference
+    pygent/algorithms/mbrl.py:450-509, Adagrad :71-73): flat fp32 `params` / `state_sum` / `bucket` buffers in torch's
+    parameter order, the operand-image workspace of the tensor-core GEMMs, the data set and its moments on the device.
+    There is no host path: construction fails without a CUDA device."""
+
+    def __init__(self, dims, params, max_rows=512, device=None):
+        if device is None or torch.device(device).type != "cuda" or not torch.cuda.is_available():
+            raise PygentB200Error("the dynamics training step runs on the B200 only; there is no CPU fallback")
+        self.device = torch.device(device)
+        self.dims, self.max_rows = dims, int(max_rows)
+        self.count = int(dll().pg_mlp_train_param_count(ctypes.byref(dims)))
+        if self.count <= 0 or params.numel() != self.count:
+            raise PygentB200Error("flat parameter buffer: expected %d floats, got %d" % (self.count, params.numel()))
+        if not (params.is_cuda and params.is_contiguous() and params.dtype == torch.float32):
+            raise PygentB200Error("params must be a contiguous fp32 CUDA tensor")
+        self.params = params
+        self.state_sum = torch.zeros_like(params)
+        self.bucket = torch.zeros(self.count + 1, dtype=torch.float32, device=self.device)  # gradient + loss
+        self.ws_bytes = int(dll().pg_mlp_train_workspace_bytes(self.max_rows))
+        self._raw = torch.empty(self.ws_bytes + 1024, dtype=torch.uint8, device=self.device)
+        self._ws_ptr = self._raw.data_ptr() + (-self._raw.data_ptr()) % 1024
+        self.moments = torch.zeros(48, dtype=torch.float32, device=self.device)
+        self.data = None
+        self.launches = 0
+        self.repack()
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def repack(self):
+        """(Re)build the fp16 hi/lo operand images of W2 from `params` -- after construction and after any outside change."""
+        _check(dll().pg_mlp_train_init(ctypes.byref(self.dims), ctypes.c_void_p(self.params.data_ptr()), ctypes.c_void_p(self._ws_ptr),
+                                       self.ws_bytes, self.max_rows, self._stream()), "pg_mlp_train_init")
+        self.launches += 1
+
+    def set_moments(self, o_mean, o_var, u_mean, u_var, dx_mean, dx_var):
+        m = np.zeros(48, dtype=np.float32)
+        m[16:32] = 1.0
+        m[34:36] = 1.0
+        m[40:44] = 1.0
+        for off, v in ((0, o_mean), (16, o_var), (32, u_mean), (34, u_var), (36, dx_mean), (40, dx_var)):
+            v = np.asarray(v, dtype=np.float32).ravel()
+            m[off:off + len(v)] = v
+        self.moments.copy_(torch.from_numpy(m))
+
+    def set_data(self, col):
+        """col: {"x_", "x", "o_", "u"} -> float32 [N, dim] arrays (DataSet.columns()); one upload per training call."""
+        self.data = {k: torch.as_tensor(np.ascontiguousarray(col[k], dtype=np.float32), device=self.device) for k in ("x_", "x", "o_", "u")}
+
+    def grad(self, idx, n_total):
+        """idx: int32 CUDA tensor of data-set rows (this rank's slice of the batch).  Fills `bucket`."""
+        R = int(idx.numel())
+        if R > self.max_rows:
+            raise PygentB200Error("batch of %d rows exceeds max_rows=%d" % (R, self.max_rows))
+        d = self.data
+        _check(dll().pg_mlp_train_grad(ctypes.byref(self.dims), ctypes.c_void_p(self.params.data_ptr()), ctypes.c_void_p(self.moments.data_ptr()),
+                                       ctypes.c_void_p(d["x_"].data_ptr()), ctypes.c_void_p(d["x"].data_ptr()),
+                                       ctypes.c_void_p(d["o_"].data_ptr()), ctypes.c_void_p(d["u"].data_ptr()),
+                                       ctypes.c_void_p(idx.data_ptr()) if R else None, R, int(n_total), ctypes.c_void_p(self._ws_ptr),
+                                       self.ws_bytes, self.max_rows, ctypes.c_void_p(self.bucket.data_ptr()), self._stream()),
+               "pg_mlp_train_grad")
+        self.launches += 5
+
+    def update(self, lr, weight_decay, eps=1e-10):
+        _check(dll().pg_mlp_train_update(ctypes.byref(self.dims), ctypes.c_void_p(self.params.data_ptr()), ctypes.c_void_p(self.state_sum.data_ptr()),
+                                         ctypes.c_void_p(self.bucket.data_ptr()), lr, weight_decay, eps, ctypes.c_void_p(self._ws_ptr),
+                                         self.ws_bytes, self.max_rows, self._stream()), "pg_mlp_train_update")
+        self.launches += 1
+
+    def step(self, idx, lr, weight_decay, eps=1e-10):
+        """pg_mlp_train_step: the single-GPU optimiser step in one C call (six launches)."""
+        R = int(idx.numel())
+        d = self.data
+        _check(dll().pg_mlp_train_step(ctypes.byref(self.dims), ctypes.c_void_p(self.params.data_ptr()), ctypes.c_void_p(self.state_sum.data_ptr()),
+                                       ctypes.c_void_p(self.moments.data_ptr()), ctypes.c_void_p(d["x_"].data_ptr()),
+                                       ctypes.c_void_p(d["x"].data_ptr()), ctypes.c_void_p(d["o_"].data_ptr()), ctypes.c_void_p(d["u"].data_ptr()),
+                                       ctypes.c_void_p(idx.data_ptr()) if R else None, R, lr, weight_decay, eps, ctypes.c_void_p(self._ws_ptr),
+                                       self.ws_bytes, self.max_rows, ctypes.c_void_p(self.bucket.data_ptr()), self._stream()),
+               "pg_mlp_train_step")
+        self.launches += 6

@@ -1,6 +1,8 @@
-"""Dynamics-model training (pygent_b200/algorithms/mbrl.py) against the unmodified reference's training step
-(tests/golden/mlp_training.npz, made by oracle/make_golden_train.py), and its data-parallel form on a world_size-2
-gloo group.  CPU only: the algebra is library GEMMs through torch; the GPU planner path is tested in test_gpu_mlp.py."""
+"""Dynamics-model training, CPU side: (1) the torch restatement oracle/train_oracle.py against the unmodified reference's
+training step (tests/golden/mlp_training.npz, made by oracle/make_golden_train.py); (2) the product's HOST logic
+(pygent_b200/algorithms/mbrl.py `DynamicsTrainer`: moments, batching, strided data-parallel slices, ONE bucket all-reduce
+per step) driven through that oracle as an injected backend, single process and on a world_size-2 gloo group.  The product's
+own backend is CUDA kernels only (tests/test_gpu_training.py); without a GPU it must refuse to construct."""
 import os
 import socket
 
@@ -12,45 +14,23 @@ import torch.multiprocessing as mp
 
 from oracle import mlp_oracle as mo
 from oracle.make_golden_train import synthetic_transitions
+from oracle.train_oracle import TorchBackend
 from pygent_b200.algorithms.mbrl import DynamicsTrainer
 from pygent_b200.data import DataSet
-from pygent_b200.nn_models import NNDynamics
+from pygent_b200.nn_models import NNDynamics  # noqa: F401
+from train_cases import dataset, fresh_net, run_fixed_batches
 
 
-def fresh_net():
-    w = mo.make_weights(6, 2)
-    net = NNDynamics(4, 1, dxDim=2, oDim=5, xIsAngle=[False, True, False, False])
-    with torch.no_grad():
-        for i, l in enumerate((net.layer1, net.layer2, net.layer3), 1):
-            l.weight.copy_(torch.from_numpy(w["W%d" % i]))
-            l.bias.copy_(torch.from_numpy(w["b%d" % i]))
-    return net
+def oracle_trainer(net, **kw):
+    return DynamicsTrainer(net, dyn_lr=1e-3, weight_decay=1e-3, backend=TorchBackend(net), **kw)
 
 
-def dataset():
-    D = DataSet(10 ** 6)
-    for s in synthetic_transitions():
-        D.force_add_sample(s)
-    return D
-
-
-def run_fixed_batches(trainer, D, epochs=2):
-    trainer.nn_dynamics.eval()
-    trainer.set_moments(D)
-    col = D.columns()
-    losses = []
-    for _ in range(epochs):
-        for idx in D.batch_indices(512, shuffle=False):
-            losses.append(float(trainer.train_step({k: v[idx] for k, v in col.items()})))
-    return losses
-
-
-def test_training_step_matches_reference(golden):
+def test_training_oracle_matches_reference(golden):
     """Moments, standardised MSE and six Adagrad steps (weight decay 1e-3) on fixed batches of 512/512/176."""
     torch.set_num_threads(1)
     g = golden("mlp_training")
     net = fresh_net()
-    tr = DynamicsTrainer(net, dyn_lr=1e-3, weight_decay=1e-3)
+    tr = oracle_trainer(net)
     losses = run_fixed_batches(tr, dataset())
     for k in ("xMean", "xVar", "dxMean", "dxVar", "oMean", "oVar", "uMean", "uVar"):
         assert np.allclose(getattr(net, k).numpy(), g[k], rtol=1e-6, atol=1e-7), k
@@ -64,6 +44,17 @@ def test_training_step_matches_reference(golden):
     s = dataset().data[3]
     dx_n, f = tr.training_data([s])
     assert abs(tr.pred_loss(s) - float(np.linalg.norm((f - dx_n).detach().numpy(), 2))) < 1e-6
+
+
+def test_trainer_has_no_cpu_fallback():
+    """Without a CUDA device the product's trainer refuses to construct (its only backend is the sm_100a kernels)."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from pygent_b200.lib import PygentB200Error
+    with pytest.raises(PygentB200Error):
+        DynamicsTrainer(fresh_net(), dyn_lr=1e-3, weight_decay=1e-3)
+    with pytest.raises(PygentB200Error):
+        DynamicsTrainer(fresh_net(), dyn_lr=1e-3, weight_decay=1e-3, device="cpu")
 
 
 def test_dataset_mirrors_reference_fifo_and_batching():
@@ -86,7 +77,7 @@ def _dp_worker(rank, world, port, q):
     try:
         torch.set_num_threads(1)
         net = fresh_net()
-        tr = DynamicsTrainer(net, dyn_lr=1e-3, weight_decay=1e-3)
+        tr = oracle_trainer(net)
         losses = run_fixed_batches(tr, dataset(), epochs=1)
         q.put((rank, losses, net.layer3.weight.detach().numpy().copy(), float(net.layer2.weight.detach().double().sum()), tr.collectives))
     finally:
@@ -111,7 +102,7 @@ def test_data_parallel_training_equals_single_process(golden):
         assert p.exitcode == 0
     torch.set_num_threads(1)
     net = fresh_net()
-    single = run_fixed_batches(DynamicsTrainer(net, dyn_lr=1e-3, weight_decay=1e-3), dataset(), epochs=1)
+    single = run_fixed_batches(oracle_trainer(net), dataset(), epochs=1)
     for rank, losses, W3, w2sum, ncoll in res:
         assert ncoll == 3  # one collective per optimiser step
         assert np.allclose(losses, single, rtol=1e-5) and np.allclose(losses, g["losses"][:3], rtol=2e-5)
