@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define PG_ABI_VERSION 5
+#define PG_ABI_VERSION 6
 
 #define PG_F64 0
 #define PG_F32 1
@@ -99,8 +99,10 @@ int pg_rollout(int dtype, int integrator, int64_t B, int32_t T, int32_t S, doubl
  * (32-trajectory group, 20-step time chunk) units from a ticket queue, so that all schedulers carry the same
  * load even when B/32 is not a multiple of the scheduler count (65,536 envs: 3.46 warps per scheduler).
  * Results are bit-identical to pg_rollout.  xN and cost are required (they carry the state between chunks);
- * workspace: device scratch of at least pg_rollout_workspace_bytes(B, T) bytes, contents irrelevant.
- * workspace[8..12) holds an error flag afterwards (non-zero: a worker gave up waiting -- never expected). */
+ * workspace: device scratch of at least pg_rollout_workspace_bytes(B, T) bytes; it must not be shared by calls that may run
+ * concurrently.  Bytes [0, 4) are a STICKY status word (i32): zero it once after allocation; a worker that gives up waiting for
+ * its unit (~2 s; never expected) sets it to 1 and no launch ever clears it, so the caller can test it whenever it next
+ * synchronises -- non-zero means the results of some earlier launch on this workspace are incomplete. */
 int64_t pg_rollout_workspace_bytes(int64_t B, int32_t T);
 int pg_rollout_balanced(int dtype, int integrator, int64_t B, int32_t T, int32_t S, double dt, double t0,
                         const void* x0, const void* U, void* X, void* xN, void* cost, uint8_t* terminated,
@@ -146,8 +148,8 @@ int pg_ilqr_forward(int dtype, int integrator, int64_t B, int32_t T, int32_t S, 
 /* pg_ilqr_forward for large line searches, load-balanced like pg_rollout_balanced: persistent worker warps pull
  * (32-entry group of the work list, alpha, 20-step time chunk) units from a ticket queue.  Costs and flags only (no
  * X_out / U_out); cost_out, diverged_out and xN_out are required (they carry a candidate between chunks).  Bit-identical
- * to pg_ilqr_forward.  workspace: device scratch of at least pg_ilqr_forward_workspace_bytes(B, T, n_alpha) bytes;
- * workspace[8..12) holds an error flag afterwards (non-zero: a worker gave up waiting -- never expected). */
+ * to pg_ilqr_forward.  workspace: device scratch of at least pg_ilqr_forward_workspace_bytes(B, T, n_alpha) bytes, with the
+ * same sticky status word in bytes [0, 4) as pg_rollout_balanced. */
 int64_t pg_ilqr_forward_workspace_bytes(int64_t B, int32_t T, int32_t n_alpha);
 int pg_ilqr_forward_balanced(int dtype, int integrator, int64_t B, int32_t T, int32_t S, double dt,
                              int32_t n_alpha, const double* alphas, const void* alpha_dev,

@@ -547,7 +547,7 @@ class iLQR(Algorithm):
         graph = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
+        with torch.cuda.stream(side), lib.workspace_stream(torch.cuda.current_stream(dev)):
             graph.capture_begin(capture_error_mode="thread_local")  # other threads (NCCL watchdog, samplers) may call CUDA
             try:
                 self.iterate()
@@ -579,6 +579,7 @@ class iLQR(Algorithm):
         if self.final_backpass:
             self._final_backpass()
         self.iterations = int(st["iters"].max().item())
+        self.lib.check_queues()  # a line-search worker that gave up waiting would have left stale candidate costs
         xx, uu = self.xx, self.uu
         self.agent.set_history(uu)
         if self.printing:

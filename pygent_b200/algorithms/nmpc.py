@@ -329,7 +329,7 @@ class NMPC(Algorithm):
             graph = torch.cuda.CUDAGraph()
             side = torch.cuda.Stream(device=env.device)
             side.wait_stream(torch.cuda.current_stream(env.device))
-            with torch.cuda.stream(side):
+            with torch.cuda.stream(side), lib.workspace_stream(torch.cuda.current_stream(env.device)):
                 graph.capture_begin(capture_error_mode="thread_local")  # other threads (NCCL watchdog, samplers) may call CUDA
                 try:
                     u_g = agent.take_action_device(x_in)

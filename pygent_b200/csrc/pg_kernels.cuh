@@ -260,7 +260,8 @@ struct QueueArgs {
     RolloutArgs<T> r;
     int n_groups, n_chunks;
     int bounds[MAX_CHUNKS + 1];  // chunk c covers control intervals [bounds[c], bounds[c + 1])
-    int* counters;   // [0] next ticket, [1] next free queue slot, [2] error flag
+    int* status;     // sticky error word: a worker that gives up waiting sets it; launches never clear it, the host reads it
+    int* counters;   // [0] next ticket, [1] next free queue slot
     int* queue;      // [n_groups * (n_chunks - 1)], zero = not yet published, else group + 1
     int* progress;   // [n_groups] next chunk of the group
     T* tq;           // [n_groups] simulation time of the group
@@ -288,7 +289,7 @@ __global__ void __launch_bounds__(128, 3) rollout_queue_kernel(const QueueArgs<T
                 while ((v = *slot) == 0) {
                     __nanosleep(128);
                     if (++spins > (1 << 24)) {  // ~2 s: something is wrong, do not hang the GPU
-                        atomicExch(&q.counters[2], 1);
+                        atomicExch(q.status, 1);
                         break;
                     }
                 }
@@ -586,7 +587,8 @@ struct ForwardQueueArgs {
     ForwardArgs<T> f;
     int n_chunks;
     int bounds[MAX_CHUNKS + 1];
-    int* counters;  // [0] next ticket, [1] next free queue slot, [2] error flag
+    int* status;    // sticky error word (see QueueArgs)
+    int* counters;  // [0] next ticket, [1] next free queue slot
     int* queue;
     int* progress;  // [n_alpha * ceil(B / 32)]
     T* tq;
@@ -617,7 +619,7 @@ __global__ void __launch_bounds__(128, 3) ilqr_forward_queue_kernel(const Forwar
                 while ((v = *slot) == 0) {
                     __nanosleep(128);
                     if (++spins > (1 << 24)) {
-                        atomicExch(&q.counters[2], 1);
+                        atomicExch(q.status, 1);
                         break;
                     }
                 }

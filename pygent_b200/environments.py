@@ -252,6 +252,7 @@ class StateSpaceModel(Environment):
             t = t + self.dt
             self.tt.append(t)
         term = r["terminated"].cpu().numpy().astype(bool)
+        L.check_queues()  # we have just synchronised: a queue worker that gave up must not go unnoticed
         self.terminated = term if self.batched else bool(term[0])
         return r
 
@@ -301,6 +302,7 @@ class StateSpaceModel(Environment):
         if xN_out is not None:
             xN_out.copy_(st["x"][i % 2], non_blocking=True)
         comp.synchronize()
+        L.check_queues()
         return {"cost": cost_out, "xN": xN_out}
 
     def terminate(self, x):

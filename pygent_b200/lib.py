@@ -104,6 +104,26 @@ def _host_doubles(vals):
     return (ctypes.c_double * len(vals))(*vals)
 
 
+_WS_STREAM_ALIAS = None
+
+
+class workspace_stream(object):
+    """While a CUDA graph is captured on a side stream that is forked from and joined back into `stream`, queue
+    workspaces are looked up as if the calls were made on `stream` (the captured kernels logically run there), so the
+    capture allocates nothing and the graph uses the buffers the eager iterations already own."""
+
+    def __init__(self, stream):
+        self.id = stream.cuda_stream
+
+    def __enter__(self):
+        global _WS_STREAM_ALIAS
+        self.prev, _WS_STREAM_ALIAS = _WS_STREAM_ALIAS, self.id
+
+    def __exit__(self, *exc):
+        global _WS_STREAM_ALIAS
+        _WS_STREAM_ALIAS = self.prev
+
+
 class ProblemLibrary:
     """One loaded `pg_<system>_<key>.so`."""
 
@@ -121,6 +141,7 @@ class ProblemLibrary:
         self.dll.pg_ilqr_num_snapshots.argtypes = [_i32]
         self.dll.pg_ilqr_num_snapshots.restype = _i32
         self._workspace = {}
+        self._retired = []
         info = ProblemInfo()
         self._check(self.dll.pg_get_problem_info(ctypes.byref(info)), "pg_get_problem_info")
         self.info = info
@@ -137,6 +158,33 @@ class ProblemLibrary:
         if rc > 0:
             raise PygentB200Error("%s: CUDA error %d (%s)" % (what, rc, _cuda_error_name(rc)))
         raise PygentB200Error("%s: %s" % (what, {-1: "bad argument", -2: "not supported by this problem"}.get(rc, rc)))
+
+    def _queue_workspace(self, kind, dev, nbytes):
+        """Ticket-queue scratch of the balanced kernels: one buffer per (kernel kind, device, STREAM) -- this handle is
+        shared by every solver and environment of the problem, and calls on different streams must not share counters.
+        A buffer that has to grow is replaced, but the old one is kept alive: its address may be baked into a captured
+        CUDA graph.  Bytes [0, 4) are the sticky status word the workers set when they give up waiting (queue_status)."""
+        key = (kind, dev, _WS_STREAM_ALIAS if _WS_STREAM_ALIAS is not None else torch.cuda.current_stream(dev).cuda_stream)
+        ws = self._workspace.get(key)
+        if ws is None or ws.numel() < nbytes:
+            if ws is not None:
+                self._retired.append(ws)
+            ws = self._workspace[key] = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=dev)
+        return ws
+
+    def queue_status_words(self):
+        """int32 views of the status words of every live queue workspace (device tensors; reading them synchronises)."""
+        return [ws[:4].view(torch.int32) for ws in list(self._workspace.values()) + self._retired]
+
+    def check_queues(self):
+        """Raise if a worker of a balanced (ticket-queue) kernel ever gave up waiting for its unit: the results of that
+        launch are incomplete.  Never expected (GPU time-slicing under a debugger or MPS contention could do it); callers
+        that already synchronise with the device check here so that the failure is loud instead of silent."""
+        for w in self.queue_status_words():
+            if int(w.item()) != 0:
+                w.zero_()
+                raise PygentB200Error("%s: a queue worker timed out waiting for its work unit; the results of that launch "
+                                      "are incomplete" % self.name)
 
     @staticmethod
     def _work(work, B):
@@ -182,9 +230,7 @@ class ProblemLibrary:
             balanced = use_balanced_rollout(B, T, dev)
         if balanced and cost is not None and T >= 1 and B > 0:
             nbytes = int(self.dll.pg_rollout_workspace_bytes(B, T))
-            ws = self._workspace.get(dev)
-            if ws is None or ws.numel() < nbytes:
-                ws = self._workspace[dev] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            ws = self._queue_workspace("ro", dev, nbytes)
             rc = self.dll.pg_rollout_balanced(_dtype_code(dtype), integrator, B, T, S, dt, t0,
                                               _ptr(x0, dtype, (n, B), "x0"), _ptr(U, dtype, (T, m, B), "U"),
                                               _ptr(X, dtype, (T + 1, n, B), "X"), _ptr(xN, dtype, (n, B), "xN"),
@@ -244,9 +290,7 @@ class ProblemLibrary:
             if xN is None:
                 xN = torch.empty((n_alpha, n, B), dtype=dtype, device=dev)
             nbytes = int(self.dll.pg_ilqr_forward_workspace_bytes(B, T, n_alpha))
-            ws = self._workspace.get(("fw", dev))
-            if ws is None or ws.numel() < nbytes:
-                ws = self._workspace[("fw", dev)] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            ws = self._queue_workspace("fw", dev, nbytes)
             rc = self.dll.pg_ilqr_forward_balanced(
                 _dtype_code(dtype), integrator, B, T, S, dt, n_alpha, _host_doubles(alphas),
                 _ptr(alpha_dev, dtype, (B,), "alpha_dev"), _ptr(x0, dtype, (n, B), "x0"),

@@ -169,13 +169,35 @@ def test_balanced_rollout_is_bit_identical(B, T, dtype):
     assert same(a["xN"], b["xN"]) and same(a["cost"], b["cost"]) and torch.equal(a["terminated"], b["terminated"])
     if hist:
         assert same(a["X"], b["X"])
-    ws = L._workspace[x0d.device]
-    assert int(ws[8:12].view(torch.int32).item()) == 0  # no worker ever gave up waiting
+    assert all(int(w.item()) == 0 for w in L.queue_status_words())  # no worker ever gave up waiting
+    L.check_queues()
     # continuation of an accumulated cost (the host-pipelined path) and the Euler integrator
     c0 = torch.full((B,), 1.5, dtype=dtype, device="cuda")
     a2 = L.rollout(a["xN"], Ud, S=4, dt=0.02, t0=1.0, integrator=1, accumulate_cost=True, out={"cost": c0.clone()}, balanced=False)
     b2 = L.rollout(a["xN"], Ud, S=4, dt=0.02, t0=1.0, integrator=1, accumulate_cost=True, out={"cost": c0.clone()}, balanced=True)
     assert same(a2["xN"], b2["xN"]) and same(a2["cost"], b2["cost"])
+
+
+def test_queue_worker_timeout_is_reported(monkeypatch):
+    """a worker of the ticket-queue kernels that gives up waiting (~2 s) must not go unnoticed.  PG_QUEUE_FAULT=1
+    makes the launch skip the first-chunk tickets, so every worker waits for a unit nobody publishes; the kernel still ends
+    (no hang, no trap), the sticky status word of the workspace is set, and the next host-side check raises."""
+    alg = solver("cart_pole", 10)
+    L = alg.lib
+    B, T = 4096, 60
+    x0 = torch.zeros((4, B), dtype=torch.float64, device="cuda")
+    U = torch.zeros((T, 1, B), dtype=torch.float64, device="cuda")
+    L.rollout(x0, U, S=4, dt=0.02, balanced=True)
+    L.check_queues()
+    monkeypatch.setenv("PG_QUEUE_FAULT", "1")
+    L.rollout(x0, U, S=4, dt=0.02, balanced=True)
+    monkeypatch.delenv("PG_QUEUE_FAULT")
+    L.rollout(x0, U, S=4, dt=0.02, balanced=True)  # a later good launch on the same workspace does not clear the word
+    with pytest.raises(pglib.PygentB200Error, match="timed out"):
+        L.check_queues()
+    L.check_queues()  # reported once, then cleared
+    r = L.rollout(x0, U, S=4, dt=0.02, balanced=True)
+    assert torch.equal(r["xN"], L.rollout(x0, U, S=4, dt=0.02, balanced=False)["xN"])
 
 
 @pytest.mark.parametrize("run", sorted(ILQR_RUNS))
@@ -332,11 +354,27 @@ def test_ilqr_iterations_in_lockstep_with_oracle(case, T, parallel, constrained,
             assert rel(r["X"].cpu().numpy(), alg._xbar.cpu().numpy()) < 1e-11  # other kernel: FMA contraction may differ
 
 
+def free_running_agreement(alg, so, cost_tol, max_iter_diff):
+    """A GPU solve against the oracle's solve of the same starts, both running free.  Every iteration is checked in lock
+    step elsewhere (test_ilqr_iterations_in_lockstep_with_oracle: the GPU's numbers match the oracle's to 1e-8 and its
+    decisions are the reference's decisions on those numbers); free-running, the two differ in rounding (the GPU contracts
+    to FMA, the oracle is compiled with -ffp-contract=off), which can only move a decision whose margin is at rounding
+    level: the `dcost < tolFun` stopping test near the optimum, i.e. WHEN a trajectory stops, not WHERE.  So: every final
+    cost agrees to `cost_tol`, every iteration count to within `max_iter_diff`, and no trajectory ends above its start."""
+    rc = np.abs(alg.cost - so["cost"]) / np.abs(so["cost"])
+    assert np.all(rc <= cost_tol), (rc.max(), np.where(rc > cost_tol)[0])
+    di = np.abs(alg.iters - so["iters"])
+    assert di.max() <= max_iter_diff, (di.max(), np.where(di > max_iter_diff)[0])
+    same = di == 0
+    if same.any():  # same number of iterations: same arithmetic up to rounding
+        assert rc[same].max() <= 1e-6
+    assert np.all(alg.cost <= so["cost0"] * (1 + 1e-12))
+    return float(same.mean())
+
+
 @pytest.mark.parametrize("case,T,parallel", [("cart_pole", 100, False), ("acrobot", 80, True), ("double_parallel", 100, False)])
 def test_ilqr_batch_converges_like_oracle(case, T, parallel):
-    """Full solves of a batch of random starts.  Swing-up optimisation amplifies rounding (the GPU contracts to
-    FMA, the oracle does not), so late line-search decisions may flip and the iteration count can differ by a few;
-    the optimum reached must not: same cost to 1e-6 wherever both stopped on a convergence test."""
+    """Full solves of a batch of random starts, every trajectory (no percentile thresholds): see free_running_agreement."""
     rng = np.random.default_rng(5)
     n = len(CASES[case][4])
     B = 48
@@ -345,12 +383,78 @@ def test_ilqr_batch_converges_like_oracle(case, T, parallel):
     alg.run_optim()
     p = oracle_problem(case, S=4)
     so = oracle.ilqr_solve(p, oracle.ilqr_params(max_iters=200, parallel=parallel), x0, T, nthreads=8)
-    both = np.isin(alg.status, (1, 2)) & np.isin(so["status"], (1, 2))
-    assert both.mean() > 0.8
-    assert np.mean(np.abs(alg.iters - so["iters"]) <= 3) > 0.7
-    close = np.abs(alg.cost - so["cost"]) / so["cost"] < 1e-5
-    assert close[both].mean() > 0.9, (alg.cost[both], so["cost"][both])
-    assert np.all(alg.cost <= so["cost0"] * (1 + 1e-12))
+    free_running_agreement(alg, so, cost_tol=1e-5, max_iter_diff=8)
+
+
+FULL_SIZE = {  # BASELINE.json configs[2] and configs[3] as bench.py builds them (per-GPU shard of rank 0)
+    "c3": ("cart_pole", 16384, False, 500, 1000, [0, np.pi, 0, 0], [.5, .3, .5, .5]),
+    "c4_double": ("double_parallel", 8192, True, 100, 4000, [0, np.pi, np.pi, 0, 0, 0], [.1] * 6),
+    "c4_acrobot": ("acrobot", 8192, True, 100, 4000, [np.pi, 0, 0, 0], [.1] * 4),
+}
+
+
+@pytest.mark.parametrize("name", sorted(FULL_SIZE))
+def test_full_size_ilqr_solves_match_oracle_on_a_sample(name):
+    """The solves bench.py times, at their full sizes (16,384 swing-ups with the serial line search; 8,192 n = 6 / acrobot
+    trajectories with `parallel=True`): (1) 256 sampled trajectories solved ALONE are bit-identical to their rows of the
+    full batch -- costs, iteration counts, statuses, trajectories -- although the full batch runs the two-phase line search,
+    the tail variant and CUDA-graph replay and the sample does not; (2) the oracle's free-running solves of the sample
+    agree with them trajectory by trajectory (observed: C3 costs <= 1.3e-7, 178/256 identical iteration counts, max
+    difference 6; C4 n = 6: all 256 iteration counts identical, costs 2e-15; acrobot: 254/256, costs 1e-12)."""
+    case, B, par, iters, seed, nominal, spread = FULL_SIZE[name]
+    rng = np.random.default_rng(seed)
+    x0 = np.array(nominal) + rng.uniform(-1, 1, (B, len(nominal))) * np.array(spread)
+    alg = solver(case, 100, x0=x0, maxIters=iters, parallel=par)
+    alg.run_optim()
+    sel = np.sort(np.random.default_rng(7).choice(B, 256, replace=False))
+    sub = solver(case, 100, x0=x0[sel], maxIters=iters, parallel=par)
+    sub.run_optim()
+    assert np.array_equal(sub.cost, alg.cost[sel]) and np.array_equal(sub.iters, alg.iters[sel])
+    assert np.array_equal(sub.status, alg.status[sel])
+    assert np.array_equal(np.asarray(sub.xx), np.asarray(alg.xx)[sel]) and np.array_equal(np.asarray(sub.uu), np.asarray(alg.uu)[sel])
+    so = oracle.ilqr_solve(oracle_problem(case, S=4), oracle.ilqr_params(max_iters=iters, parallel=par), x0[sel], 100, nthreads=16)
+    same = free_running_agreement(sub, so, cost_tol=1e-6, max_iter_diff=8 if name == "c3" else 2)
+    assert same >= (0.6 if name == "c3" else 0.97)
+
+
+@pytest.mark.parametrize("case", ["cart_pole", "double_parallel"])
+def test_fp32_ilqr_kernels_within_stated_tolerance(case):
+    """The float instantiation of K2/K3/K4 (`dtype=torch.float32` environments) against the fp64 kernels on the same
+    starts.  Stated tolerance: from identical nominal trajectories, ONE iteration -- gains K, k within 5e-5 of their largest
+    entry, expected reductions within 5e-5, sane line-search candidate costs within 1e-5 (observed 3e-6 / 5e-6 / 4e-6 /
+    9e-7: fp32 rounding over a 100-interval Riccati sweep and 400 RK4 substeps).  Whole solves: fp32 cannot resolve the
+    reference's stopping test dcost < 1e-7 on costs of ~70, so it stops on the regularisation limit or the iteration cap
+    instead, after more iterations; it must still reach the fp64 optimum: final costs within 1e-3 on >= 97 % of the
+    trajectories (observed 1e-4 on 255/256) and never above the initial cost."""
+    rng = np.random.default_rng(5)
+    n = len(CASES[case][4])
+    B, T = 256, 100
+    x0 = np.array(CASES[case][4]) + rng.uniform(-0.3, 0.3, (B, n))
+    a64 = solver(case, T, x0=x0, maxIters=200)
+    a32 = solver(case, T, x0=x0, maxIters=200, env_kw={"dtype": torch.float32})
+    assert a32._xbar.dtype == torch.float32 and a32._KKc.dtype == torch.float32
+    assert rel(a32.cost, a64.cost) < 1e-5
+    cost0 = a64.cost.copy()
+    for a in (a64, a32):
+        a._sel = a._select_params()
+        a._rearm()
+        a.iterate()
+    K64, K32, k64, k32 = host(a64._KKc), host(a32._KKc), host(a64._kkc), host(a32._kkc)
+    assert np.max(np.abs(K32 - K64) / np.max(np.abs(K64), axis=(1, 2, 3), keepdims=True)) < 5e-5
+    assert np.max(np.abs(k32 - k64) / np.max(np.abs(k64), axis=(1, 2), keepdims=True)) < 5e-5
+    d64, d32 = a64._bw["dV"].cpu().numpy(), a32._bw["dV"].double().cpu().numpy()
+    assert np.max(np.abs(d32 - d64) / np.abs(d64)) < 5e-5
+    c64, c32 = a64._fw["cost"].cpu().numpy(), a32._fw["cost"].double().cpu().numpy()
+    sane = ~a64._fw["diverged"].cpu().numpy().astype(bool) & (c64 < 50 * (np.abs(cost0) + 1))
+    assert np.array_equal(a32._fw["diverged"].cpu().numpy().astype(bool)[sane], np.zeros(int(sane.sum()), dtype=bool))
+    assert np.max((np.abs(c32 - c64) / np.abs(c64))[sane]) < 1e-5
+    a64 = solver(case, T, x0=x0, maxIters=200)
+    a32 = solver(case, T, x0=x0, maxIters=200, env_kw={"dtype": torch.float32})
+    a64.run_optim()
+    a32.run_optim()
+    rc = np.abs(a32.cost - a64.cost) / np.abs(a64.cost)
+    assert np.mean(rc <= 1e-3) >= 0.97, np.sort(rc)[-10:]
+    assert np.all(a32.cost <= cost0 * (1 + 1e-5))
 
 
 def test_ilqr_per_trajectory_control_flow():
@@ -535,7 +639,7 @@ def test_balanced_forward_is_bit_identical(case, B, T):
     b = L.ilqr_forward(*args, balanced=True, **kw)
     for k in ("cost", "diverged", "terminated", "xN"):
         assert torch.equal(a[k], b[k]), k
-    assert int(L._workspace[("fw", alg._x0.device)][8:12].view(torch.int32).item()) == 0
+    L.check_queues()
     # compacted work list: only the listed trajectories are touched
     sel = torch.as_tensor(np.sort(rng.choice(B, B // 3, replace=False)), dtype=torch.int32, device="cuda")
     idx = torch.zeros(B, dtype=torch.int32, device="cuda")
