@@ -170,6 +170,48 @@ def cpu_rollout_baseline(n_envs, threads, seed=0):
     return n_envs * T_STEPS / dt, dt
 
 
+def cpu_ilqr_baseline(n_traj, threads, seed=1000):
+    """M2 on the host: the C oracle's `run_optim` (line-by-line port of ilqr.py:399-485, RK4 x 4) on the first `n_traj` of
+    the C3 starts bench.py's `ilqr` leg solves on the GPU (rank 0's shard), OpenMP over trajectories.  Returns (it/s, s, its)."""
+    import oracle
+    from pygent_b200.examples import CASES
+    _, _, cp = CASES["cart_pole"][3]()
+    p = oracle.make_problem("cart_pole_lin", DT, S=SUBSTEPS, term_lim=[1.2, 0, 4.0, 0], **cp)
+    rng = np.random.default_rng(seed)
+    xi = np.array([0, np.pi, 0, 0]) + rng.uniform(-1, 1, (ILQR_B, 4)) * np.array([.5, .3, .5, .5])
+    t0 = time.perf_counter()
+    so = oracle.ilqr_solve(p, oracle.ilqr_params(max_iters=500), xi[:n_traj], ILQR_T, nthreads=threads)
+    secs = time.perf_counter() - t0
+    its = int(so["iters"].sum())
+    return its / secs, secs, its
+
+
+def cpu_ilqr_report(threads):
+    """`ilqr.cpu_baseline` of the bench line: the oracle port on all host threads and on one, and -- when oracle/_ref (the
+    pip-installed unmodified reference, oracle/install_ref.py) is present -- the reference's own Python path on C1."""
+    n = 512
+    v, secs, its = cpu_ilqr_baseline(n, threads)
+    v1, secs1, its1 = cpu_ilqr_baseline(32, 1)
+    out = {"value": v, "unit": "iLQR iterations/s", "cores": threads, "kind": "port", "single_core": v1,
+           "sample": "first %d of the 16,384 C3 swing-ups to convergence (%d iterations, %.1f s), C oracle, OpenMP over %d threads; "
+                     "single_core: first 32 on one thread (%d iterations, %.1f s)" % (n, its, secs, threads, its1, secs1)}
+    try:
+        from oracle import ref_bench
+        if ref_bench.available():
+            r = ref_bench.run_c1()
+            out["reference_python"] = {"value": r["iterations"] / r["seconds"], "unit": "iLQR iterations/s", "cores": 1, "kind": "reference",
+                                       "iterations": r["iterations"], "final_cost": r["cost"], "seconds": r["seconds"],
+                                       "expected": {"iterations": ref_bench.C1_ITERATIONS, "final_cost": ref_bench.C1_COST},
+                                       "matches_known_answer": bool(r["iterations"] == ref_bench.C1_ITERATIONS and abs(r["cost"] - ref_bench.C1_COST) < 1e-9),
+                                       "sample": "BASELINE.json configs[0]: the unmodified reference (oracle/_ref), one cart-pole swing-up, "
+                                                 "horizon 100, RK45, lambdified sympy, one Python thread"}
+        else:
+            out["reference_python"] = {"unavailable": "oracle/_ref not installed (python -m oracle.install_ref needs /root/reference)"}
+    except Exception as e:  # the baseline must never take the bench line down
+        out["reference_python"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+    return out
+
+
 def run_reference(args, rank):
     """Reference arm: the reference's algorithm on the host cores (oracle port), same metric and config."""
     if rank != 0:
@@ -185,13 +227,15 @@ def run_reference(args, rank):
         el += cpu_rollout_baseline(n, threads)[1]
     value = n * T_STEPS * args.steps / el
     sample = "%d of the 65,536 envs x 500 steps per step (RK4 x 4), OpenMP over all host threads" % n
+    ilqr_cpu = cpu_ilqr_report(threads)
     emit({
         "impl": "reference", "metric": "rk4_env_steps_per_s", "value": value, "unit": "env-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": CONFIG,
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "ilqr": {"metric": "ilqr_iterations_per_s", "value": ilqr_cpu["value"], "unit": "iLQR iterations/s", "cpu_baseline": ilqr_cpu}})
 
 
 
@@ -619,6 +663,36 @@ def main():
                               "(one launch of all 11 once fewer than 64 x SMs trajectories are live)"}
         ilqr["full_batch"] = ilqr_full_batch_roofline(xi, dev)
 
+    # ---- config 3 AS SPECIFIED: 16,384 initial states in total, sharded over the N GPUs (strong scaling) --------
+    ilqr_c3 = None
+    if not args.no_ilqr:
+        rng = np.random.default_rng(1000)  # one global batch; rank r solves rows [r * B/N, (r + 1) * B/N)
+        x_all = np.array([0, np.pi, 0, 0]) + rng.uniform(-1, 1, (ILQR_B, 4)) * np.array([.5, .3, .5, .5])
+        per = ILQR_B // world
+        xi = x_all[rank * per:(rank + 1) * per]
+        solver = make_ilqr("cart_pole", ILQR_T, x0=xi, env_kw={"device": dev}, maxIters=500)
+        solver.run_optim()
+        solver.environment.reset(xi)
+        solver.reset()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        solver.run_optim()
+        b.record()
+        barrier()
+        ms, total_iters = a.elapsed_time(b), int(solver.iters.sum())
+        if world > 1:
+            t = torch.tensor([ms, -float(total_iters)], dtype=torch.float64, device=dev)
+            tm, ts = t.clone(), t.clone()
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+            ms, total_iters = float(tm[0]), int(-ts[1])
+        bc3, bi3, br3 = pgd.gather_best(torch.as_tensor(solver.cost, device=dev), offset=rank * per)
+        ilqr_c3 = {"metric": "ilqr_iterations_per_s", "value": total_iters / (ms * 1e-3), "unit": "iLQR iterations/s",
+                   "trajectories_total": ILQR_B, "trajectories_per_gpu": per, "scaling": "strong", "horizon": ILQR_T, "ms": ms,
+                   "iterations_total": total_iters, "best": {"cost": bc3, "trajectory": bi3, "rank": br3},
+                   "note": "BASELINE.json configs[2]: 16,384 initial states in total, sharded over the GPUs of the run"}
+
     # ---- config 4: n = 6 double pendulum / acrobot, parallel line search -------------------------------
     ilqr_c4 = None
     if not args.no_ilqr:
@@ -715,6 +789,8 @@ def main():
             res["nmpc"] = nmpc
         if ilqr_c4:
             res["ilqr_c4"] = ilqr_c4
+        if ilqr_c3 is not None:
+            res["ilqr_c3_sharded"] = ilqr_c3
         if train is not None:
             res["train"] = train
         if not args.no_cpu:
@@ -724,6 +800,8 @@ def main():
             n = B_ENVS  # the whole step: 65,536 envs x 500 control intervals (a few seconds on the host cores)
             v, secs = cpu_rollout_baseline(n, threads)
             v1, secs1 = cpu_rollout_baseline(1024, 1)
+            if ilqr is not None:
+                ilqr["cpu_baseline"] = cpu_ilqr_report(threads)
             res["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port",
                                    "sample": "all %d envs x 500 steps of one step (RK4 x 4), C oracle, OpenMP over %d threads; %.1f s" % (n, threads, secs),
                                    "single_core": v1}

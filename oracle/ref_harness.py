@@ -1,9 +1,10 @@
 """Import the UNMODIFIED reference (mpritzkoleit/pygent, /root/reference) in this container.
 
-TEST TOOLING ONLY.  This module exists so that `oracle/make_golden.py` can run the real
-reference and freeze its outputs under `tests/golden/`.  It is never imported by the product
-(`pygent_b200/`), by `-m gpu` tests, by `bench.py` or by `smoke()`: `/root/reference` does not
-exist on the GPU box.
+TEST / BASELINE TOOLING ONLY.  This module exists so that `oracle/make_golden.py` can run the real
+reference and freeze its outputs under `tests/golden/`, and so that `bench.py`'s CPU legs (`cpu_baseline`,
+`--impl reference`) can time the reference itself (oracle/ref_bench.py).  It is never imported by the product
+(`pygent_b200/`), by `-m gpu` tests or by `smoke()`.  `/root/reference` does not exist on the GPU box; the
+pip-installed copy oracle/_ref/ (oracle/install_ref.py; git-ignored, travels with the tree) does.
 
 What it does:
   1. registers permissive stub modules for the reference's absent, import-time-only
@@ -21,7 +22,18 @@ import pickle
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("PYGENT_REFERENCE", "/root/reference")
+_INSTALLED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def reference_root():
+    """Directory that contains the reference's `pygent` package: $PYGENT_REFERENCE, /root/reference, or oracle/_ref."""
+    for cand in (os.environ.get("PYGENT_REFERENCE"), "/root/reference", _INSTALLED):
+        if cand and os.path.isfile(os.path.join(cand, "pygent", "algorithms", "ilqr.py")):
+            return cand
+    return None
+
+
+REFERENCE_ROOT = reference_root() or "/root/reference"
 
 
 class _Stub(types.ModuleType):
@@ -82,7 +94,7 @@ def load_reference():
     if _loaded is not None:
         return _loaded
     if not os.path.isdir(REFERENCE_ROOT):
-        raise RuntimeError("reference tree %s not present (it never is on the GPU box)" % REFERENCE_ROOT)
+        raise RuntimeError("reference tree %s not present (run `python -m oracle.install_ref` where /root/reference exists)" % REFERENCE_ROOT)
     sys.dont_write_bytecode = True
     for name in _STUBS:
         if name not in sys.modules:
