@@ -14,7 +14,11 @@
  *     x' = x + dt * [x[n/2:], dv / dt]                         fp64
  * precision PG_MLP_FP32: layer 2 in fp32 FFMA (tracks the reference's fp32 torch path to ~1e-6);
  * precision PG_MLP_BF16: layer 2 on the 5th-generation tensor cores (tcgen05.mma, bf16 operands, fp32
- *                        accumulation in TMEM), weights streamed from L2 by bulk async copies.
+ *                        accumulation in TMEM), weights streamed from L2 by bulk async copies.  LOWER precision than the
+ *                        reference's fp32 network (2e-2 per evaluation): an explicitly approximate fast path.
+ * precision PG_MLP_F16X3: layer 2 on the tensor cores at the REFERENCE's precision: H1 and W2 are split x = hi + lo into two
+ *                        fp16 numbers (22 mantissa bits) and the product is formed as Ah Wh + Al Wh + Ah Wl with fp32
+ *                        accumulation; layer 1 in fp32 on the CUDA cores.  Tracks the fp32 network to ~1e-6 (stated: 1e-5).
  *
  * All pointers are device pointers owned by the caller; state arrays are trajectory-minor ([n, R], R fastest),
  * fp64; every function enqueues on `stream` and returns 0 / a cudaError_t / a negative PG_E_* code.
@@ -30,6 +34,7 @@ extern "C" {
 
 #define PG_MLP_FP32 0
 #define PG_MLP_BF16 1
+#define PG_MLP_F16X3 2
 
 #define PG_MLP_HIDDEN 500     /* the reference's layer width (nn_models.py:179-181) */
 #define PG_MLP_HPAD 512       /* padded width used by the kernels */
@@ -93,7 +98,7 @@ int pg_mlp_forward_balanced(int precision, const pg_mlp_dims_t* dims, const void
  *   PG_MLP_LIN_FD       central differences with eps = 1e-3 through 2(n+m) network evaluations -- what the reference does
  *                       (helpers.system_linearization, pygent/helpers.py:130-148); any precision, meant for PG_MLP_FP32;
  *   PG_MLP_LIN_ANALYTIC the exact derivative of the piecewise-linear network by the chain rule, on the tensor cores
- *                       (PG_MLP_BF16 only): one forward GEMM for the ReLU masks + one transposed GEMM per output. */
+ *                       (PG_MLP_BF16 or PG_MLP_F16X3): one forward GEMM for the ReLU masks + one transposed GEMM per output. */
 #define PG_MLP_LIN_ANALYTIC 0
 #define PG_MLP_LIN_FD 1
 int pg_mlp_linearize(int precision, int lin_mode, const pg_mlp_dims_t* dims, const void* packed, int64_t B, int32_t T,

@@ -173,7 +173,8 @@ class MBRL(Algorithm):
     the learned model is (re)trained on `D_rand + D_RL`, episodes are planned on the learned model (iLQR / NMPC on
     `LearnedStateSpaceModel`, tensor-core rollouts and Jacobians) and executed on the real environment, and transitions
     the model predicts badly are added to `D_RL`.  Same constructor arguments and method names as the reference; plotting
-    and animation are out of scope.  `precision` selects the planner's network path ("bf16": tensor cores)."""
+    and animation are out of scope.  `precision` selects the planner's network path ("f16x3": tensor cores at the reference's
+    fp32 precision; "bf16": lower-precision tensor cores; "fp32": CUDA cores)."""
 
     def __init__(self, environment, t, dt,
                  test_t=0.,
@@ -202,7 +203,7 @@ class MBRL(Algorithm):
                  ou_sigma=0.2,
                  maxIters=500,
                  sparse_dyn=True,
-                 precision="bf16",
+                 precision="f16x3",
                  seed=0):
         from ..data import DataSet
         from ..environments import LearnedStateSpaceModel

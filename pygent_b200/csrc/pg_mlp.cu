@@ -45,6 +45,10 @@ struct alignas(1024) MlpPacked {
     uint16_t W2bT[N_CHUNKS][CHUNK_BYTES / 2];  // the same for W2^T (contraction over layer 2's OUTPUT index)
     uint16_t W1img[4][CHUNK_BYTES / 2];        // layer 1 as ONE k-block for the tensor core: per output quarter [128 n x 64 k],
                                                // k = 16 seg + j: seg 0 hi(W1b[n][j]), 1 lo(...), 2 hi(...), 3 zero (see layer1_operand)
+    uint16_t W2h[N_CHUNKS][CHUNK_BYTES / 2];   // PG_MLP_F16X3: W2 = hi + lo in fp16, same chunk images as W2b
+    uint16_t W2l[N_CHUNKS][CHUNK_BYTES / 2];
+    uint16_t W2hT[N_CHUNKS][CHUNK_BYTES / 2];  // ... and of W2^T
+    uint16_t W2lT[N_CHUNKS][CHUNK_BYTES / 2];
     float W2t[H][H];                          // [k][n] fp32 (FFMA path)
     float W1[H][MAXIN];                       // [k][input]
     float b1[H];
@@ -65,6 +69,14 @@ inline uint16_t f32_to_bf16(float f) {  // round to nearest even
     if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
     u += 0x7fffu + ((u >> 16) & 1u);
     return (uint16_t)(u >> 16);
+}
+
+inline void f32_to_f16_pair(float f, uint16_t& hi, uint16_t& lo) {  // f ~ hi + lo, both fp16 (round to nearest even)
+    const float c = f > 65000.0f ? 65000.0f : (f < -65000.0f ? -65000.0f : f);
+    const __half h = __float2half_rn(c);
+    const __half l = __float2half_rn(c - __half2float(h));
+    hi = __half_as_ushort(h);
+    lo = __half_as_ushort(l);
 }
 
 inline float bf16_to_f32(uint16_t h) {
@@ -1132,24 +1144,571 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_j
     }
 }
 
+// ---- reference-precision tensor-core path (PG_MLP_F16X3) -----------------------------------------------------------------
+// The reference's network is fp32 (nn_models.py:179-202).  Here every operand of the 500 x 500 layer is split x = hi + lo
+// into two fp16 numbers (22 mantissa bits) and the product is formed as Ah Wh + Al Wh + Ah Wl with fp32 accumulation in
+// TMEM: fp32-class results (the dropped term is 2^-22) at a third of the fp16 tensor rate.  Twice the operand bytes do not
+// fit the "whole A image in shared memory" design above (2 x 128 KB), so the GEMM runs K-BLOCK-MAJOR instead:
+//   for each block of 64 hidden units kb:  all 512 threads compute layer 1 for (128 rows x 64 units) on the CUDA cores in
+//   fp32 -- exactly the reference's arithmetic for that layer -- and write it, split, into one of two 32 KB A buffers;
+//   the leader's issuing thread then multiplies it against the four 16 KB weight chunks of that block (two 256-column
+//   halves x {hi, lo}; cta_group::2, M = 256 = both CTAs' rows, N = 256) into ALL 512 accumulator columns,
+// and layer 1 of block kb + 1 overlaps the MMAs of block kb.  No layer-1 GEMM pass, no TMEM -> smem conversion of H1, an
+// 8-stage weight ring (2 x 4 chunks) where the bf16 kernel has room for 4.
+constexpr int X_NST = 8;
+constexpr int X_ABUF_BYTES = 2 * CHUNK_BYTES;  // A_hi | A_lo of one k-block: [128 rows x 64 k] fp16 each
+constexpr int X_SMEM = 2 * X_ABUF_BYTES + X_NST * CHUNK_BYTES + T_INS_BYTES + T_CONST_BYTES + 256;
+constexpr uint32_t X_IDESC_2SM = umma_idesc_f16(0u, 256u, 256u);
+static_assert(X_SMEM <= 232448, "x3 kernels: shared memory");
+
+struct XPipe {
+    uint8_t* Ab;       // 2 A buffers
+    uint8_t* Bs;       // weight ring
+    uint64_t *full, *empty, *pfull;  // [X_NST]
+    uint64_t *a_full, *a_empty;      // [2]
+    uint64_t* accum;
+    uint32_t tmem_base;
+    uint32_t c;       // k-steps issued so far by this CTA (barrier phases derive from it)
+    uint32_t total;   // k-steps this CTA will run in total (no weight chunk is requested beyond it)
+    uint32_t passes;  // GEMMs completed (phase of `accum`)
+};
+
+// weight chunks of k-step `c` (hidden-unit block kb of the image sets imgh/imgl) -> ring set c & 1.  Producer thread only.
+__device__ __forceinline__ void x_request(const XPipe& p, uint32_t c, const uint16_t (*imgh)[CHUNK_BYTES / 2],
+                                          const uint16_t (*imgl)[CHUNK_BYTES / 2], int kb, uint32_t rank) {
+    const uint32_t set = c & 1, u = c >> 1;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {  // j = 2 * (column half) + (lo part)
+        const uint32_t s = set * 4 + j;
+        mbar_wait(&p.empty[s], (u & 1) ^ 1);
+        mbar_expect_tx(&p.full[s], CHUNK_BYTES);
+        const uint16_t(*img)[CHUNK_BYTES / 2] = (j & 1) ? imgl : imgh;
+        bulk_g2s(p.Bs + s * CHUNK_BYTES, &img[(2 * (j >> 1) + rank) * 8 + kb][0], CHUNK_BYTES, &p.full[s]);
+    }
+}
+
+// Call after the A block of k-step p.c is in A buffer p.c & 1, fenced (fence.proxy.async) and the CTA has synchronised.
+// (nh, nl, nkb): image sets and block of the NEXT k-step, whose weights are requested now (nullptr: there is none).
+__device__ __forceinline__ void x_issue(XPipe& p, int kb, bool last, const uint16_t (*nh)[CHUNK_BYTES / 2],
+                                        const uint16_t (*nl)[CHUNK_BYTES / 2], int nkb, int t, uint32_t rank) {
+    const uint32_t c = p.c, set = c & 1, u = c >> 1;
+    if (t == 0 && rank != 0) mbar_arrive_remote(&p.a_full[set], 0);  // the peer's half of the A block is written
+    if (t == PRODUCER_THREAD && nh != nullptr && c + 1 < p.total) x_request(p, c + 1, nh, nl, nkb, rank);
+    if (t == ISSUER_THREAD) {
+        if (rank != 0) {  // peer: tell the leader when a stage of OUR ring is full
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                mbar_wait(&p.full[set * 4 + j], u & 1);
+                mbar_arrive_remote(&p.pfull[set * 4 + j], 0);
+            }
+        } else {  // leader: one thread drives both tensor cores
+            mbar_wait(&p.a_full[set], u & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = smem_u32(p.Ab + set * X_ABUF_BYTES), a_lo = a_hi + CHUNK_BYTES;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t s = set * 4 + j;
+                mbar_wait(&p.full[s], u & 1);
+                mbar_wait(&p.pfull[s], u & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t b = smem_u32(p.Bs + s * CHUNK_BYTES), d = p.tmem_base + (j >> 1) * 256;
+                if ((j & 1) == 0) {  // Wh: Al Wh (small) first, then Ah Wh
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++)
+                        umma_f16_2sm(d, umma_desc_sw128(a_lo + ks * 32), umma_desc_sw128(b + ks * 32), X_IDESC_2SM, (kb > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++)
+                        umma_f16_2sm(d, umma_desc_sw128(a_hi + ks * 32), umma_desc_sw128(b + ks * 32), X_IDESC_2SM, 1u);
+                } else {  // Wl: Ah Wl
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++)
+                        umma_f16_2sm(d, umma_desc_sw128(a_hi + ks * 32), umma_desc_sw128(b + ks * 32), X_IDESC_2SM, 1u);
+                }
+                umma_commit_2sm(&p.empty[s], CL_MASK);  // frees the stage in both CTAs
+            }
+            umma_commit_2sm(&p.a_empty[set], CL_MASK);  // ... and the A buffer
+            if (last) umma_commit_2sm(p.accum, CL_MASK);  // all 512 accumulator columns final in both CTAs
+        }
+    }
+    p.c = c + 1;
+}
+
+// every thread: wait until the A buffer of the coming k-step is free (the MMAs of two k-steps ago have read it)
+__device__ __forceinline__ uint8_t* x_abuf(const XPipe& p) {
+    const uint32_t set = p.c & 1, u = p.c >> 1;
+    mbar_wait(&p.a_empty[set], (u & 1) ^ 1);
+    return p.Ab + set * X_ABUF_BYTES;
+}
+
+// 16 values of this thread (its row, hidden units kb * 64 + part * 16 .. + 15) -> split -> the A buffer
+__device__ __forceinline__ void x_store16(const float (&v)[16], uint8_t* abuf, int row, int part) {
+#pragma unroll
+    for (int uu = 0; uu < 2; uu++) {
+        float e8[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) e8[e] = v[uu * 8 + e];
+        uint4 hi, lo;
+        f16_split8(e8, hi, lo);
+        const int off = chunk_off(row, part * 16 + uu * 8);
+        *reinterpret_cast<uint4*>(abuf + off) = hi;
+        *reinterpret_cast<uint4*>(abuf + CHUNK_BYTES + off) = lo;
+    }
+}
+
+// Layer 1 of one block of 64 hidden units in fp32 on the CUDA cores (weights with the bias folded into slot n_in, the input
+// vector carries a 1 there; warp-uniform 128-bit reads, broadcast) -> h1 = relu(.) -> A buffer; returns the 16 ReLU mask bits.
+template <int NQ>
+__device__ __forceinline__ uint32_t x_l1_block(const float* w1, int w1_stride, const float (&in)[16], int kb, int row, int part,
+                                              uint8_t* abuf) {
+    float v[16];
+    uint32_t bits = 0;
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+        const int k = kb * 64 + part * 16 + e;
+        const float4* wr = reinterpret_cast<const float4*>(w1 + (size_t)k * w1_stride);
+        float acc = 0.0f;
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            const float4 ww = wr[q];
+            acc = fmaf(ww.x, in[q * 4 + 0], acc);
+            acc = fmaf(ww.y, in[q * 4 + 1], acc);
+            acc = fmaf(ww.z, in[q * 4 + 2], acc);
+            acc = fmaf(ww.w, in[q * 4 + 3], acc);
+        }
+        const bool pos = k < HID && acc > 0.0f;
+        v[e] = pos ? acc : 0.0f;
+        bits |= (pos ? 1u : 0u) << e;
+    }
+    x_store16(v, abuf, row, part);
+    return bits;
+}
+
+__device__ __forceinline__ uint32_t x_l1_dispatch(int nin, const MlpPacked* w, const float* w1s, const float (&in)[16], int kb, int row,
+                                                 int part, uint8_t* abuf) {
+    const int nq = (nin + 1 + 3) >> 2;  // inputs + the constant 1, in float4 units
+    if (nq <= 1) return x_l1_block<1>(w1s, W1S_FLOATS, in, kb, row, part, abuf);
+    if (nq == 2) return x_l1_block<2>(w1s, W1S_FLOATS, in, kb, row, part, abuf);
+    if (nq == 3) return x_l1_block<3>(&w->W1b[0][0], MAXIN, in, kb, row, part, abuf);
+    return x_l1_block<4>(&w->W1b[0][0], MAXIN, in, kb, row, part, abuf);
+}
+
+struct XSmem {
+    uint8_t *Ab, *Bs;
+    uint64_t *full, *empty, *pfull, *a_full, *a_empty, *accum;
+    uint32_t* tmem_slot;
+};
+
+__device__ __forceinline__ void x_barriers(uint8_t* base, XSmem& m) {
+    m.full = reinterpret_cast<uint64_t*>(base);
+    m.empty = m.full + X_NST;
+    m.pfull = m.empty + X_NST;
+    m.a_full = m.pfull + X_NST;
+    m.a_empty = m.a_full + 2;
+    m.accum = m.a_empty + 2;
+    m.tmem_slot = reinterpret_cast<uint32_t*>(m.accum + 1);
+}
+
+__device__ __forceinline__ void x_setup(const XSmem& m, int t, int warp) {
+    if (t == 0) {
+        for (int s = 0; s < X_NST; s++) {
+            mbar_init(&m.full[s], 1);
+            mbar_init(&m.empty[s], 1);
+            mbar_init(&m.pfull[s], 1);
+        }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&m.a_full[s], 1);
+            mbar_init(&m.a_empty[s], 1);
+        }
+        mbar_init(m.accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {  // the whole accumulator file of the SM pair: 128 lanes x 512 fp32 columns per CTA
+        asm volatile(PG_TMEM_ALLOC_2SM ::"r"(smem_u32(m.tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+}
+
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_x3_kernel(const MlpArgs a) {
+    extern __shared__ __align__(1024) uint8_t tsm[];
+    XSmem sm;
+    sm.Ab = tsm;
+    sm.Bs = tsm + 2 * X_ABUF_BYTES;
+    float* ins = reinterpret_cast<float*>(sm.Bs + X_NST * CHUNK_BYTES);
+    float* yp = ins;  // partial layer-3 sums [T_SPLIT][T_ROWS][MAXDX]: the input tile is in registers by then
+    float4* eps = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(ins) + T_INS_BYTES);
+    float* w1s = reinterpret_cast<float*>(eps + H);
+    x_barriers(reinterpret_cast<uint8_t*>(w1s) + T_W1_BYTES, sm);
+    const MlpPacked* w = a.w;
+    const int t = threadIdx.x, warp = t >> 5, row = t & (T_ROWS - 1), part = t >> 7;
+    const int steps = steps_of(a);
+    const int64_t pairs = (total_rows(a) + CL * T_ROWS - 1) / (CL * T_ROWS), slot = blockIdx.x / CL;
+    int64_t lo, hi;
+    if (a.progress) {  // balanced schedule: see mlp_bf16_kernel
+        const int64_t slots = min((int64_t)(gridDim.x / CL), pairs);
+        if (slot >= slots) return;
+        lo = slot * (pairs * steps) / slots;
+        hi = (slot + 1) * (pairs * steps) / slots;
+    } else {
+        if (slot >= pairs) return;
+        lo = slot * steps;
+        hi = lo + steps;
+    }
+    const bool owner = t < T_ROWS;
+    const int nin = a.d.n_obs + a.d.m;
+    const pg::MathCtx<double> mc;
+    const uint32_t rank = cluster_ctarank();
+
+    x_setup(sm, t, warp);
+    stage_constants(w, eps, w1s, t);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync();  // the peer's barriers are initialised before anything arrives on them
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    XPipe pipe = {sm.Ab, sm.Bs, sm.full, sm.empty, sm.pfull, sm.a_full, sm.a_empty, sm.accum, *sm.tmem_slot, 0u, (uint32_t)((hi - lo) * 8), 0u};
+    const uint32_t tmem_base = pipe.tmem_base;
+    if (t == PRODUCER_THREAD && pipe.total > 0) x_request(pipe, 0, w->W2h, w->W2l, 0, rank);
+
+    double x[8], u[2], xe[8], ue[2], fplus[8];
+    if (steps == 0 && owner) {  // T = 0: only the initial states
+        Row r0 = decode_row(a, (int64_t)blockIdx.x * T_ROWS + row);
+        load_row(a, r0, x, u);
+    }
+    bool first = true;
+    for (int64_t pos = hi; pos > lo;) {
+    const int64_t pair = (pos - 1) / steps, base = pair * steps;
+    const int k_begin = (int)(max(lo, base) - base), k_end = (int)(pos - base);
+    pos = base + k_begin;
+    const int64_t tile = pair * CL + (blockIdx.x % CL);
+    Row rw = decode_row(a, tile * T_ROWS + row);
+    rw.valid = rw.valid && owner;
+    if (k_begin > 0) {  // continue where another cluster left this tile
+        if (t == 0) wait_progress(&a.progress[tile], k_begin);
+        __syncthreads();
+    }
+    if (owner) {
+        if (k_begin == 0) load_row(a, rw, x, u);
+        else reload_row(a, rw, k_begin, x, u);
+    }
+    for (int k = k_begin; k < k_end; k++) {
+        if (!first) __syncthreads();  // the previous interval's partial sums (they alias `ins`) have been consumed
+        first = false;
+        if (owner) {
+            pre_step(a, rw, k, x, u, xe, ue);
+            float in[MAXIN];
+            network_input(a, mc, xe, ue, in);
+#pragma unroll
+            for (int j = 0; j < MAXIN; j += 4)
+                *reinterpret_cast<float4*>(&ins[row * INS_STRIDE + j]) = make_float4(in[j], in[j + 1], in[j + 2], in[j + 3]);
+        }
+        __syncthreads();
+        float in[16];
+#pragma unroll
+        for (int j = 0; j < MAXIN; j += 4) {
+            const float4 v4 = *reinterpret_cast<const float4*>(&ins[row * INS_STRIDE + j]);
+            in[j] = v4.x; in[j + 1] = v4.y; in[j + 2] = v4.z; in[j + 3] = v4.w;
+        }
+        for (int kb = 0; kb < 8; kb++) {
+            uint8_t* abuf = x_abuf(pipe);
+            x_l1_dispatch(nin, w, w1s, in, kb, row, part, abuf);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA unit
+            __syncthreads();
+            x_issue(pipe, kb, kb == 7, w->W2h, w->W2l, (kb + 1) & 7, t, rank);
+        }
+        // epilogue: TMEM lane = row; this thread's quarter of the 512 columns: +b2, ReLU, layer 3
+        mbar_wait(pipe.accum, pipe.passes & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {
+            float y[MAXDX] = {0.0f, 0.0f, 0.0f, 0.0f};
+            for (int cb = part * (H / 32 / T_SPLIT); cb < (part + 1) * (H / 32 / T_SPLIT); cb++) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + cb * 32, v);
+#pragma unroll
+                for (int c = 0; c < 32; c++) {
+                    const int nn = cb * 32 + c;
+                    const float4 e4 = eps[nn];  // {b2, W3[nn][0..2]}: one 128-bit smem broadcast per column
+                    const float h2 = fmaxf(__uint_as_float(v[c]) + e4.x, 0.0f);
+                    y[0] = fmaf(h2, e4.y, y[0]);
+                    y[1] = fmaf(h2, e4.z, y[1]);
+                    y[2] = fmaf(h2, e4.w, y[2]);
+                    if (a.d.dx_dim > 3) y[3] = fmaf(h2, w->W3[nn][3], y[3]);
+                }
+            }
+            *reinterpret_cast<float4*>(&yp[(part * T_ROWS + row) * MAXDX]) = make_float4(y[0], y[1], y[2], y[3]);
+        }
+        pipe.passes++;
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();  // every lane has read its accumulators before the next interval's MMAs overwrite them
+        if (owner) {
+            float y[MAXDX];
+#pragma unroll
+            for (int j = 0; j < MAXDX; j++) {
+                float v = 0.0f;
+#pragma unroll
+                for (int q = 0; q < T_SPLIT; q++) v += yp[(q * T_ROWS + row) * MAXDX + j];
+                y[j] = v;
+            }
+            post_step(a, rw, k, y, x, u, xe, fplus);
+        }
+    }
+    if (a.progress && k_end < steps) {  // the head of a pair: publish that X holds the states up to interval k_end
+        __threadfence();
+        __syncthreads();
+        if (t == 0) publish_progress(&a.progress[tile], k_end);
+    }
+    }
+    __syncthreads();
+    cluster_sync();  // no CTA leaves while its peer may still signal its barriers
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
+// Analytic Jacobian at reference precision: the passes of mlp_jac_kernel on the k-block-major split-fp16 GEMM.
+constexpr int XJ_SMEM = 2 * X_ABUF_BYTES + X_NST * CHUNK_BYTES + T_W1_BYTES + J_MASK_BYTES + 256;
+static_assert(XJ_SMEM <= 232448 && J_MASK_BYTES >= T_INS_BYTES, "jacobian x3 kernel: shared memory");
+
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_jac_x3_kernel(const MlpArgs a) {
+    extern __shared__ __align__(1024) uint8_t tsm[];
+    XSmem sm;
+    sm.Ab = tsm;
+    sm.Bs = tsm + 2 * X_ABUF_BYTES;
+    float* w1s = reinterpret_cast<float*>(sm.Bs + X_NST * CHUNK_BYTES);
+    uint32_t* m1 = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(w1s) + T_W1_BYTES);
+    uint32_t* m2 = m1 + T_ROWS * J_MASK_WORDS;
+    float* ins = reinterpret_cast<float*>(m1);  // the input tile lives in the mask area until every thread has it in registers
+    x_barriers(reinterpret_cast<uint8_t*>(m1) + J_MASK_BYTES, sm);
+    const MlpPacked* w = a.w;
+    const int t = threadIdx.x, warp = t >> 5, row = t & (T_ROWS - 1), part = t >> 7;
+    if ((int64_t)(blockIdx.x / CL) * CL * T_ROWS >= total_rows(a)) return;  // surplus clusters
+    const bool owner = t < T_ROWS;
+    Row rw = decode_row(a, (int64_t)blockIdx.x * T_ROWS + row);
+    rw.valid = rw.valid && owner;
+    const int n = a.d.n, nh = a.d.n / 2, m = a.d.m, nin = a.d.n_obs + a.d.m;
+    const pg::MathCtx<double> mc;
+    const uint32_t rank = cluster_ctarank();
+
+    x_setup(sm, t, warp);
+    for (int i = t; i < H * (W1S_FLOATS / 4); i += T_THREADS) {
+        const int k = i / (W1S_FLOATS / 4), q = i % (W1S_FLOATS / 4);
+        reinterpret_cast<float4*>(w1s)[i] = reinterpret_cast<const float4*>(&w->W1b[k][0])[q];
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    XPipe pipe = {sm.Ab, sm.Bs, sm.full, sm.empty, sm.pfull, sm.a_full, sm.a_empty, sm.accum, *sm.tmem_slot, 0u, (uint32_t)(8 * (1 + nh)), 0u};
+    const uint32_t tmem_base = pipe.tmem_base;
+    if (t == PRODUCER_THREAD) x_request(pipe, 0, w->W2h, w->W2l, 0, rank);
+
+    double x[8], u[2];
+    if (owner) {
+        load_row(a, rw, x, u);
+        float in[MAXIN];
+        network_input(a, mc, x, u, in);
+#pragma unroll
+        for (int j = 0; j < MAXIN; j++) ins[row * INS_STRIDE + j] = in[j];
+    }
+    __syncthreads();
+    float in[16];
+#pragma unroll
+    for (int j = 0; j < MAXIN; j++) in[j] = ins[row * INS_STRIDE + j];
+    __syncthreads();  // the mask words alias the input tile
+    uint16_t* m1h = reinterpret_cast<uint16_t*>(m1);
+    // pass 0: forward, ReLU masks of both layers
+    for (int kb = 0; kb < 8; kb++) {
+        uint8_t* abuf = x_abuf(pipe);
+        const uint32_t bits = x_l1_dispatch(nin, w, w1s, in, kb, row, part, abuf);
+        m1h[row * (2 * J_MASK_WORDS) + kb * 4 + part] = (uint16_t)bits;  // hidden units kb * 64 + part * 16 .. + 15
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (kb < 7) x_issue(pipe, kb, false, w->W2h, w->W2l, kb + 1, t, rank);
+        else x_issue(pipe, kb, true, w->W2hT, w->W2lT, 0, t, rank);
+    }
+    mbar_wait(pipe.accum, pipe.passes & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int cb = part * (H / 32 / T_SPLIT); cb < (part + 1) * (H / 32 / T_SPLIT); cb++) {  // mask of layer 2: [acc + b2 > 0]
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + cb * 32, v);
+        uint32_t mw = 0;
+#pragma unroll
+        for (int c = 0; c < 32; c++) {
+            const int nn = cb * 32 + c;
+            mw |= ((nn < HID && __uint_as_float(v[c]) + w->b2[nn] > 0.0f) ? 1u : 0u) << c;
+        }
+        m2[row * J_MASK_WORDS + cb] = mw;
+    }
+    pipe.passes++;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+
+    double sx[8], cx[8];  // sin/cos of the angle states for the chain rule
+    if (owner) {
+        for (int i = 0; i < n; i++) {
+            sx[i] = 0.0;
+            cx[i] = 1.0;
+            if (a.d.is_angle[i]) mc.sincos(x[i], sx[i], cx[i]);
+        }
+    }
+    float* partial = reinterpret_cast<float*>(sm.Ab);  // [T_SPLIT][T_ROWS][MAXIN]: valid between a pass's last MMA and the next A block
+    for (int j = 0; j < nh; j++) {
+        for (int kb = 0; kb < 8; kb++) {  // A block: g2 = W3[j, :] * m2
+            uint8_t* abuf = x_abuf(pipe);
+            const int k0 = kb * 64 + part * 16;
+            const uint32_t bits = (m2[row * J_MASK_WORDS + (k0 >> 5)] >> (k0 & 31)) & 0xffffu;
+            float v[16];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const float4 w4 = *reinterpret_cast<const float4*>(&w->W3T[j][k0 + q * 4]);
+                v[q * 4 + 0] = ((bits >> (q * 4 + 0)) & 1u) ? w4.x : 0.0f;
+                v[q * 4 + 1] = ((bits >> (q * 4 + 1)) & 1u) ? w4.y : 0.0f;
+                v[q * 4 + 2] = ((bits >> (q * 4 + 2)) & 1u) ? w4.z : 0.0f;
+                v[q * 4 + 3] = ((bits >> (q * 4 + 3)) & 1u) ? w4.w : 0.0f;
+            }
+            x_store16(v, abuf, row, part);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            const bool more = kb < 7 || j + 1 < nh;
+            x_issue(pipe, kb, kb == 7, more ? w->W2hT : nullptr, w->W2lT, (kb + 1) & 7, t, rank);
+        }
+        mbar_wait(pipe.accum, pipe.passes & 1);  // every MMA of the pass is complete: the A buffers may be reused as scratch
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {  // epilogue: g1 = acc * m1, gin = g1 W1 (this thread's quarter of the hidden units)
+            float gin[MAXIN];
+#pragma unroll
+            for (int c = 0; c < MAXIN; c++) gin[c] = 0.0f;
+            for (int cb = part * (H / 32 / T_SPLIT); cb < (part + 1) * (H / 32 / T_SPLIT); cb++) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + cb * 32, v);
+                const uint32_t mw = m1[row * J_MASK_WORDS + cb];
+#pragma unroll
+                for (int c = 0; c < 32; c++) {
+                    const float g1 = ((mw >> c) & 1u) ? __uint_as_float(v[c]) : 0.0f;
+                    const float4* w1 = nin + 1 <= W1S_FLOATS ? reinterpret_cast<const float4*>(w1s + (cb * 32 + c) * W1S_FLOATS)
+                                                             : reinterpret_cast<const float4*>(&w->W1[cb * 32 + c][0]);
+#pragma unroll
+                    for (int q = 0; q < MAXIN / 4; q++) {
+                        if (q * 4 < nin) {
+                            const float4 ww = w1[q];
+                            gin[q * 4 + 0] = fmaf(g1, ww.x, gin[q * 4 + 0]);
+                            gin[q * 4 + 1] = fmaf(g1, ww.y, gin[q * 4 + 1]);
+                            gin[q * 4 + 2] = fmaf(g1, ww.z, gin[q * 4 + 2]);
+                            gin[q * 4 + 3] = fmaf(g1, ww.w, gin[q * 4 + 3]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < MAXIN; c++) partial[(part * T_ROWS + row) * MAXIN + c] = gin[c];
+        }
+        pipe.passes++;
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (rw.valid) {
+            float gin[MAXIN];
+#pragma unroll
+            for (int c = 0; c < MAXIN; c++) {
+                float v = 0.0f;
+#pragma unroll
+                for (int q = 0; q < T_SPLIT; q++) v += partial[(q * T_ROWS + row) * MAXIN + c];
+                gin[c] = v;
+            }
+            // d rhs[nh + j] / d(x, u) = (1/dt) dxVar_j * sum_c gin_c * d in_c / d(x, u)
+            const double sc = (double)((float)(1.0 / a.dt) * w->dx_var[j]);
+            const int64_t B = a.Bs, b = rw.b;
+            int c = 0;
+            for (int i = 0; i < n; i++) {
+                double dcol;
+                if (a.d.is_angle[i]) {
+                    dcol = (double)gin[c] * (-sx[i]) / (double)w->o_var[c] + (double)gin[c + 1] * cx[i] / (double)w->o_var[c + 1];
+                    c += 2;
+                } else {
+                    dcol = (double)gin[c] / (double)w->o_var[c];
+                    c++;
+                }
+                a.A[(((int64_t)rw.k * n + nh + j) * n + i) * B + b] = sc * dcol;
+            }
+            for (int jj = 0; jj < m; jj++) {
+                a.Bm[(((int64_t)rw.k * n + nh + j) * m + jj) * B + b] = sc * (double)gin[c] / (double)w->u_var[jj];
+                c++;
+            }
+        }
+        __syncthreads();  // the partial sums are consumed before the next pass writes its A blocks over them
+    }
+    if (rw.valid) {  // position half: d x[nh + i] / dx
+        const int64_t B = a.Bs, b = rw.b;
+        for (int i = 0; i < nh; i++) {
+            for (int c = 0; c < n; c++) a.A[(((int64_t)rw.k * n + i) * n + c) * B + b] = (c == nh + i) ? 1.0 : 0.0;
+            for (int jj = 0; jj < m; jj++) a.Bm[(((int64_t)rw.k * n + i) * m + jj) * B + b] = 0.0;
+        }
+    }
+    __syncthreads();
+    cluster_sync();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
 int64_t max_rows(const MlpArgs& a) {  // upper bound of total_rows() known on the host (the work list may be shorter)
     if (a.mode == MODE_ROLLOUT) return a.R * a.n_alpha;
     if (a.mode == MODE_LIN_FD || a.mode == MODE_LIN_AN) return a.R * a.T;
     return a.R;
 }
 
+// rollouts on a tensor-core kernel (bf16 or split fp16), plain or with the balanced schedule
+template <typename K>
+int launch_tc(K kernel, int smem, int* resident, bool* attr_set, const MlpArgs& a, int64_t rows, cudaStream_t st) {
+    if (!*attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        *attr_set = true;
+    }
+    int64_t clusters = (rows + CL * T_ROWS - 1) / (CL * T_ROWS);
+    if (a.progress) {  // balanced rollout: at most one cluster per pair of SMs, all of them resident at once
+        if (!*resident) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(CL * 1024);
+            cfg.blockDim = dim3(T_THREADS);
+            cfg.dynamicSmemBytes = smem;
+            cudaLaunchAttribute at;
+            at.id = cudaLaunchAttributeClusterDimension;
+            at.val.clusterDim.x = CL;
+            at.val.clusterDim.y = at.val.clusterDim.z = 1;
+            cfg.attrs = &at;
+            cfg.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n < 1) {
+                (void)cudaGetLastError();
+                return PG_E_UNSUPPORTED;
+            }
+            *resident = n;
+        }
+        cudaError_t e = cudaMemsetAsync(a.progress, 0, sizeof(int32_t) * (size_t)(clusters * CL), st);
+        if (e != cudaSuccess) return (int)e;
+        if (clusters > *resident) clusters = *resident;
+    }
+    kernel<<<(unsigned)(clusters * CL), T_THREADS, smem, st>>>(a);
+    return 0;
+}
+
 int launch(int precision, const MlpArgs& a, cudaStream_t st) {
     const int64_t rows = max_rows(a);
     if (rows == 0) return 0;
     if (a.mode == MODE_LIN_AN) {
-        if (precision != PG_MLP_BF16) return PG_E_BADARG;  // the analytic chain exists on the tensor-core path only
-        static bool set = false;
-        if (!set) {
-            cudaError_t e = cudaFuncSetAttribute(mlp_jac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, J_SMEM);
-            if (e != cudaSuccess) return (int)e;
-            set = true;
+        // the analytic chain exists on the tensor-core paths only
+        if (precision != PG_MLP_BF16 && precision != PG_MLP_F16X3) return PG_E_BADARG;
+        static bool set = false, setx = false;
+        const unsigned grid = (unsigned)((rows + CL * T_ROWS - 1) / (CL * T_ROWS)) * CL;
+        if (precision == PG_MLP_BF16) {
+            if (!set) {
+                cudaError_t e = cudaFuncSetAttribute(mlp_jac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, J_SMEM);
+                if (e != cudaSuccess) return (int)e;
+                set = true;
+            }
+            mlp_jac_kernel<<<grid, T_THREADS, J_SMEM, st>>>(a);
+        } else {
+            if (!setx) {
+                cudaError_t e = cudaFuncSetAttribute(mlp_jac_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XJ_SMEM);
+                if (e != cudaSuccess) return (int)e;
+                setx = true;
+            }
+            mlp_jac_x3_kernel<<<grid, T_THREADS, XJ_SMEM, st>>>(a);
         }
-        mlp_jac_kernel<<<(unsigned)((rows + CL * T_ROWS - 1) / (CL * T_ROWS)) * CL, T_THREADS, J_SMEM, st>>>(a);
     } else if (precision == PG_MLP_FP32) {
         const int smem = (F_ROWS * F_HSTR + F_ROWS * MAXIN + F_ROWS * MAXDX) * 4;
         static bool set = false;
@@ -1161,37 +1720,14 @@ int launch(int precision, const MlpArgs& a, cudaStream_t st) {
         mlp_fp32_kernel<<<(unsigned)((rows + F_ROWS - 1) / F_ROWS), 256, smem, st>>>(a);
     } else if (precision == PG_MLP_BF16) {
         static bool set = false;
-        if (!set) {
-            cudaError_t e = cudaFuncSetAttribute(mlp_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM);
-            if (e != cudaSuccess) return (int)e;
-            set = true;
-        }
-        int64_t clusters = (rows + CL * T_ROWS - 1) / (CL * T_ROWS);
-        if (a.progress) {  // balanced rollout: at most one cluster per pair of SMs, all of them resident at once
-            static int resident = 0;
-            if (!resident) {
-                cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3(CL * 1024);
-                cfg.blockDim = dim3(T_THREADS);
-                cfg.dynamicSmemBytes = T_SMEM;
-                cudaLaunchAttribute at;
-                at.id = cudaLaunchAttributeClusterDimension;
-                at.val.clusterDim.x = CL;
-                at.val.clusterDim.y = at.val.clusterDim.z = 1;
-                cfg.attrs = &at;
-                cfg.numAttrs = 1;
-                int n = 0;
-                if (cudaOccupancyMaxActiveClusters(&n, mlp_bf16_kernel, &cfg) != cudaSuccess || n < 1) {
-                    (void)cudaGetLastError();
-                    return PG_E_UNSUPPORTED;
-                }
-                resident = n;
-            }
-            cudaError_t e = cudaMemsetAsync(a.progress, 0, sizeof(int32_t) * (size_t)(clusters * CL), st);
-            if (e != cudaSuccess) return (int)e;
-            if (clusters > resident) clusters = resident;
-        }
-        mlp_bf16_kernel<<<(unsigned)(clusters * CL), T_THREADS, T_SMEM, st>>>(a);
+        static int resident = 0;
+        const int rc = launch_tc(mlp_bf16_kernel, T_SMEM, &resident, &set, a, rows, st);
+        if (rc) return rc;
+    } else if (precision == PG_MLP_F16X3) {
+        static bool set = false;
+        static int resident = 0;
+        const int rc = launch_tc(mlp_x3_kernel, X_SMEM, &resident, &set, a, rows, st);
+        if (rc) return rc;
     } else {
         return PG_E_BADARG;
     }
@@ -1255,8 +1791,11 @@ int pg_mlp_pack(const pg_mlp_dims_t* d, const float* W1, const float* b1, const 
                 for (int kk = 0; kk < 64; kk++) {
                     const int n = qt * CHUNK_N + nl, k = kb * 64 + kk;
                     const int off = (nl >> 3) * 1024 + (nl & 7) * 128 + (((kk >> 3) ^ (nl & 7)) << 4) + (kk & 7) * 2;
-                    img[off >> 1] = f32_to_bf16((n < HID && k < HID) ? W2[n * HID + k] : 0.0f);
-                    imgT[off >> 1] = f32_to_bf16((k < HID && n < HID) ? W2[k * HID + n] : 0.0f);
+                    const float wv = (n < HID && k < HID) ? W2[n * HID + k] : 0.0f, wt = (k < HID && n < HID) ? W2[k * HID + n] : 0.0f;
+                    img[off >> 1] = f32_to_bf16(wv);
+                    imgT[off >> 1] = f32_to_bf16(wt);
+                    f32_to_f16_pair(wv, p->W2h[qt * 8 + kb][off >> 1], p->W2l[qt * 8 + kb][off >> 1]);
+                    f32_to_f16_pair(wt, p->W2hT[qt * 8 + kb][off >> 1], p->W2lT[qt * 8 + kb][off >> 1]);
                 }
         }
     // layer 1 for the tensor core: W1b split into bf16 hi + lo parts (x w ~ xh wh + xh wl + xl wh, error ~2^-16)
@@ -1358,7 +1897,7 @@ int pg_mlp_forward_balanced(int precision, const pg_mlp_dims_t* dims, const void
                             double* U_out, const int32_t* index, const int32_t* count, void* workspace,
                             int64_t workspace_bytes, void* stream) {
     if (B == 0) return 0;
-    if (precision != PG_MLP_BF16) return PG_E_UNSUPPORTED;  // the schedule exists in the tensor-core kernel only
+    if (precision != PG_MLP_BF16 && precision != PG_MLP_F16X3) return PG_E_UNSUPPORTED;  // the schedule exists in the tensor-core kernels only
     if (!workspace || n_alpha < 1 || workspace_bytes < pg_mlp_forward_workspace_bytes(B, n_alpha)) return PG_E_BADARG;
     return forward_impl(precision, dims, packed, B, T, dt, n_alpha, alphas, x0, U, KK, kk, xbar, ubar, ulim, X, U_out, index,
                         count, (int32_t*)workspace, stream);

@@ -1,6 +1,7 @@
 // tcgen05 / mbarrier / bulk-copy primitives shared by the learned-dynamics kernels (pg_mlp.cu: planner rollouts and
 // Jacobians; pg_train.cu: the dynamics training step).  sm_100a only; everything is inline PTX.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -79,6 +80,33 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // 1024 B, a row = 128 B = eight 16-byte units, unit index XOR (row mod 8).
 __host__ __device__ constexpr int chunk_off(int rl, int kl) {
     return (rl >> 3) * 1024 + (rl & 7) * 128 + ((((kl >> 3) ^ (rl & 7))) << 4) + (kl & 7) * 2;
+}
+
+// The CTA pair as ONE MMA unit (cta_group::2), issued by the leader CTA's thread: D rows 0-127 in the leader's TMEM, 128-255 in
+// the peer's; A = each CTA's own 128 rows (same smem offset), B = N/2 rows from the leader's smem + N/2 from the peer's.
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// x = hi + lo with hi, lo fp16 (22 mantissa bits together; |x| clamped to fp16's range): eight values -> two 16-byte units
+__device__ __forceinline__ void f16_split8(const float (&v)[8], uint4& hi, uint4& lo) {
+    __half2 h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const float a = fminf(fmaxf(v[2 * e], -65000.0f), 65000.0f), b = fminf(fmaxf(v[2 * e + 1], -65000.0f), 65000.0f);
+        h[e] = __floats2half2_rn(a, b);
+        const float2 hf = __half22float2(h[e]);
+        l[e] = __floats2half2_rn(a - hf.x, b - hf.y);
+    }
+    hi = make_uint4(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[1]), *reinterpret_cast<uint32_t*>(&h[2]),
+                    *reinterpret_cast<uint32_t*>(&h[3]));
+    lo = make_uint4(*reinterpret_cast<uint32_t*>(&l[0]), *reinterpret_cast<uint32_t*>(&l[1]), *reinterpret_cast<uint32_t*>(&l[2]),
+                    *reinterpret_cast<uint32_t*>(&l[3]));
 }
 
 }  // namespace pgtc

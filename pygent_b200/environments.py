@@ -333,11 +333,12 @@ class LearnedStateSpaceModel(StateSpaceModel):
 
     `net` is a `pygent_b200.nn_models.NNDynamics` (sparse_dyn: dxDim = xDim / 2).  Rollouts and linearisation run in
     the learned-dynamics library (include/pygent_b200_mlp.h); the problem library compiled from `cost` supplies the
-    cost, its expansion and the iLQR kernels.  precision "fp32" follows the reference's fp32 network, "bf16" puts the
-    500 x 500 layer on the tensor cores; linearization "fd" is the reference's central differences, "analytic" the
-    chain rule on the tensor cores (bf16 only)."""
+    cost, its expansion and the iLQR kernels.  precision "f16x3" (default) puts the 500 x 500 layer on the tensor cores at
+    the reference's fp32 precision (fp16 hi/lo split operands, ~1e-6 per evaluation), "fp32" is the CUDA-core FFMA path,
+    "bf16" the lower-precision tensor-core path (2e-2 per evaluation); linearization "fd" is the reference's central
+    differences (helpers.py:130-148), "analytic" the exact chain rule on the tensor cores (f16x3 / bf16)."""
 
-    def __init__(self, net, cost, x0, uDim, dt, terminal_cost=0., precision="bf16", linearization=None, device=None):
+    def __init__(self, net, cost, x0, uDim, dt, terminal_cost=0., precision="f16x3", linearization=None, device=None):
         n = int(np.array(x0() if callable(x0) else x0).shape[-1])
         if net.xDim != n or net.uDim != uDim or net.dxDim * 2 != n:
             raise ValueError("network dimensions (x %d, u %d, dx %d) do not match the environment (n %d, m %d, sparse_dyn)"
@@ -352,9 +353,9 @@ class LearnedStateSpaceModel(StateSpaceModel):
                                                      device=device, dtype=torch.float64)
         self.net = net
         self.precision = precision
-        self.linearization = linearization or ("analytic" if precision == "bf16" else "fd")
-        if self.linearization == "analytic" and precision != "bf16":
-            raise ValueError("the analytic Jacobian chain runs on the tensor-core path (precision='bf16'); use linearization='fd'")
+        self.linearization = linearization or ("analytic" if precision in ("bf16", "f16x3") else "fd")
+        if self.linearization == "analytic" and precision not in ("bf16", "f16x3"):
+            raise ValueError("the analytic Jacobian chain runs on the tensor-core paths (precision='f16x3' or 'bf16'); use linearization='fd'")
         self.learned = True
 
     @property

@@ -2,7 +2,10 @@
 environment that integrates `MBRL.ode` (pygent/algorithms/mbrl.py:125-130) with forward Euler.
 
 `precision="fp32"`: layer 2 in fp32 FFMA -- tracks the reference's fp32 torch network to ~1e-6;
-`precision="bf16"`: layer 2 on the tcgen05 tensor cores (bf16 operands, fp32 accumulation in TMEM).
+`precision="f16x3"`: layer 2 on the tcgen05 tensor cores at the reference's precision (fp16 hi/lo split operands, three MMAs
+                     per product, fp32 accumulation in TMEM): ~1e-6 -- the default of the planner;
+`precision="bf16"`: layer 2 on the tensor cores with bf16 operands: 3x fewer MMAs, 2e-2 per evaluation -- an explicitly
+                    lower-precision extra.
 """
 import ctypes
 import hashlib
@@ -15,7 +18,8 @@ import torch
 from . import build as pgbuild
 from .lib import PygentB200Error
 
-PRECISIONS = {"fp32": 0, "bf16": 1}
+PRECISIONS = {"fp32": 0, "bf16": 1, "f16x3": 2}
+TENSOR_CORE = ("bf16", "f16x3")
 _CU = [os.path.join(pgbuild.CSRC, "pg_mlp.cu"), os.path.join(pgbuild.CSRC, "pg_train.cu")]
 _SRC = _CU + [os.path.join(pgbuild.CSRC, "pg_math.cuh"), os.path.join(pgbuild.CSRC, "pg_tc.cuh"),
               os.path.join(pgbuild.INCLUDE, "pygent_b200_mlp.h")]
@@ -191,7 +195,7 @@ class MLPDynamics:
         Uo = torch.empty((T, self.m, B), dtype=torch.float64, device=self.device) if want_u else None
         KK, kk, xbar, ubar = gains if gains is not None else (None, None, None, None)
         lim = None if ulim is None else (ctypes.c_double * len(ulim))(*[float(v) for v in ulim])
-        if precision == "bf16" and self.balanced:
+        if precision in TENSOR_CORE and self.balanced:
             ws, nb = self._workspace(B, 1)
             al = (ctypes.c_double * 1)(float(alpha))
             _check(dll().pg_mlp_forward_balanced(PRECISIONS[precision], ctypes.byref(self.dims), ctypes.c_void_p(self.packed.data_ptr()),
@@ -217,7 +221,7 @@ class MLPDynamics:
         al = (ctypes.c_double * A)(*[float(v) for v in alphas])
         lim = None if ulim is None else (ctypes.c_double * len(ulim))(*[float(v) for v in ulim])
         idx, cnt = (None, None) if work is None else (ctypes.c_void_p(work[0].data_ptr()), ctypes.c_void_p(work[1].data_ptr()))
-        if precision == "bf16" and self.balanced:
+        if precision in TENSOR_CORE and self.balanced:
             ws, nb = self._workspace(B, A)
             _check(dll().pg_mlp_forward_balanced(PRECISIONS[precision], ctypes.byref(self.dims), ctypes.c_void_p(self.packed.data_ptr()),
                                                  B, T, dt, A, al, _ptr(x0), None, _ptr(KK), _ptr(kk), _ptr(xbar), _ptr(ubar), lim,
