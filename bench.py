@@ -275,7 +275,7 @@ def ilqr_full_batch_roofline(xi, dev, n_iter=8):
     return res
 
 
-def nmpc_bench(dev, rank, world, barrier, plants=4096, steps=50, horizon=1.0):
+def nmpc_bench(dev, rank, world, barrier, plants=4096, steps=102, horizon=1.0):
     """examples/nmpc/cart_pole.py for a batch: every plant has its own MPCAgent state; the planner's terminal value is
     solved once on the host (cache_terminal_value) so the control loop never leaves the device: after two eager control
     steps the step is captured into a CUDA graph and replayed (NMPC.run), which keeps the host out of the timed loop."""
@@ -289,7 +289,7 @@ def nmpc_bench(dev, rank, world, barrier, plants=4096, steps=50, horizon=1.0):
     alg = NMPC(make_env("cart_pole", x0=x0, device=dev), make_env("cart_pole", x0=x0, device=dev), steps * DT, DT, horizon,
                fcost=c_N, constrained=False, maxIters=100, step_iterations=1, cache_terminal_value=True)
     opt = alg.agent.traj_optimizer
-    alg.run(steps=5, printing=False)  # warm-up
+    alg.run(steps=steps, printing=False)  # warm-up; captures the 10-control-step CUDA graph that the timed run replays
     alg.agent.init_optim(x0)
     barrier()
     l0 = opt.lib.launches + alg.environment.library().launches
@@ -639,9 +639,38 @@ def main():
         tmax = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         e2e_s = float(tmax.item())
-    e2e_value = world * B_ENVS * T_STEPS * e2e_steps / e2e_s
+    e2e_host_value = world * B_ENVS * T_STEPS * e2e_steps / e2e_s
+    e2e_host_gbs = (U_pin.numel() + x0_pin.numel()) * 8 * e2e_steps / e2e_s / 1e9   # per GPU
     assert torch.equal(xN_pin, out["xN"].cpu()), "e2e path and resident path disagree on the final states"
     assert torch.allclose(cost_pin, out["cost"].cpu(), rtol=1e-12, atol=0), "e2e path and resident path disagree"
+
+    # ---- end to end with the actions drawn in the kernel ("or in-kernel Philox ... validated against the host
+    # stream"): per step the host sends the start states (2 MB) and a seed, and reads cost and final states back ----------
+    cost_pin2 = torch.empty((B_ENVS,), dtype=torch.float64).pin_memory()
+    xN_pin2 = torch.empty((4, B_ENVS), dtype=torch.float64).pin_memory()
+    seed0 = 0x5EED0000 + rank
+    for i in range(2):
+        env.rollout_host_random(x0_pin, T_STEPS, seed0 + i, cost_out=cost_pin2, xN_out=xN_pin2)
+    barrier()
+    e2e_r_steps = max(3, min(args.steps, 50))
+    t0 = time.perf_counter()
+    for i in range(e2e_r_steps):
+        env.rollout_host_random(x0_pin, T_STEPS, seed0 + i, cost_out=cost_pin2, xN_out=xN_pin2)
+    barrier()
+    e2e_r_s = time.perf_counter() - t0
+    if world > 1:
+        tmax = torch.tensor([e2e_r_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_r_s = float(tmax.item())
+    e2e_value = world * B_ENVS * T_STEPS * e2e_r_steps / e2e_r_s
+    # the stream is the documented one: the last step again over the materialised controls, and 512 environments of it
+    # against the host restatement (pygent_b200/random_actions.py)
+    from pygent_b200.random_actions import random_actions as host_actions
+    U_chk = L.random_actions(B_ENVS, T_STEPS, seed0 + e2e_r_steps - 1, [U_MAX], device=dev)
+    r_chk = L.rollout(x0, U_chk, S=SUBSTEPS, dt=DT)
+    assert torch.equal(r_chk["xN"].cpu(), xN_pin2) and torch.equal(r_chk["cost"].cpu(), cost_pin2), "in-kernel action stream != materialised stream"
+    assert np.array_equal(U_chk[:, :, :512].cpu().numpy(), host_actions(512, T_STEPS, seed0 + e2e_r_steps - 1, [U_MAX])), "device stream != host stream"
+    del U_chk, r_chk
 
     # ---- final cost / argmin gather: the only collective of the path -----------------------
     from pygent_b200 import distributed as pgd
@@ -773,8 +802,17 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": CONFIG, "clocks": clocks, "gpu_launches": gpu_launches,
             "e2e": {"value": e2e_value, "unit": "env-steps/s",
-                    "h2d_bytes_per_step": int(U_pin.numel() * 8 + x0_pin.numel() * 8),
-                    "d2h_bytes_per_step": int(cost_pin.numel() * 8 + xN_pin.numel() * 8), "steps": e2e_steps},
+                    "h2d_bytes_per_step": int(x0_pin.numel() * 8 + 8),
+                    "d2h_bytes_per_step": int(cost_pin2.numel() * 8 + xN_pin2.numel() * 8), "steps": e2e_r_steps,
+                    "api": "StateSpaceModel.rollout_host_random(x0_pinned, T, seed): start states from pinned host memory, the random "
+                           "actions of config 2 drawn inside the kernel (Philox4x32-10 stream, bit-identical to pygent_b200/random_actions.py "
+                           "on the host: checked in this run), cost + final states back to pinned host memory; every step a new seed"},
+            "e2e_host_actions": {"value": e2e_host_value, "unit": "env-steps/s",
+                                 "h2d_bytes_per_step": int(U_pin.numel() * 8 + x0_pin.numel() * 8),
+                                 "d2h_bytes_per_step": int(cost_pin.numel() * 8 + xN_pin.numel() * 8), "steps": e2e_steps,
+                                 "h2d_gb_per_s_per_gpu": e2e_host_gbs,
+                                 "api": "StateSpaceModel.rollout_host(x0_pinned, U_pinned): the same workload with the 262 MB action array "
+                                        "supplied by the host every step (PCIe-bound: compare h2d_gb_per_s_per_gpu with the link)"},
             "roofline": {"bound": "fp64", "kernel": "rollout_queue_kernel<Problem,double,RK4,1>", "achieved": achieved,
                          "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "peak_source": peak_src,
                          "flops_per_launch": flops, "kernel_ms": kernel_ms, "traffic": NCU_TRAFFIC_BYTES,

@@ -104,6 +104,18 @@ int pg_rollout(int dtype, int integrator, int64_t B, int32_t T, int32_t S, doubl
  * its unit (~2 s; never expected) sets it to 1 and no launch ever clears it, so the caller can test it whenever it next
  * synchronises -- non-zero means the results of some earlier launch on this workspace are incomplete. */
 int64_t pg_rollout_workspace_bytes(int64_t B, int32_t T);
+
+/* pg_rollout / pg_rollout_balanced with the controls drawn INSIDE the kernel instead of read from U (SURVEY.md 8(d), config 2:
+ * "u[k,b] ~ U(-uMax, uMax) ... or in-kernel Philox with the same counter scheme, validated against the host stream"):
+ *     u[k, j, b] = (2 U - 1) * u_max[j],   U = 53-bit uniform from Philox4x32-10 with counter (b mod 2^32, b div 2^32,
+ *     k_offset + k, j) and the 64-bit key `seed`.
+ * u_max: host array [m].  workspace == NULL: the plain kernel; else the ticket-queue kernel (pg_rollout_balanced's rules).
+ * pg_random_actions writes the same stream to U [T, m, B] (for validation and for kernels that read U); the host-side
+ * restatement is pygent_b200/random_actions.py.  A rollout over pg_random_actions' U equals pg_rollout_random bit for bit. */
+int pg_rollout_random(int dtype, int integrator, int64_t B, int32_t T, int32_t S, double dt, double t0, const void* x0, uint64_t seed,
+                      int32_t k_offset, const double* u_max, void* X, void* xN, void* cost, uint8_t* terminated, double terminal_cost,
+                      int32_t flags, void* workspace, int64_t workspace_bytes, void* stream);
+int pg_random_actions(int dtype, int64_t B, int32_t T, uint64_t seed, int32_t k_offset, const double* u_max, void* U, void* stream);
 int pg_rollout_balanced(int dtype, int integrator, int64_t B, int32_t T, int32_t S, double dt, double t0,
                         const void* x0, const void* U, void* X, void* xN, void* cost, uint8_t* terminated,
                         double terminal_cost, int32_t flags, void* workspace, int64_t workspace_bytes, void* stream);

@@ -137,6 +137,22 @@ int pg_mlp_train_grad(const pg_mlp_dims_t* dims, const float* params, const floa
                       int64_t workspace_bytes, int32_t max_rows, float* bucket, void* stream);
 int pg_mlp_train_update(const pg_mlp_dims_t* dims, float* params, float* state_sum, const float* bucket, float lr, float weight_decay,
                         float eps, void* workspace, int64_t workspace_bytes, int32_t max_rows, void* stream);
+/* Data-parallel exchange over NVLink peer memory, fused with the optimiser (instead of an NCCL all-reduce + pg_mlp_train_update):
+ * every rank allocates an exchange block with pg_mlp_train_p2p_alloc (cudaMalloc + CUDA IPC handle, 64 bytes), the handles are
+ * exchanged by the host (e.g. torch.distributed.all_gather), every rank maps its peers' blocks with pg_mlp_train_p2p_open, and
+ * passes pg_mlp_train_grad the bucket  (float*)own_block + (step & 1) * npad,  npad = (count + 1) rounded up to 256.
+ * pg_mlp_train_update_p2p(step) then publishes "my gradient of `step` is complete" into every peer's flag array and runs ONE
+ * kernel that waits for all ranks, sums element i of the world's buckets by peer loads in rank order (bit-identical on every
+ * rank) and applies Adagrad to it.  blocks: host array [world] of the mapped block pointers (own block at index rank);
+ * steps must be numbered 0, 1, 2, ... identically on all ranks.  loss_out (device, 1 float) receives the summed loss.  A rank
+ * that waits more than ~4 s gives up and sets the status word (i32 at byte 2 * npad * 4 + 256 of its own block). */
+int64_t pg_mlp_train_p2p_bytes(const pg_mlp_dims_t* dims);
+int pg_mlp_train_p2p_alloc(int64_t bytes, void** ptr, void* ipc_handle_out);
+int pg_mlp_train_p2p_open(const void* ipc_handle, void** ptr);
+int pg_mlp_train_p2p_close(void* ptr, int32_t own);
+int pg_mlp_train_update_p2p(const pg_mlp_dims_t* dims, float* params, float* state_sum, void* const* blocks, int32_t world, int32_t rank,
+                            int64_t step, float lr, float weight_decay, float eps, float* loss_out, void* workspace,
+                            int64_t workspace_bytes, int32_t max_rows, void* stream);
 int pg_mlp_train_step(const pg_mlp_dims_t* dims, float* params, float* state_sum, const float* moments, const float* x_,
                       const float* x, const float* o_, const float* u, const int32_t* idx, int32_t R, float lr, float weight_decay,
                       float eps, void* workspace, int64_t workspace_bytes, int32_t max_rows, float* bucket, void* stream);

@@ -60,6 +60,15 @@ class _KernelBackend(object):
     def grad_device(self, idx, n_total):
         self.k.grad(idx, n_total)
 
+    def enable_p2p(self, group=None):
+        self.k.enable_p2p(group)
+        self.p2p = True
+
+    def step_p2p(self, idx, n_total, lr, weight_decay, eps=1e-10):
+        """Gradient of this rank's slice straight into its NVLink exchange block, then the fused peer-sum + Adagrad kernel."""
+        self.k.grad(torch.as_tensor(np.ascontiguousarray(idx, dtype=np.int32), device=self.device), n_total, bucket=self.k.p2p_bucket())
+        return self.k.update_p2p(lr, weight_decay, eps)
+
     def update(self, lr, weight_decay, eps=1e-10):
         self.k.update(lr, weight_decay, eps)
 
@@ -69,7 +78,7 @@ class DynamicsTrainer(object):
     device.  `backend` is for tests only (a CPU stand-in that speaks the same protocol drives the host logic on gloo)."""
 
     def __init__(self, nn_dynamics, dyn_lr=1e-3, weight_decay=1e-3, batch_size=512, training_epochs=60, sparse_dyn=True,
-                 device=None, process_group=None, backend=None):
+                 device=None, process_group=None, backend=None, exchange=None):
         if not sparse_dyn:
             raise NotImplementedError("the GPU network path implements the sparse_dyn model (velocity half, mbrl.py:54-57)")
         self.nn_dynamics = nn_dynamics
@@ -85,6 +94,11 @@ class DynamicsTrainer(object):
         self.device = getattr(self.backend, "device", torch.device("cpu"))
         self.collectives = 0
         self.steps = 0
+        # gradient exchange of the data-parallel step: "nccl" = one all-reduce of the bucket + the Adagrad kernel; "p2p" = the
+        # fused peer-memory kernel (pg_mlp_train_update_p2p): every rank reads the others' buckets over NVLink and updates
+        self.exchange = exchange or os.environ.get("PG_TRAIN_EXCHANGE", "nccl")
+        if self.world > 1 and self.exchange == "p2p":
+            self.backend.enable_p2p(process_group)
 
     # -- moments (mbrl.py:487-509): mean / unbiased std over the data set --------------------------------------------
     def set_moments(self, dataSet):
@@ -141,6 +155,9 @@ class DynamicsTrainer(object):
         ONE sum-all-reduce of the flat bucket (255,002 gradient floats + the loss) follows, and every rank applies the
         identical Adagrad update.  Returns the batch's MSE loss (a view of the bucket's last slot: read it before the next step)."""
         idx = np.asarray(idx)
+        if self.world > 1 and self.exchange == "p2p":
+            self.steps += 1
+            return self.backend.step_p2p(idx[self.rank::self.world], len(idx), self.dyn_lr, self.weight_decay)[0]
         self.backend.grad(idx[self.rank::self.world], len(idx))
         if self.world > 1:
             dist.all_reduce(self.backend.bucket, op=dist.ReduceOp.SUM, group=self.group)  # NCCL, on the compute stream

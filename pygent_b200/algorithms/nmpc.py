@@ -319,40 +319,69 @@ class NMPC(Algorithm):
                       out={"xN": X[i + 1], "cost": C[i], "terminated": term})
             t_plant = t_plant + self.dt
         if eager < n_steps:
-            x_in, x_out = X[eager].clone(), torch.empty_like(X[0])
-            c_out = torch.empty_like(C[0])
-            n_before = len(agent._u_dev)
-            libs = {id(l): l for l in (L, agent.traj_optimizer.lib)}.values()
-            launched = [l.launches for l in libs]
-            # capture on a side stream with the raw API: `with torch.cuda.graph(...)` would first empty the caching
-            # allocator (hundreds of ms of cudaFree when another solver has just released its buffers)
-            graph = torch.cuda.CUDAGraph()
-            side = torch.cuda.Stream(device=env.device)
-            side.wait_stream(torch.cuda.current_stream(env.device))
-            with torch.cuda.stream(side), lib.workspace_stream(torch.cuda.current_stream(env.device)):
-                graph.capture_begin(capture_error_mode="thread_local")  # other threads (NCCL watchdog, samplers) may call CUDA
-                try:
-                    u_g = agent.take_action_device(x_in)
-                    L.rollout(x_in, u_g[None], S=env.substeps, dt=self.dt, t0=0.0, terminal_cost=float(env.terminal_cost),
-                              out={"xN": x_out, "cost": c_out, "terminated": term})
-                    x_in.copy_(x_out)
-                finally:
-                    graph.capture_end()
-            torch.cuda.current_stream(env.device).wait_stream(side)
-            del agent._u_dev[n_before:]  # capture recorded (did not run) one step: undo its host-side bookkeeping
-            del agent.tt[-1:]
-            for l, n0 in zip(libs, launched):  # the capture launched nothing; every replay launches the captured kernels
-                l.launches = n0 + (l.launches - n0) * (n_steps - eager)
-            # the capture did not execute: restore nothing, the planner state is untouched; replay from step `eager`
-            Uh = torch.empty((n_steps - eager,) + tuple(u_g.shape), dtype=u_g.dtype, device=u_g.device)
-            for i in range(eager, n_steps):
+            K = max(1, min(int(os.environ.get("PG_NMPC_GRAPH_STEPS", "10")), n_steps - eager))
+            libs = list({id(l): l for l in (L, agent.traj_optimizer.lib)}.values())
+            g = getattr(self, "_graph_state", None)
+            if g is None or g["K"] != K or g["B"] != B or g["planner"] is not agent.traj_optimizer:
+                # K consecutive control steps per graph: one replay + three copies per K steps on the host instead of per
+                # step, so a busy host (8 ranks, clock samplers) does not pace the loop.  Captured on a side stream with
+                # the raw API: `with torch.cuda.graph(...)` would first empty the caching allocator (hundreds of ms of
+                # cudaFree when another solver has just released its buffers).  The graph is kept for later run() calls.
+                x_in = X[eager].clone()
+                Xs = torch.empty((K, env.xDim, B), dtype=env.dtype, device=env.device)
+                Cs = torch.empty((K, B), dtype=env.dtype, device=env.device)
+                Us, gterm = None, torch.empty((B,), dtype=torch.uint8, device=env.device)
+                n_before, tt_before = len(agent._u_dev), len(agent.tt)
+                launched = [l.launches for l in libs]
+                graph = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream(device=env.device)
+                side.wait_stream(torch.cuda.current_stream(env.device))
+                with torch.cuda.stream(side), lib.workspace_stream(torch.cuda.current_stream(env.device)):
+                    graph.capture_begin(capture_error_mode="thread_local")  # other threads (NCCL watchdog, samplers) may call CUDA
+                    try:
+                        for k in range(K):
+                            u_g = agent.take_action_device(x_in)
+                            if Us is None:
+                                Us = torch.empty((K,) + tuple(u_g.shape), dtype=u_g.dtype, device=u_g.device)
+                            L.rollout(x_in, u_g[None], S=env.substeps, dt=self.dt, t0=0.0, terminal_cost=float(env.terminal_cost),
+                                      out={"xN": Xs[k], "cost": Cs[k], "terminated": gterm})
+                            Us[k].copy_(u_g)
+                            x_in.copy_(Xs[k])
+                    finally:
+                        graph.capture_end()
+                torch.cuda.current_stream(env.device).wait_stream(side)
+                del agent._u_dev[n_before:]  # the capture recorded (did not run) K steps: undo their host-side bookkeeping
+                del agent.tt[tt_before:]
+                per_replay = [l.launches - n0 for l, n0 in zip(libs, launched)]
+                for l, n0 in zip(libs, launched):
+                    l.launches = n0
+                g = self._graph_state = {"K": K, "B": B, "planner": agent.traj_optimizer, "graph": graph, "x_in": x_in, "Xs": Xs, "Cs": Cs,
+                                         "Us": Us, "term": gterm, "per_replay": per_replay}
+            else:
+                g["x_in"].copy_(X[eager])
+            graph, Xs, Cs, Us = g["graph"], g["Xs"], g["Cs"], g["Us"]
+            n_rep = (n_steps - eager) // K
+            Uh = torch.empty((n_rep * K,) + tuple(Us.shape[1:]), dtype=Us.dtype, device=Us.device)
+            i = eager
+            for r in range(n_rep):
                 graph.replay()
-                X[i + 1].copy_(x_in)
-                C[i].copy_(c_out)
-                Uh[i - eager].copy_(u_g)
-                agent._u_dev.append(Uh[i - eager])
-                agent.tt.extend([agent.tt[-1] + self.dt])
-            self._graph = graph  # keep the captured buffers alive until the results have been read
+                X[i + 1:i + 1 + K].copy_(Xs)
+                C[i:i + K].copy_(Cs)
+                Uh[r * K:(r + 1) * K].copy_(Us)
+                for k in range(K):
+                    agent._u_dev.append(Uh[r * K + k])
+                    agent.tt.extend([agent.tt[-1] + self.dt])
+                i += K
+            for l, per in zip(libs, g["per_replay"]):
+                l.launches += per * n_rep
+            if n_rep:
+                term.copy_(g["term"])
+                t_plant = t_plant + self.dt * n_rep * K
+            for i in range(i, n_steps):  # the remainder that does not fill a graph: eager control steps
+                u = agent.take_action_device(X[i])
+                L.rollout(X[i], u[None], S=env.substeps, dt=self.dt, t0=t_plant, terminal_cost=float(env.terminal_cost),
+                          out={"xN": X[i + 1], "cost": C[i], "terminated": term})
+                t_plant = t_plant + self.dt
         Xh = X.detach().to("cpu", torch.float64).numpy()
         env._hist = [Xh[k].T.copy() for k in range(n_steps + 1)]
         env._xd_prev, env._xd = X[n_steps - 1].clone(), X[n_steps].clone()

@@ -176,6 +176,44 @@ __device__ __forceinline__ void env_step(const typename P::template Ctx<T>& m, T
     env_step_multi<P, T, INTEG, 1>(m, reinterpret_cast<T(&)[1][P::N]>(x), reinterpret_cast<const T(&)[1][P::M]>(u), dt, h, S);
 }
 
+// ---- in-kernel action stream ("u[k,b] ~ U(-uMax, uMax) ... or in-kernel Philox with the same counter scheme,
+// validated against the host stream") --------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11): counter
+// (b mod 2^32, b div 2^32, control interval k, input j), key = the 64-bit seed.  The first two output words make one
+// 53-bit uniform U in [0, 1); the action is (2 U - 1) * uMax, all in IEEE double (exact up to the two final roundings), so
+// pygent_b200/random_actions.py reproduces the stream bit for bit on the host.  The fp32 kernels use the top 24 bits of the
+// same draw and float arithmetic (random_actions(..., dtype=np.float32) on the host).
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t& r0,
+                                              uint32_t& r1) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    r0 = c0;
+    r1 = c1;
+}
+
+template <typename T>
+__device__ __forceinline__ T philox_action(uint32_t seed_lo, uint32_t seed_hi, int64_t b, int k, int j, double u_max) {
+    uint32_t r0, r1;
+    philox4x32_10((uint32_t)((uint64_t)b & 0xffffffffu), (uint32_t)((uint64_t)b >> 32), (uint32_t)k, (uint32_t)j, seed_lo, seed_hi, r0, r1);
+    if constexpr (sizeof(T) == 8) {
+        const uint64_t bits = (((uint64_t)r1 << 32) | (uint64_t)r0) >> 11;
+        const double U = (double)bits * 1.1102230246251565e-16;  // 2^-53
+        return (T)((2.0 * U - 1.0) * u_max);
+    } else {  // the fp32 instantiation holds no fp64 arithmetic: the top 24 bits of the same 64-bit draw, in float
+        const float U = (float)(r1 >> 8) * 5.9604644775390625e-08f;  // 2^-24
+        return (T)((2.0f * U - 1.0f) * (float)u_max);
+    }
+}
+
 // ---- K1: open-loop rollout ----------------------------------------------------------------------
 template <typename T>
 struct RolloutArgs {
@@ -183,6 +221,10 @@ struct RolloutArgs {
     int T_steps, S;
     T dt, t0, terminal_cost;
     int add_final_cost, accumulate_cost;
+    int rng;                      // 1: controls come from the Philox stream (U is ignored)
+    uint32_t seed_lo, seed_hi;
+    int k_offset;                 // control interval of the stream that this launch's interval 0 is
+    double u_max[2];
     const T* x0;
     const T* U;
     T* X;
@@ -190,6 +232,13 @@ struct RolloutArgs {
     T* cost;
     uint8_t* terminated;
 };
+
+// control j of trajectory b in control interval k: the action stream, the U array, or zero
+template <typename T>
+__device__ __forceinline__ T control_in(const RolloutArgs<T>& a, int k, int j, int64_t b, int M) {
+    if (a.rng) return philox_action<T>(a.seed_lo, a.seed_hi, b, a.k_offset + k, j, a.u_max[j]);
+    return a.U ? a.U[((int64_t)k * M + j) * a.B + b] : T(0);
+}
 
 template <typename P, typename T, int INTEG>
 __global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs<T> a) {
@@ -210,12 +259,12 @@ __global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs<T> a) {
     T cost = (a.accumulate_cost && a.cost) ? a.cost[b] : T(0), t = a.t0;
     bool term = false;
 #pragma unroll
-    for (int j = 0; j < M; j++) un[j] = (a.U && a.T_steps > 0) ? a.U[j * B + b] : T(0);
+    for (int j = 0; j < M; j++) un[j] = a.T_steps > 0 ? control_in(a, 0, j, b, M) : T(0);
     for (int k = 0; k < a.T_steps; k++) {
         copy(u, un);
-        if (a.U && k + 1 < a.T_steps) {  // prefetch next control
+        if ((a.U || a.rng) && k + 1 < a.T_steps) {  // prefetch next control
 #pragma unroll
-            for (int j = 0; j < M; j++) un[j] = a.U[((int64_t)(k + 1) * M + j) * B + b];
+            for (int j = 0; j < M; j++) un[j] = control_in(a, k + 1, j, b, M);
         }
         T xp[N];
         copy(xp, x);
@@ -327,7 +376,7 @@ __global__ void __launch_bounds__(128, 3) rollout_queue_kernel(const QueueArgs<T
                 cost[e] = __ldcg(&a.cost[bb[e]]);
             }
 #pragma unroll
-            for (int j = 0; j < M; j++) un[e][j] = (a.U && k0 < k1) ? a.U[((int64_t)k0 * M + j) * B + bb[e]] : T(0);
+            for (int j = 0; j < M; j++) un[e][j] = k0 < k1 ? control_in(a, k0, j, bb[e], M) : T(0);
         }
         t = (c == 0) ? a.t0 : __ldcg(&q.tq[g]);
         bool term[E];
@@ -338,9 +387,9 @@ __global__ void __launch_bounds__(128, 3) rollout_queue_kernel(const QueueArgs<T
 #pragma unroll
             for (int e = 0; e < E; e++) {
                 copy(u[e], un[e]);
-                if (a.U && k + 1 < k1) {
+                if ((a.U || a.rng) && k + 1 < k1) {
 #pragma unroll
-                    for (int j = 0; j < M; j++) un[e][j] = a.U[((int64_t)(k + 1) * M + j) * B + bb[e]];
+                    for (int j = 0; j < M; j++) un[e][j] = control_in(a, k + 1, j, bb[e], M);
                 }
                 copy(xp[e], x[e]);
             }
@@ -379,6 +428,17 @@ __global__ void __launch_bounds__(128, 3) rollout_queue_kernel(const QueueArgs<T
             }
         }
     }
+}
+
+// U [T, m, B] <- the action stream (validation against the host stream; feeding kernels that read U)
+template <typename T>
+__global__ void __launch_bounds__(256) random_actions_kernel(int64_t B, int T_steps, int M, uint32_t seed_lo, uint32_t seed_hi, int k_offset,
+                                                             double um0, double um1, T* __restrict__ U) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)T_steps * M * B) return;
+    const int64_t b = i % B;
+    const int j = (int)((i / B) % M), k = (int)(i / (B * M));
+    U[i] = philox_action<T>(seed_lo, seed_hi, b, k_offset + k, j, j == 0 ? um0 : um1);
 }
 
 // ---- K2: closed-loop line-search rollouts (iLQR.forward_pass, ilqr.py:187-231) ---------------------

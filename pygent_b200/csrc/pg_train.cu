@@ -589,6 +589,77 @@ __global__ void __launch_bounds__(256) train_adagrad_kernel(float* params, float
     if (i >= L.oW2 && i < L.ob2) pack_w2(w, (i - L.oW2) / HID, (i - L.oW2) % HID, p);
 }
 
+// ---- data-parallel exchange over NVLink peer memory, fused with the optimiser --------------------------------------------------
+// Every rank owns an exchange block in its own HBM, mapped into all ranks (CUDA IPC): two gradient buckets [NPAD] (step parity)
+// and a flag word per rank.  After its gradient kernels a rank stores (step + 1) into ITS slot of every peer's flag array; the
+// update kernel waits until all of its own slots show the step, then every thread sums element i of the WORLD buckets -- peer
+// loads through NVLink / NVSwitch, in rank order, so all ranks form bit-identical sums -- and applies Adagrad at once: one
+// kernel is the all-reduce and the optimiser, and the gradients cross the links exactly once (world - 1 reads per element, no
+// reduce-scatter / all-gather round trips, no host in the loop).  Reuse of a parity slot is safe: a rank writes the bucket of
+// step s + 2 only after its update of step s + 1, which waited for every peer's gradient of step s + 1, which in stream order
+// follows that peer's update (the reader) of step s.
+constexpr int P2P_MAX_WORLD = 16;
+
+struct P2PTable {
+    const float* bucket[P2P_MAX_WORLD];  // peer r's exchange block (bucket of parity p at + p * npad)
+    uint32_t* flags[P2P_MAX_WORLD];      // peer r's flag array [P2P_MAX_WORLD]
+    int world, rank;
+    int64_t npad;
+};
+
+__global__ void train_p2p_signal_kernel(P2PTable t, uint32_t step1) {
+    const int r = threadIdx.x;
+    if (r < t.world) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(t.flags[r] + t.rank), "r"(step1) : "memory");
+    }
+}
+
+__global__ void __launch_bounds__(256) train_adagrad_p2p_kernel(float* params, float* state_sum, float* loss_out, int32_t* status, Layout L, Ws w,
+                                                                P2PTable t, uint32_t step1, float lr, float wd, float eps) {
+    __shared__ int ok;
+    if (threadIdx.x == 0) {  // wait until every rank has published its gradient of this step
+        int good = 1;
+        unsigned long long t0 = 0;
+        for (int r = 0; r < t.world && good; r++) {
+            const uint32_t* f = t.flags[t.rank] + r;
+            for (uint32_t spins = 0;; spins++) {
+                uint32_t v;
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                if ((int32_t)(v - step1) >= 0) break;
+                if ((spins & 1023) == 1023) {  // a rank that never arrives must not hang the GPU: give up after ~4 s
+                    unsigned long long now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    if (t0 == 0) t0 = now;
+                    else if (now - t0 > 4000000000ull) { good = 0; break; }
+                }
+            }
+        }
+        ok = good;
+    }
+    __syncthreads();
+    if (!ok) {
+        if (threadIdx.x == 0 && blockIdx.x == 0) atomicExch(status, 1);
+        return;
+    }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > L.NP) return;
+    const size_t off = (size_t)((step1 - 1) & 1) * t.npad + i;
+    float g = 0.0f;
+    for (int r = 0; r < t.world; r++) g += __ldcv(t.bucket[r] + off);  // fixed rank order: identical on every rank
+    if (i == L.NP) {  // the loss rides in the bucket's last slot
+        *loss_out = g;
+        return;
+    }
+    float p = params[i];
+    const float gr = fmaf(wd, p, g);
+    const float s = fmaf(gr, gr, state_sum[i]);
+    p = p - lr * (gr / (sqrtf(s) + eps));
+    state_sum[i] = s;
+    params[i] = p;
+    if (i >= L.oW2 && i < L.ob2) pack_w2(w, (i - L.oW2) / HID, (i - L.oW2) % HID, p);
+}
+
 int check_last() {
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
@@ -672,6 +743,64 @@ int pg_mlp_train_update(const pg_mlp_dims_t* dims, float* params, float* state_s
     if (ws_layout(&w, (uint8_t*)workspace, rmax) > workspace_bytes) return PG_E_BADARG;
     const Layout L = make_layout(dims);
     train_adagrad_kernel<<<(L.NP + 255) / 256, 256, 0, (cudaStream_t)stream>>>(params, state_sum, bucket, L, w, lr, weight_decay, eps);
+    return check_last();
+}
+
+int64_t pg_mlp_train_p2p_bytes(const pg_mlp_dims_t* dims) {
+    if (!dims_ok(dims)) return PG_E_BADARG;
+    const int64_t npad = (make_layout(dims).NP + 1 + 255) / 256 * 256;
+    return 2 * npad * 4 + 1024;  // two buckets + the flag words (+ a status word)
+}
+
+int pg_mlp_train_p2p_alloc(int64_t bytes, void** ptr, void* ipc_handle_out) {
+    if (bytes <= 0 || !ptr || !ipc_handle_out) return PG_E_BADARG;
+    cudaError_t e = cudaMalloc(ptr, (size_t)bytes);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemset(*ptr, 0, (size_t)bytes);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaIpcGetMemHandle((cudaIpcMemHandle_t*)ipc_handle_out, *ptr);
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+int pg_mlp_train_p2p_open(const void* ipc_handle, void** ptr) {
+    if (!ipc_handle || !ptr) return PG_E_BADARG;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, sizeof(h));
+    const cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+int pg_mlp_train_p2p_close(void* ptr, int32_t own) {
+    if (!ptr) return 0;
+    const cudaError_t e = own ? cudaFree(ptr) : cudaIpcCloseMemHandle(ptr);
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+int pg_mlp_train_update_p2p(const pg_mlp_dims_t* dims, float* params, float* state_sum, void* const* blocks, int32_t world, int32_t rank,
+                            int64_t step, float lr, float weight_decay, float eps, float* loss_out, void* workspace,
+                            int64_t workspace_bytes, int32_t max_rows, void* stream) {
+    if (!dims_ok(dims) || !params || !state_sum || !blocks || world < 1 || world > P2P_MAX_WORLD || rank < 0 || rank >= world || step < 0 ||
+        !loss_out || !workspace || max_rows < 1)
+        return PG_E_BADARG;
+    const int rmax = (max_rows + 127) / 128 * 128;
+    Ws w;
+    if (ws_layout(&w, (uint8_t*)workspace, rmax) > workspace_bytes) return PG_E_BADARG;
+    const Layout L = make_layout(dims);
+    P2PTable t;
+    memset(&t, 0, sizeof(t));
+    t.world = world;
+    t.rank = rank;
+    t.npad = (L.NP + 1 + 255) / 256 * 256;
+    for (int r = 0; r < world; r++) {
+        if (!blocks[r]) return PG_E_BADARG;
+        t.bucket[r] = (const float*)blocks[r];
+        t.flags[r] = (uint32_t*)((char*)blocks[r] + 2 * t.npad * 4);
+    }
+    int32_t* status = (int32_t*)(t.flags[rank] + 64);
+    const uint32_t step1 = (uint32_t)(step + 1);
+    cudaStream_t st = (cudaStream_t)stream;
+    train_p2p_signal_kernel<<<1, 32, 0, st>>>(t, step1);
+    train_adagrad_p2p_kernel<<<(L.NP + 1 + 255) / 256, 256, 0, st>>>(params, state_sum, loss_out, status, L, w, t, step1, lr, weight_decay, eps);
     return check_last();
 }
 

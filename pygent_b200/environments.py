@@ -305,6 +305,32 @@ class StateSpaceModel(Environment):
         L.check_queues()
         return {"cost": cost_out, "xN": xN_out}
 
+    def rollout_host_random(self, x0, T, seed, cost_out=None, xN_out=None, u_max=None, fast=False):
+        """End-to-end rollout under RANDOM actions from HOST start states: x0 `[n, B]` (pinned torch tensor) crosses PCIe,
+        the T controls per environment are drawn inside the kernel (Philox stream of pygent_b200/random_actions.py, keyed
+        by `seed`: u ~ U(-uMax, uMax)) -- 2 MB of input per step at the benchmark size instead of the
+        264 MB a materialised U would be -- and cost `[B]` / final states `[n, B]` come back into the pinned outputs.
+        Synchronises before returning.  `random_actions.random_actions(B, T, seed, uMax)` reproduces the controls on the host."""
+        L = self.library()
+        n, B = x0.shape
+        dev, dt_ = self.device, self.dtype
+        st = getattr(self, "_host_rand", None)
+        if st is None or st["B"] != B:
+            st = self._host_rand = {"B": B, "x": torch.empty((n, B), dtype=dt_, device=dev), "xN": torch.empty((n, B), dtype=dt_, device=dev),
+                                    "cost": torch.empty((B,), dtype=dt_, device=dev), "term": torch.empty((B,), dtype=torch.uint8, device=dev)}
+        um = np.ravel(self.uMax if u_max is None else u_max).astype(float)
+        st["x"].copy_(x0, non_blocking=True)
+        L.rollout(st["x"], None, T=int(T), S=self.substeps, dt=self.dt, t0=0.0, integrator=lib.INTEG_EULER if fast else lib.INTEG_RK4,
+                  terminal_cost=float(self.terminal_cost), out={"xN": st["xN"], "cost": st["cost"], "terminated": st["term"]},
+                  actions=(seed, um))
+        if cost_out is not None:
+            cost_out.copy_(st["cost"], non_blocking=True)
+        if xN_out is not None:
+            xN_out.copy_(st["xN"], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        L.check_queues()
+        return {"cost": cost_out, "xN": xN_out}
+
     def terminate(self, x):
         """True where `x` (`[n]` or `[B, n]`) is a terminal state (reference: environments.py:278-288)."""
         x = np.asarray(x, dtype=float)

@@ -8,6 +8,7 @@ import ctypes
 import functools
 import os
 
+import numpy as np
 import torch
 
 from . import build
@@ -46,6 +47,9 @@ SIGNATURES = {
     "pg_get_problem_info": [ctypes.POINTER(ProblemInfo)],
     "pg_rollout": [_i32, _i32, _i64, _i32, _i32, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _i32, _vp],
     "pg_rollout_balanced": [_i32, _i32, _i64, _i32, _i32, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _i32, _vp, _i64, _vp],
+    "pg_rollout_random": [_i32, _i32, _i64, _i32, _i32, _f64, _f64, _vp, ctypes.c_uint64, _i32, _dp, _vp, _vp, _vp, _vp, _f64, _i32,
+                          _vp, _i64, _vp],
+    "pg_random_actions": [_i32, _i64, _i32, ctypes.c_uint64, _i32, _dp, _vp, _vp],
     "pg_ilqr_forward": [_i32, _i32, _i64, _i32, _i32, _f64, _i32, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _dp, _f64,
                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "pg_ilqr_forward_balanced": [_i32, _i32, _i64, _i32, _i32, _f64, _i32, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _dp, _f64,
@@ -200,11 +204,13 @@ class ProblemLibrary:
     # -- K1 ------------------------------------------------------------------------------------
     def rollout(self, x0, U=None, T=None, S=4, dt=0.02, t0=0.0, integrator=INTEG_RK4, history=False,
                 want_cost=True, terminal_cost=0.0, add_final_cost=False, accumulate_cost=False, out=None,
-                balanced=None):
+                balanced=None, actions=None):
         """x0 [n,B], U [T,m,B] or None -> dict(xN [n,B], cost [B], terminated [B] u8, X [T+1,n,B]).
 
         balanced: use the work-queue kernel (pg_rollout_balanced); default: when the batch fills the GPU but
-        is not a whole number of warps per scheduler and the horizon has several chunks."""
+        is not a whole number of warps per scheduler and the horizon has several chunks.
+        actions = (seed, u_max [m][, k_offset]): the controls are drawn inside the kernel from the Philox stream of
+        pygent_b200/random_actions.py (pg_rollout_random) instead of being read from U."""
         n, m = self.n, self.m
         dtype, dev = x0.dtype, x0.device
         B = x0.shape[1]
@@ -228,6 +234,25 @@ class ProblemLibrary:
         flags = int(add_final_cost) | (2 if accumulate_cost else 0)
         if balanced is None:
             balanced = use_balanced_rollout(B, T, dev)
+        if actions is not None:
+            if U is not None:
+                raise PygentB200Error("rollout: pass U or actions=(seed, u_max), not both")
+            seed, u_max = int(actions[0]), [float(v) for v in np.ravel(actions[1])]
+            k_off = int(actions[2]) if len(actions) > 2 else 0
+            if len(u_max) != m:
+                raise PygentB200Error("actions: u_max needs %d entries" % m)
+            ws, nbytes = None, 0
+            if balanced and cost is not None and T >= 1 and B > 0:
+                nbytes = int(self.dll.pg_rollout_workspace_bytes(B, T))
+                ws = self._queue_workspace("ro", dev, nbytes)
+            rc = self.dll.pg_rollout_random(_dtype_code(dtype), integrator, B, T, S, dt, t0, _ptr(x0, dtype, (n, B), "x0"),
+                                            ctypes.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), k_off, _host_doubles(u_max),
+                                            _ptr(X, dtype, (T + 1, n, B), "X"), _ptr(xN, dtype, (n, B), "xN"),
+                                            _ptr(cost, dtype, (B,), "cost"), _ptr(term, torch.uint8, (B,), "terminated"),
+                                            terminal_cost, flags, _ptr(ws) if ws is not None else None, nbytes, self._stream())
+            self._check(rc, "pg_rollout_random")
+            self.launches += 1
+            return {"xN": xN, "cost": cost, "terminated": term, "X": X}
         if balanced and cost is not None and T >= 1 and B > 0:
             nbytes = int(self.dll.pg_rollout_workspace_bytes(B, T))
             ws = self._queue_workspace("ro", dev, nbytes)
@@ -247,6 +272,16 @@ class ProblemLibrary:
         self._check(rc, "pg_rollout")
         self.launches += 1
         return {"xN": xN, "cost": cost, "terminated": term, "X": X}
+
+    def random_actions(self, B, T, seed, u_max, k_offset=0, dtype=torch.float64, device=None):
+        """U [T, m, B] of the in-kernel action stream (pg_random_actions), materialised."""
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        U = torch.empty((T, self.m, B), dtype=dtype, device=dev)
+        rc = self.dll.pg_random_actions(_dtype_code(dtype), B, T, ctypes.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), int(k_offset),
+                                        _host_doubles([float(v) for v in np.ravel(u_max)]), _ptr(U, dtype, (T, self.m, B), "U"), self._stream())
+        self._check(rc, "pg_random_actions")
+        self.launches += 1
+        return U
 
     # -- K2 ------------------------------------------------------------------------------------
     def ilqr_forward(self, x0, xbar, ubar, KK, kk, alphas=None, alpha_dev=None, S=4, dt=0.02,

@@ -72,6 +72,10 @@ _f32 = ctypes.c_float
 SIGNATURES["pg_mlp_train_init"] = [_dims_p, _vp, _vp, _i64, _i32, _vp]
 SIGNATURES["pg_mlp_train_grad"] = [_dims_p, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _i64, _i32, _vp, _vp]
 SIGNATURES["pg_mlp_train_update"] = [_dims_p, _vp, _vp, _vp, _f32, _f32, _f32, _vp, _i64, _i32, _vp]
+SIGNATURES["pg_mlp_train_p2p_alloc"] = [_i64, ctypes.POINTER(ctypes.c_void_p), _vp]
+SIGNATURES["pg_mlp_train_p2p_open"] = [_vp, ctypes.POINTER(ctypes.c_void_p)]
+SIGNATURES["pg_mlp_train_p2p_close"] = [_vp, _i32]
+SIGNATURES["pg_mlp_train_update_p2p"] = [_dims_p, _vp, _vp, ctypes.POINTER(ctypes.c_void_p), _i32, _i32, _i64, _f32, _f32, _f32, _vp, _vp, _i64, _i32, _vp]
 SIGNATURES["pg_mlp_train_step"] = [_dims_p, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _vp, _i64, _i32, _vp, _vp]
 LIN_MODES = {"analytic": 0, "fd": 1}
 _dll = None
@@ -88,6 +92,7 @@ def dll():
         _dll.pg_mlp_forward_workspace_bytes.argtypes, _dll.pg_mlp_forward_workspace_bytes.restype = [_i64, _i32], ctypes.c_int64
         _dll.pg_mlp_train_param_count.argtypes, _dll.pg_mlp_train_param_count.restype = [_dims_p], ctypes.c_int64
         _dll.pg_mlp_train_workspace_bytes.argtypes, _dll.pg_mlp_train_workspace_bytes.restype = [_i32], ctypes.c_int64
+        _dll.pg_mlp_train_p2p_bytes.argtypes, _dll.pg_mlp_train_p2p_bytes.restype = [_dims_p], ctypes.c_int64
     return _dll
 
 
@@ -310,8 +315,9 @@ class TrainKernels:
         """col: {"x_", "x", "o_", "u"} -> float32 [N, dim] arrays (DataSet.columns()); one upload per training call."""
         self.data = {k: torch.as_tensor(np.ascontiguousarray(col[k], dtype=np.float32), device=self.device) for k in ("x_", "x", "o_", "u")}
 
-    def grad(self, idx, n_total):
-        """idx: int32 CUDA tensor of data-set rows (this rank's slice of the batch).  Fills `bucket`."""
+    def grad(self, idx, n_total, bucket=None):
+        """idx: int32 CUDA tensor of data-set rows (this rank's slice of the batch).  Fills `bucket` (default: self.bucket)."""
+        bucket = self.bucket if bucket is None else bucket
         R = int(idx.numel())
         if R > self.max_rows:
             raise PygentB200Error("batch of %d rows exceeds max_rows=%d" % (R, self.max_rows))
@@ -320,7 +326,7 @@ class TrainKernels:
                                        ctypes.c_void_p(d["x_"].data_ptr()), ctypes.c_void_p(d["x"].data_ptr()),
                                        ctypes.c_void_p(d["o_"].data_ptr()), ctypes.c_void_p(d["u"].data_ptr()),
                                        ctypes.c_void_p(idx.data_ptr()) if R else None, R, int(n_total), ctypes.c_void_p(self._ws_ptr),
-                                       self.ws_bytes, self.max_rows, ctypes.c_void_p(self.bucket.data_ptr()), self._stream()),
+                                       self.ws_bytes, self.max_rows, ctypes.c_void_p(bucket.data_ptr()), self._stream()),
                "pg_mlp_train_grad")
         self.launches += 5
 
@@ -329,6 +335,60 @@ class TrainKernels:
                                          ctypes.c_void_p(self.bucket.data_ptr()), lr, weight_decay, eps, ctypes.c_void_p(self._ws_ptr),
                                          self.ws_bytes, self.max_rows, self._stream()), "pg_mlp_train_update")
         self.launches += 1
+
+    # -- data parallel over NVLink peer memory (pg_mlp_train_update_p2p) ---------------------------------------------------------
+    def enable_p2p(self, group=None):
+        """Allocate this rank's exchange block, swap CUDA IPC handles with the other ranks of `group` (one all_gather of 64
+        bytes) and map their blocks.  Afterwards `grad` writes into the block's parity slot and `update_p2p` replaces the
+        NCCL all-reduce + `update` pair.  Raises PygentB200Error if peer mapping is not possible on this node."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        nbytes = int(dll().pg_mlp_train_p2p_bytes(ctypes.byref(self.dims)))
+        own, handle = ctypes.c_void_p(), (ctypes.c_uint8 * 64)()
+        _check(dll().pg_mlp_train_p2p_alloc(nbytes, ctypes.byref(own), handle), "pg_mlp_train_p2p_alloc")
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
+        every = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine, group=group)
+        blocks = (ctypes.c_void_p * world)()
+        for r in range(world):
+            if r == rank:
+                blocks[r] = own.value
+            else:
+                h = (ctypes.c_uint8 * 64)(*every[r].cpu().tolist())
+                p = ctypes.c_void_p()
+                _check(dll().pg_mlp_train_p2p_open(h, ctypes.byref(p)), "pg_mlp_train_p2p_open (rank %d's block)" % r)
+                blocks[r] = p.value
+        self._p2p = {"world": world, "rank": rank, "blocks": blocks, "own": own.value, "npad": (self.count + 1 + 255) // 256 * 256, "step": 0,
+                     "nbytes": nbytes}
+
+        class _Mem(object):  # the own block as a torch tensor (not owned by torch: freed in close_p2p)
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        self._p2p["view"] = torch.as_tensor(_Mem(own.value, nbytes // 4), device=self.device)
+        self.loss_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
+        dist.barrier(group=group)  # nobody publishes into a block that is not mapped yet
+        return self
+
+    def p2p_bucket(self):
+        """The slot of the exchange block that this step's gradient goes to (a view of count + 1 floats)."""
+        p = self._p2p
+        off = (p["step"] & 1) * p["npad"]
+        return p["view"][off:off + self.count + 1]
+
+    def update_p2p(self, lr, weight_decay, eps=1e-10):
+        p = self._p2p
+        _check(dll().pg_mlp_train_update_p2p(ctypes.byref(self.dims), ctypes.c_void_p(self.params.data_ptr()), ctypes.c_void_p(self.state_sum.data_ptr()),
+                                             p["blocks"], p["world"], p["rank"], p["step"], lr, weight_decay, eps,
+                                             ctypes.c_void_p(self.loss_dev.data_ptr()), ctypes.c_void_p(self._ws_ptr), self.ws_bytes, self.max_rows,
+                                             self._stream()), "pg_mlp_train_update_p2p")
+        p["step"] += 1
+        self.launches += 2
+        return self.loss_dev
+
+    def p2p_status(self):
+        """Non-zero: this rank gave up waiting for a peer's gradient (synchronises)."""
+        p = self._p2p
+        return int(p["view"][2 * p["npad"] + 64:2 * p["npad"] + 65].view(torch.int32).item())
 
     def step(self, idx, lr, weight_decay, eps=1e-10):
         """pg_mlp_train_step: the single-GPU optimiser step in one C call (six launches)."""

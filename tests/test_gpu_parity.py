@@ -178,6 +178,44 @@ def test_balanced_rollout_is_bit_identical(B, T, dtype):
     assert same(a2["xN"], b2["xN"]) and same(a2["cost"], b2["cost"])
 
 
+@pytest.mark.parametrize("case,B,T", [("cart_pole", 40001, 130), ("car", 777, 33), ("cart_pole", 64, 7)])
+def test_in_kernel_action_stream(case, B, T):
+    """"in-kernel Philox with the same counter scheme, validated against the host stream".
+    (1) pg_random_actions on the device == pygent_b200/random_actions.py on the host, bit for bit (m = 1 and m = 2, with
+    offsets); (2) a rollout that draws its controls in the kernel (pg_rollout_random, plain and ticket-queue kernel) ==
+    the rollout over the materialised U, bit for bit, fp64 and fp32."""
+    from pygent_b200.random_actions import random_actions
+    alg = solver(case, 10)
+    L = alg.lib
+    m, n = L.m, L.n
+    u_max = [10.0, 0.7][:m]
+    seed = 0x1234_5678_9ABC_DEF0 + B
+    U = L.random_actions(B, T, seed, u_max)
+    Uh = random_actions(B, T, seed, u_max)
+    assert np.array_equal(U.cpu().numpy(), Uh)
+    assert np.array_equal(L.random_actions(B, 5, seed, u_max, k_offset=T - 5).cpu().numpy(), Uh[T - 5:])
+    rng = np.random.default_rng(B)
+    x0 = torch.as_tensor(np.array(CASES[case][4])[:, None] + rng.uniform(-0.2, 0.2, (n, B)), device="cuda")
+    for dtype in (torch.float64, torch.float32):
+        x0d, Ud = x0.to(dtype), L.random_actions(B, T, seed, u_max, dtype=dtype)
+        if dtype == torch.float32:
+            assert np.array_equal(Ud.cpu().numpy(), random_actions(B, T, seed, u_max, dtype=np.float32))
+        for balanced in (False, True):
+            a = L.rollout(x0d, Ud, S=4, dt=0.02, history=B < 1000, balanced=balanced)
+            b = L.rollout(x0d, None, T=T, S=4, dt=0.02, history=B < 1000, balanced=balanced, actions=(seed, u_max))
+            assert torch.equal(a["xN"], b["xN"]) and torch.equal(a["cost"], b["cost"]) and torch.equal(a["terminated"], b["terminated"])
+            if B < 1000:
+                assert torch.equal(a["X"], b["X"])
+    # a horizon split into two launches continues the same stream (k_offset)
+    a = L.rollout(x0, None, T=T, S=4, dt=0.02, balanced=False, actions=(seed, u_max))
+    h = T // 2
+    p1 = L.rollout(x0, None, T=h, S=4, dt=0.02, balanced=False, actions=(seed, u_max))
+    p2 = L.rollout(p1["xN"], None, T=T - h, S=4, dt=0.02, t0=h * 0.02, balanced=False, accumulate_cost=True, out={"cost": p1["cost"].clone()},
+                   actions=(seed, u_max, h))
+    assert torch.equal(a["xN"], p2["xN"])
+    L.check_queues()
+
+
 def test_queue_worker_timeout_is_reported(monkeypatch):
     """a worker of the ticket-queue kernels that gives up waiting (~2 s) must not go unnoticed.  PG_QUEUE_FAULT=1
     makes the launch skip the first-chunk tickets, so every worker waits for a unit nobody publishes; the kernel still ends

@@ -214,3 +214,21 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "rk4_env_steps_per_s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_host_action_stream_known_answers():
+    """pygent_b200/random_actions.py: Philox4x32-10 against the Random123 known-answer vectors (kat_vectors: philox4x32 10),
+    and the shape / range / determinism of the action stream built on it."""
+    from pygent_b200.random_actions import philox4x32_10, random_actions
+    kats = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+            ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kats:
+        got = philox4x32_10(*ctr, *key)
+        assert tuple(int(g) for g in got) == want
+    U = random_actions(257, 40, seed=12345, u_max=[10.0, 0.5])
+    assert U.shape == (40, 2, 257) and np.all(np.abs(U[:, 0]) <= 10.0) and np.all(np.abs(U[:, 1]) <= 0.5)
+    assert abs(U[:, 0].mean()) < 0.2 and abs(U[:, 0].std() - 10 / np.sqrt(3)) < 0.2
+    assert np.array_equal(U[10:], random_actions(257, 30, seed=12345, u_max=[10.0, 0.5], k_offset=10))      # the stream is indexed, not stateful
+    assert np.array_equal(U[:, :, 100:], random_actions(157, 40, seed=12345, u_max=[10.0, 0.5], b_offset=100))
+    assert not np.array_equal(U, random_actions(257, 40, seed=12346, u_max=[10.0, 0.5]))
