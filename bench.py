@@ -462,6 +462,29 @@ def train_bench(dev, rank, world, barrier, steps=300, with_cpu=True):
     b.record()
     barrier()
     ms_local = a.elapsed_time(b)
+    # ---- the same step with the fused NVLink peer-memory exchange (pg_mlp_train_update_p2p) instead of NCCL + update ----
+    p2p = None
+    if world > 1:
+        try:
+            k.enable_p2p()
+            for i in range(10):
+                k.grad(idx_dev[i % 8], gb, bucket=k.p2p_bucket())
+                k.update_p2p(1e-3, 1e-3)
+            barrier()
+            a.record()
+            for i in range(steps):
+                k.grad(idx_dev[i % 8], gb, bucket=k.p2p_bucket())
+                k.update_p2p(1e-3, 1e-3)
+            b.record()
+            barrier()
+            t = torch.tensor([a.elapsed_time(b), float(k.p2p_status())], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            p2p = {"value": steps / (float(t[0]) * 1e-3), "unit": "optimiser steps/s", "us_per_step": float(t[0]) * 1e3 / steps,
+                   "gave_up_waiting": int(t[1]), "loss_last": float(k.loss_dev[0]),
+                   "exchange": "each rank writes its gradient into its own NVLink-mapped block; ONE kernel waits for all ranks, sums the "
+                               "world's buckets by peer loads in rank order and applies Adagrad (no NCCL call in the step)"}
+        except Exception as e:  # noqa: BLE001 -- peer mapping unavailable on this node: the NCCL figures stand
+            p2p = {"unavailable": "%s: %s" % (type(e).__name__, e)}
     flops = 3 * 2.0 * TRAIN_ROWS * 500 * 500 + 2 * 2.0 * TRAIN_ROWS * 500 * (6 + 2) * 1.5  # layer-2 fwd/dgrad/wgrad + the thin layers
     res = {"metric": "dynamics_train_steps_per_s", "value": steps / (ms * 1e-3), "unit": "optimiser steps/s",
            "samples_per_s": world * TRAIN_ROWS * steps / (ms * 1e-3), "us_per_step": ms * 1e3 / steps,
@@ -471,6 +494,8 @@ def train_bench(dev, rank, world, barrier, steps=300, with_cpu=True):
            "bucket_floats": int(k.count + 1), "collective": "one NCCL all-reduce(sum) of the flat gradient bucket + loss per step" if world > 1 else None,
            "gpu_launches": launches, "launches_per_step": launches / steps, "loss_first": loss0, "loss_last": loss1,
            "tflops_per_gpu": flops / (ms * 1e-3 / steps) / 1e12}
+    if p2p is not None:
+        res["p2p"] = p2p
     if with_cpu and rank == 0:
         # the reference's own path for this step: torch autograd + torch.optim.Adagrad on the host cores (oracle/train_oracle.py)
         from oracle.train_oracle import TorchBackend
