@@ -288,6 +288,55 @@ int pg_ilqr_commit_chunked(int dtype, int integrator, int64_t B, int32_t T, int3
                            void* xbar, void* ubar, const void* KK, const void* kk, const double* ulim, const void* xS,
                            void* KK_acc, void* kk_acc, const int32_t* index, const int32_t* count, void* stream);
 
+/* Terminal value of the FINAL backward pass, per trajectory, on the device (iLQR.backward_pass(final=True), ilqr.py:246-260):
+ *   x* = argmin fcost(x) started at the trajectory's terminal state (the reference: scipy.optimize.minimize; here Newton's method
+ *        on the generated gradient and Hessian of the final cost -- one step for the quadratic final costs of the examples),
+ *   Ad = I + A(x*, 0) dt, Bd = B(x*, 0) dt, (Q, R, N) = the expansion of c dt at (x*, 0, t_final)   (ilqr.py:250-256),
+ *   P  = scipy.linalg.solve_discrete_are(Ad, Bd, Q, R, s=N), by the structure-preserving doubling algorithm.
+ * xbar [T+1, n, B] -> P [n, n, B] (symmetric; hand it to pg_ilqr_backward as Vxx_T), x_eq [n, B] or NULL, ok [B] (u8: both
+ * iterations converged).  fp64 only; lin_mode 0 (analytic Jacobians) or 1 (central differences). */
+int pg_ilqr_terminal_value(int dtype, int64_t B, int32_t T, double dt, double t_final, int32_t lin_mode, const void* xbar, void* P,
+                           void* x_eq, uint8_t* ok, const int32_t* index, const int32_t* count, void* stream);
+
+/* Fused tail solver (the "persistent fused loop" of iLQR.run_optim, ilqr.py:399-485): ONE launch that finishes every trajectory
+ * of a work list.  A warp owns a trajectory and iterates backward sweep (lane 0) -> all n_alpha line-search candidates side by
+ * side (one lane each) -> the reference's decision logic -> winner copied into the nominal trajectory, until that
+ * trajectory stops (status != 0 or iters == select.max_iters), then takes the next one.  The arithmetic and every decision
+ * are those of pg_ilqr_backward / pg_ilqr_forward / pg_ilqr_select / pg_ilqr_commit (bit-identical results), without the
+ * launch boundaries, the host and the slowest trajectory pacing everybody; meant for the tail of a solve, when the running
+ * trajectories no longer fill the GPU.  All arrays as in those functions; the struct holds plain pointers and sizes only.
+ * Supported: fp64, lin_mode 0 / 1 (no PG_LIN_COST_FD), no externally supplied Jacobians or terminal value; else
+ * PG_E_UNSUPPORTED (run the launch-per-step functions instead). */
+typedef struct {
+    int32_t dtype, integrator, T, S, n_alpha, reg_type, lin_mode, constrained; /* constrained: clip with ulim (both passes) */
+    int64_t B;
+    double dt, terminal_cost;
+    double ulim[2];
+    pg_select_params_t select;
+    const void* x0;                                   /* [n, B] */
+    void *xbar, *ubar, *KK, *kk;                      /* nominal trajectory and accepted gains: in / out */
+    void *KKc, *kkc, *dV, *gnorm;                     /* candidate gains and backward-pass outputs (scratch, as pg_ilqr_backward) */
+    uint8_t* bw_success;
+    void* cost_cand;                                  /* [n_alpha, B] line-search outputs (scratch, as pg_ilqr_forward) */
+    uint8_t *diverged, *terminated;
+    void* xN;                                         /* [n_alpha, n, B] or NULL */
+    void *cost, *mu, *mu_d, *dcost;                   /* solver state, as pg_ilqr_select */
+    uint8_t* success_gradient;
+    int32_t *status, *iters;
+    void* alpha_best;
+    uint8_t *accept, *active;
+    int32_t* last_tried;                              /* or NULL */
+    const int32_t *index, *count;                     /* work list (device) and its length (device, <= max_count) */
+    int32_t max_count;
+    void* workspace;                                  /* pg_ilqr_solve_workspace_bytes(T, max_count) bytes */
+    int64_t workspace_bytes;
+} pg_ilqr_solve_t;
+int64_t pg_ilqr_solve_workspace_bytes(int32_t T, int32_t max_count);
+/* Trajectories the fused solver works on simultaneously (one resident warp each); a longer work list is handed out through a
+ * ticket counter as warps become free.  Switching to pg_ilqr_solve pays once the running trajectories fit. */
+int32_t pg_ilqr_solve_capacity(void);
+int pg_ilqr_solve(const pg_ilqr_solve_t* args, void* stream);
+
 /* o [n_obs,B] = observation(x [n,B]) : angle -> [cos, sin] (helpers.py:20-29). */
 int pg_observe(int dtype, int64_t B, const void* x, void* o, void* stream);
 

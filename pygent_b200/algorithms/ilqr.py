@@ -173,7 +173,14 @@ class iLQR(Algorithm):
         self._have_gains = False
         # serial line search in two launches: work lists "backward pass succeeded" and "no success among the first alphas"
         self.first_alphas = 4
-        self.tail_threshold = int(os.environ.get("PG_ILQR_TAIL", "2048"))  # live trajectories below which iterate() runs its tail variant
+        # live trajectories below which the solve switches to its tail form: the fused per-trajectory solver once they all fit
+        # on the GPU at one warp each (lib.solve_capacity(): 1,184 on a B200), else iterate()'s one-launch line search
+        cap = self.lib.solve_capacity() if (self.environment.device.type == "cuda" and not self.learned) else 0
+        self.tail_threshold = int(os.environ.get("PG_ILQR_TAIL", str(cap if cap > 0 else 2048)))
+        self.final_on_device = None  # final backward pass: None = per-trajectory on the device when B > 32, host (scipy) otherwise
+        self.final_status = None
+        self._trace = None  # list: (iteration, live trajectories, host time) per readback, for tools/time_fused_tail.py
+        self.fused_tail = os.environ.get("PG_ILQR_FUSED_TAIL", "1") != "0"  # ... or, better, the fused per-trajectory solver finishes the solve
         self._tail = False
         self._ls_small = lib.split_search_threshold(self._x0.device)
         self._ls_idx = [i32(B), i32(B)]
@@ -237,6 +244,7 @@ class iLQR(Algorithm):
         """Initial trajectory with u = 0 (ilqr.py:501-516): cost = sum c*dt + fcost(x_N)*dt."""
         self._x0 = self.environment._to_dev(self.environment._x0_host, self.xDim)
         self._ubar.zero_()
+        self._have_nominal = True
         if self.learned:
             env = self.environment
             X = env.dynamics.rollout_device(self._x0, self.dt, T=self.steps, precision=env.precision)
@@ -260,7 +268,7 @@ class iLQR(Algorithm):
         self._st["iters"].zero_()
         self._st["active"].fill_(1)
         self._st["success_gradient"].zero_()
-        if self.init:
+        if self.init or not getattr(self, "_have_nominal", False):  # the reference also initialises when it has no plan yet
             self.init_trajectory()
 
     def cost_fnc(self, x, u, t, mod):
@@ -338,16 +346,42 @@ class iLQR(Algorithm):
             P = np.broadcast_to(P[0], (self.B,) + P.shape[1:])
         return torch.as_tensor(np.ascontiguousarray(np.moveaxis(P, 0, -1)), dtype=self.dtype, device=self.environment.device)
 
+    def _terminal_value_device(self):
+        """P [n, n, B] per trajectory on the device (lib.terminal_value: Newton on the final cost + the doubling algorithm
+        for the Riccati equation); (P, ok [B] bool) or None where the device route does not apply (learned dynamics, fp32,
+        `finite_diff=True`)."""
+        if self.learned or self.finite_diff or self.dtype != torch.float64:
+            return None
+        r = self.lib.terminal_value(self._xbar, self.dt, float(self.tt[-1]), lin_mode=self.lin_mode)
+        if r is None:
+            return None
+        return r["P"], r["ok"].bool()
+
     def _final_backpass(self):
-        """`self.mu = 0; backward_pass(final=True); if success: self.KK, self.kk = KK, kk` for every trajectory."""
-        try:
-            P = self._P_cache if self._P_cache is not None else self._terminal_value()
-        except (np.linalg.LinAlgError, ValueError):  # no stabilising solution: the reference would raise here
-            return
+        """`self.mu = 0; backward_pass(final=True); if success: self.KK, self.kk = KK, kk` for every trajectory.
+        Batches larger than 32 solve their equilibrium / Riccati problems on the device, one per trajectory
+        (`final_on_device`; small batches keep the host route, which calls the reference's own scipy functions)."""
+        converged = None
+        if self._P_cache is not None:
+            P = self._P_cache
+        else:
+            dev_route = self._terminal_value_device() if (self.final_on_device if self.final_on_device is not None else self.B > 32) else None
+            if dev_route is not None:
+                P, converged = dev_route
+            else:
+                try:
+                    P = self._terminal_value()
+                except (np.linalg.LinAlgError, ValueError) as e:
+                    # no stabilising solution: the reference raises here (scipy.linalg.solve_discrete_are); so do we
+                    self.final_status = "failed: %s" % e
+                    raise
         if self.cache_terminal_value:
             self._P_cache = P
         r = self._backward(Vxx_T=P)
         ok = r["success"].bool()
+        if converged is not None:
+            ok = ok & converged  # no terminal value, no final gains for that trajectory (its iLQR gains stay)
+        self.final_status = "ok"
         self._KK.copy_(torch.where(ok, self._KKc, self._KK))
         self._kk.copy_(torch.where(ok, self._kkc, self._kk))
         self._st["mu"].zero_()
@@ -530,12 +564,39 @@ class iLQR(Algorithm):
             if pending is not None:
                 pending[0].synchronize()
                 live = int(flags[pending[1]])
+                if self._trace is not None:
+                    self._trace.append((it - n, live, time.perf_counter()))  # count after iteration it - n, seen now
                 if live == 0:
                     break
                 if not self._tail and not self.learned and live <= self.tail_threshold:
+                    if self.fused_tail and self._solve_tail():
+                        # the fused tail solver (pg_ilqr_solve) has been enqueued behind the iterations already in flight: it
+                        # finishes every trajectory that is still running when it starts, in one launch
+                        break
                     self._tail, graph = True, None  # the count only falls: switch the line search for good (new graph)
             pending = (ev, slot)
         self._graph = graph  # keep it alive until the results have been read
+
+    def _solve_tail(self):
+        """Finish the solve with ONE launch of the fused per-trajectory solver (lib.ilqr_solve): every trajectory on the
+        current work list is iterated to its stopping test by a warp of its own.  Results and decisions are bit-identical to
+        continuing with iterate() (same device functions).  Returns False where the fused kernel does not apply."""
+        if self.learned or self.finite_diff or self.dtype != torch.float64 or self.lin_mode not in (0, 1) or self.lib.m != 1:
+            # (m = 2: the Car's active-set sweep rounds differently once inlined into the fused kernel -- iteration counts then
+            # differ by rounding-level decisions; it keeps the launch-per-step tail, which is bit-identical by the tests)
+            return False
+        cur = self._cur
+        work = (self._idx[cur], self._cnt[cur])
+        ok = self.lib.ilqr_solve(self._sel, self._x0, self._xbar, self._ubar, self._KK, self._kk, self._KKc, self._kkc, self._bw,
+                                 self._fw, self._st, work, max_count=min(self.B, max(self.tail_threshold, 1)), S=self.substeps, dt=self.dt,
+                                 integrator=self.integrator, reg_type=self.regType, lin_mode=self.lin_mode, ulim=self._ulim(),
+                                 terminal_cost=float(self.environment.terminal_cost), last_tried=self._last_tried)
+        if ok:
+            self._cnt[1 - cur].zero_()
+            self._cur = 1 - cur
+            self._n_active = self._cnt[self._cur]
+            self._have_gains = True
+        return ok
 
     def _capture_two_iterations(self):
         """CUDA graph of iterate(); iterate() -- raw capture on a side stream (`with torch.cuda.graph` would first empty

@@ -62,8 +62,10 @@ def build_problem(spec, force=False, verbose=False, extra_flags=()):
             "there is no CPU fallback (run __graft_entry__.build() where nvcc exists)" % so)
     os.makedirs(CACHE, exist_ok=True)
     hdr = os.path.join(CACHE, "pg_%s_%s.cuh" % (spec.system.name, key))
-    with open(hdr, "w") as fh:
+    hdr_tmp = hdr + ".tmp%d" % os.getpid()  # several ranks may build the same problem at once: never expose a half-written header
+    with open(hdr_tmp, "w") as fh:
         fh.write(spec.header(key))
+    os.replace(hdr_tmp, hdr)
     tmp = so + ".tmp%d" % os.getpid()
     cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ["-DPG_PROBLEM_HEADER=\"%s\"" % hdr,
                                                       os.path.join(CSRC, "pg_abi.cu"), "-o", tmp]

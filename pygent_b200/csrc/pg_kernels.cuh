@@ -521,28 +521,14 @@ struct Nominal {  // gains and nominal point of one control interval
 template <typename P>
 constexpr int forward_alphas_per_cta() { return P::N >= 8 ? 8 : MAX_ALPHAS; }
 
+// The closed-loop rollout of ONE (trajectory b, candidate ia) pair -- the body of K2, and what lane ia of a warp runs in the
+// fused tail solver.  Trajectory outputs go to Xo / Uo, whose element (k, i) lives at Xo[(k * N + i) * os + oo]: the nominal
+// arrays and the candidate arrays of K2 have os = B, oo = b; the fused solver keeps a warp's candidates lane-minor.
 template <typename P, typename T, int INTEG, bool COMMIT>
-__global__ void __launch_bounds__(32 * forward_alphas_per_cta<P>()) ilqr_forward_kernel(const ForwardArgs<T> a) {
-    const typename P::template Ctx<T> m;
+__device__ __forceinline__ void forward_body(const typename P::template Ctx<T>& m, const ForwardArgs<T>& a, const int64_t b, const int ia,
+                                             T* Xo, T* Uo, const int64_t os, const int64_t oo) {
     constexpr int N = P::N, M = P::M;
     const int64_t B = a.B;
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int ia = blockIdx.y * blockDim.y + threadIdx.y;
-    int64_t b = tid;
-    if (a.index) {  // compacted list of running trajectories (written by ilqr_select_kernel)
-        if (tid >= *a.count) return;
-        b = a.index[tid];
-    } else if (b >= B) {
-        return;
-    }
-    if constexpr (COMMIT) {
-        if (!a.accept[b]) return;
-    } else {
-        if (a.active && !a.active[b]) return;
-        int lo, hi;
-        alpha_window(a, lo, hi);
-        if (ia < lo || ia >= hi) return;
-    }
     const T alpha = a.alpha_dev ? a.alpha_dev[b] : a.alphas[ia];
     const T* xbar = COMMIT ? a.xbar_io : a.xbar;
     const T* ubar = COMMIT ? a.ubar_io : a.ubar;
@@ -552,15 +538,6 @@ __global__ void __launch_bounds__(32 * forward_alphas_per_cta<P>()) ilqr_forward
     bool div = false;
 #pragma unroll
     for (int i = 0; i < N; i++) div |= (x[i] > T(1e8));
-    T* Xo = nullptr;
-    T* Uo = nullptr;
-    if constexpr (COMMIT) {
-        Xo = a.xbar_io;
-        Uo = a.ubar_io;
-    } else {
-        if (a.X_out) Xo = a.X_out + (int64_t)ia * (a.T_steps + 1) * N * B;
-        if (a.U_out) Uo = a.U_out + (int64_t)ia * a.T_steps * M * B;
-    }
     const T h = a.dt / T(a.S);
     T cost = T(0), t = T(0);  // environment.reset(x0) => tt = [0] (ilqr.py:199)
     bool term = false;
@@ -568,7 +545,7 @@ __global__ void __launch_bounds__(32 * forward_alphas_per_cta<P>()) ilqr_forward
     if (a.T_steps > 0) nxt.load(a.KK, a.kk, xbar, ubar, 0, B, b);
     if (Xo) {
 #pragma unroll
-        for (int i = 0; i < N; i++) Xo[i * B + b] = x[i];
+        for (int i = 0; i < N; i++) Xo[i * os + oo] = x[i];
     }
     int sc = 0;  // next snapshot
     for (int k = 0; k < a.T_steps; k++) {
@@ -600,7 +577,7 @@ __global__ void __launch_bounds__(32 * forward_alphas_per_cta<P>()) ilqr_forward
         }
         if (Xo) {
 #pragma unroll
-            for (int i = 0; i < N; i++) Xo[((int64_t)(k + 1) * N + i) * B + b] = x[i];
+            for (int i = 0; i < N; i++) Xo[((int64_t)(k + 1) * N + i) * os + oo] = x[i];
         }
         if constexpr (!COMMIT) {
             if (a.xS && sc < a.n_snap && k + 1 == a.snap[sc + 1]) {  // end of chunk sc
@@ -611,7 +588,7 @@ __global__ void __launch_bounds__(32 * forward_alphas_per_cta<P>()) ilqr_forward
         }
         if (Uo) {
 #pragma unroll
-            for (int r = 0; r < M; r++) Uo[((int64_t)k * M + r) * B + b] = u[r];
+            for (int r = 0; r < M; r++) Uo[((int64_t)k * M + r) * os + oo] = u[r];
         }
         if constexpr (COMMIT) {
             if (k < a.Tk) {  // self.KK = KK; self.kk = kk (ilqr.py:463-464)
@@ -633,6 +610,40 @@ __global__ void __launch_bounds__(32 * forward_alphas_per_cta<P>()) ilqr_forward
             for (int i = 0; i < N; i++) a.xN_out[((int64_t)ia * N + i) * B + b] = x[i];
         }
     }
+}
+
+template <typename P, typename T, int INTEG, bool COMMIT>
+__global__ void __launch_bounds__(32 * forward_alphas_per_cta<P>()) ilqr_forward_kernel(const ForwardArgs<T> a) {
+    const typename P::template Ctx<T> m;
+    constexpr int N = P::N, M = P::M;
+    const int64_t B = a.B;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int ia = blockIdx.y * blockDim.y + threadIdx.y;
+    int64_t b = tid;
+    if (a.index) {  // compacted list of running trajectories (written by ilqr_select_kernel)
+        if (tid >= *a.count) return;
+        b = a.index[tid];
+    } else if (b >= B) {
+        return;
+    }
+    if constexpr (COMMIT) {
+        if (!a.accept[b]) return;
+    } else {
+        if (a.active && !a.active[b]) return;
+        int lo, hi;
+        alpha_window(a, lo, hi);
+        if (ia < lo || ia >= hi) return;
+    }
+    T* Xo = nullptr;
+    T* Uo = nullptr;
+    if constexpr (COMMIT) {
+        Xo = a.xbar_io;
+        Uo = a.ubar_io;
+    } else {
+        if (a.X_out) Xo = a.X_out + (int64_t)ia * (a.T_steps + 1) * N * B;
+        if (a.U_out) Uo = a.U_out + (int64_t)ia * a.T_steps * M * B;
+    }
+    forward_body<P, T, INTEG, COMMIT>(m, a, b, ia, Xo, Uo, B, b);
 }
 
 // ---- K2b: the candidate rollouts, load-balanced -----------------------------------------------------------------
@@ -1011,21 +1022,12 @@ __device__ __forceinline__ bool np_isclose(T a, T b, T atol) {  // np.isclose(a,
     return fabs(a - b) <= atol + T(1e-5) * fabs(b);
 }
 
+// The backward sweep of ONE trajectory b (the body of K3; also lane 0's part of the fused tail solver ilqr_solve_kernel).
 template <typename P, typename T, int LIN, bool CFD = false>
-__global__ void __launch_bounds__(128) ilqr_backward_kernel(const BackwardArgs<T> a) {
-    const typename P::template Ctx<T> m;
+__device__ __forceinline__ void backward_body(const typename P::template Ctx<T>& m, const BackwardArgs<T>& a, const int64_t b) {
     constexpr int N = P::N, M = P::M;
     static_assert(M <= 2, "control dimension > 2 not supported by the closed-form Quu solve");
     const int64_t B = a.B;
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t b = tid;
-    if (a.index) {
-        if (tid >= *a.count) return;
-        b = a.index[tid];
-    } else if (b >= B) {
-        return;
-    }
-    if (a.active && !a.active[b]) return;
     const T mu = a.mu[b];
     const T dt = a.dt;
     const int Ts = a.T_steps;
@@ -1382,6 +1384,253 @@ __global__ void __launch_bounds__(128) ilqr_backward_kernel(const BackwardArgs<T
     a.success[b] = ok ? 1 : 0;
 }
 
+template <typename P, typename T, int LIN, bool CFD = false>
+__global__ void __launch_bounds__(128) ilqr_backward_kernel(const BackwardArgs<T> a) {
+    const typename P::template Ctx<T> m;
+    const int64_t B = a.B;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t b = tid;
+    if (a.index) {
+        if (tid >= *a.count) return;
+        b = a.index[tid];
+    } else if (b >= B) {
+        return;
+    }
+    if (a.active && !a.active[b]) return;
+    backward_body<P, T, LIN, CFD>(m, a, b);
+}
+
+// ---- terminal value of the final backward pass (iLQR.backward_pass(final=True), ilqr.py:246-260) ---------------------------
+// Per trajectory, on the device: (1) the equilibrium of the final cost, x* = argmin fcost(x) started at x_N (the reference
+// calls scipy.optimize.minimize; here Newton's method on the generated gradient / Hessian, exact in one step for the
+// quadratic final costs of every shipped example); (2) Ad, Bd and the cost expansion at (x*, u = 0, t = t_N) exactly as the
+// backward sweep forms them; (3) P = the stabilising solution of the discrete algebraic Riccati equation
+//       P = Ad' P Ad - (Ad' P Bd + N)(R + Bd' P Bd)^-1 (Bd' P Ad + N') + Q         (scipy.linalg.solve_discrete_are(A, B, Q, R, s=N))
+// by the structure-preserving doubling algorithm on (A0, G0, H0) = (Ad - Bd R^-1 N', Bd R^-1 Bd', Q - N R^-1 N'):
+//       W = I + G H;  A+ = A W^-1 A;  G+ = G + A W^-1 G A';  H+ = H + A' H W^-1 A;      H_k -> P quadratically
+// (Chu, Fan, Lin, Wang 2004).  One thread per trajectory, n <= 8 matrices in registers / local memory.
+template <typename T>
+struct TerminalArgs {
+    int64_t B;
+    int T_steps;
+    T dt, t_final;
+    const T* xbar;   // [T+1, n, B]
+    T* P_out;        // [n, n, B]
+    T* xeq_out;      // [n, B] or NULL
+    uint8_t* ok_out; // [B]: 1 = Newton and the doubling iteration converged
+    const int32_t* index;
+    const int32_t* count;
+};
+
+// solve W Z = R in place (Gauss elimination with partial pivoting), W [n x n], R [n x nr]; returns false if singular
+template <typename T, int N, int NR>
+__device__ __forceinline__ bool gauss_solve(T (&W)[N * N], T (&R)[N * NR]) {
+    for (int c = 0; c < N; c++) {
+        int piv = c;
+        T best = fabs(W[c * N + c]);
+        for (int r = c + 1; r < N; r++) {
+            const T v = fabs(W[r * N + c]);
+            if (v > best) {
+                best = v;
+                piv = r;
+            }
+        }
+        if (!(best > T(0))) return false;
+        if (piv != c) {
+            for (int j = 0; j < N; j++) {
+                const T t = W[c * N + j];
+                W[c * N + j] = W[piv * N + j];
+                W[piv * N + j] = t;
+            }
+            for (int j = 0; j < NR; j++) {
+                const T t = R[c * NR + j];
+                R[c * NR + j] = R[piv * NR + j];
+                R[piv * NR + j] = t;
+            }
+        }
+        const T inv = T(1) / W[c * N + c];
+        for (int r = c + 1; r < N; r++) {
+            const T f = W[r * N + c] * inv;
+            if (f != T(0)) {
+                for (int j = c + 1; j < N; j++) W[r * N + j] -= f * W[c * N + j];
+                for (int j = 0; j < NR; j++) R[r * NR + j] -= f * R[c * NR + j];
+            }
+        }
+    }
+    for (int c = N - 1; c >= 0; c--) {
+        const T inv = T(1) / W[c * N + c];
+        for (int j = 0; j < NR; j++) {
+            T acc = R[c * NR + j];
+            for (int k = c + 1; k < N; k++) acc -= W[c * N + k] * R[k * NR + j];
+            R[c * NR + j] = acc * inv;
+        }
+    }
+    return true;
+}
+
+template <typename P, typename T, int LIN>
+__global__ void __launch_bounds__(64) terminal_value_kernel(const TerminalArgs<T> a) {
+    const typename P::template Ctx<T> m;
+    constexpr int N = P::N, M = P::M;
+    const int64_t B = a.B;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t b = tid;
+    if (a.index) {
+        if (tid >= *a.count) return;
+        b = a.index[tid];
+    } else if (b >= B) {
+        return;
+    }
+    T x[N], u[M];
+#pragma unroll
+    for (int i = 0; i < N; i++) x[i] = a.xbar[((int64_t)a.T_steps * N + i) * B + b];
+#pragma unroll
+    for (int r = 0; r < M; r++) u[r] = T(0);
+    bool ok = true;
+    // (1) equilibrium of the final cost: Newton steps x <- x - Cfxx^-1 cfx
+    for (int it = 0; it < 50; it++) {
+        T g[N], Hm[N * N];
+        P::fcost_derivs(m, x, g, Hm);
+        T gmax = T(0);
+#pragma unroll
+        for (int i = 0; i < N; i++) gmax = fmax(gmax, fabs(g[i]));
+        if (!(gmax > T(0))) break;
+        T rhs[N * 1];
+#pragma unroll
+        for (int i = 0; i < N; i++) rhs[i] = g[i];
+        if (!gauss_solve<T, N, 1>(Hm, rhs)) {
+            ok = false;
+            break;
+        }
+        T dmax = T(0), xmax = T(0);
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            x[i] -= rhs[i];
+            dmax = fmax(dmax, fabs(rhs[i]));
+            xmax = fmax(xmax, fabs(x[i]));
+        }
+        if (dmax <= T(1e-14) * (xmax + T(1))) break;
+        if (it == 49) ok = false;
+    }
+    // (2) linearisation and cost expansion at (x*, 0, t_N), as the backward sweep forms them
+    T A[N * N], Bd[N * M];
+    if constexpr (LIN == 0) P::AB(m, x, u, A, Bd);
+    else fd_AB<P, T>(m, x, u, A, Bd);
+    const T dt = a.dt;
+#pragma unroll
+    for (int i = 0; i < N; i++)
+#pragma unroll
+        for (int j = 0; j < N; j++) A[i * N + j] = A[i * N + j] * dt + (i == j ? T(1) : T(0));
+#pragma unroll
+    for (int i = 0; i < N * M; i++) Bd[i] = Bd[i] * dt;
+    T cx[N], cu[M], Q[N * N], R[M * M], Nx[N * M];
+    P::cost_derivs(m, x, u, a.t_final, cx, cu, Q, R, Nx);
+#pragma unroll
+    for (int i = 0; i < N * N; i++) Q[i] *= dt;
+#pragma unroll
+    for (int i = 0; i < M * M; i++) R[i] *= dt;
+#pragma unroll
+    for (int i = 0; i < N * M; i++) Nx[i] *= dt;
+    // R^-1 (m <= 2)
+    T Ri[M * M];
+    if constexpr (M == 1) {
+        Ri[0] = T(1) / R[0];
+    } else {
+        const T det = R[0] * R[3] - R[1] * R[2];
+        Ri[0] = R[3] / det;
+        Ri[1] = -R[1] / det;
+        Ri[2] = -R[2] / det;
+        Ri[3] = R[0] / det;
+    }
+    // BR = Bd R^-1 [n x m], NR = N R^-1 [n x m]
+    T BR[N * M], NR[N * M];
+    for (int i = 0; i < N; i++)
+        for (int r = 0; r < M; r++) {
+            T s1 = T(0), s2 = T(0);
+            for (int q = 0; q < M; q++) {
+                s1 += Bd[i * M + q] * Ri[q * M + r];
+                s2 += Nx[i * M + q] * Ri[q * M + r];
+            }
+            BR[i * M + r] = s1;
+            NR[i * M + r] = s2;
+        }
+    // A0 = Ad - BR N', G0 = BR Bd', H0 = Q - NR N'
+    T G[N * N], H[N * N];
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < N; j++) {
+            T s1 = T(0), s2 = T(0), s3 = T(0);
+            for (int r = 0; r < M; r++) {
+                s1 += BR[i * M + r] * Nx[j * M + r];
+                s2 += BR[i * M + r] * Bd[j * M + r];
+                s3 += NR[i * M + r] * Nx[j * M + r];
+            }
+            A[i * N + j] -= s1;
+            G[i * N + j] = s2;
+            H[i * N + j] = Q[i * N + j] - s3;
+        }
+    // (3) doubling
+    bool conv = false;
+    for (int it = 0; it < 60 && !conv; it++) {
+        T W[N * N], Z[N * 2 * N];  // Z = [A | G] -> W^-1 [A | G]
+        for (int i = 0; i < N; i++)
+            for (int j = 0; j < N; j++) {
+                T s = (i == j) ? T(1) : T(0);
+                for (int k = 0; k < N; k++) s += G[i * N + k] * H[k * N + j];
+                W[i * N + j] = s;
+                Z[i * 2 * N + j] = A[i * N + j];
+                Z[i * 2 * N + N + j] = G[i * N + j];
+            }
+        if (!gauss_solve<T, N, 2 * N>(W, Z)) {
+            ok = false;
+            break;
+        }
+        // A+ = A Z1; G+ = G + A Z2 A'; H+ = H + A' H Z1
+        T A1[N * N], HZ[N * N], AZ2[N * N];
+        for (int i = 0; i < N; i++)
+            for (int j = 0; j < N; j++) {
+                T s1 = T(0), s2 = T(0), s3 = T(0);
+                for (int k = 0; k < N; k++) {
+                    s1 += A[i * N + k] * Z[k * 2 * N + j];
+                    s2 += H[i * N + k] * Z[k * 2 * N + j];
+                    s3 += A[i * N + k] * Z[k * 2 * N + N + j];
+                }
+                A1[i * N + j] = s1;
+                HZ[i * N + j] = s2;
+                AZ2[i * N + j] = s3;
+            }
+        T dmax = T(0), hmax = T(0);
+        T G1[N * N], H1[N * N];
+        for (int i = 0; i < N; i++)
+            for (int j = 0; j < N; j++) {
+                T s1 = T(0), s2 = T(0);
+                for (int k = 0; k < N; k++) {
+                    s1 += AZ2[i * N + k] * A[j * N + k];
+                    s2 += A[k * N + i] * HZ[k * N + j];
+                }
+                G1[i * N + j] = G[i * N + j] + s1;
+                H1[i * N + j] = H[i * N + j] + s2;
+                dmax = fmax(dmax, fabs(s2));
+                hmax = fmax(hmax, fabs(H1[i * N + j]));
+            }
+        for (int i = 0; i < N * N; i++) {
+            A[i] = A1[i];
+            G[i] = G1[i];
+            H[i] = H1[i];
+        }
+        conv = dmax <= T(1e-15) * hmax;
+        if (!(hmax == hmax) || hmax > T(1e300)) {
+            ok = false;
+            break;
+        }
+    }
+    ok = ok && conv;
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < N; j++) a.P_out[((int64_t)(i * N + j)) * B + b] = T(0.5) * (H[i * N + j] + H[j * N + i]);
+    if (a.xeq_out)
+        for (int i = 0; i < N; i++) a.xeq_out[(int64_t)i * B + b] = x[i];
+    a.ok_out[b] = ok ? 1 : 0;
+}
+
 // ---- K4: line-search decision, mu schedule, stopping tests (iLQR.run_optim, ilqr.py:407-485) -------
 struct SelectParams {
     int n_alpha, parallel, iteration, max_iters;
@@ -1467,15 +1716,21 @@ __device__ __forceinline__ int select_one(const SelectArgs<T>& a, const int64_t 
         }
         if (a.last_tried) a.last_tried[b] = n_tried - 1;
         if (success_fw) {
-            // best_idx = np.argmin(cost_list): first minimum, a NaN wins (ilqr.py:458)
-            int best = 0;
-            T bc = a.cost_cand[b];
-            for (int i = 1; i < n_tried; i++) {
+            // best_idx = np.argmin(cost_list): first minimum (ilqr.py:458).  A NaN candidate never wins here: the reference
+            // cannot produce one on this path (numpy's sin/cos are finite for any finite angle), while pg::sincos returns NaN
+            // beyond |x| >= 2^30 -- a candidate that diverged towards -inf, which the one-sided test x > 1e8 does not flag.
+            int best = -1;
+            T bc = T(0);
+            for (int i = 0; i < n_tried; i++) {
                 const T c = a.cost_cand[(int64_t)i * B + b];
-                if (!(bc != bc) && (c < bc || c != c)) {
+                if (c == c && (best < 0 || c < bc)) {
                     bc = c;
                     best = i;
                 }
+            }
+            if (best < 0) {  // every tried candidate is NaN (cannot pass the z-test, so this is unreachable): keep alpha 0
+                best = 0;
+                bc = a.cost_cand[b];
             }
             a.cost[b] = bc;
             a.alpha_best[b] = T(p.alphas[best]);
@@ -1521,6 +1776,149 @@ __global__ void ilqr_select_kernel(const SelectArgs<T> a) {
         if (lane == __ffs(ballot) - 1) base = atomicAdd(a.n_active, __popc(ballot));
         base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
         if (keep && a.index_out) a.index_out[base + __popc(ballot & ((1u << lane) - 1))] = (int32_t)b;
+    }
+}
+
+// ---- fused tail solver: one warp finishes one trajectory (iLQR.run_optim, ilqr.py:399-485) ---------------------------------
+// Once few trajectories are still running, an iteration is a chain of dependent launches (backward sweep -> line search ->
+// decision -> commit), each a latency-bound chain of T steps, with launch gaps between them and the slowest trajectory
+// pacing everybody.  Trajectories are independent, so here ONE launch finishes them: a warp owns a trajectory and loops
+//     lane 0        backward sweep (backward_body: exactly K3's arithmetic)
+//     lanes 0..10   the 11 line-search candidates side by side (forward_body: exactly K2's arithmetic), each lane keeping
+//                   its trajectory in the warp's candidate block (lane-minor: a warp store is one 128-byte line)
+// on a compact private copy of the trajectory (nominal states and controls, gains), written back when it stops,
+//     lane 0        the reference's decision logic (select_one: exactly K4's)
+//     all lanes     winner -> nominal trajectory, candidate gains -> accepted gains (a copy: no re-integration)
+// until the trajectory stops (converged / mu_max / max_iters), then takes the next one from the list.  No grid-wide
+// synchronisation, no host in the loop, every decision bit-identical to the launch-per-step path (same device functions).
+template <typename T>
+struct SolveArgs {
+    BackwardArgs<T> bw;
+    ForwardArgs<T> fw;
+    SelectArgs<T> sel;
+    T* xbar;      // nominal trajectory, updated in place when a candidate is accepted
+    T* ubar;
+    T* KK_acc;    // accepted gains
+    T* kk_acc;
+    T* cand;      // [warps of the grid][solve_block_doubles(T)]: the private block of each warp (see ilqr_solve_kernel)
+    int32_t* ticket;  // next entry of the work list to hand out (zeroed by the host before the launch)
+    const int32_t* index;
+    const int32_t* count;
+};
+
+// Doubles of a warp's private block: the trajectory it is working on, compact (the batch-strided arrays give one useful word
+// per 32-byte sector once the running trajectories are sparse in the batch: the tail of a 16,384-trajectory solve then
+// misses L2 on every dependent load), its candidate and accepted gains, 16 scalars, and the 16 candidates lane-minor.
+template <typename P>
+__host__ __device__ constexpr size_t solve_block_doubles(int Ts) {
+    return (size_t)P::N + (size_t)(Ts + 1) * P::N + (size_t)Ts * P::M + 2 * ((size_t)Ts * P::M * P::N + (size_t)Ts * P::M) + 64 +
+           ((size_t)(Ts + 1) * P::N + (size_t)Ts * P::M) * 16;
+}
+
+template <typename P, typename T, int INTEG, int LIN>
+__global__ void __launch_bounds__(128) ilqr_solve_kernel(const SolveArgs<T> a) {
+    const typename P::template Ctx<T> m;
+    constexpr int N = P::N, M = P::M;
+    const int lane = threadIdx.x & 31;
+    const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int64_t B = a.fw.B;
+    const int Ts = a.fw.T_steps, nA = a.fw.n_alpha;
+    const int cnt = *a.count;
+    const int nX = (Ts + 1) * N, nU = Ts * M, nK = Ts * M * N;
+    // the warp's private block
+    T* px0 = a.cand + (size_t)warp * solve_block_doubles<P>(Ts);
+    T* pX = px0 + N;
+    T* pU = pX + nX;
+    T* pKc = pU + nU;
+    T* pkc = pKc + nK;
+    T* pKa = pkc + nU;
+    T* pka = pKa + nK;
+    T* ps = pka + nU;  // [0] mu, [1..2] dV, [3] gnorm, [16..31] candidate costs
+    uint8_t* pflag = reinterpret_cast<uint8_t*>(ps + 32);  // [0] backward success, [16..31] diverged, [32..47] terminated
+    T* Xc = ps + 64;
+    T* Uc = Xc + (size_t)nX * 16;
+    // the kernels' argument blocks, redirected to the private copy: batch size 1, trajectory 0
+    BackwardArgs<T> bw = a.bw;
+    bw.B = 1;
+    bw.mu = ps;
+    bw.xbar = pX;
+    bw.ubar = pU;
+    bw.KK = pKc;
+    bw.kk = pkc;
+    bw.dV = ps + 1;
+    bw.gnorm = ps + 3;
+    bw.success = pflag;
+    ForwardArgs<T> fw = a.fw;
+    fw.B = 1;
+    fw.x0 = px0;
+    fw.xbar = pX;
+    fw.ubar = pU;
+    fw.KK = pKc;
+    fw.kk = pkc;
+    fw.cost_out = ps + 16;
+    fw.diverged_out = pflag + 16;
+    fw.terminated_out = pflag + 32;
+    fw.xN_out = nullptr;
+    for (;;) {
+        // trajectories are handed out one at a time: a warp whose trajectory stops early takes the next one, so the few
+        // that run to max_iters never queue up behind each other on one warp
+        int w = 0;
+        if (lane == 0) w = atomicAdd(a.ticket, 1);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= cnt) break;
+        const int64_t b = a.index[w];
+        for (int e = lane; e < N; e += 32) px0[e] = a.fw.x0[(int64_t)e * B + b];
+        for (int e = lane; e < nX; e += 32) pX[e] = a.xbar[(int64_t)e * B + b];
+        for (int e = lane; e < nU; e += 32) pU[e] = a.ubar[(int64_t)e * B + b];
+        bool any_accept = false;
+        __syncwarp();
+        for (;;) {
+            if (lane == 0) {
+                ps[0] = a.sel.mu[b];
+                backward_body<P, T, LIN, false>(m, bw, 0);
+                a.bw.dV[b] = ps[1];
+                a.bw.dV[B + b] = ps[2];
+                a.bw.gnorm[b] = ps[3];
+                a.bw.success[b] = pflag[0];
+            }
+            __syncwarp();
+            if (pflag[0] && lane < nA) {
+                forward_body<P, T, INTEG, false>(m, fw, 0, lane, Xc, Uc, 16, lane);
+                a.fw.cost_out[(int64_t)lane * B + b] = ps[16 + lane];
+                a.fw.diverged_out[(int64_t)lane * B + b] = pflag[16 + lane];
+                if (a.fw.terminated_out) a.fw.terminated_out[(int64_t)lane * B + b] = pflag[32 + lane];
+                if (a.fw.xN_out) {
+#pragma unroll
+                    for (int i = 0; i < N; i++) a.fw.xN_out[((int64_t)lane * N + i) * B + b] = Xc[((size_t)Ts * N + i) * 16 + lane];
+                }
+            }
+            __syncwarp();
+            int status = 0;
+            if (lane == 0) status = select_one(a.sel, b);
+            status = __shfl_sync(0xffffffffu, status, 0);
+            if (a.sel.accept[b]) {  // self.xx, self.uu, self.KK, self.kk = the best candidate (ilqr.py:458-464)
+                const T ab = a.sel.alpha_best[b];
+                int best = 0;
+                for (int i = 0; i < nA; i++)
+                    if (T(a.sel.p.alphas[i]) == ab) best = i;
+                for (int e = lane; e < nX; e += 32) pX[e] = Xc[(size_t)e * 16 + best];
+                for (int e = lane; e < nU; e += 32) pU[e] = Uc[(size_t)e * 16 + best];
+                for (int e = lane; e < nK; e += 32) pKa[e] = pKc[e];
+                for (int e = lane; e < nU; e += 32) pka[e] = pkc[e];
+                any_accept = true;
+            }
+            __syncwarp();
+            if (status != 0) break;
+        }
+        if (any_accept) {  // the result back into the batch arrays
+            for (int e = lane; e < nX; e += 32) a.xbar[(int64_t)e * B + b] = pX[e];
+            for (int e = lane; e < nU; e += 32) a.ubar[(int64_t)e * B + b] = pU[e];
+            for (int e = lane; e < nK; e += 32) a.KK_acc[(int64_t)e * B + b] = pKa[e];
+            for (int e = lane; e < nU; e += 32) a.kk_acc[(int64_t)e * B + b] = pka[e];
+        }
+        for (int e = lane; e < nK; e += 32) a.bw.KK[(int64_t)e * B + b] = pKc[e];  // the last candidate gains (as K3 leaves them)
+        for (int e = lane; e < nU; e += 32) a.bw.kk[(int64_t)e * B + b] = pkc[e];
+        __syncwarp();
     }
 }
 

@@ -55,7 +55,8 @@ __device__ const double PG_SC_TABLE[16] = {
 // warps per scheduler and are bound by that chain, not by the pipe).  Coefficients are held in
 // registers (see opaque_load()).  Accuracy <= 1.6 ulp, absolute error < 1.8e-16, for |x| < 2^30
 // (checked against long-double libm on 2e7 points); outside that range, and for non-finite
-// input, the result is NaN -- the mechanical systems here flag |x| > 1e8 as diverged long before.
+// input, the result is NaN.  The line search's divergence test is one-sided (x > 1e8, as in the reference), so a state that
+// diverges towards -inf gets here: its cost is NaN, fails the z-test and is skipped by the argmin (select_one).
 // There is deliberately no call to the CUDA library slow path: its ABI spill sat in the hot loop.
 template <typename T>
 struct MathCtx;

@@ -37,6 +37,18 @@ class SelectParams(ctypes.Structure):
                 ("mu_min", _f64), ("mu_max", _f64), ("mu_d0", _f64)]
 
 
+class SolveArgs(ctypes.Structure):
+    """pg_ilqr_solve_t (include/pygent_b200.h): every array of the fused tail solver."""
+    _fields_ = [("dtype", _i32), ("integrator", _i32), ("T", _i32), ("S", _i32), ("n_alpha", _i32), ("reg_type", _i32),
+                ("lin_mode", _i32), ("constrained", _i32), ("B", _i64), ("dt", _f64), ("terminal_cost", _f64), ("ulim", _f64 * 2),
+                ("select", SelectParams), ("x0", _vp), ("xbar", _vp), ("ubar", _vp), ("KK", _vp), ("kk", _vp), ("KKc", _vp),
+                ("kkc", _vp), ("dV", _vp), ("gnorm", _vp), ("bw_success", _vp), ("cost_cand", _vp), ("diverged", _vp),
+                ("terminated", _vp), ("xN", _vp), ("cost", _vp), ("mu", _vp), ("mu_d", _vp), ("dcost", _vp),
+                ("success_gradient", _vp), ("status", _vp), ("iters", _vp), ("alpha_best", _vp), ("accept", _vp), ("active", _vp),
+                ("last_tried", _vp), ("index", _vp), ("count", _vp), ("max_count", _i32), ("workspace", _vp),
+                ("workspace_bytes", _i64)]
+
+
 # name -> argtypes (restype is always int); mirrors include/pygent_b200.h
 class AlphaWindow(ctypes.Structure):
     """pg_alpha_window (include/pygent_b200.h): which alphas one launch of a split serial line search evaluates."""
@@ -50,6 +62,8 @@ SIGNATURES = {
     "pg_rollout_random": [_i32, _i32, _i64, _i32, _i32, _f64, _f64, _vp, ctypes.c_uint64, _i32, _dp, _vp, _vp, _vp, _vp, _f64, _i32,
                           _vp, _i64, _vp],
     "pg_random_actions": [_i32, _i64, _i32, ctypes.c_uint64, _i32, _dp, _vp, _vp],
+    "pg_ilqr_solve": [ctypes.POINTER(SolveArgs), _vp],
+    "pg_ilqr_terminal_value": [_i32, _i64, _i32, _f64, _f64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "pg_ilqr_forward": [_i32, _i32, _i64, _i32, _i32, _f64, _i32, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _dp, _f64,
                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "pg_ilqr_forward_balanced": [_i32, _i32, _i64, _i32, _i32, _f64, _i32, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _dp, _f64,
@@ -142,6 +156,10 @@ class ProblemLibrary:
         self.dll.pg_rollout_workspace_bytes.restype = _i64
         self.dll.pg_ilqr_forward_workspace_bytes.argtypes = [_i64, _i32, _i32]
         self.dll.pg_ilqr_forward_workspace_bytes.restype = _i64
+        self.dll.pg_ilqr_solve_capacity.argtypes = []
+        self.dll.pg_ilqr_solve_capacity.restype = _i32
+        self.dll.pg_ilqr_solve_workspace_bytes.argtypes = [_i32, _i32]
+        self.dll.pg_ilqr_solve_workspace_bytes.restype = _i64
         self.dll.pg_ilqr_num_snapshots.argtypes = [_i32]
         self.dll.pg_ilqr_num_snapshots.restype = _i32
         self._workspace = {}
@@ -178,7 +196,8 @@ class ProblemLibrary:
 
     def queue_status_words(self):
         """int32 views of the status words of every live queue workspace (device tensors; reading them synchronises)."""
-        return [ws[:4].view(torch.int32) for ws in list(self._workspace.values()) + self._retired]
+        return [ws[:4].view(torch.int32) for k, ws in self._workspace.items() if k[0] != "solve"] + \
+               [ws[:4].view(torch.int32) for ws in self._retired]
 
     def check_queues(self):
         """Raise if a worker of a balanced (ticket-queue) kernel ever gave up waiting for its unit: the results of that
@@ -349,6 +368,66 @@ class ProblemLibrary:
         self._check(rc, "pg_ilqr_forward")
         self.launches += 1
         return {"cost": cost, "diverged": div, "terminated": term, "X": X, "U": Uo, "xN": xN}
+
+    def terminal_value(self, xbar, dt, t_final, lin_mode=0, work=None):
+        """pg_ilqr_terminal_value: xbar [T+1, n, B] -> dict(P [n, n, B], x_eq [n, B], ok [B] u8); None if this problem /
+        dtype is not supported on the device (the caller then uses the host route)."""
+        dtype, dev = xbar.dtype, xbar.device
+        T, n, B = xbar.shape[0] - 1, self.n, xbar.shape[2]
+        P = torch.empty((n, n, B), dtype=dtype, device=dev)
+        xe = torch.empty((n, B), dtype=dtype, device=dev)
+        ok = torch.zeros((B,), dtype=torch.uint8, device=dev)
+        rc = self.dll.pg_ilqr_terminal_value(_dtype_code(dtype), B, T, dt, t_final, lin_mode & 3, _ptr(xbar, dtype, (T + 1, n, B), "xbar"),
+                                             _ptr(P, dtype, (n, n, B), "P"), _ptr(xe, dtype, (n, B), "x_eq"), _ptr(ok, torch.uint8, (B,), "ok"),
+                                             *self._work(work, B), self._stream())
+        if rc == -2:
+            return None
+        self._check(rc, "pg_ilqr_terminal_value")
+        self.launches += 1
+        return {"P": P, "x_eq": xe, "ok": ok}
+
+    # -- fused tail solver -----------------------------------------------------------------------
+    def solve_capacity(self):
+        """Trajectories pg_ilqr_solve works on at once (resident warps of the fused solver on this device)."""
+        if not torch.cuda.is_available():
+            return 0
+        return int(self.dll.pg_ilqr_solve_capacity())
+
+    def ilqr_solve(self, sel, x0, xbar, ubar, KK, kk, KKc, kkc, bw, fw, st, work, max_count, S=4, dt=0.02, integrator=INTEG_RK4,
+                   reg_type=2, lin_mode=0, ulim=None, terminal_cost=0.0, last_tried=None):
+        """pg_ilqr_solve: ONE launch that finishes every trajectory of the work list `work` = (index, count) -- a warp per
+        trajectory loops backward sweep / 11 candidates side by side / decision / commit until the trajectory stops.
+        bw = dict(dV, gnorm, success), fw = dict(cost, diverged, terminated, xN), st = the solver state dict of ilqr_select.
+        Returns False if this configuration is not supported by the fused kernel (the caller keeps iterating)."""
+        dtype, dev = x0.dtype, x0.device
+        T, B = ubar.shape[0], x0.shape[1]
+        nbytes = int(self.dll.pg_ilqr_solve_workspace_bytes(T, int(max_count)))
+        key = ("solve", dev, _WS_STREAM_ALIAS if _WS_STREAM_ALIAS is not None else torch.cuda.current_stream(dev).cuda_stream)
+        ws = self._workspace.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = self._workspace[key] = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=dev)
+        a = SolveArgs()
+        a.dtype, a.integrator, a.T, a.S, a.n_alpha = _dtype_code(dtype), integrator, T, S, sel.n_alpha
+        a.reg_type, a.lin_mode, a.constrained, a.B = reg_type, lin_mode, 1 if ulim is not None else 0, B
+        a.dt, a.terminal_cost = dt, terminal_cost
+        for i, v in enumerate(ulim or []):
+            a.ulim[i] = float(v)
+        a.select = sel
+        p = lambda t: None if t is None else t.data_ptr()
+        a.x0, a.xbar, a.ubar, a.KK, a.kk, a.KKc, a.kkc = p(x0), p(xbar), p(ubar), p(KK), p(kk), p(KKc), p(kkc)
+        a.dV, a.gnorm, a.bw_success = p(bw["dV"]), p(bw["gnorm"]), p(bw["success"])
+        a.cost_cand, a.diverged, a.terminated, a.xN = p(fw["cost"]), p(fw["diverged"]), p(fw.get("terminated")), p(fw.get("xN"))
+        a.cost, a.mu, a.mu_d, a.dcost = p(st["cost"]), p(st["mu"]), p(st["mu_d"]), p(st["dcost"])
+        a.success_gradient, a.status, a.iters = p(st["success_gradient"]), p(st["status"]), p(st["iters"])
+        a.alpha_best, a.accept, a.active, a.last_tried = p(st["alpha_best"]), p(st["accept"]), p(st["active"]), p(last_tried)
+        a.index, a.count, a.max_count = p(work[0]), p(work[1]), int(max_count)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes
+        rc = self.dll.pg_ilqr_solve(ctypes.byref(a), self._stream())
+        if rc == -2:
+            return False
+        self._check(rc, "pg_ilqr_solve")
+        self.launches += 1
+        return True
 
     # -- K3 ------------------------------------------------------------------------------------
     def ilqr_backward(self, xbar, ubar, mu, dt=0.02, reg_type=2, lin_mode=None, ulim=None, active=None, out=None,

@@ -753,6 +753,7 @@ def test_tail_variant_changes_nothing():
     for thr in (0, 10 ** 9, 300):   # never / from the first count the host sees / when most have converged
         alg = solver("cart_pole", T, x0=x0, maxIters=80)
         alg.tail_threshold = thr
+        alg.fused_tail = False
         alg._ls_small = 64
         alg.run_optim()
         assert alg._tail == (thr > 0) or thr == 300   # (300: only if the host saw the count while it was that low)
@@ -761,3 +762,87 @@ def test_tail_variant_changes_nothing():
     for other in res[1:]:
         for p, q in zip(res[0], other):
             assert np.array_equal(p, q)
+
+
+@pytest.mark.parametrize("case,kw", [("cart_pole", {}), ("cart_pole", {"constrained": True}), ("double_parallel", {"parallel": True}),
+                                     ("pendulum", {"constrained": True}), ("car", {"constrained": True}), ("acrobot", {"regType": 1})])
+def test_fused_tail_solver_changes_nothing(case, kw):
+    """pg_ilqr_solve -- one launch in which a warp per trajectory loops backward sweep / all candidates side by side /
+    decision / commit until its trajectory stops -- against the launch-per-step loop: iteration counts, statuses, costs,
+    trajectories, gains, mu and the accepted alphas must be exactly equal, whether the fused solver takes over from the
+    first count the host sees or only once most trajectories have stopped (serial and parallel search, box constraints with
+    m = 1 and m = 2, analytic and finite-difference Jacobians, both regularisation types)."""
+    B, T = 600, 60
+    rng = np.random.default_rng(78)
+    n = len(CASES[case][4])
+    x0 = np.array(CASES[case][4]) + rng.uniform(-0.3, 0.3, (B, n))
+    res = []
+    for fused, thr in ((False, 0), (True, 10 ** 9), (True, 200)):
+        alg = solver(case, T, x0=x0, maxIters=60, **kw)
+        alg.tail_threshold, alg.fused_tail = thr, fused
+        launches0 = alg.lib.launches
+        alg.run_optim()
+        res.append((alg.iters.copy(), alg.status.copy(), np.array(alg.cost), np.array(alg.xx), np.array(alg.uu), np.array(alg.KK),
+                    np.array(alg.kk), np.array(alg.mu), np.array(alg.current_alpha)))
+        if fused and thr > 10 ** 6 and alg.lib.m == 1:  # (m = 2 keeps the launch-per-step tail, see iLQR._solve_tail)
+            assert alg.lib.launches - launches0 < 12 * alg.check_every  # one block of iterations, then ONE launch
+    assert res[0][0].max() > 10
+    for other in res[1:]:
+        for p, q in zip(res[0], other):
+            assert np.array_equal(p, q)
+
+
+@pytest.mark.parametrize("case,T", [("cart_pole", 60), ("double_parallel", 60), ("double_serial", 40), ("pendulum", 40), ("car", 40), ("triple", 30),
+                                    ("acrobot", 40)])
+def test_terminal_value_on_device_matches_scipy(case, T):
+    """pg_ilqr_terminal_value (Newton on the final cost + the doubling algorithm for the discrete Riccati equation, one
+    thread per trajectory) against the reference's own route, scipy.optimize.minimize + scipy.linalg.solve_discrete_are
+    (ilqr.py:246-260, `iLQR._terminal_value`), trajectory by trajectory; then the whole final backward pass: the gains of
+    `final_on_device=True` against those of the host route."""
+    rng = np.random.default_rng(9)
+    n = len(CASES[case][4])
+    B = 24
+    x0 = np.array(CASES[case][4]) + rng.uniform(-0.2, 0.2, (B, n))
+    alg = solver(case, T, x0=x0, maxIters=4, final_backpass=False)
+    alg.run_optim()
+    P_host = alg._terminal_value().cpu().numpy()                      # [n, n, B], per trajectory (B <= 32)
+    r = alg.lib.terminal_value(alg._xbar, alg.dt, float(alg.tt[-1]), lin_mode=alg.lin_mode)
+    assert r is not None and bool(r["ok"].all())
+    P_dev = r["P"].cpu().numpy()
+    scale = np.abs(P_host).max(axis=(0, 1), keepdims=True)
+    # scipy's BFGS stops at gtol = 1e-5, Newton at 1e-14: the equilibria differ by ~1e-6, which moves P only where the
+    # dynamics are nonlinear at x*; the Riccati solutions themselves agree to ~1e-10
+    assert np.max(np.abs(P_dev - P_host) / scale) < 1e-6, np.max(np.abs(P_dev - P_host) / scale)
+    assert np.max(np.abs(P_dev - np.swapaxes(P_dev, 0, 1))) == 0.0
+    assert np.max(np.abs(r["x_eq"].cpu().numpy())) < 1e-9             # quadratic final costs: the minimiser is the origin
+    gains = []
+    for on_device in (False, True):
+        a2 = solver(case, T, x0=x0, maxIters=4, final_backpass=True)
+        a2.final_on_device = on_device
+        a2.run_optim()
+        assert a2.final_status == "ok"
+        gains.append((np.array(a2.KK), np.array(a2.kk), np.array(a2.mu)))
+    assert rel(gains[1][0], gains[0][0]) < 1e-6 and rel(gains[1][1], gains[0][1]) < 1e-6
+    assert np.array_equal(gains[0][2], gains[1][2])
+
+
+def test_final_backward_pass_of_a_large_batch_is_per_trajectory():
+    """B > 32 used to share ONE terminal value (trajectory 0's): now every trajectory gets its own, on the device.  Checked
+    on a final cost whose minimiser depends on nothing but whose Riccati solution does not either -- so the per-trajectory
+    values must all be equal to the host value of trajectory 0 -- and on sampled trajectories against scipy."""
+    rng = np.random.default_rng(10)
+    B, T = 4096, 50
+    x0 = np.array(CASES["cart_pole"][4]) + rng.uniform(-0.3, 0.3, (B, 4))
+    alg = solver("cart_pole", T, x0=x0, maxIters=6, final_backpass=True)
+    assert alg.final_on_device is None
+    alg.run_optim()
+    assert alg.final_status == "ok"
+    r = alg.lib.terminal_value(alg._xbar, alg.dt, float(alg.tt[-1]), lin_mode=alg.lin_mode)
+    P = r["P"].cpu().numpy()
+    assert bool(r["ok"].all())
+    sub = solver("cart_pole", T, x0=x0[:8], maxIters=6, final_backpass=True)
+    sub.final_on_device = False
+    sub.run_optim()
+    Ph = sub._terminal_value().cpu().numpy()
+    assert np.max(np.abs(P[..., :8] - Ph) / np.abs(Ph).max()) < 1e-6
+    assert rel(np.array(alg.KK)[:8], np.array(sub.KK)) < 1e-6
