@@ -805,9 +805,30 @@ def test_terminal_value_on_device_matches_scipy(case, T):
     x0 = np.array(CASES[case][4]) + rng.uniform(-0.2, 0.2, (B, n))
     alg = solver(case, T, x0=x0, maxIters=4, final_backpass=False)
     alg.run_optim()
-    P_host = alg._terminal_value().cpu().numpy()                      # [n, n, B], per trajectory (B <= 32)
     r = alg.lib.terminal_value(alg._xbar, alg.dt, float(alg.tt[-1]), lin_mode=alg.lin_mode)
-    assert r is not None and bool(r["ok"].all())
+    assert r is not None
+    try:
+        P_host = alg._terminal_value().cpu().numpy()                  # [n, n, B], per trajectory (B <= 32)
+    except np.linalg.LinAlgError:
+        # scipy finds no stabilising solution here (a mode on the unit circle the final cost does not see: the reference's
+        # run_optim raises at this point).  The device route must then either say so per trajectory, or return a
+        # symmetric solution of the Riccati equation: checked through the equation's residual.
+        ok = r["ok"].cpu().numpy().astype(bool)
+        if ok.any():
+            P = np.moveaxis(r["P"].cpu().numpy(), -1, 0)[ok]
+            xe = r["x_eq"].cpu().numpy().T[ok]
+            u0 = np.zeros((len(xe), alg.uDim))
+            Ad, Bd, _ = alg.linearization(xe, u0)
+            Cxx, Cuu, Cxu, _, _ = alg.cost_lin(xe, u0, float(alg.tt[-1]))
+            Ad, Bd, Cxx, Cuu, Cxu = (np.asarray(a).reshape((len(xe),) + np.asarray(a).shape[-2:]) for a in (Ad, Bd, Cxx, Cuu, Cxu))
+            for i in range(len(xe)):
+                G = Cuu[i] + Bd[i].T @ P[i] @ Bd[i]
+                H = Bd[i].T @ P[i] @ Ad[i] + Cxu[i].T.reshape(G.shape[0], -1)
+                res = Ad[i].T @ P[i] @ Ad[i] - P[i] - H.T @ np.linalg.solve(G, H) + Cxx[i]
+                assert np.max(np.abs(res)) < 1e-7 * max(1.0, np.abs(P[i]).max()), np.max(np.abs(res))
+                assert np.array_equal(P[i], P[i].T)
+        return
+    assert bool(r["ok"].all())
     P_dev = r["P"].cpu().numpy()
     scale = np.abs(P_host).max(axis=(0, 1), keepdims=True)
     # scipy's BFGS stops at gtol = 1e-5, Newton at 1e-14: the equilibria differ by ~1e-6, which moves P only where the
