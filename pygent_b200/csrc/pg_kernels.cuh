@@ -1400,6 +1400,263 @@ __global__ void __launch_bounds__(128) ilqr_backward_kernel(const BackwardArgs<T
     backward_body<P, T, LIN, CFD>(m, a, b);
 }
 
+// ---- the backward sweep of ONE trajectory by the lanes of a warp (ilqr_solve_kernel) ---------------------------------------
+// The sweep of backward_body, value for value, laid over a warp in two phases per chunk of 32 control intervals:
+//   A  the linearisation and the cost expansion do not depend on the value function, only on the nominal point: lane s
+//      evaluates them for interval k_hi - s and leaves (Ad, Bd, the raw cost derivatives, u) in row s of the warp's
+//      shared-memory staging area -- 32 intervals for the instructions of one;
+//   B  the Riccati recursion walks the rows: lane j owns COLUMN j of W = Vxx Ad, of Qux, of K and of the new Vxx; the
+//      scalars (Quu, k, dV) are computed by every lane.  Two exchanges per interval through shared memory: (K, Qux) of all
+//      columns before the value update, the new columns (and vx) after it.
+// Bit-identical to backward_body: every sum runs over the same terms in the same order (the structural zeros the
+// single-thread code skips are exact zeros here: x + v * 0 == x), products meet their addends in the same expressions,
+// so the compiler contracts the same multiply-adds.  M == 1 (the fused solver's scope).
+template <typename P>
+struct LaneSweep {
+    static constexpr int N = P::N, M = P::M;
+    static constexpr int oAd = 0, oCxx = oAd + N * N, oBd = oCxx + N * N, oCxu = oBd + N * M, oCx = oCxu + N * M, oCu = oCx + N,
+                         oCuu = oCu + M, oU = oCuu + M * M, E = oU + M;
+    // row stride in words of T: even (16-byte rows) and = 2 mod 4, so that the 32 rows phase A writes side by side fall on 8
+    // distinct 16-byte bank groups (2-way conflicts at most)
+    __host__ __device__ static constexpr int stride() {
+        int s = (E + 1) & ~1;
+        while (s % 4 != 2) s += 2;
+        return s;
+    }
+    static constexpr int xVn = 0, xVx = xVn + N * N + (N * N & 1), xKt = xVx + N + (N & 1), xQux = xKt + N + (N & 1),
+                         X = xQux + N + (N & 1);
+    __host__ __device__ static constexpr int warp_words() { return 32 * stride() + X; }
+};
+
+template <typename T, int K, bool ALIGNED>
+__device__ __forceinline__ void lds_vec(const T* p, T (&d)[K]) {
+    if constexpr (ALIGNED && sizeof(T) == 8 && K % 2 == 0) {
+#pragma unroll
+        for (int q = 0; q < K / 2; q++) {
+            const double2 v = reinterpret_cast<const double2*>(p)[q];
+            d[2 * q] = v.x;
+            d[2 * q + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < K; q++) d[q] = p[q];
+    }
+}
+
+template <typename P, typename T, int LIN>
+__device__ __forceinline__ void backward_lanes(const typename P::template Ctx<T>& m, const BackwardArgs<T>& a, T* sm, const int lane) {
+    using L = LaneSweep<P>;
+    constexpr int N = P::N, M = P::M, S = L::stride();
+    static_assert(M == 1, "lane-parallel sweep: one control input");
+    const int j = lane % N;      // lanes >= N repeat the work of lane j (uniform control flow); only lanes < N publish
+    const bool writer = lane < N;
+    T* ex = sm + 32 * S;
+    const T mu = a.mu[0];
+    const T dt = a.dt;
+    const int Ts = a.T_steps;
+    T vx[N], Vxx[N * N];
+    {
+        T x[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) x[i] = a.xbar[(int64_t)Ts * N + i];
+        P::fcost_derivs(m, x, vx, Vxx);
+#pragma unroll
+        for (int i = 0; i < N; i++) vx[i] *= dt;
+#pragma unroll
+        for (int i = 0; i < N * N; i++) Vxx[i] = P::cfxx_nz(i) ? Vxx[i] * dt : T(0);
+    }
+    T sV1 = T(0), sV2 = T(0);
+    T gmax[M];
+#pragma unroll
+    for (int r = 0; r < M; r++) gmax[r] = T(0);
+    bool ok = true;
+    auto bdnz = [](int l, int r) constexpr { return LIN != 0 || P::b_nz(l * M + r); };
+    for (int k_hi = Ts - 1; k_hi >= 0 && ok; k_hi -= 32) {
+        __syncwarp();  // the rows of the previous chunk have been consumed
+        {              // phase A: lane s <-> interval k_hi - s
+            const int k = k_hi - lane;
+            if (k >= 0) {
+                T x[N], u[M];
+#pragma unroll
+                for (int i = 0; i < N; i++) x[i] = a.xbar[(int64_t)k * N + i];
+#pragma unroll
+                for (int r = 0; r < M; r++) u[r] = a.ubar[(int64_t)k * M + r];
+                T Ad[N * N], Bd[N * M];
+                if constexpr (LIN == 0) P::AB(m, x, u, Ad, Bd);
+                else fd_AB<P, T>(m, x, u, Ad, Bd);
+#pragma unroll
+                for (int i = 0; i < N; i++)
+#pragma unroll
+                    for (int c = 0; c < N; c++) Ad[i * N + c] = Ad[i * N + c] * dt + (i == c ? T(1) : T(0));
+#pragma unroll
+                for (int i = 0; i < N * M; i++) Bd[i] = Bd[i] * dt;
+                T cx[N], cu[M], Cxx[N * N], Cuu[M * M], Cxu[N * M];
+                P::cost_derivs(m, x, u, T(k) * dt, cx, cu, Cxx, Cuu, Cxu);
+                T* row = sm + lane * S;
+#pragma unroll
+                for (int i = 0; i < N * N; i++) row[L::oAd + i] = Ad[i];
+#pragma unroll
+                for (int i = 0; i < N * N; i++) row[L::oCxx + i] = Cxx[i];
+#pragma unroll
+                for (int i = 0; i < N * M; i++) row[L::oBd + i] = Bd[i];
+#pragma unroll
+                for (int i = 0; i < N * M; i++) row[L::oCxu + i] = Cxu[i];
+#pragma unroll
+                for (int i = 0; i < N; i++) row[L::oCx + i] = cx[i];
+#pragma unroll
+                for (int r = 0; r < M; r++) row[L::oCu + r] = cu[r];
+#pragma unroll
+                for (int i = 0; i < M * M; i++) row[L::oCuu + i] = Cuu[i];
+#pragma unroll
+                for (int r = 0; r < M; r++) row[L::oU + r] = u[r];
+            }
+        }
+        __syncwarp();
+        const int nk = k_hi + 1 < 32 ? k_hi + 1 : 32;
+        for (int s = 0; s < nk; s++) {  // phase B: the recursion over the staged intervals
+            const int k = k_hi - s;
+            const T* e = sm + s * S;
+            T Ad[N * N], Acol[N], Bd[N * M];
+            lds_vec<T, N * N, true>(e + L::oAd, Ad);
+            lds_vec<T, N * M, (L::oBd % 2 == 0)>(e + L::oBd, Bd);
+#pragma unroll
+            for (int l = 0; l < N; l++) Acol[l] = e[L::oAd + l * N + j];
+            const T cxj = e[L::oCx + j] * dt;
+            const T cu0 = e[L::oCu] * dt;
+            const T Cuu0 = e[L::oCuu] * dt;
+            const T u0 = e[L::oU];
+            // column j of W = Vxx Ad; g = Vxx Bd
+            T W[N], g[N];
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                T acc = T(0);
+#pragma unroll
+                for (int l = 0; l < N; l++) acc += Vxx[i * N + l] * Acol[l];
+                W[i] = acc;
+                T acg = T(0);
+#pragma unroll
+                for (int l = 0; l < N; l++)
+                    if (bdnz(l, 0)) acg += Vxx[i * N + l] * Bd[l];
+                g[i] = acg;
+            }
+            // qx[j], qu
+            T qxj, qu;
+            {
+                T acc = T(0);
+#pragma unroll
+                for (int l = 0; l < N; l++) acc += Acol[l] * vx[l];
+                qxj = cxj + acc;
+                T acu = T(0);
+#pragma unroll
+                for (int l = 0; l < N; l++)
+                    if (bdnz(l, 0)) acu += Bd[l] * vx[l];
+                qu = cu0 + acu;
+            }
+            // Quu, Qux[j]
+            T Quu, Quxj, QuuR, QuxRj;
+            {
+                T acc = T(0);
+#pragma unroll
+                for (int l = 0; l < N; l++)
+                    if (bdnz(l, 0)) acc += Bd[l] * g[l];
+                Quu = Cuu0 + acc;
+                T acx = T(0);
+#pragma unroll
+                for (int l = 0; l < N; l++)
+                    if (bdnz(l, 0)) acx += Bd[l] * W[l];
+                Quxj = e[L::oCxu + j] * dt + acx;
+            }
+            if (a.reg_type == 1) {
+                T acc = T(0);
+#pragma unroll
+                for (int l = 0; l < N; l++)
+                    if (bdnz(l, 0)) acc += Bd[l] * (g[l] + mu * Bd[l]);
+                QuuR = Cuu0 + acc;
+                T acx = T(0);
+#pragma unroll
+                for (int l = 0; l < N; l++)
+                    if (bdnz(l, 0)) acx += Bd[l] * (W[l] + mu * Acol[l]);
+                QuxRj = e[L::oCxu + j] * dt + acx;
+            } else {
+                QuuR = Quu + (a.reg_type == 2 ? mu : T(0));
+                QuxRj = Quxj;
+            }
+            if (!(QuuR > T(0))) {
+                ok = false;
+                break;
+            }
+            T kt = -(qu / QuuR);
+            T Ktj = -(QuxRj / QuuR);
+            if (a.constrained) {
+                const T up = a.ulim[0] - u0, lo = a.ulim[0] + u0;
+                kt = pg::clamp(kt, -lo, up);
+                const bool clamped = np_isclose(kt, up, T(1e-3)) || np_isclose(kt, lo, T(1e-3));
+                if (clamped) Ktj = T(0);
+            }
+            if (writer) {
+                ex[L::xKt + j] = Ktj;
+                ex[L::xQux + j] = Quxj;
+            }
+            T Qk = T(0);
+            Qk += Quu * kt;
+            T dV1 = T(0), dV2 = T(0);
+            dV1 += kt * qu;
+            dV2 += kt * Qk;
+            sV1 += dV1;
+            sV2 += T(0.5) * dV2;
+            T vxn;
+            {
+                T t1 = T(0), t2 = T(0), t3 = T(0);
+                t1 += Ktj * Qk;
+                t2 += Ktj * qu;
+                t3 += Quxj * kt;
+                vxn = ((qxj + t1) + t2) + t3;
+            }
+            T QKj = T(0);
+            QKj += Quu * Ktj;
+            __syncwarp();
+            T Kt[N], Qux[N];
+            lds_vec<T, N, true>(ex + L::xKt, Kt);
+            lds_vec<T, N, true>(ex + L::xQux, Qux);
+            T Vn[N];
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                T acc = T(0);
+#pragma unroll
+                for (int l = 0; l < N; l++) acc += Ad[l * N + i] * W[l];
+                T q = e[L::oCxx + i * N + j] * dt + acc;
+                T t1 = T(0), t2 = T(0), t3 = T(0);
+                t1 += Kt[i] * QKj;
+                t2 += Kt[i] * Quxj;
+                t3 += Qux[i] * Ktj;
+                Vn[i] = ((q + t1) + t2) + t3;
+            }
+            if (writer) {
+#pragma unroll
+                for (int i = 0; i < N; i++) ex[L::xVn + i * N + j] = Vn[i];
+                ex[L::xVx + j] = vxn;
+                a.KK[(int64_t)k * N + j] = Ktj;
+                if (lane == 0) a.kk[k] = kt;
+            }
+            gmax[0] = fmax(gmax[0], fabs(kt) / (fabs(u0) + T(1)));
+            __syncwarp();
+            T Vf[N * N];
+            lds_vec<T, N * N, true>(ex + L::xVn, Vf);
+            lds_vec<T, N, true>(ex + L::xVx, vx);
+#pragma unroll
+            for (int i = 0; i < N; i++)
+#pragma unroll
+                for (int l = 0; l < N; l++) Vxx[i * N + l] = T(0.5) * (Vf[i * N + l] + Vf[l * N + i]);
+        }
+    }
+    if (lane == 0) {
+        a.dV[0] = sV1;
+        a.dV[1] = sV2;
+        a.gnorm[0] = gmax[0] / T(M);
+        a.success[0] = ok ? 1 : 0;
+    }
+}
+
 // ---- terminal value of the final backward pass (iLQR.backward_pass(final=True), ilqr.py:246-260) ---------------------------
 // Per trajectory, on the device: (1) the equilibrium of the final cost, x* = argmin fcost(x) started at x_N (the reference
 // calls scipy.optimize.minimize; here Newton's method on the generated gradient / Hessian, exact in one step for the
@@ -1498,6 +1755,14 @@ __global__ void __launch_bounds__(64) terminal_value_kernel(const TerminalArgs<T
         T rhs[N * 1];
 #pragma unroll
         for (int i = 0; i < N; i++) rhs[i] = g[i];
+        // a final cost that does not weigh every state (the pendulum chains: velocities) has a singular Hessian; the gradient
+        // vanishes along those directions and the minimiser keeps x_N's components there, as scipy's BFGS does: a relative
+        // 1e-14 on the diagonal makes the step well defined (and costs one more iteration elsewhere)
+        T hdiag = T(0);
+#pragma unroll
+        for (int i = 0; i < N; i++) hdiag = fmax(hdiag, fabs(Hm[i * N + i]));
+#pragma unroll
+        for (int i = 0; i < N; i++) Hm[i * N + i] += T(1e-14) * hdiag;
         if (!gauss_solve<T, N, 1>(Hm, rhs)) {
             ok = false;
             break;
@@ -1825,6 +2090,8 @@ __global__ void __launch_bounds__(128) ilqr_solve_kernel(const SolveArgs<T> a) {
     const int Ts = a.fw.T_steps, nA = a.fw.n_alpha;
     const int cnt = *a.count;
     const int nX = (Ts + 1) * N, nU = Ts * M, nK = Ts * M * N;
+    extern __shared__ __align__(16) unsigned char solve_smem[];  // M == 1: the staging rows of backward_lanes, per warp
+    T* sm = reinterpret_cast<T*>(solve_smem) + (threadIdx.x >> 5) * LaneSweep<P>::warp_words();
     // the warp's private block
     T* px0 = a.cand + (size_t)warp * solve_block_doubles<P>(Ts);
     T* pX = px0 + N;
@@ -1873,9 +2140,16 @@ __global__ void __launch_bounds__(128) ilqr_solve_kernel(const SolveArgs<T> a) {
         bool any_accept = false;
         __syncwarp();
         for (;;) {
+            if constexpr (M == 1) {  // the sweep laid over the lanes (backward_lanes)
+                bw.mu = a.sel.mu + b;
+                backward_lanes<P, T, LIN>(m, bw, sm, lane);
+            } else {
+                if (lane == 0) {
+                    ps[0] = a.sel.mu[b];
+                    backward_body<P, T, LIN, false>(m, bw, 0);
+                }
+            }
             if (lane == 0) {
-                ps[0] = a.sel.mu[b];
-                backward_body<P, T, LIN, false>(m, bw, 0);
                 a.bw.dV[b] = ps[1];
                 a.bw.dV[B + b] = ps[2];
                 a.bw.gnorm[b] = ps[3];
