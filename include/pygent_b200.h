@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define PG_ABI_VERSION 6
+#define PG_ABI_VERSION 7
 
 #define PG_F64 0
 #define PG_F32 1
@@ -299,7 +299,7 @@ int pg_ilqr_terminal_value(int dtype, int64_t B, int32_t T, double dt, double t_
                            void* x_eq, uint8_t* ok, const int32_t* index, const int32_t* count, void* stream);
 
 /* Fused tail solver (the "persistent fused loop" of iLQR.run_optim, ilqr.py:399-485): ONE launch that finishes every trajectory
- * of a work list.  A warp owns a trajectory and iterates backward sweep (lane 0) -> all n_alpha line-search candidates side by
+ * of a work list.  A warp owns a trajectory and iterates backward sweep (laid over the lanes: one column of the value Hessian each) -> all n_alpha line-search candidates side by
  * side (one lane each) -> the reference's decision logic -> winner copied into the nominal trajectory, until that
  * trajectory stops (status != 0 or iters == select.max_iters), then takes the next one.  The arithmetic and every decision
  * are those of pg_ilqr_backward / pg_ilqr_forward / pg_ilqr_select / pg_ilqr_commit (bit-identical results), without the
@@ -330,6 +330,14 @@ typedef struct {
     int32_t max_count;
     void* workspace;                                  /* pg_ilqr_solve_workspace_bytes(T, max_count) bytes */
     int64_t workspace_bytes;
+    /* Rounds: with round_iters > 0 a launch gives every trajectory of the list at most that many iterations and writes those
+     * still running to index_out / count_out (device; count_out is zeroed by the call; order unspecified), the work list of
+     * the next call.  Each call deals the trajectories to the warps anew -- the first 4 x SMs of the list get a warp scheduler
+     * of their own -- so a few long-running trajectories never share a scheduler for the rest of a solve; a list of at most
+     * 4 x SMs trajectories is finished by the call that finds it, whatever round_iters says.  0: run to the end. */
+    int32_t round_iters;
+    int32_t* index_out;
+    int32_t* count_out;
 } pg_ilqr_solve_t;
 int64_t pg_ilqr_solve_workspace_bytes(int32_t T, int32_t max_count);
 /* Trajectories the fused solver works on simultaneously (one resident warp each); a longer work list is handed out through a

@@ -180,6 +180,8 @@ class iLQR(Algorithm):
         self.final_on_device = None  # final backward pass: None = per-trajectory on the device when B > 32, host (scipy) otherwise
         self.final_status = None
         self._trace = None  # list: (iteration, live trajectories, host time) per readback, for tools/time_fused_tail.py
+        self._round_trace = []
+        self.tail_round = int(os.environ.get("PG_ILQR_TAIL_ROUND", "32"))  # iterations per launch of the fused tail solver
         self.fused_tail = os.environ.get("PG_ILQR_FUSED_TAIL", "1") != "0"  # ... or, better, the fused per-trajectory solver finishes the solve
         self._tail = False
         self._ls_small = lib.split_search_threshold(self._x0.device)
@@ -190,7 +192,17 @@ class iLQR(Algorithm):
             self._cand = {"X": z(A, T + 1, n, B), "U": z(A, T, m, B)}
 
     def _host(self, t, batch_axis_last=True):
-        a = t.detach().to("cpu", torch.float64).numpy()
+        t = t.detach()
+        if t.is_cuda and t.dtype == torch.float64 and t.numel() >= (1 << 17):
+            # large results (the nominal trajectories of a 16,384-trajectory batch are 66 MB) go through page-locked memory:
+            # ~50 GB/s instead of the ~3 GB/s of a copy into pageable memory.  The array owns its buffer (torch's caching
+            # host allocator hands the block out again once the array is gone).
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t, non_blocking=True)
+            torch.cuda.current_stream(t.device).synchronize()
+            a = h.numpy()
+        else:
+            a = t.to("cpu", torch.float64).numpy()
         a = np.moveaxis(a, -1, 0)  # [B, ...]
         return a if self.batched else a[0]
 
@@ -569,7 +581,7 @@ class iLQR(Algorithm):
                 if live == 0:
                     break
                 if not self._tail and not self.learned and live <= self.tail_threshold:
-                    if self.fused_tail and self._solve_tail():
+                    if self.fused_tail and self._solve_tail(self.max_iters - it):
                         # the fused tail solver (pg_ilqr_solve) has been enqueued behind the iterations already in flight: it
                         # finishes every trajectory that is still running when it starts, in one launch
                         break
@@ -577,26 +589,37 @@ class iLQR(Algorithm):
             pending = (ev, slot)
         self._graph = graph  # keep it alive until the results have been read
 
-    def _solve_tail(self):
-        """Finish the solve with ONE launch of the fused per-trajectory solver (lib.ilqr_solve): every trajectory on the
-        current work list is iterated to its stopping test by a warp of its own.  Results and decisions are bit-identical to
-        continuing with iterate() (same device functions).  Returns False where the fused kernel does not apply."""
+    def _solve_tail(self, remaining):
+        """Finish the solve with the fused per-trajectory solver (lib.ilqr_solve): every trajectory on the current work
+        list is iterated to its stopping test by a warp of its own -- in rounds of `tail_round` iterations (one launch
+        each, all enqueued now: `remaining` iterations at most are left), because every launch deals the trajectories that
+        are still running to the warps anew, and a short list gives each a warp scheduler of its own.  Results and
+        decisions are bit-identical to continuing with iterate() (same device functions).  Returns False where the fused
+        kernel does not apply."""
         if self.learned or self.finite_diff or self.dtype != torch.float64 or self.lin_mode not in (0, 1) or self.lib.m != 1:
             # (m = 2: the Car's active-set sweep rounds differently once inlined into the fused kernel -- iteration counts then
             # differ by rounding-level decisions; it keeps the launch-per-step tail, which is bit-identical by the tests)
             return False
-        cur = self._cur
-        work = (self._idx[cur], self._cnt[cur])
-        ok = self.lib.ilqr_solve(self._sel, self._x0, self._xbar, self._ubar, self._KK, self._kk, self._KKc, self._kkc, self._bw,
-                                 self._fw, self._st, work, max_count=min(self.B, max(self.tail_threshold, 1)), S=self.substeps, dt=self.dt,
-                                 integrator=self.integrator, reg_type=self.regType, lin_mode=self.lin_mode, ulim=self._ulim(),
-                                 terminal_cost=float(self.environment.terminal_cost), last_tried=self._last_tried)
-        if ok:
-            self._cnt[1 - cur].zero_()
+        R = max(1, int(self.tail_round))
+        rounds = max(1, -(-int(remaining) // R))
+        for _ in range(rounds):
+            cur = self._cur
+            work = (self._idx[cur], self._cnt[cur])
+            if self._trace is not None:  # tools/time_fused_tail.py: (event, live count) at the start of every round
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                self._round_trace.append((ev, self._cnt[cur].clone()))
+            ok = self.lib.ilqr_solve(self._sel, self._x0, self._xbar, self._ubar, self._KK, self._kk, self._KKc, self._kkc, self._bw,
+                                     self._fw, self._st, work, max_count=min(self.B, max(self.tail_threshold, 1)), S=self.substeps,
+                                     dt=self.dt, integrator=self.integrator, reg_type=self.regType, lin_mode=self.lin_mode,
+                                     ulim=self._ulim(), terminal_cost=float(self.environment.terminal_cost),
+                                     last_tried=self._last_tried, round_iters=R, work_out=(self._idx[1 - cur], self._cnt[1 - cur]))
+            if not ok:
+                return False
             self._cur = 1 - cur
             self._n_active = self._cnt[self._cur]
             self._have_gains = True
-        return ok
+        return True
 
     def _capture_two_iterations(self):
         """CUDA graph of iterate(); iterate() -- raw capture on a side stream (`with torch.cuda.graph` would first empty
@@ -622,8 +645,10 @@ class iLQR(Algorithm):
             l.launches = b
         return graph
 
-    def run_optim(self):
-        """Trajectory optimisation (ilqr.py:399-499).  Returns (xx, uu, cost)."""
+    def run_optim(self, host_results=True):
+        """Trajectory optimisation (ilqr.py:399-499).  Returns (xx, uu, cost) as host arrays, like the reference; with
+        `host_results=False` the results stay on the device (`_xbar`, `_ubar`, `_st["cost"]`; the properties `xx`, `uu`,
+        `cost` fetch them on demand) and None is returned -- a 16,384-trajectory batch otherwise copies 66 MB per call."""
         start_time = time.time()
         st = self._st
         if self.reset_mu:
@@ -641,6 +666,8 @@ class iLQR(Algorithm):
             self._final_backpass()
         self.iterations = int(st["iters"].max().item())
         self.lib.check_queues()  # a line-search worker that gave up waiting would have left stale candidate costs
+        if not host_results and not self.printing and not self.saving:
+            return None
         xx, uu = self.xx, self.uu
         self.agent.set_history(uu)
         if self.printing:

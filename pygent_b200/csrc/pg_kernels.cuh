@@ -2066,9 +2066,14 @@ struct SolveArgs {
     T* KK_acc;    // accepted gains
     T* kk_acc;
     T* cand;      // [warps of the grid][solve_block_doubles(T)]: the private block of each warp (see ilqr_solve_kernel)
-    int32_t* ticket;  // next entry of the work list to hand out (zeroed by the host before the launch)
+    int32_t* ticket;  // [0] next of the first n_first work-list entries, [1] next of the others (zeroed before the launch)
+    int32_t* sm_rank; // [SMs] CTAs that have arrived on each SM (zeroed before the launch)
+    int n_first;      // 4 x SMs: the entries that can each have a warp scheduler of their own
+    int round_iters;  // iterations per trajectory in this launch; a trajectory still running after them goes on index_out
     const int32_t* index;
     const int32_t* count;
+    int32_t* index_out;
+    int32_t* count_out;
 };
 
 // Doubles of a warp's private block: the trajectory it is working on, compact (the batch-strided arrays give one useful word
@@ -2126,20 +2131,44 @@ __global__ void __launch_bounds__(128) ilqr_solve_kernel(const SolveArgs<T> a) {
     fw.diverged_out = pflag + 16;
     fw.terminated_out = pflag + 32;
     fw.xN_out = nullptr;
+    // Placement: a 4-warp CTA puts one warp on each scheduler of its SM, and two CTAs fit an SM.  The first CTA to arrive on an
+    // SM serves the first n_first = 4 x SMs entries of the work list, so that a list that short gives every trajectory a
+    // scheduler of its own (two latency-bound warps on one scheduler run 1.5-2x slower each -- and the launch lasts as long
+    // as its slowest trajectory); later arrivals serve the entries beyond, and so does everybody once the first are gone.
+    __shared__ int s_rank;
+    if (threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        s_rank = atomicAdd(a.sm_rank + smid, 1);
+    }
+    __syncthreads();
+    bool first_open = s_rank == 0;
+    const int n_first = cnt < a.n_first ? cnt : a.n_first;
+    // a list that short needs no further dealing: this launch finishes it (and the launches queued behind it find it empty)
+    const int round_iters = cnt > a.n_first ? a.round_iters : INT32_MAX;
     for (;;) {
         // trajectories are handed out one at a time: a warp whose trajectory stops early takes the next one, so the few
         // that run to max_iters never queue up behind each other on one warp
         int w = 0;
-        if (lane == 0) w = atomicAdd(a.ticket, 1);
+        if (lane == 0) {
+            w = cnt;
+            if (first_open) w = atomicAdd(a.ticket, 1);
+            if (!first_open || w >= n_first) w = n_first + atomicAdd(a.ticket + 1, 1);
+        }
         w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= n_first) first_open = false;
         if (w >= cnt) break;
         const int64_t b = a.index[w];
         for (int e = lane; e < N; e += 32) px0[e] = a.fw.x0[(int64_t)e * B + b];
         for (int e = lane; e < nX; e += 32) pX[e] = a.xbar[(int64_t)e * B + b];
         for (int e = lane; e < nU; e += 32) pU[e] = a.ubar[(int64_t)e * B + b];
-        bool any_accept = false;
+        bool any_accept = false, running = false;
         __syncwarp();
-        for (;;) {
+        for (int it = 0;; it++) {
+            if (it == round_iters) {  // this launch's share is done: the next launch deals the trajectory again
+                running = true;
+                break;
+            }
             if constexpr (M == 1) {  // the sweep laid over the lanes (backward_lanes)
                 bw.mu = a.sel.mu + b;
                 backward_lanes<P, T, LIN>(m, bw, sm, lane);
@@ -2192,6 +2221,7 @@ __global__ void __launch_bounds__(128) ilqr_solve_kernel(const SolveArgs<T> a) {
         }
         for (int e = lane; e < nK; e += 32) a.bw.KK[(int64_t)e * B + b] = pKc[e];  // the last candidate gains (as K3 leaves them)
         for (int e = lane; e < nU; e += 32) a.bw.kk[(int64_t)e * B + b] = pkc[e];
+        if (running && lane == 0) a.index_out[atomicAdd(a.count_out, 1)] = (int32_t)b;
         __syncwarp();
     }
 }

@@ -46,7 +46,7 @@ class SolveArgs(ctypes.Structure):
                 ("terminated", _vp), ("xN", _vp), ("cost", _vp), ("mu", _vp), ("mu_d", _vp), ("dcost", _vp),
                 ("success_gradient", _vp), ("status", _vp), ("iters", _vp), ("alpha_best", _vp), ("accept", _vp), ("active", _vp),
                 ("last_tried", _vp), ("index", _vp), ("count", _vp), ("max_count", _i32), ("workspace", _vp),
-                ("workspace_bytes", _i64)]
+                ("workspace_bytes", _i64), ("round_iters", _i32), ("index_out", _vp), ("count_out", _vp)]
 
 
 # name -> argtypes (restype is always int); mirrors include/pygent_b200.h
@@ -394,9 +394,11 @@ class ProblemLibrary:
         return int(self.dll.pg_ilqr_solve_capacity())
 
     def ilqr_solve(self, sel, x0, xbar, ubar, KK, kk, KKc, kkc, bw, fw, st, work, max_count, S=4, dt=0.02, integrator=INTEG_RK4,
-                   reg_type=2, lin_mode=0, ulim=None, terminal_cost=0.0, last_tried=None):
+                   reg_type=2, lin_mode=0, ulim=None, terminal_cost=0.0, last_tried=None, round_iters=0, work_out=None):
         """pg_ilqr_solve: ONE launch that finishes every trajectory of the work list `work` = (index, count) -- a warp per
-        trajectory loops backward sweep / 11 candidates side by side / decision / commit until the trajectory stops.
+        trajectory loops backward sweep / 11 candidates side by side / decision / commit until the trajectory stops -- or,
+        with `round_iters` > 0, gives each at most that many iterations and leaves the list of those still running in
+        `work_out` = (index, count) for the next call.
         bw = dict(dV, gnorm, success), fw = dict(cost, diverged, terminated, xN), st = the solver state dict of ilqr_select.
         Returns False if this configuration is not supported by the fused kernel (the caller keeps iterating)."""
         dtype, dev = x0.dtype, x0.device
@@ -422,6 +424,8 @@ class ProblemLibrary:
         a.alpha_best, a.accept, a.active, a.last_tried = p(st["alpha_best"]), p(st["accept"]), p(st["active"]), p(last_tried)
         a.index, a.count, a.max_count = p(work[0]), p(work[1]), int(max_count)
         a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes
+        if round_iters > 0:
+            a.round_iters, a.index_out, a.count_out = int(round_iters), p(work_out[0]), p(work_out[1])
         rc = self.dll.pg_ilqr_solve(ctypes.byref(a), self._stream())
         if rc == -2:
             return False

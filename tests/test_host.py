@@ -38,7 +38,7 @@ def test_header_declares_what_the_library_exports(built):
             assert hasattr(dll, name), (p, name)
     L = lib.ProblemLibrary(paths[0])
     assert (L.n, L.m, L.n_obs, L.has_ab) == (4, 1, 5, True) and L.name == "cart_pole_lin"
-    assert L.info.abi_version == 6
+    assert L.info.abi_version == 7
 
 
 def test_mlp_header_declares_what_the_library_exports():

@@ -17,7 +17,7 @@ def timed(alg, xi, reps=3):
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        alg.run_optim()
+        alg.run_optim(host_results=False)
         b.record()
         torch.cuda.synchronize()
         best = min(best, a.elapsed_time(b))
@@ -57,6 +57,13 @@ def trace():
     print("live trajectories as the host saw them (iteration, live, ms since start):")
     print("  " + "  ".join("%d:%d@%.1f" % (i, l, (t - t0) * 1e3) for i, l, t in alg._trace))
     print("  total %.1f ms" % ((t1 - t0) * 1e3))
+    if alg._round_trace:
+        end = torch.cuda.Event(enable_timing=True)
+        end.record()
+        torch.cuda.synchronize()
+        evs = [e for e, _ in alg._round_trace] + [end]
+        print("rounds of the fused tail solver (live at start: ms):")
+        print("  " + "  ".join("%d:%.2f" % (int(c), evs[i].elapsed_time(evs[i + 1])) for i, (_, c) in enumerate(alg._round_trace)))
     it = np.sort(alg.iters)
     print("iterations per trajectory: median %d, 90%% %d, 99%% %d, max %d; trajectories at max: %d" % (
         np.median(it), it[int(0.9 * len(it))], it[int(0.99 * len(it))], it[-1], int((it == it[-1]).sum())))
