@@ -1240,6 +1240,12 @@ __device__ __forceinline__ uint8_t* x_abuf(const XPipe& p) {
     return p.Ab + set * X_ABUF_BYTES;
 }
 
+__device__ __forceinline__ uint8_t* x_abuf_parked(const XPipe& p) {
+    const uint32_t set = p.c & 1, u = p.c >> 1;
+    mbar_wait_parked(&p.a_empty[set], (u & 1) ^ 1);
+    return p.Ab + set * X_ABUF_BYTES;
+}
+
 // 16 values of this thread (its row, hidden units kb * 64 + part * 16 .. + 15) -> split -> the A buffer
 __device__ __forceinline__ void x_store16(const float (&v)[16], uint8_t* abuf, int row, int part) {
 #pragma unroll
@@ -1308,7 +1314,7 @@ __device__ __forceinline__ void x_barriers(uint8_t* base, XSmem& m) {
     m.tmem_slot = reinterpret_cast<uint32_t*>(m.accum + 1);
 }
 
-__device__ __forceinline__ void x_setup(const XSmem& m, int t, int warp) {
+__device__ __forceinline__ void x_setup(const XSmem& m, int t, int warp, uint32_t a_full_count = 1) {
     if (t == 0) {
         for (int s = 0; s < X_NST; s++) {
             mbar_init(&m.full[s], 1);
@@ -1316,7 +1322,7 @@ __device__ __forceinline__ void x_setup(const XSmem& m, int t, int warp) {
             mbar_init(&m.pfull[s], 1);
         }
         for (int s = 0; s < 2; s++) {
-            mbar_init(&m.a_full[s], 1);
+            mbar_init(&m.a_full[s], a_full_count);
             mbar_init(&m.a_empty[s], 1);
         }
         mbar_init(m.accum, 1);
@@ -1328,7 +1334,93 @@ __device__ __forceinline__ void x_setup(const XSmem& m, int t, int warp) {
     }
 }
 
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_x3_kernel(const MlpArgs a) {
+// The rollout kernel keeps the tensor core's feed out of the compute warps: two more warps hold one control thread each --
+// warp 16 issues the MMAs (leader) or relays "my stage is full" (peer), warp 17 requests the weight chunks -- and the 16
+// compute warps hand each A block over through an mbarrier (one arrival per warp of BOTH CTAs on the leader's a_full) instead
+// of a CTA barrier.  With the control threads inside compute warps every k-block cost layer 1 PLUS the time the issuing
+// thread is held by the tensor core's queue: 37 % of all warp samples sat at that barrier
+// (profiles/r02_mlp_x3_ncu_summary.txt).  The two control threads must not share a warp either: a thread held at the issue of
+// a tcgen05.mma holds its warp, so a producer in a sibling lane only ran while the issuer waited -- the refills then followed
+// the MMAs instead of overlapping them (tools/mlp_timing.py: "wait weights" = "issuing").
+constexpr int XC_THREADS = T_THREADS + 64;
+// -DPG_MLP_TIMING (tools/mlp_timing.py; never in the product build): cycles per phase of mlp_x3_kernel, summed per CTA --
+// compute thread 0: [0] owner phase + input hand-over, [1] the eight layer-1 blocks incl. waits for a free A buffer,
+// [2] waiting for the last MMAs, [3] epilogue, [4] partial sums + state update; the leader's issuing thread: [8] waiting
+// for an A block, [9] waiting for weight stages, [10] issuing; [15] intervals.
+#ifdef PG_MLP_TIMING
+__device__ unsigned long long pg_mlp_timing_buf[1024 * 16];
+#define PG_TIME_DECL long long tm_last = clock64()
+#define PG_TIME_ADD(slot)                                                                          \
+    do {                                                                                           \
+        const long long tm_now = clock64();                                                        \
+        atomicAdd(&pg_mlp_timing_buf[(blockIdx.x & 1023) * 16 + (slot)], (unsigned long long)(tm_now - tm_last)); \
+        tm_last = tm_now;                                                                          \
+    } while (0)
+#else
+#define PG_TIME_DECL
+#define PG_TIME_ADD(slot)
+#endif
+__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(T_THREADS) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void x_control(const XPipe& p, const MlpPacked* w, int cwarp, int lane, uint32_t rank) {
+    if (lane != 0) {
+    } else if (cwarp == 1) {  // producer: a stage is requested again as soon as the MMAs that read it have retired
+        for (uint32_t c = 0; c < p.total; c++) x_request(p, c, w->W2h, w->W2l, (int)(c & 7), rank);
+    } else if (rank != 0) {  // peer: tell the leader when a stage of OUR ring is full
+        for (uint32_t c = 0; c < p.total; c++) {
+            const uint32_t set = c & 1, u = c >> 1;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                mbar_wait(&p.full[set * 4 + j], u & 1);
+                mbar_arrive_remote(&p.pfull[set * 4 + j], 0);
+            }
+        }
+    } else {  // leader: one thread drives both tensor cores
+        PG_TIME_DECL;
+        for (uint32_t c = 0; c < p.total; c++) {
+            const uint32_t set = c & 1, u = c >> 1;
+            const int kb = (int)(c & 7);
+            PG_TIME_ADD(10);
+            mbar_wait(&p.a_full[set], u & 1);
+            PG_TIME_ADD(8);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // descriptors: the start address sits in the low 14 bits in 16-byte units, so the k-slice ks (+32 bytes) is + 2 * ks
+            const uint64_t da_hi = umma_desc_sw128(smem_u32(p.Ab + set * X_ABUF_BYTES)), da_lo = da_hi + (CHUNK_BYTES >> 4);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t s = set * 4 + j;
+                PG_TIME_ADD(10);
+                mbar_wait(&p.full[s], u & 1);
+#ifdef PG_MLP_TIMING
+                PG_TIME_ADD(9);
+#endif
+                mbar_wait(&p.pfull[s], u & 1);
+                PG_TIME_ADD(11);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t db = umma_desc_sw128(smem_u32(p.Bs + s * CHUNK_BYTES));
+                const uint32_t d = p.tmem_base + (j >> 1) * 256;
+                if ((j & 1) == 0) {  // Wh: Al Wh (small) first, then Ah Wh
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++) umma_f16_2sm(d, da_lo + 2 * ks, db + 2 * ks, X_IDESC_2SM, (kb > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++) umma_f16_2sm(d, da_hi + 2 * ks, db + 2 * ks, X_IDESC_2SM, 1u);
+                } else {  // Wl: Ah Wl
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++) umma_f16_2sm(d, da_hi + 2 * ks, db + 2 * ks, X_IDESC_2SM, 1u);
+                }
+                umma_commit_2sm(&p.empty[s], CL_MASK);  // frees the stage in both CTAs
+            }
+            umma_commit_2sm(&p.a_empty[set], CL_MASK);  // ... and the A buffer
+            if (kb == 7) umma_commit_2sm(p.accum, CL_MASK);  // all 512 accumulator columns final in both CTAs
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(XC_THREADS, 1) mlp_x3_kernel(const MlpArgs a) {
     extern __shared__ __align__(1024) uint8_t tsm[];
     XSmem sm;
     sm.Ab = tsm;
@@ -1358,15 +1450,17 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_x
     const pg::MathCtx<double> mc;
     const uint32_t rank = cluster_ctarank();
 
-    x_setup(sm, t, warp);
-    stage_constants(w, eps, w1s, t);
+    x_setup(sm, t, warp, CL * (T_THREADS / 32));
+    if (t < T_THREADS) stage_constants(w, eps, w1s, t);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     cluster_sync();  // the peer's barriers are initialised before anything arrives on them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     XPipe pipe = {sm.Ab, sm.Bs, sm.full, sm.empty, sm.pfull, sm.a_full, sm.a_empty, sm.accum, *sm.tmem_slot, 0u, (uint32_t)((hi - lo) * 8), 0u};
     const uint32_t tmem_base = pipe.tmem_base;
-    if (t == PRODUCER_THREAD && pipe.total > 0) x_request(pipe, 0, w->W2h, w->W2l, 0, rank);
+    if (warp >= T_THREADS / 32) {  // the control warps
+        x_control(pipe, w, warp - T_THREADS / 32, t & 31, rank);
+    } else {
 
     double x[8], u[2], xe[8], ue[2], fplus[8];
     if (steps == 0 && owner) {  // T = 0: only the initial states
@@ -1374,6 +1468,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_x
         load_row(a, r0, x, u);
     }
     bool first = true;
+    PG_TIME_DECL;
     for (int64_t pos = hi; pos > lo;) {
     const int64_t pair = (pos - 1) / steps, base = pair * steps;
     const int k_begin = (int)(max(lo, base) - base), k_end = (int)(pos - base);
@@ -1383,14 +1478,14 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_x
     rw.valid = rw.valid && owner;
     if (k_begin > 0) {  // continue where another cluster left this tile
         if (t == 0) wait_progress(&a.progress[tile], k_begin);
-        __syncthreads();
+        compute_sync();
     }
     if (owner) {
         if (k_begin == 0) load_row(a, rw, x, u);
         else reload_row(a, rw, k_begin, x, u);
     }
     for (int k = k_begin; k < k_end; k++) {
-        if (!first) __syncthreads();  // the previous interval's partial sums (they alias `ins`) have been consumed
+        if (!first) compute_sync();  // the previous interval's partial sums (they alias `ins`) have been consumed
         first = false;
         if (owner) {
             pre_step(a, rw, k, x, u, xe, ue);
@@ -1400,7 +1495,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_x
             for (int j = 0; j < MAXIN; j += 4)
                 *reinterpret_cast<float4*>(&ins[row * INS_STRIDE + j]) = make_float4(in[j], in[j + 1], in[j + 2], in[j + 3]);
         }
-        __syncthreads();
+        compute_sync();
+        if (t == 0) PG_TIME_ADD(0);
         float in[16];
 #pragma unroll
         for (int j = 0; j < MAXIN; j += 4) {
@@ -1408,14 +1504,20 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_x
             in[j] = v4.x; in[j + 1] = v4.y; in[j + 2] = v4.z; in[j + 3] = v4.w;
         }
         for (int kb = 0; kb < 8; kb++) {
-            uint8_t* abuf = x_abuf(pipe);
+            uint8_t* abuf = x_abuf_parked(pipe);
             x_l1_dispatch(nin, w, w1s, in, kb, row, part, abuf);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA unit
-            __syncthreads();
-            x_issue(pipe, kb, kb == 7, w->W2h, w->W2l, (kb + 1) & 7, t, rank);
+            __syncwarp();
+            if ((t & 31) == 0) {  // this warp's share of the A block is written: one of the 2 x 16 arrivals the issuer waits for
+                if (rank == 0) mbar_arrive_local(&pipe.a_full[pipe.c & 1]);
+                else mbar_arrive_remote(&pipe.a_full[pipe.c & 1], 0);
+            }
+            pipe.c++;
         }
         // epilogue: TMEM lane = row; this thread's quarter of the 512 columns: +b2, ReLU, layer 3
-        mbar_wait(pipe.accum, pipe.passes & 1);
+        if (t == 0) PG_TIME_ADD(1);
+        mbar_wait_parked(pipe.accum, pipe.passes & 1);
+        if (t == 0) PG_TIME_ADD(2);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         {
             float y[MAXDX] = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -1437,7 +1539,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_x
         }
         pipe.passes++;
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();  // every lane has read its accumulators before the next interval's MMAs overwrite them
+        compute_sync();  // every lane has read its accumulators before the next interval's MMAs overwrite them
+        if (t == 0) PG_TIME_ADD(3);
         if (owner) {
             float y[MAXDX];
 #pragma unroll
@@ -1449,13 +1552,20 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_x
             }
             post_step(a, rw, k, y, x, u, xe, fplus);
         }
+#ifdef PG_MLP_TIMING
+        if (t == 0) {
+            PG_TIME_ADD(4);
+            atomicAdd(&pg_mlp_timing_buf[(blockIdx.x & 1023) * 16 + 15], 1ull);
+        }
+#endif
     }
     if (a.progress && k_end < steps) {  // the head of a pair: publish that X holds the states up to interval k_end
         __threadfence();
-        __syncthreads();
+        compute_sync();
         if (t == 0) publish_progress(&a.progress[tile], k_end);
     }
     }
+    }  // compute warps
     __syncthreads();
     cluster_sync();  // no CTA leaves while its peer may still signal its barriers
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
@@ -1652,7 +1762,7 @@ int64_t max_rows(const MlpArgs& a) {  // upper bound of total_rows() known on th
 
 // rollouts on a tensor-core kernel (bf16 or split fp16), plain or with the balanced schedule
 template <typename K>
-int launch_tc(K kernel, int smem, int* resident, bool* attr_set, const MlpArgs& a, int64_t rows, cudaStream_t st) {
+int launch_tc(K kernel, int smem, int* resident, bool* attr_set, const MlpArgs& a, int64_t rows, cudaStream_t st, int threads = T_THREADS) {
     if (!*attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
@@ -1663,7 +1773,7 @@ int launch_tc(K kernel, int smem, int* resident, bool* attr_set, const MlpArgs& 
         if (!*resident) {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(CL * 1024);
-            cfg.blockDim = dim3(T_THREADS);
+            cfg.blockDim = dim3(threads);
             cfg.dynamicSmemBytes = smem;
             cudaLaunchAttribute at;
             at.id = cudaLaunchAttributeClusterDimension;
@@ -1682,7 +1792,7 @@ int launch_tc(K kernel, int smem, int* resident, bool* attr_set, const MlpArgs& 
         if (e != cudaSuccess) return (int)e;
         if (clusters > *resident) clusters = *resident;
     }
-    kernel<<<(unsigned)(clusters * CL), T_THREADS, smem, st>>>(a);
+    kernel<<<(unsigned)(clusters * CL), threads, smem, st>>>(a);
     return 0;
 }
 
@@ -1726,7 +1836,7 @@ int launch(int precision, const MlpArgs& a, cudaStream_t st) {
     } else if (precision == PG_MLP_F16X3) {
         static bool set = false;
         static int resident = 0;
-        const int rc = launch_tc(mlp_x3_kernel, X_SMEM, &resident, &set, a, rows, st);
+        const int rc = launch_tc(mlp_x3_kernel, X_SMEM, &resident, &set, a, rows, st, XC_THREADS);
         if (rc) return rc;
     } else {
         return PG_E_BADARG;
@@ -1929,3 +2039,15 @@ int pg_mlp_linearize(int precision, int lin_mode, const pg_mlp_dims_t* dims, con
 }
 
 }  // extern "C"
+
+#ifdef PG_MLP_TIMING
+extern "C" int pg_mlp_timing_read(unsigned long long* out, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out, pg_mlp_timing_buf, sizeof(unsigned long long) * 1024 * 16);
+    if (e != cudaSuccess) return (int)e;
+    if (reset) {
+        static unsigned long long zeros[1024 * 16];
+        e = cudaMemcpyToSymbol(pg_mlp_timing_buf, zeros, sizeof(zeros));
+    }
+    return (int)e;
+}
+#endif

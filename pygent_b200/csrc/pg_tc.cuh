@@ -29,6 +29,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (!ok && spins > (1u << 26)) __trap();  // a lost arrival must not hang the GPU
     }
 }
+// The same for the many threads of a compute phase: the hint lets the hardware park the warp until the phase completes (or
+// ~20 us pass) instead of returning after its short default limit -- sixteen warps polling in a loop took a third of the
+// issue slots of mlp_x3_kernel, and with them the slots its two control threads needed (profiles/r02_mlp_x3_v2).
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok = 0;
+    for (uint32_t spins = 0; !ok; spins++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity), "r"(20000u)
+            : "memory");
+        if (!ok && spins > (1u << 20)) __trap();  // a lost arrival must not hang the GPU
+    }
+}
 // plain bulk copy global -> own smem, completion on an own mbarrier
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
