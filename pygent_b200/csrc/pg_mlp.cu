@@ -1289,6 +1289,47 @@ __device__ __forceinline__ uint32_t x_l1_block(const float* w1, int w1_stride, c
     return bits;
 }
 
+// The same block with packed arithmetic (fma.rn.f32x2: two hidden units per instruction; per unit the same sequence of
+// fused multiply-adds as x_l1_block, so the values are identical), for the rollout kernel, whose layer 1 took as long as the
+// tensor core needs for the block (tools/mlp_timing.py).  w1p: the weight rows of a PAIR of units interleaved,
+// w1p[(k / 2) * 16 + 2 i + (k & 1)] = W1b[k][i], i < 8 (stage_w1_pairs); in2[i] = {in[i], in[i]}.  Inputs + 1 <= 8.
+__device__ __forceinline__ void ffma2(float2& acc, const float2 a, const float2 b) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%0, %1};\n\t"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rc;\n\t}"
+        : "+f"(acc.x), "+f"(acc.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+}
+
+__device__ __forceinline__ void stage_w1_pairs(const MlpPacked* w, float* w1p, int t) {
+    for (int i = t; i < H * W1S_FLOATS; i += T_THREADS) {
+        const int k = i / W1S_FLOATS, c = i % W1S_FLOATS;
+        w1p[(k >> 1) * (2 * W1S_FLOATS) + 2 * c + (k & 1)] = w->W1b[k][c];
+    }
+}
+
+template <int NQ>
+__device__ __forceinline__ void x_l1_block_pairs(const float* w1p, const float2 (&in2)[8], int kb, int row, int part, uint8_t* abuf) {
+    float v[16];
+#pragma unroll
+    for (int e = 0; e < 16; e += 2) {
+        const int k = kb * 64 + part * 16 + e;
+        const float4* wr = reinterpret_cast<const float4*>(w1p + (size_t)(k >> 1) * (2 * W1S_FLOATS));
+        float2 acc = make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int q = 0; q < 2 * NQ; q++) {  // inputs 2 q, 2 q + 1 of both units
+            const float4 ww = wr[q];
+            ffma2(acc, make_float2(ww.x, ww.y), in2[2 * q]);
+            ffma2(acc, make_float2(ww.z, ww.w), in2[2 * q + 1]);
+        }
+        // relu; the rows of the padding units (k >= HID) are zero
+        v[e] = fmaxf(acc.x, 0.0f);
+        v[e + 1] = fmaxf(acc.y, 0.0f);
+    }
+    x_store16(v, abuf, row, part);
+}
+
 __device__ __forceinline__ uint32_t x_l1_dispatch(int nin, const MlpPacked* w, const float* w1s, const float (&in)[16], int kb, int row,
                                                  int part, uint8_t* abuf) {
     const int nq = (nin + 1 + 3) >> 2;  // inputs + the constant 1, in float4 units
@@ -1314,7 +1355,7 @@ __device__ __forceinline__ void x_barriers(uint8_t* base, XSmem& m) {
     m.tmem_slot = reinterpret_cast<uint32_t*>(m.accum + 1);
 }
 
-__device__ __forceinline__ void x_setup(const XSmem& m, int t, int warp, uint32_t a_full_count = 1) {
+__device__ __forceinline__ void x_setup(const XSmem& m, int t, int warp, uint32_t a_full_count = 1, uint32_t issuers = 1) {
     if (t == 0) {
         for (int s = 0; s < X_NST; s++) {
             mbar_init(&m.full[s], 1);
@@ -1323,9 +1364,9 @@ __device__ __forceinline__ void x_setup(const XSmem& m, int t, int warp, uint32_
         }
         for (int s = 0; s < 2; s++) {
             mbar_init(&m.a_full[s], a_full_count);
-            mbar_init(&m.a_empty[s], 1);
+            mbar_init(&m.a_empty[s], issuers);
         }
-        mbar_init(m.accum, 1);
+        mbar_init(m.accum, issuers);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {  // the whole accumulator file of the SM pair: 128 lanes x 512 fp32 columns per CTA
@@ -1342,9 +1383,9 @@ __device__ __forceinline__ void x_setup(const XSmem& m, int t, int warp, uint32_
 // (profiles/r02_mlp_x3_ncu_summary.txt).  The two control threads must not share a warp either: a thread held at the issue of
 // a tcgen05.mma holds its warp, so a producer in a sibling lane only ran while the issuer waited -- the refills then followed
 // the MMAs instead of overlapping them (tools/mlp_timing.py: "wait weights" = "issuing").
-constexpr int XC_THREADS = T_THREADS + 64;
+constexpr int XC_THREADS = T_THREADS + 96;
 // -DPG_MLP_TIMING (tools/mlp_timing.py; never in the product build): cycles per phase of mlp_x3_kernel, summed per CTA --
-// compute thread 0: [0] owner phase + input hand-over, [1] the eight layer-1 blocks incl. waits for a free A buffer,
+// compute thread 0: [0] owner phase + input hand-over, [1] the eight layer-1 blocks, [5] their waits for a free A buffer,
 // [2] waiting for the last MMAs, [3] epilogue, [4] partial sums + state update; the leader's issuing thread: [8] waiting
 // for an A block, [9] waiting for weight stages, [10] issuing; [15] intervals.
 #ifdef PG_MLP_TIMING
@@ -1365,21 +1406,26 @@ __device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
     asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// cwarp 0 / 1: the issuer of accumulator half 0 / 1 (weight stages j = 2 * half, 2 * half + 1 of every k-step: the halves are
+// disjoint TMEM columns, so two threads can feed the tensor cores side by side -- one thread needed longer to wait for and
+// issue a k-step than the MMAs take); cwarp 2: the producer.
 __device__ __forceinline__ void x_control(const XPipe& p, const MlpPacked* w, int cwarp, int lane, uint32_t rank) {
+    const int jh = 2 * cwarp;
     if (lane != 0) {
-    } else if (cwarp == 1) {  // producer: a stage is requested again as soon as the MMAs that read it have retired
+    } else if (cwarp == 2) {  // producer: a stage is requested again as soon as the MMAs that read it have retired
         for (uint32_t c = 0; c < p.total; c++) x_request(p, c, w->W2h, w->W2l, (int)(c & 7), rank);
     } else if (rank != 0) {  // peer: tell the leader when a stage of OUR ring is full
         for (uint32_t c = 0; c < p.total; c++) {
             const uint32_t set = c & 1, u = c >> 1;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
+            for (int j = jh; j < jh + 2; j++) {
                 mbar_wait(&p.full[set * 4 + j], u & 1);
                 mbar_arrive_remote(&p.pfull[set * 4 + j], 0);
             }
         }
-    } else {  // leader: one thread drives both tensor cores
+    } else {  // leader: drives both tensor cores (its half of the accumulator columns)
         PG_TIME_DECL;
+        (void)0;
         for (uint32_t c = 0; c < p.total; c++) {
             const uint32_t set = c & 1, u = c >> 1;
             const int kb = (int)(c & 7);
@@ -1390,7 +1436,7 @@ __device__ __forceinline__ void x_control(const XPipe& p, const MlpPacked* w, in
             // descriptors: the start address sits in the low 14 bits in 16-byte units, so the k-slice ks (+32 bytes) is + 2 * ks
             const uint64_t da_hi = umma_desc_sw128(smem_u32(p.Ab + set * X_ABUF_BYTES)), da_lo = da_hi + (CHUNK_BYTES >> 4);
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
+            for (int j = jh; j < jh + 2; j++) {
                 const uint32_t s = set * 4 + j;
                 PG_TIME_ADD(10);
                 mbar_wait(&p.full[s], u & 1);
@@ -1401,7 +1447,7 @@ __device__ __forceinline__ void x_control(const XPipe& p, const MlpPacked* w, in
                 PG_TIME_ADD(11);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint64_t db = umma_desc_sw128(smem_u32(p.Bs + s * CHUNK_BYTES));
-                const uint32_t d = p.tmem_base + (j >> 1) * 256;
+                const uint32_t d = p.tmem_base + (uint32_t)cwarp * 256;
                 if ((j & 1) == 0) {  // Wh: Al Wh (small) first, then Ah Wh
 #pragma unroll
                     for (int ks = 0; ks < 4; ks++) umma_f16_2sm(d, da_lo + 2 * ks, db + 2 * ks, X_IDESC_2SM, (kb > 0 || ks > 0) ? 1u : 0u);
@@ -1450,8 +1496,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(XC_THREADS, 1) mlp_
     const pg::MathCtx<double> mc;
     const uint32_t rank = cluster_ctarank();
 
-    x_setup(sm, t, warp, CL * (T_THREADS / 32));
-    if (t < T_THREADS) stage_constants(w, eps, w1s, t);
+    x_setup(sm, t, warp, CL * (T_THREADS / 32), 2);
+    const int nq = (nin + 1 + 3) >> 2;  // inputs + the constant 1, in float4 units
+    if (t < T_THREADS) {
+        stage_constants(w, eps, nq <= 2 ? nullptr : w1s, t);
+        if (nq <= 2) stage_w1_pairs(w, w1s, t);
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     cluster_sync();  // the peer's barriers are initialised before anything arrives on them
@@ -1503,9 +1553,16 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(XC_THREADS, 1) mlp_
             const float4 v4 = *reinterpret_cast<const float4*>(&ins[row * INS_STRIDE + j]);
             in[j] = v4.x; in[j + 1] = v4.y; in[j + 2] = v4.z; in[j + 3] = v4.w;
         }
+        float2 in2[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) in2[j] = make_float2(in[j], in[j]);
         for (int kb = 0; kb < 8; kb++) {
+            if (t == 0) PG_TIME_ADD(1);
             uint8_t* abuf = x_abuf_parked(pipe);
-            x_l1_dispatch(nin, w, w1s, in, kb, row, part, abuf);
+            if (t == 0) PG_TIME_ADD(5);
+            if (nq <= 1) x_l1_block_pairs<1>(w1s, in2, kb, row, part, abuf);
+            else if (nq == 2) x_l1_block_pairs<2>(w1s, in2, kb, row, part, abuf);
+            else x_l1_dispatch(nin, w, w1s, in, kb, row, part, abuf);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA unit
             __syncwarp();
             if ((t & 31) == 0) {  // this warp's share of the A block is written: one of the 2 x 16 arrivals the issuer waits for

@@ -43,15 +43,15 @@ dll.pg_mlp_timing_read(buf, 0)
 a = np.array(buf, dtype=np.float64).reshape(1024, 16)
 a = a[a[:, 15] > 0]
 n = a[:, 15].sum()
-names = {0: "owner phase + inputs", 1: "8 layer-1 blocks (incl. A-buffer waits)", 2: "wait for the last MMAs", 3: "epilogue",
+names = {0: "owner phase + inputs", 1: "8 layer-1 blocks", 5: "waits for a free A buffer", 2: "wait for the last MMAs", 3: "epilogue",
          4: "partial sums + update", 8: "issuer: wait A block", 9: "issuer: wait own weight stage", 10: "issuer: issuing", 11: "issuer: wait the peer's stage (relay)"}
 print("rows %d: CTAs %d, intervals per CTA %.1f; cycles per interval (mean over CTAs):" % (R, len(a), a[:, 15].mean()))
 tot = 0.0
-for k in (0, 1, 2, 3, 4):
+for k in (0, 1, 5, 2, 3, 4):
     v = a[:, k].sum() / n
     tot += v
     print("  %-42s %8.0f" % (names[k], v))
 print("  %-42s %8.0f  (%.2f us at 1.9 GHz)" % ("sum", tot, tot / 1900))
 lead = a[a[:, 10] > 0]
 for k in (8, 9, 11, 10):
-    print("  %-42s %8.0f" % (names[k], lead[:, k].sum() / lead[:, 15].sum()))
+    print("  %-42s %8.0f  (two issuing threads: mean)" % (names[k], lead[:, k].sum() / lead[:, 15].sum() / 2))
