@@ -792,6 +792,29 @@ def test_fused_tail_solver_changes_nothing(case, kw):
             assert np.array_equal(p, q)
 
 
+@pytest.mark.parametrize("case,rounds", [("cart_pole", 1), ("cart_pole", 7), ("double_parallel", 5), ("pendulum", 3)])
+def test_fused_tail_rounds_change_nothing(case, rounds):
+    """The fused solver in rounds (pg_ilqr_solve.round_iters): every launch gives each running trajectory at most `rounds`
+    iterations, writes the list of those still running and the next launch deals them to the warps anew (more trajectories
+    than 4 x SMs, so that both ticket ranges and the re-dealing are exercised; lists at most that long are finished by the
+    launch that finds them).  Whatever the round length, the solve must be the one of the launch-per-step loop, bit for bit."""
+    B, T = 900, 50
+    rng = np.random.default_rng(79)
+    n = len(CASES[case][4])
+    x0 = np.array(CASES[case][4]) + rng.uniform(-0.3, 0.3, (B, n))
+    res = []
+    for fused, r in ((False, 0), (True, rounds), (True, 10 ** 6)):
+        alg = solver(case, T, x0=x0, maxIters=40)
+        alg.tail_threshold, alg.fused_tail, alg.tail_round = 10 ** 9, fused, max(r, 1)
+        alg.run_optim(host_results=False)
+        res.append((alg.iters.copy(), alg.status.copy(), np.array(alg.cost), np.array(alg.xx), np.array(alg.uu), np.array(alg.KK),
+                    np.array(alg.kk), np.array(alg.mu), np.array(alg.current_alpha)))
+    assert res[0][0].max() > 10 and (res[0][0] < 40).any()
+    for other in res[1:]:
+        for p, q in zip(res[0], other):
+            assert np.array_equal(p, q)
+
+
 @pytest.mark.parametrize("case,T", [("cart_pole", 60), ("double_parallel", 60), ("double_serial", 40), ("pendulum", 40), ("car", 40), ("triple", 30),
                                     ("acrobot", 40)])
 def test_terminal_value_on_device_matches_scipy(case, T):
