@@ -1240,12 +1240,6 @@ __device__ __forceinline__ uint8_t* x_abuf(const XPipe& p) {
     return p.Ab + set * X_ABUF_BYTES;
 }
 
-__device__ __forceinline__ uint8_t* x_abuf_parked(const XPipe& p) {
-    const uint32_t set = p.c & 1, u = p.c >> 1;
-    mbar_wait_parked(&p.a_empty[set], (u & 1) ^ 1);
-    return p.Ab + set * X_ABUF_BYTES;
-}
-
 // 16 values of this thread (its row, hidden units kb * 64 + part * 16 .. + 15) -> split -> the A buffer
 __device__ __forceinline__ void x_store16(const float (&v)[16], uint8_t* abuf, int row, int part) {
 #pragma unroll
@@ -1401,6 +1395,58 @@ __device__ unsigned long long pg_mlp_timing_buf[1024 * 16];
 #define PG_TIME_DECL
 #define PG_TIME_ADD(slot)
 #endif
+// Ring geometry of the rollout kernel: THREE A buffers and a SIX-stage weight ring in the 192 KB the two A buffers and eight
+// stages of the Jacobian kernel take.  With two A buffers layer 1 of block c + 2 could not start before the MMAs of block c
+// had retired, and those of block c + 2 not before it was written: ~9 k of the 50 k cycles of an interval were fill and
+// drain of that ping-pong.  Weight stage of (k-step c, chunk j): g = 4 c + j -> stage g % 6, use g / 6; the stages were
+// never late (tools/mlp_timing.py), and six still cover more than a k-step of MMAs.
+constexpr int XR_NST = 6, XR_ABUFS = 3;
+static_assert(XR_ABUFS * X_ABUF_BYTES + XR_NST * CHUNK_BYTES == 2 * X_ABUF_BYTES + X_NST * CHUNK_BYTES, "rollout ring: same shared memory");
+__device__ __forceinline__ void xr_barriers(uint8_t* base, XSmem& m) {
+    m.full = reinterpret_cast<uint64_t*>(base);
+    m.empty = m.full + XR_NST;
+    m.pfull = m.empty + XR_NST;
+    m.a_full = m.pfull + XR_NST;
+    m.a_empty = m.a_full + XR_ABUFS;
+    m.accum = m.a_empty + XR_ABUFS;
+    m.tmem_slot = reinterpret_cast<uint32_t*>(m.accum + 1);
+}
+__device__ __forceinline__ void xr_setup(const XSmem& m, int t, int warp, uint32_t a_full_count, uint32_t issuers) {
+    if (t == 0) {
+        for (int s = 0; s < XR_NST; s++) {
+            mbar_init(&m.full[s], 1);
+            mbar_init(&m.empty[s], 1);
+            mbar_init(&m.pfull[s], 1);
+        }
+        for (int s = 0; s < XR_ABUFS; s++) {
+            mbar_init(&m.a_full[s], a_full_count);
+            mbar_init(&m.a_empty[s], issuers);
+        }
+        mbar_init(m.accum, issuers);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {  // the whole accumulator file of the SM pair: 128 lanes x 512 fp32 columns per CTA
+        asm volatile(PG_TMEM_ALLOC_2SM ::"r"(smem_u32(m.tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+}
+// weight chunks of k-step c -> their ring stages.  Producer thread only.
+__device__ __forceinline__ void xr_request(const XPipe& p, uint32_t c, const uint16_t (*imgh)[CHUNK_BYTES / 2],
+                                           const uint16_t (*imgl)[CHUNK_BYTES / 2], int kb, uint32_t rank) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {  // j = 2 * (column half) + (lo part)
+        const uint32_t g = 4 * c + j, s = g % XR_NST, n = g / XR_NST;
+        mbar_wait(&p.empty[s], (n & 1) ^ 1);
+        mbar_expect_tx(&p.full[s], CHUNK_BYTES);
+        const uint16_t(*img)[CHUNK_BYTES / 2] = (j & 1) ? imgl : imgh;
+        bulk_g2s(p.Bs + s * CHUNK_BYTES, &img[(2 * (j >> 1) + rank) * 8 + kb][0], CHUNK_BYTES, &p.full[s]);
+    }
+}
+__device__ __forceinline__ uint8_t* xr_abuf_parked(const XPipe& p) {
+    const uint32_t set = p.c % XR_ABUFS, u = p.c / XR_ABUFS;
+    mbar_wait_parked(&p.a_empty[set], (u & 1) ^ 1);
+    return p.Ab + set * X_ABUF_BYTES;
+}
 __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(T_THREADS) : "memory"); }
 __device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
     asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -1413,21 +1459,20 @@ __device__ __forceinline__ void x_control(const XPipe& p, const MlpPacked* w, in
     const int jh = 2 * cwarp;
     if (lane != 0) {
     } else if (cwarp == 2) {  // producer: a stage is requested again as soon as the MMAs that read it have retired
-        for (uint32_t c = 0; c < p.total; c++) x_request(p, c, w->W2h, w->W2l, (int)(c & 7), rank);
+        for (uint32_t c = 0; c < p.total; c++) xr_request(p, c, w->W2h, w->W2l, (int)(c & 7), rank);
     } else if (rank != 0) {  // peer: tell the leader when a stage of OUR ring is full
         for (uint32_t c = 0; c < p.total; c++) {
-            const uint32_t set = c & 1, u = c >> 1;
 #pragma unroll
             for (int j = jh; j < jh + 2; j++) {
-                mbar_wait(&p.full[set * 4 + j], u & 1);
-                mbar_arrive_remote(&p.pfull[set * 4 + j], 0);
+                const uint32_t g = 4 * c + j, s = g % XR_NST, n = g / XR_NST;
+                mbar_wait(&p.full[s], n & 1);
+                mbar_arrive_remote(&p.pfull[s], 0);
             }
         }
     } else {  // leader: drives both tensor cores (its half of the accumulator columns)
         PG_TIME_DECL;
-        (void)0;
         for (uint32_t c = 0; c < p.total; c++) {
-            const uint32_t set = c & 1, u = c >> 1;
+            const uint32_t set = c % XR_ABUFS, u = c / XR_ABUFS;
             const int kb = (int)(c & 7);
             PG_TIME_ADD(10);
             mbar_wait(&p.a_full[set], u & 1);
@@ -1437,13 +1482,13 @@ __device__ __forceinline__ void x_control(const XPipe& p, const MlpPacked* w, in
             const uint64_t da_hi = umma_desc_sw128(smem_u32(p.Ab + set * X_ABUF_BYTES)), da_lo = da_hi + (CHUNK_BYTES >> 4);
 #pragma unroll
             for (int j = jh; j < jh + 2; j++) {
-                const uint32_t s = set * 4 + j;
+                const uint32_t g = 4 * c + j, s = g % XR_NST, n = g / XR_NST;
                 PG_TIME_ADD(10);
-                mbar_wait(&p.full[s], u & 1);
+                mbar_wait(&p.full[s], n & 1);
 #ifdef PG_MLP_TIMING
                 PG_TIME_ADD(9);
 #endif
-                mbar_wait(&p.pfull[s], u & 1);
+                mbar_wait(&p.pfull[s], n & 1);
                 PG_TIME_ADD(11);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint64_t db = umma_desc_sw128(smem_u32(p.Bs + s * CHUNK_BYTES));
@@ -1470,12 +1515,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(XC_THREADS, 1) mlp_
     extern __shared__ __align__(1024) uint8_t tsm[];
     XSmem sm;
     sm.Ab = tsm;
-    sm.Bs = tsm + 2 * X_ABUF_BYTES;
-    float* ins = reinterpret_cast<float*>(sm.Bs + X_NST * CHUNK_BYTES);
+    sm.Bs = tsm + XR_ABUFS * X_ABUF_BYTES;
+    float* ins = reinterpret_cast<float*>(sm.Bs + XR_NST * CHUNK_BYTES);
     float* yp = ins;  // partial layer-3 sums [T_SPLIT][T_ROWS][MAXDX]: the input tile is in registers by then
     float4* eps = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(ins) + T_INS_BYTES);
     float* w1s = reinterpret_cast<float*>(eps + H);
-    x_barriers(reinterpret_cast<uint8_t*>(w1s) + T_W1_BYTES, sm);
+    xr_barriers(reinterpret_cast<uint8_t*>(w1s) + T_W1_BYTES, sm);
     const MlpPacked* w = a.w;
     const int t = threadIdx.x, warp = t >> 5, row = t & (T_ROWS - 1), part = t >> 7;
     const int steps = steps_of(a);
@@ -1496,7 +1541,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(XC_THREADS, 1) mlp_
     const pg::MathCtx<double> mc;
     const uint32_t rank = cluster_ctarank();
 
-    x_setup(sm, t, warp, CL * (T_THREADS / 32), 2);
+    xr_setup(sm, t, warp, CL * (T_THREADS / 32), 2);
     const int nq = (nin + 1 + 3) >> 2;  // inputs + the constant 1, in float4 units
     if (t < T_THREADS) {
         stage_constants(w, eps, nq <= 2 ? nullptr : w1s, t);
@@ -1558,7 +1603,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(XC_THREADS, 1) mlp_
         for (int j = 0; j < 8; j++) in2[j] = make_float2(in[j], in[j]);
         for (int kb = 0; kb < 8; kb++) {
             if (t == 0) PG_TIME_ADD(1);
-            uint8_t* abuf = x_abuf_parked(pipe);
+            uint8_t* abuf = xr_abuf_parked(pipe);
             if (t == 0) PG_TIME_ADD(5);
             if (nq <= 1) x_l1_block_pairs<1>(w1s, in2, kb, row, part, abuf);
             else if (nq == 2) x_l1_block_pairs<2>(w1s, in2, kb, row, part, abuf);
@@ -1566,8 +1611,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(XC_THREADS, 1) mlp_
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA unit
             __syncwarp();
             if ((t & 31) == 0) {  // this warp's share of the A block is written: one of the 2 x 16 arrivals the issuer waits for
-                if (rank == 0) mbar_arrive_local(&pipe.a_full[pipe.c & 1]);
-                else mbar_arrive_remote(&pipe.a_full[pipe.c & 1], 0);
+                if (rank == 0) mbar_arrive_local(&pipe.a_full[pipe.c % XR_ABUFS]);
+                else mbar_arrive_remote(&pipe.a_full[pipe.c % XR_ABUFS], 0);
             }
             pipe.c++;
         }
