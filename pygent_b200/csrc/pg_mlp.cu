@@ -1150,11 +1150,13 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_j
 // TMEM: fp32-class results (the dropped term is 2^-22) at a third of the fp16 tensor rate.  Twice the operand bytes do not
 // fit the "whole A image in shared memory" design above (2 x 128 KB), so the GEMM runs K-BLOCK-MAJOR instead:
 //   for each block of 64 hidden units kb:  all 512 threads compute layer 1 for (128 rows x 64 units) on the CUDA cores in
-//   fp32 -- exactly the reference's arithmetic for that layer -- and write it, split, into one of two 32 KB A buffers;
-//   the leader's issuing thread then multiplies it against the four 16 KB weight chunks of that block (two 256-column
-//   halves x {hi, lo}; cta_group::2, M = 256 = both CTAs' rows, N = 256) into ALL 512 accumulator columns,
-// and layer 1 of block kb + 1 overlaps the MMAs of block kb.  No layer-1 GEMM pass, no TMEM -> smem conversion of H1, an
-// 8-stage weight ring (2 x 4 chunks) where the bf16 kernel has room for 4.
+//   fp32 -- exactly the reference's arithmetic for that layer -- and write it, split, into one of three 32 KB A buffers;
+//   the leader's two issuing threads (one per 256-column half of the accumulators, in control warps of their own) multiply
+//   it against the four 16 KB weight chunks of that block (two 256-column halves x {hi, lo}; cta_group::2, M = 256 = both
+//   CTAs' rows, N = 256) into ALL 512 accumulator columns,
+// and layer 1 of the blocks ahead overlaps the MMAs of block kb.  No layer-1 GEMM pass, no TMEM -> smem conversion of H1, a
+// 6-stage weight ring where the bf16 kernel has room for 4.  (X_NST / "2 x" below: the budget the geometry was first written
+// for -- two A buffers + eight stages; XR_ABUFS / XR_NST further down redistribute the same 192 KB.)
 constexpr int X_NST = 8;
 constexpr int X_ABUF_BYTES = 2 * CHUNK_BYTES;  // A_hi | A_lo of one k-block: [128 rows x 64 k] fp16 each
 constexpr int X_SMEM = 2 * X_ABUF_BYTES + X_NST * CHUNK_BYTES + T_INS_BYTES + T_CONST_BYTES + 256;
@@ -1162,83 +1164,16 @@ constexpr uint32_t X_IDESC_2SM = umma_idesc_f16(0u, 256u, 256u);
 static_assert(X_SMEM <= 232448, "x3 kernels: shared memory");
 
 struct XPipe {
-    uint8_t* Ab;       // 2 A buffers
+    uint8_t* Ab;       // XR_ABUFS A buffers
     uint8_t* Bs;       // weight ring
-    uint64_t *full, *empty, *pfull;  // [X_NST]
-    uint64_t *a_full, *a_empty;      // [2]
+    uint64_t *full, *empty, *pfull;  // [XR_NST]
+    uint64_t *a_full, *a_empty;      // [XR_ABUFS]
     uint64_t* accum;
     uint32_t tmem_base;
     uint32_t c;       // k-steps issued so far by this CTA (barrier phases derive from it)
     uint32_t total;   // k-steps this CTA will run in total (no weight chunk is requested beyond it)
     uint32_t passes;  // GEMMs completed (phase of `accum`)
 };
-
-// weight chunks of k-step `c` (hidden-unit block kb of the image sets imgh/imgl) -> ring set c & 1.  Producer thread only.
-__device__ __forceinline__ void x_request(const XPipe& p, uint32_t c, const uint16_t (*imgh)[CHUNK_BYTES / 2],
-                                          const uint16_t (*imgl)[CHUNK_BYTES / 2], int kb, uint32_t rank) {
-    const uint32_t set = c & 1, u = c >> 1;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {  // j = 2 * (column half) + (lo part)
-        const uint32_t s = set * 4 + j;
-        mbar_wait(&p.empty[s], (u & 1) ^ 1);
-        mbar_expect_tx(&p.full[s], CHUNK_BYTES);
-        const uint16_t(*img)[CHUNK_BYTES / 2] = (j & 1) ? imgl : imgh;
-        bulk_g2s(p.Bs + s * CHUNK_BYTES, &img[(2 * (j >> 1) + rank) * 8 + kb][0], CHUNK_BYTES, &p.full[s]);
-    }
-}
-
-// Call after the A block of k-step p.c is in A buffer p.c & 1, fenced (fence.proxy.async) and the CTA has synchronised.
-// (nh, nl, nkb): image sets and block of the NEXT k-step, whose weights are requested now (nullptr: there is none).
-__device__ __forceinline__ void x_issue(XPipe& p, int kb, bool last, const uint16_t (*nh)[CHUNK_BYTES / 2],
-                                        const uint16_t (*nl)[CHUNK_BYTES / 2], int nkb, int t, uint32_t rank) {
-    const uint32_t c = p.c, set = c & 1, u = c >> 1;
-    if (t == 0 && rank != 0) mbar_arrive_remote(&p.a_full[set], 0);  // the peer's half of the A block is written
-    if (t == PRODUCER_THREAD && nh != nullptr && c + 1 < p.total) x_request(p, c + 1, nh, nl, nkb, rank);
-    if (t == ISSUER_THREAD) {
-        if (rank != 0) {  // peer: tell the leader when a stage of OUR ring is full
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                mbar_wait(&p.full[set * 4 + j], u & 1);
-                mbar_arrive_remote(&p.pfull[set * 4 + j], 0);
-            }
-        } else {  // leader: one thread drives both tensor cores
-            mbar_wait(&p.a_full[set], u & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_hi = smem_u32(p.Ab + set * X_ABUF_BYTES), a_lo = a_hi + CHUNK_BYTES;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t s = set * 4 + j;
-                mbar_wait(&p.full[s], u & 1);
-                mbar_wait(&p.pfull[s], u & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t b = smem_u32(p.Bs + s * CHUNK_BYTES), d = p.tmem_base + (j >> 1) * 256;
-                if ((j & 1) == 0) {  // Wh: Al Wh (small) first, then Ah Wh
-#pragma unroll
-                    for (int ks = 0; ks < 4; ks++)
-                        umma_f16_2sm(d, umma_desc_sw128(a_lo + ks * 32), umma_desc_sw128(b + ks * 32), X_IDESC_2SM, (kb > 0 || ks > 0) ? 1u : 0u);
-#pragma unroll
-                    for (int ks = 0; ks < 4; ks++)
-                        umma_f16_2sm(d, umma_desc_sw128(a_hi + ks * 32), umma_desc_sw128(b + ks * 32), X_IDESC_2SM, 1u);
-                } else {  // Wl: Ah Wl
-#pragma unroll
-                    for (int ks = 0; ks < 4; ks++)
-                        umma_f16_2sm(d, umma_desc_sw128(a_hi + ks * 32), umma_desc_sw128(b + ks * 32), X_IDESC_2SM, 1u);
-                }
-                umma_commit_2sm(&p.empty[s], CL_MASK);  // frees the stage in both CTAs
-            }
-            umma_commit_2sm(&p.a_empty[set], CL_MASK);  // ... and the A buffer
-            if (last) umma_commit_2sm(p.accum, CL_MASK);  // all 512 accumulator columns final in both CTAs
-        }
-    }
-    p.c = c + 1;
-}
-
-// every thread: wait until the A buffer of the coming k-step is free (the MMAs of two k-steps ago have read it)
-__device__ __forceinline__ uint8_t* x_abuf(const XPipe& p) {
-    const uint32_t set = p.c & 1, u = p.c >> 1;
-    mbar_wait(&p.a_empty[set], (u & 1) ^ 1);
-    return p.Ab + set * X_ABUF_BYTES;
-}
 
 // 16 values of this thread (its row, hidden units kb * 64 + part * 16 .. + 15) -> split -> the A buffer
 __device__ __forceinline__ void x_store16(const float (&v)[16], uint8_t* abuf, int row, int part) {
@@ -1339,36 +1274,6 @@ struct XSmem {
     uint32_t* tmem_slot;
 };
 
-__device__ __forceinline__ void x_barriers(uint8_t* base, XSmem& m) {
-    m.full = reinterpret_cast<uint64_t*>(base);
-    m.empty = m.full + X_NST;
-    m.pfull = m.empty + X_NST;
-    m.a_full = m.pfull + X_NST;
-    m.a_empty = m.a_full + 2;
-    m.accum = m.a_empty + 2;
-    m.tmem_slot = reinterpret_cast<uint32_t*>(m.accum + 1);
-}
-
-__device__ __forceinline__ void x_setup(const XSmem& m, int t, int warp, uint32_t a_full_count = 1, uint32_t issuers = 1) {
-    if (t == 0) {
-        for (int s = 0; s < X_NST; s++) {
-            mbar_init(&m.full[s], 1);
-            mbar_init(&m.empty[s], 1);
-            mbar_init(&m.pfull[s], 1);
-        }
-        for (int s = 0; s < 2; s++) {
-            mbar_init(&m.a_full[s], a_full_count);
-            mbar_init(&m.a_empty[s], issuers);
-        }
-        mbar_init(m.accum, issuers);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {  // the whole accumulator file of the SM pair: 128 lanes x 512 fp32 columns per CTA
-        asm volatile(PG_TMEM_ALLOC_2SM ::"r"(smem_u32(m.tmem_slot)) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
-}
-
 // The rollout kernel keeps the tensor core's feed out of the compute warps: two more warps hold one control thread each --
 // warp 16 issues the MMAs (leader) or relays "my stage is full" (peer), warp 17 requests the weight chunks -- and the 16
 // compute warps hand each A block over through an mbarrier (one arrival per warp of BOTH CTAs on the leader's a_full) instead
@@ -1455,11 +1360,16 @@ __device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
 // cwarp 0 / 1: the issuer of accumulator half 0 / 1 (weight stages j = 2 * half, 2 * half + 1 of every k-step: the halves are
 // disjoint TMEM columns, so two threads can feed the tensor cores side by side -- one thread needed longer to wait for and
 // issue a k-step than the MMAs take); cwarp 2: the producer.
+// JAC: the Jacobian kernel's sequence -- the first GEMM (8 k-steps) against W2, the others against its transpose.
+template <bool JAC>
 __device__ __forceinline__ void x_control(const XPipe& p, const MlpPacked* w, int cwarp, int lane, uint32_t rank) {
     const int jh = 2 * cwarp;
     if (lane != 0) {
     } else if (cwarp == 2) {  // producer: a stage is requested again as soon as the MMAs that read it have retired
-        for (uint32_t c = 0; c < p.total; c++) xr_request(p, c, w->W2h, w->W2l, (int)(c & 7), rank);
+        for (uint32_t c = 0; c < p.total; c++) {
+            if (JAC && c >= 8) xr_request(p, c, w->W2hT, w->W2lT, (int)(c & 7), rank);
+            else xr_request(p, c, w->W2h, w->W2l, (int)(c & 7), rank);
+        }
     } else if (rank != 0) {  // peer: tell the leader when a stage of OUR ring is full
         for (uint32_t c = 0; c < p.total; c++) {
 #pragma unroll
@@ -1554,7 +1464,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(XC_THREADS, 1) mlp_
     XPipe pipe = {sm.Ab, sm.Bs, sm.full, sm.empty, sm.pfull, sm.a_full, sm.a_empty, sm.accum, *sm.tmem_slot, 0u, (uint32_t)((hi - lo) * 8), 0u};
     const uint32_t tmem_base = pipe.tmem_base;
     if (warp >= T_THREADS / 32) {  // the control warps
-        x_control(pipe, w, warp - T_THREADS / 32, t & 31, rank);
+        x_control<false>(pipe, w, warp - T_THREADS / 32, t & 31, rank);
     } else {
 
     double x[8], u[2], xe[8], ue[2], fplus[8];
@@ -1677,16 +1587,16 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(XC_THREADS, 1) mlp_
 constexpr int XJ_SMEM = 2 * X_ABUF_BYTES + X_NST * CHUNK_BYTES + T_W1_BYTES + J_MASK_BYTES + 256;
 static_assert(XJ_SMEM <= 232448 && J_MASK_BYTES >= T_INS_BYTES, "jacobian x3 kernel: shared memory");
 
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_jac_x3_kernel(const MlpArgs a) {
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(XC_THREADS, 1) mlp_jac_x3_kernel(const MlpArgs a) {
     extern __shared__ __align__(1024) uint8_t tsm[];
     XSmem sm;
     sm.Ab = tsm;
-    sm.Bs = tsm + 2 * X_ABUF_BYTES;
-    float* w1s = reinterpret_cast<float*>(sm.Bs + X_NST * CHUNK_BYTES);
+    sm.Bs = tsm + XR_ABUFS * X_ABUF_BYTES;  // ring geometry and control warps of mlp_x3_kernel
+    float* w1s = reinterpret_cast<float*>(sm.Bs + XR_NST * CHUNK_BYTES);
     uint32_t* m1 = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(w1s) + T_W1_BYTES);
     uint32_t* m2 = m1 + T_ROWS * J_MASK_WORDS;
     float* ins = reinterpret_cast<float*>(m1);  // the input tile lives in the mask area until every thread has it in registers
-    x_barriers(reinterpret_cast<uint8_t*>(m1) + J_MASK_BYTES, sm);
+    xr_barriers(reinterpret_cast<uint8_t*>(m1) + J_MASK_BYTES, sm);
     const MlpPacked* w = a.w;
     const int t = threadIdx.x, warp = t >> 5, row = t & (T_ROWS - 1), part = t >> 7;
     if ((int64_t)(blockIdx.x / CL) * CL * T_ROWS >= total_rows(a)) return;  // surplus clusters
@@ -1697,8 +1607,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_j
     const pg::MathCtx<double> mc;
     const uint32_t rank = cluster_ctarank();
 
-    x_setup(sm, t, warp);
-    for (int i = t; i < H * (W1S_FLOATS / 4); i += T_THREADS) {
+    xr_setup(sm, t, warp, CL * (T_THREADS / 32), 2);
+    for (int i = t; i < H * (W1S_FLOATS / 4) && t < T_THREADS; i += T_THREADS) {
         const int k = i / (W1S_FLOATS / 4), q = i % (W1S_FLOATS / 4);
         reinterpret_cast<float4*>(w1s)[i] = reinterpret_cast<const float4*>(&w->W1b[k][0])[q];
     }
@@ -1708,7 +1618,19 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_j
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     XPipe pipe = {sm.Ab, sm.Bs, sm.full, sm.empty, sm.pfull, sm.a_full, sm.a_empty, sm.accum, *sm.tmem_slot, 0u, (uint32_t)(8 * (1 + nh)), 0u};
     const uint32_t tmem_base = pipe.tmem_base;
-    if (t == PRODUCER_THREAD) x_request(pipe, 0, w->W2h, w->W2l, 0, rank);
+    if (warp >= T_THREADS / 32) {  // the control warps
+        x_control<true>(pipe, w, warp - T_THREADS / 32, t & 31, rank);
+    } else {
+    // one of the 2 x 16 warp arrivals the issuers wait for: this warp's share of the A block of k-step pipe.c is written
+    auto hand_over = [&]() {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if ((t & 31) == 0) {
+            if (rank == 0) mbar_arrive_local(&pipe.a_full[pipe.c % XR_ABUFS]);
+            else mbar_arrive_remote(&pipe.a_full[pipe.c % XR_ABUFS], 0);
+        }
+        pipe.c++;
+    };
 
     double x[8], u[2];
     if (owner) {
@@ -1718,23 +1640,20 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_j
 #pragma unroll
         for (int j = 0; j < MAXIN; j++) ins[row * INS_STRIDE + j] = in[j];
     }
-    __syncthreads();
+    compute_sync();
     float in[16];
 #pragma unroll
     for (int j = 0; j < MAXIN; j++) in[j] = ins[row * INS_STRIDE + j];
-    __syncthreads();  // the mask words alias the input tile
+    compute_sync();  // the mask words alias the input tile
     uint16_t* m1h = reinterpret_cast<uint16_t*>(m1);
     // pass 0: forward, ReLU masks of both layers
     for (int kb = 0; kb < 8; kb++) {
-        uint8_t* abuf = x_abuf(pipe);
+        uint8_t* abuf = xr_abuf_parked(pipe);
         const uint32_t bits = x_l1_dispatch(nin, w, w1s, in, kb, row, part, abuf);
         m1h[row * (2 * J_MASK_WORDS) + kb * 4 + part] = (uint16_t)bits;  // hidden units kb * 64 + part * 16 .. + 15
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        if (kb < 7) x_issue(pipe, kb, false, w->W2h, w->W2l, kb + 1, t, rank);
-        else x_issue(pipe, kb, true, w->W2hT, w->W2lT, 0, t, rank);
+        hand_over();
     }
-    mbar_wait(pipe.accum, pipe.passes & 1);
+    mbar_wait_parked(pipe.accum, pipe.passes & 1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     for (int cb = part * (H / 32 / T_SPLIT); cb < (part + 1) * (H / 32 / T_SPLIT); cb++) {  // mask of layer 2: [acc + b2 > 0]
         uint32_t v[32];
@@ -1749,7 +1668,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_j
     }
     pipe.passes++;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    compute_sync();
 
     double sx[8], cx[8];  // sin/cos of the angle states for the chain rule
     if (owner) {
@@ -1762,7 +1681,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_j
     float* partial = reinterpret_cast<float*>(sm.Ab);  // [T_SPLIT][T_ROWS][MAXIN]: valid between a pass's last MMA and the next A block
     for (int j = 0; j < nh; j++) {
         for (int kb = 0; kb < 8; kb++) {  // A block: g2 = W3[j, :] * m2
-            uint8_t* abuf = x_abuf(pipe);
+            uint8_t* abuf = xr_abuf_parked(pipe);
             const int k0 = kb * 64 + part * 16;
             const uint32_t bits = (m2[row * J_MASK_WORDS + (k0 >> 5)] >> (k0 & 31)) & 0xffffu;
             float v[16];
@@ -1775,12 +1694,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_j
                 v[q * 4 + 3] = ((bits >> (q * 4 + 3)) & 1u) ? w4.w : 0.0f;
             }
             x_store16(v, abuf, row, part);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncthreads();
-            const bool more = kb < 7 || j + 1 < nh;
-            x_issue(pipe, kb, kb == 7, more ? w->W2hT : nullptr, w->W2lT, (kb + 1) & 7, t, rank);
+            hand_over();
         }
-        mbar_wait(pipe.accum, pipe.passes & 1);  // every MMA of the pass is complete: the A buffers may be reused as scratch
+        mbar_wait_parked(pipe.accum, pipe.passes & 1);  // every MMA of the pass is complete: the A buffers may be reused as scratch
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         {  // epilogue: g1 = acc * m1, gin = g1 W1 (this thread's quarter of the hidden units)
             float gin[MAXIN];
@@ -1812,7 +1728,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_j
         }
         pipe.passes++;
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
+        compute_sync();
         if (rw.valid) {
             float gin[MAXIN];
 #pragma unroll
@@ -1842,7 +1758,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_j
                 c++;
             }
         }
-        __syncthreads();  // the partial sums are consumed before the next pass writes its A blocks over them
+        compute_sync();  // the partial sums are consumed before the next pass writes its A blocks over them
     }
     if (rw.valid) {  // position half: d x[nh + i] / dx
         const int64_t B = a.Bs, b = rw.b;
@@ -1851,6 +1767,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T_THREADS, 1) mlp_j
             for (int jj = 0; jj < m; jj++) a.Bm[(((int64_t)rw.k * n + i) * m + jj) * B + b] = 0.0;
         }
     }
+    }  // compute warps
     __syncthreads();
     cluster_sync();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
@@ -1919,7 +1836,7 @@ int launch(int precision, const MlpArgs& a, cudaStream_t st) {
                 if (e != cudaSuccess) return (int)e;
                 setx = true;
             }
-            mlp_jac_x3_kernel<<<grid, T_THREADS, XJ_SMEM, st>>>(a);
+            mlp_jac_x3_kernel<<<grid, XC_THREADS, XJ_SMEM, st>>>(a);
         }
     } else if (precision == PG_MLP_FP32) {
         const int smem = (F_ROWS * F_HSTR + F_ROWS * MAXIN + F_ROWS * MAXDX) * 4;
