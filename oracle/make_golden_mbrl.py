@@ -1,0 +1,72 @@
+"""Golden vectors of the MBRL outer loop's deterministic pieces from the UNMODIFIED reference:
+`MBRL.run_random_episode` (pygent/algorithms/mbrl.py:211-249: random actions through `MPCAgent.take_random_action`,
+nmpc.py:279-296, `CartPole.step`, the noisy transition record, `DataSet.force_add_sample`, the episode statistics) and
+`MBRL.pred_loss` (:189-209), each called UNBOUND on a stand-in `self` that carries exactly the attributes the method
+reads (the reference's own `MBRL.__init__` passes a float layer width to torch and no longer constructs).  The global
+numpy generator is seeded, so an implementation that draws in the reference's order -- action, then the noise of x_, u, x,
+o_, o -- reproduces every number.     python -m oracle.make_golden_mbrl"""
+import os
+import types
+
+import numpy as np
+import torch
+
+from . import mlp_oracle as mo
+from . import ref_harness as rh
+from .make_golden import GOLDEN
+
+SEED, T_EPISODE, DT, DATA_NOISE = 123, 1.2, 0.02, 1e-3
+
+
+def c_k(x, u, mod):  # examples/mbrl/cart_pole_hpc.py:24-28
+    x1, x2, x3, x4 = x
+    u1, = u
+    return 10 * x1 ** 2 + 5 * x2 ** 2 + .01 * x3 ** 2 + .01 * x4 ** 2 + 0.1 * u1 ** 2
+
+
+def main():
+    pg = rh.load_reference()
+    import pygent.nn_models as nnm
+    from pygent.algorithms.mbrl import MBRL
+    from pygent.algorithms.nmpc import MPCAgent
+    from pygent.data import DataSet
+    torch.set_num_threads(1)
+    with rh.quiet():
+        env = pg.environments.CartPole(c_k, [0, np.pi, 0, 0], DT)
+    agent = types.SimpleNamespace(uMax=env.uMax, uDim=env.uDim, history=np.zeros([1, env.uDim]), tt=[0], u=None)
+    agent.take_random_action = lambda dt, ou_noise=True: MPCAgent.take_random_action(agent, dt, ou_noise=ou_noise)
+
+    def agent_reset():
+        agent.history, agent.tt = np.zeros([1, env.uDim]), [0]
+    agent.reset = agent_reset
+    stub = types.SimpleNamespace(environment=env, agent=agent, t=T_EPISODE, dt=DT, data_noise=DATA_NOISE, episode=0,
+                                 D_rand=DataSet(10 ** 6), meanCost=[], totalCost=[], episode_steps=[])
+    np.random.seed(SEED)
+    with rh.quiet():
+        MBRL.run_random_episode(stub)
+        MBRL.run_random_episode(stub)   # a second episode: reset semantics, data set growth
+    data = stub.D_rand.data
+    col = lambda k: np.array([np.asarray(s[k], dtype=float).ravel() for s in data])
+    out = {k: col(k) for k in ("x_", "u", "x", "o_", "o", "c")}
+    out["terminated"] = col("t")
+    out.update(meanCost=np.array(stub.meanCost), totalCost=np.array(stub.totalCost), episode_steps=np.array(stub.episode_steps),
+               episode=stub.episode, seed=SEED, t_episode=T_EPISODE, dt=DT, data_noise=DATA_NOISE, x0=np.array([0, np.pi, 0, 0.]))
+
+    # pred_loss of the first 16 transitions under a fixed network and the data set's moments
+    w = mo.make_weights(6, 2)
+    net = nnm.NNDynamics(4, 1, dxDim=2, oDim=5, xIsAngle=[False, True, False, False])
+    with torch.no_grad():
+        for i, l in enumerate((net.layer1, net.layer2, net.layer3), 1):
+            l.weight.copy_(torch.from_numpy(w["W%d" % i]))
+            l.bias.copy_(torch.from_numpy(w["b%d" % i]))
+    stub2 = types.SimpleNamespace(nn_dynamics=net, sparse_dyn=True)
+    MBRL.set_moments(stub2, stub.D_rand)
+    net.eval()
+    out["pred_loss"] = np.array([float(MBRL.pred_loss(stub2, s)) for s in data[:16]])
+    np.savez_compressed(os.path.join(GOLDEN, "mbrl_warmup.npz"), **out)
+    print("mbrl_warmup.npz: %d transitions, episode steps %s, mean costs %s, pred_loss[0] %.6f" % (
+        len(data), stub.episode_steps, np.round(stub.meanCost, 6), out["pred_loss"][0]))
+
+
+if __name__ == "__main__":
+    main()

@@ -386,3 +386,45 @@ def test_mbrl_outer_loop_runs_end_to_end(tmp_path):
     other.load()
     assert torch.equal(other.nn_dynamics.layer2.weight.detach().cpu(), w) and len(other.D_rand.data) == n_rand
     assert other.episode == alg.episode
+
+
+def test_mbrl_warm_up_episodes_and_pred_loss_match_reference(tmp_path, golden):
+    """The deterministic pieces of the MBRL outer loop against the UNMODIFIED reference (oracle/make_golden_mbrl.py):
+    two `run_random_episode` calls (mbrl.py:211-249) with the numpy generator seeded like the reference's global one --
+    random actions, plant steps (the reference: native RK45; here RK4 x 4), the noisy transition records in the reference's
+    draw order (x_, u, x, o_, o), the episode statistics -- and `pred_loss` (:189-209) of the first transitions under a
+    fixed network and the data set's moments, through the training kernels' forward pass."""
+    from pygent_b200.algorithms.mbrl import MBRL
+    from pygent_b200.environments import CartPole
+    g = golden("mbrl_warmup")
+
+    def cost(x, u, mod):
+        x1, x2, x3, x4 = x
+        u1, = u
+        return 10 * x1 ** 2 + 5 * x2 ** 2 + .01 * x3 ** 2 + .01 * x4 ** 2 + 0.1 * u1 ** 2
+    env = CartPole(cost, list(g["x0"]), float(g["dt"]))
+    alg = MBRL(env, float(g["t_episode"]), float(g["dt"]), path=str(tmp_path) + "/", data_noise=float(g["data_noise"]), fcost=c_N, maxIters=4)
+    alg.rng = alg.agent.rng = np.random.RandomState(int(g["seed"]))   # ONE stream for actions and noise, as in the reference
+    alg.run_random_episode()
+    alg.run_random_episode()
+    data = alg.D_rand.data
+    assert len(data) == len(g["x_"]) and alg.episode == int(g["episode"])
+    assert list(alg.episode_steps) == list(g["episode_steps"])
+    col = lambda k: np.array([np.asarray(s[k], dtype=float).ravel() for s in data])
+    assert np.array_equal(col("t"), g["terminated"])
+    assert np.max(np.abs(col("u") - g["u"])) < 1e-12                      # the same draws
+    for k in ("x_", "x", "o_", "o"):                                      # noise identical, states to the integrator's tolerance
+        assert np.max(np.abs(col(k) - g[k])) < 2e-5, (k, np.max(np.abs(col(k) - g[k])))
+    assert rel(col("c"), g["c"]) < 1e-5
+    assert rel(np.array(alg.meanCost), g["meanCost"]) < 1e-5 and rel(np.array(alg.totalCost), g["totalCost"]) < 1e-5
+    # pred_loss: the golden's network, moments from the data set as MBRL.set_moments computes them
+    w = mo.make_weights(6, 2)
+    with torch.no_grad():
+        for i, l in enumerate((alg.nn_dynamics.layer1, alg.nn_dynamics.layer2, alg.nn_dynamics.layer3), 1):
+            l.weight.copy_(torch.from_numpy(w["W%d" % i]).to(l.weight.device))
+            l.bias.copy_(torch.from_numpy(w["b%d" % i]).to(l.bias.device))
+    alg.nn_dynamics.invalidate()
+    alg.trainer.set_moments(alg.D_rand)
+    golden_tr = [{k: g[k][i] for k in ("x_", "u", "x", "o_", "o")} for i in range(len(g["pred_loss"]))]
+    mine = np.array([alg.pred_loss(tr) for tr in golden_tr])
+    assert rel(mine, g["pred_loss"]) < 1e-4, rel(mine, g["pred_loss"])
