@@ -39,7 +39,7 @@ def main():
     def agent_reset():
         agent.history, agent.tt = np.zeros([1, env.uDim]), [0]
     agent.reset = agent_reset
-    stub = types.SimpleNamespace(environment=env, agent=agent, t=T_EPISODE, dt=DT, data_noise=DATA_NOISE, episode=0,
+    stub = types.SimpleNamespace(environment=env, agent=agent, t=T_EPISODE, dt=DT, data_noise=DATA_NOISE, episode=1,   # Algorithm.__init__ (core.py:26)
                                  D_rand=DataSet(10 ** 6), meanCost=[], totalCost=[], episode_steps=[])
     np.random.seed(SEED)
     with rh.quiet():
