@@ -77,6 +77,8 @@ class Environment(object):
         self._xd = None          # device state, created lazily (so that construction works without a GPU)
         self._xd_prev = None
         self._hist = [self._x0_host.copy()]
+        if "_obs_cur_state" not in self.__dict__:   # `o` is computed at construction and by `step`, never by `reset` (see `o_`)
+            self._obs_cur_state = self._hist[0]
         self.tt = [0]
         self.terminated = False if not self.batched else np.zeros(self.batch, dtype=bool)
 
@@ -205,6 +207,10 @@ class StateSpaceModel(Environment):
                       terminal_cost=float(self.terminal_cost))
         self._xd_prev, self._xd = x, r["xN"]
         self._hist.append(r["xN"].detach().to("cpu", torch.float64).numpy().T.copy())
+        # `o_ = o; ...; o = observe(x)` (environments.py:254-267, :311-316): the state whose observation `o_` reports is the one
+        # `o` was last computed from -- the previous step's result, or x0 at construction -- NOT necessarily x_ (see `o_`)
+        self._obs_prev_state = self._obs_cur_state
+        self._obs_cur_state = self._hist[-1]
         self.tt.extend([self.tt[-1] + dt])
         term = r["terminated"].cpu().numpy().astype(bool)
         c = r["cost"].to("cpu", torch.float64).numpy()
@@ -348,7 +354,14 @@ class StateSpaceModel(Environment):
 
     @property
     def o_(self):
-        return self.observe(self.x_)
+        """Observation before the last step.  The reference keeps `o_` / `o` as attributes that `step` shifts and `reset`
+        does not touch (environments.py:61-75): the first transition after a reset therefore carries the LAST observation
+        of the previous episode as `o_` (MBRL stores it, mbrl.py:228-234).  Kept: the data sets must equal the reference's."""
+        prev = self.__dict__.get("_obs_prev_state")
+        if prev is None:
+            return self.observe(self.x_)
+        prev = np.asarray(prev)
+        return self.observe(prev if self.batched else prev.reshape(-1))
 
 
 class LearnedStateSpaceModel(StateSpaceModel):
