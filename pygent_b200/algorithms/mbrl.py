@@ -45,8 +45,17 @@ class _KernelBackend(object):
             off += p.numel()
         self.k = mlp.TrainKernels(mlp.make_dims(net.xDim, net.uDim, net.xIsAngle), flat, max_rows=max_rows, device=device)
         self.bucket, self.count = self.k.bucket, self.k.count
+        self._seen_version = getattr(net, "_weights_version", 0)
 
     launches = property(lambda self: self.k.launches)
+
+    def _sync_weights(self):
+        """The fp16 hi/lo operand images of W2 follow the flat parameter buffer through the Adagrad kernel only: weights
+        changed from outside (`load_state_dict`, a hand-set layer) announce themselves through `net.invalidate()`."""
+        v = getattr(self.net, "_weights_version", 0)
+        if v != self._seen_version:
+            self.k.repack()
+            self._seen_version = v
 
     def set_moments(self, *a):
         self.k.set_moments(*a)
@@ -55,9 +64,11 @@ class _KernelBackend(object):
         self.k.set_data(col)
 
     def grad(self, idx, n_total):
+        self._sync_weights()
         self.k.grad(torch.as_tensor(np.ascontiguousarray(idx, dtype=np.int32), device=self.device), n_total)
 
     def grad_device(self, idx, n_total):
+        self._sync_weights()
         self.k.grad(idx, n_total)
 
     def enable_p2p(self, group=None):
@@ -66,6 +77,7 @@ class _KernelBackend(object):
 
     def step_p2p(self, idx, n_total, lr, weight_decay, eps=1e-10):
         """Gradient of this rank's slice straight into its NVLink exchange block, then the fused peer-sum + Adagrad kernel."""
+        self._sync_weights()
         self.k.grad(torch.as_tensor(np.ascontiguousarray(idx, dtype=np.int32), device=self.device), n_total, bucket=self.k.p2p_bucket())
         return self.k.update_p2p(lr, weight_decay, eps)
 

@@ -35,6 +35,7 @@ class NNDynamics(nn.Module):
         self.layer2 = nn.Linear(HIDDEN, HIDDEN)
         self.layer3 = nn.Linear(HIDDEN, self.dxDim)
         self._device_model = None
+        self._weights_version = 0
 
     def forward(self, o, u):
         h1 = F.relu(self.layer1(torch.cat((o, u), 1)))
@@ -42,8 +43,10 @@ class NNDynamics(nn.Module):
         return self.layer3(h2)
 
     def invalidate(self):
-        """Call after changing weights or moments: the packed device copy is rebuilt on next use."""
+        """Call after changing weights or moments: the packed device copy is rebuilt on next use (and the training kernels
+        rebuild their operand images of W2: `DynamicsTrainer` watches the version counter)."""
         self._device_model = None
+        self._weights_version = getattr(self, "_weights_version", 0) + 1
 
     def device_model(self, device=None):
         from . import mlp
