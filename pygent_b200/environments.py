@@ -311,31 +311,54 @@ class StateSpaceModel(Environment):
         L.check_queues()
         return {"cost": cost_out, "xN": xN_out}
 
-    def rollout_host_random(self, x0, T, seed, cost_out=None, xN_out=None, u_max=None, fast=False):
+    def rollout_host_random(self, x0, T, seed, cost_out=None, xN_out=None, u_max=None, fast=False, wait=True):
         """End-to-end rollout under RANDOM actions from HOST start states: x0 `[n, B]` (pinned torch tensor) crosses PCIe,
         the T controls per environment are drawn inside the kernel (Philox stream of pygent_b200/random_actions.py, keyed
         by `seed`: u ~ U(-uMax, uMax)) -- 2 MB of input per step at the benchmark size instead of the
         264 MB a materialised U would be -- and cost `[B]` / final states `[n, B]` come back into the pinned outputs.
-        Synchronises before returning.  `random_actions.random_actions(B, T, seed, uMax)` reproduces the controls on the host."""
+        `random_actions.random_actions(B, T, seed, uMax)` reproduces the controls on the host.
+
+        `wait=True` synchronises before returning.  `wait=False` returns a handle whose `.wait()` blocks until THIS call's
+        outputs are in host memory: copies in, kernel and copies out run on three streams over two alternating sets of
+        device buffers, so a caller that submits step i + 1 before waiting for step i overlaps the 4.7 MB of copies of one
+        step with the kernel of the next (give consecutive calls different output buffers)."""
         L = self.library()
         n, B = x0.shape
         dev, dt_ = self.device, self.dtype
         st = getattr(self, "_host_rand", None)
         if st is None or st["B"] != B:
-            st = self._host_rand = {"B": B, "x": torch.empty((n, B), dtype=dt_, device=dev), "xN": torch.empty((n, B), dtype=dt_, device=dev),
-                                    "cost": torch.empty((B,), dtype=dt_, device=dev), "term": torch.empty((B,), dtype=torch.uint8, device=dev)}
+            slot = lambda: {"x": torch.empty((n, B), dtype=dt_, device=dev), "xN": torch.empty((n, B), dtype=dt_, device=dev),
+                            "cost": torch.empty((B,), dtype=dt_, device=dev), "term": torch.empty((B,), dtype=torch.uint8, device=dev),
+                            "free": None}
+            st = self._host_rand = {"B": B, "slots": [slot(), slot()], "next": 0, "h2d": torch.cuda.Stream(device=dev),
+                                    "d2h": torch.cuda.Stream(device=dev)}
         um = np.ravel(self.uMax if u_max is None else u_max).astype(float)
-        st["x"].copy_(x0, non_blocking=True)
-        L.rollout(st["x"], None, T=int(T), S=self.substeps, dt=self.dt, t0=0.0, integrator=lib.INTEG_EULER if fast else lib.INTEG_RK4,
-                  terminal_cost=float(self.terminal_cost), out={"xN": st["xN"], "cost": st["cost"], "terminated": st["term"]},
+        sl = st["slots"][st["next"]]
+        st["next"] ^= 1
+        comp = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(st["h2d"]):
+            if sl["free"] is not None:
+                st["h2d"].wait_event(sl["free"])     # the slot's previous results have left the device
+            sl["x"].copy_(x0, non_blocking=True)
+            up = torch.cuda.Event()
+            up.record(st["h2d"])
+        comp.wait_event(up)
+        L.rollout(sl["x"], None, T=int(T), S=self.substeps, dt=self.dt, t0=0.0, integrator=lib.INTEG_EULER if fast else lib.INTEG_RK4,
+                  terminal_cost=float(self.terminal_cost), out={"xN": sl["xN"], "cost": sl["cost"], "terminated": sl["term"]},
                   actions=(seed, um))
-        if cost_out is not None:
-            cost_out.copy_(st["cost"], non_blocking=True)
-        if xN_out is not None:
-            xN_out.copy_(st["xN"], non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
-        L.check_queues()
-        return {"cost": cost_out, "xN": xN_out}
+        done = torch.cuda.Event()
+        done.record(comp)
+        with torch.cuda.stream(st["d2h"]):
+            st["d2h"].wait_event(done)
+            if cost_out is not None:
+                cost_out.copy_(sl["cost"], non_blocking=True)
+            if xN_out is not None:
+                xN_out.copy_(sl["xN"], non_blocking=True)
+            back = torch.cuda.Event()
+            back.record(st["d2h"])
+        sl["free"] = back
+        handle = _HostRollout(back, L, {"cost": cost_out, "xN": xN_out})
+        return handle.wait() if wait else handle
 
     def terminate(self, x):
         """True where `x` (`[n]` or `[B, n]`) is a terminal state (reference: environments.py:278-288)."""
@@ -362,6 +385,19 @@ class StateSpaceModel(Environment):
             return self.observe(self.x_)
         prev = np.asarray(prev)
         return self.observe(prev if self.batched else prev.reshape(-1))
+
+
+class _HostRollout(object):
+    """Handle of a non-blocking `StateSpaceModel.rollout_host_random(..., wait=False)` call."""
+
+    def __init__(self, event, library, out):
+        self._event, self._lib, self._out = event, library, out
+
+    def wait(self):
+        """Blocks until the call's outputs are in host memory; returns {"cost", "xN"} (the caller's pinned tensors)."""
+        self._event.synchronize()
+        self._lib.check_queues()
+        return self._out
 
 
 class LearnedStateSpaceModel(StateSpaceModel):

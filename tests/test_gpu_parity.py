@@ -792,6 +792,44 @@ def test_fused_tail_solver_changes_nothing(case, kw):
             assert np.array_equal(p, q)
 
 
+def test_rollout_host_random_blocking_and_pipelined():
+    """`StateSpaceModel.rollout_host_random` (the call bench.py's `e2e` times): start states from pinned host memory,
+    actions drawn in the kernel, results into pinned host memory.  The blocking call equals the device-resident rollout over
+    the materialised action stream; calls submitted with `wait=False` (two alternating output buffers, step i + 1 in flight
+    while step i is read) return, through their handles, exactly what the blocking calls return -- in every order of waiting
+    the two-slot scheme allows."""
+    from pygent_b200.examples import make_env
+    B, T = 20480, 40
+    rng = np.random.default_rng(12)
+    x0 = np.array([0, np.pi, 0, 0]) + rng.uniform(-0.2, 0.2, (B, 4))
+    env = make_env("cart_pole", x0=x0)
+    L = env.library()
+    pin = lambda *shape: torch.empty(shape, dtype=torch.float64).pin_memory()
+    x0_pin = pin(4, B)
+    x0_pin.copy_(torch.as_tensor(x0.T.copy()))
+    ref = []
+    for i in range(5):
+        c, xn = pin(B), pin(4, B)
+        r = env.rollout_host_random(x0_pin, T, 900 + i, cost_out=c, xN_out=xn)
+        assert r["cost"] is c and r["xN"] is xn
+        ref.append((c.clone(), xn.clone()))
+    U = L.random_actions(B, T, 900, np.ravel(env.uMax).astype(float))
+    d = L.rollout(dev(x0), U, S=env.substeps, dt=env.dt)
+    assert torch.equal(d["cost"].cpu(), ref[0][0]) and torch.equal(d["xN"].cpu(), ref[0][1])
+    bufs = [(pin(B), pin(4, B)) for _ in range(2)]
+    pending, got = None, []
+    for i in range(5):
+        h = env.rollout_host_random(x0_pin, T, 900 + i, cost_out=bufs[i % 2][0], xN_out=bufs[i % 2][1], wait=False)
+        if pending is not None:
+            r = pending.wait()
+            got.append((r["cost"].clone(), r["xN"].clone()))
+        pending = h
+    r = pending.wait()
+    got.append((r["cost"].clone(), r["xN"].clone()))
+    for (c0, x0_), (c1, x1) in zip(ref, got):
+        assert torch.equal(c0, c1) and torch.equal(x0_, x1)
+
+
 @pytest.mark.parametrize("case,rounds", [("cart_pole", 1), ("cart_pole", 7), ("double_parallel", 5), ("pendulum", 3)])
 def test_fused_tail_rounds_change_nothing(case, rounds):
     """The fused solver in rounds (pg_ilqr_solve.round_iters): every launch gives each running trajectory at most `rounds`
