@@ -850,7 +850,7 @@ def main():
                     "h2d_bytes_per_step": int(x0_pin.numel() * 8 + 8),
                     "d2h_bytes_per_step": int(cost_pin2.numel() * 8 + xN_pin2.numel() * 8), "steps": e2e_r_steps,
                     "api": "StateSpaceModel.rollout_host_random(x0_pinned, T, seed, wait=False): start states from pinned host memory, the random "
-                           "actions of config 2 drawn inside the kernel (Philox4x32-10 stream, bit-identical to pygent_b200/random_actions.py "
+                           "actions of config 2 drawn inside the kernel (Philox2x32-10 stream, bit-identical to pygent_b200/random_actions.py "
                            "on the host: checked in this run), cost + final states back to pinned host memory; every step a new seed; "
                            "step i + 1 is submitted before step i's results are waited for (copies overlap the next kernel)"},
             "e2e_host_actions": {"value": e2e_host_value, "unit": "env-steps/s",

@@ -107,8 +107,9 @@ int64_t pg_rollout_workspace_bytes(int64_t B, int32_t T);
 
 /* pg_rollout / pg_rollout_balanced with the controls drawn INSIDE the kernel instead of read from U (SURVEY.md 8(d), config 2:
  * "u[k,b] ~ U(-uMax, uMax) ... or in-kernel Philox with the same counter scheme, validated against the host stream"):
- *     u[k, j, b] = (2 U - 1) * u_max[j],   U = 53-bit uniform from Philox4x32-10 with counter (b mod 2^32, b div 2^32,
- *     k_offset + k, j) and the 64-bit key `seed`.
+ *     u[k, j, b] = (2 U - 1) * u_max[j],   U = ((r1 << 32 | r0) >> 11) * 2^-53,
+ *     (r0, r1) = Philox2x32-10(counter = (b, 4 (k_offset + k) + j), key = Philox2x32-10((seed mod 2^32, seed div 2^32), 0x5047454E).r0)
+ *     (one 64-bit block per action; B <= 2^32, k_offset + T <= 2^30, else PG_E_BADARG).
  * u_max: host array [m].  workspace == NULL: the plain kernel; else the ticket-queue kernel (pg_rollout_balanced's rules).
  * pg_random_actions writes the same stream to U [T, m, B] (for validation and for kernels that read U); the host-side
  * restatement is pygent_b200/random_actions.py.  A rollout over pg_random_actions' U equals pg_rollout_random bit for bit. */

@@ -354,10 +354,17 @@ class StateSpaceModel(Environment):
                 cost_out.copy_(sl["cost"], non_blocking=True)
             if xN_out is not None:
                 xN_out.copy_(sl["xN"], non_blocking=True)
+            # the queue kernels' sticky status words travel with the results (check_queues() would synchronise with the
+            # stream, i.e. with the NEXT step's kernel, and the host could not submit the step after it in time)
+            words = L.queue_status_words()
+            if "status" not in sl or sl["status"].numel() != len(words):
+                sl["status"] = torch.zeros(max(len(words), 1), dtype=torch.int32).pin_memory()
+            for i, w in enumerate(words):
+                sl["status"][i:i + 1].copy_(w.reshape(1), non_blocking=True)
             back = torch.cuda.Event()
             back.record(st["d2h"])
         sl["free"] = back
-        handle = _HostRollout(back, L, {"cost": cost_out, "xN": xN_out})
+        handle = _HostRollout(back, L, {"cost": cost_out, "xN": xN_out}, sl["status"])
         return handle.wait() if wait else handle
 
     def terminate(self, x):
@@ -390,13 +397,14 @@ class StateSpaceModel(Environment):
 class _HostRollout(object):
     """Handle of a non-blocking `StateSpaceModel.rollout_host_random(..., wait=False)` call."""
 
-    def __init__(self, event, library, out):
-        self._event, self._lib, self._out = event, library, out
+    def __init__(self, event, library, out, status):
+        self._event, self._lib, self._out, self._status = event, library, out, status
 
     def wait(self):
         """Blocks until the call's outputs are in host memory; returns {"cost", "xN"} (the caller's pinned tensors)."""
         self._event.synchronize()
-        self._lib.check_queues()
+        if int(self._status.sum()) != 0:
+            self._lib.check_queues()  # raises, and resets the words
         return self._out
 
 

@@ -217,9 +217,12 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
 
 
 def test_host_action_stream_known_answers():
-    """pygent_b200/random_actions.py: Philox4x32-10 against the Random123 known-answer vectors (kat_vectors: philox4x32 10),
-    and the shape / range / determinism of the action stream built on it."""
-    from pygent_b200.random_actions import philox4x32_10, random_actions
+    """pygent_b200/random_actions.py: Philox2x32-10 (the action stream's generator) and Philox4x32-10 against the Random123
+    known-answer vectors (kat_vectors: philox2x32 10, philox4x32 10), and the shape / range / determinism of the action stream."""
+    from pygent_b200.random_actions import philox2x32_10, philox4x32_10, random_actions
+    for ctr, key, want in [((0, 0), 0, (0xff1dae59, 0x6cd10df2)), ((0xffffffff, 0xffffffff), 0xffffffff, (0x2c3f628b, 0xab4fd7ad)),
+                           ((0x243f6a88, 0x85a308d3), 0x13198a2e, (0xdd7ce038, 0xf62a4c12))]:
+        assert tuple(int(g) for g in philox2x32_10(*ctr, key)) == want
     kats = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
             ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
             ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
