@@ -17,3 +17,12 @@ class Algorithm(object):
 
     def learning_curve(self):
         raise NotImplementedError
+
+    # Plotting and animation are out of scope; scripts written against the reference call these after a
+    # run (ilqr.py:624-644, nmpc.py:105-124), so they are accepted and do nothing.
+    def plot(self, *args, **kwargs):
+        return None
+
+    def animation(self, *args, **kwargs):
+        return None
+

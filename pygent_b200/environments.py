@@ -119,6 +119,13 @@ class Environment(object):
     def observe(self, x):
         return x
 
+    # plotting / animation: out of scope; accepted, do nothing (environments.py:81-126)
+    def plot(self, *args, **kwargs):
+        return None
+
+    def animation(self, *args, **kwargs):
+        return None
+
     def save_history(self, filename, path):
         import pickle
         with open(path + filename + ".p", "wb") as fh:
