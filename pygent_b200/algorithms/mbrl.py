@@ -106,6 +106,8 @@ class DynamicsTrainer(object):
         self.device = getattr(self.backend, "device", torch.device("cpu"))
         self.collectives = 0
         self.steps = 0
+        self.use_graph = True       # training(): replay each epoch from a CUDA graph (single process, kernel backend)
+        self._epoch_graphs = {}
         # gradient exchange of the data-parallel step: "nccl" = one all-reduce of the bucket + the Adagrad kernel; "p2p" = the
         # fused peer-memory kernel (pg_mlp_train_update_p2p): every rank reads the others' buckets over NVLink and updates
         self.exchange = exchange or os.environ.get("PG_TRAIN_EXCHANGE", "nccl")
@@ -160,6 +162,45 @@ class DynamicsTrainer(object):
         self.backend.grad(np.zeros(1, dtype=np.int32), 1)
         return float(np.sqrt(float(self.backend.bucket[-1]) * self.nn_dynamics.dxDim))
 
+    # -- a whole epoch as one CUDA graph -------------------------------------------------------------------------------
+    def _graph_ok(self):
+        return self.world == 1 and isinstance(self.backend, _KernelBackend) and self.use_graph and \
+            os.environ.get("PG_TRAIN_GRAPH", "1") != "0"
+
+    def _epoch_from_graph(self, batches):
+        """`for idx in batches: train_step(idx)` replayed from a graph keyed by the batch lengths (the last batch of an epoch
+        may be shorter): the epoch's shuffled rows go up in one copy into the static index buffer the captured kernels read.
+        Same kernels in the same order as the eager loop: identical losses and weights."""
+        be, dev = self.backend, self.device
+        lens = tuple(len(b) for b in batches)
+        st = self._epoch_graphs.get(lens)
+        if st is None:
+            be._sync_weights()
+            width = max(lens)
+            st = {"idx": torch.zeros((len(lens), width), dtype=torch.int32, device=dev),
+                  "host": torch.zeros((len(lens), width), dtype=torch.int32).pin_memory(),
+                  "run": torch.zeros(len(lens), dtype=torch.float32, device=dev), "graph": torch.cuda.CUDAGraph()}
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                st["graph"].capture_begin(capture_error_mode="thread_local")
+                try:
+                    for it, n in enumerate(lens):
+                        be.k.grad(st["idx"][it, :n], n)
+                        be.k.update(self.dyn_lr, self.weight_decay)
+                        st["run"][it:it + 1].copy_(be.bucket[-1:])
+                finally:
+                    st["graph"].capture_end()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            self._epoch_graphs[lens] = st
+        be._sync_weights()
+        for it, b in enumerate(batches):
+            st["host"][it, :len(b)] = torch.from_numpy(np.ascontiguousarray(b, dtype=np.int32))
+        st["idx"].copy_(st["host"], non_blocking=True)
+        st["graph"].replay()
+        self.steps += len(lens)
+        return float(st["run"].sum()) / max(1, len(lens) - 1)
+
     # -- one optimiser step on one batch -------------------------------------------------------------------------------
     def train_step(self, idx):
         """idx: rows of ONE full batch in the uploaded data set (identical on every rank).  Data parallel: every rank
@@ -186,6 +227,11 @@ class DynamicsTrainer(object):
         losses = []
         for epoch in range(self.training_epochs):
             batches = dataSet.batch_indices(self.batch_size, shuffle=True)
+            if self._graph_ok():
+                # one process, kernel backend: the whole epoch -- every batch's gradient, Adagrad update and loss read-out --
+                # is ONE replay of a CUDA graph over a static index buffer (the step is six launches of ~9 us: launch-bound)
+                losses.append(self._epoch_from_graph(batches))
+                continue
             run = torch.zeros(len(batches), dtype=torch.float32, device=self.device)
             it = 0
             for it, idx in enumerate(batches):

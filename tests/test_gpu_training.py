@@ -152,3 +152,21 @@ def test_trained_weights_reach_the_planner():
         f = net((t(o) - net.oMean.to(dev)) / net.oVar.to(dev), (t(u) - net.uMean.to(dev)) / net.uVar.to(dev))
         ref = (f * net.dxVar.to(dev) + net.dxMean.to(dev)).cpu().numpy()
     assert np.allclose(y, ref, rtol=1e-4, atol=1e-6)
+
+
+def test_training_epochs_replayed_from_a_graph_equal_the_eager_loop():
+    """`DynamicsTrainer.training` replays each epoch (batches of 512 / 512 / 176 here: a ragged last batch) from ONE CUDA graph
+    over a static index buffer; the eager launch-per-call loop (`use_graph = False`) must produce the same losses and the same
+    weights bit for bit -- same kernels, same order, same shuffles."""
+    D1, D2 = dataset(), dataset()
+    res = []
+    for D, graph in ((D1, True), (D2, False)):
+        net = fresh_net()
+        tr = DynamicsTrainer(net, dyn_lr=1e-3, weight_decay=1e-3, batch_size=512, training_epochs=5, device="cuda")
+        tr.use_graph = graph
+        l0 = tr.backend.launches
+        losses = tr.training(D)
+        res.append((losses, torch.cat([p.detach().reshape(-1) for p in net.parameters()]).cpu(), tr.steps, tr.backend.launches - l0))
+    assert res[0][0] == res[1][0] and torch.equal(res[0][1], res[1][1]) and res[0][2] == res[1][2] == 15
+    assert res[0][0][-1] < res[0][0][0]
+    assert len(tr._epoch_graphs) == 0 and res[0][3] < res[1][3]
