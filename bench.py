@@ -408,9 +408,17 @@ def train_bench(dev, rank, world, barrier, steps=300, with_cpu=True):
     tr = DynamicsTrainer(net, dyn_lr=1e-3, weight_decay=1e-3, batch_size=gb, device=dev)
     col = synthetic_transitions_np(8 * gb, seed=11)
 
-    class _D:  # the two DataSet methods the trainer uses
+    class _D:  # the DataSet methods the trainer uses
+        rng = np.random.RandomState(5)
+
         def columns(self):
             return col
+
+        def batch_indices(self, n, shuffle=True):
+            idx = np.arange(8 * gb)
+            if shuffle:
+                self.rng.shuffle(idx)
+            return [idx[i:i + n] for i in range(0, len(idx), n)]
     tr.set_moments(_D())
     tr.set_data(col)
     batches = [np.arange(i * gb, (i + 1) * gb) for i in range(8)]
@@ -485,6 +493,22 @@ def train_bench(dev, rank, world, barrier, steps=300, with_cpu=True):
                                "world's buckets by peer loads in rank order and applies Adagrad (no NCCL call in the step)"}
         except Exception as e:  # noqa: BLE001 -- peer mapping unavailable on this node: the NCCL figures stand
             p2p = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+    # ---- the public call: DynamicsTrainer.training(data set) -- moments, upload, `epochs` shuffled passes of 8 batches; a single
+    # process replays every epoch from one CUDA graph (host work per epoch: one shuffle, one index upload, one loss read-back)
+    api = None
+    if world == 1:
+        tr.training_epochs = 5
+        tr.training(_D())   # captures the epoch graph
+        tr.training_epochs = 40
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        losses = tr.training(_D())
+        torch.cuda.synchronize()
+        secs = time.perf_counter() - t0
+        api = {"us_per_step": secs * 1e6 / (40 * 8), "steps": 40 * 8, "value": 40 * 8 / secs, "unit": "optimiser steps/s",
+               "loss_first_epoch": losses[0], "loss_last_epoch": losses[-1],
+               "api": "DynamicsTrainer.training(data set): wall clock of the whole call (moments, upload, 40 epochs x 8 batches of 512, "
+                      "each epoch one CUDA-graph replay)"}
     flops = 3 * 2.0 * TRAIN_ROWS * 500 * 500 + 2 * 2.0 * TRAIN_ROWS * 500 * (6 + 2) * 1.5  # layer-2 fwd/dgrad/wgrad + the thin layers
     res = {"metric": "dynamics_train_steps_per_s", "value": steps / (ms * 1e-3), "unit": "optimiser steps/s",
            "samples_per_s": world * TRAIN_ROWS * steps / (ms * 1e-3), "us_per_step": ms * 1e3 / steps,
@@ -496,6 +520,8 @@ def train_bench(dev, rank, world, barrier, steps=300, with_cpu=True):
            "tflops_per_gpu": flops / (ms * 1e-3 / steps) / 1e12}
     if p2p is not None:
         res["p2p"] = p2p
+    if api is not None:
+        res["training_api"] = api
     if with_cpu and rank == 0:
         # the reference's own path for this step: torch autograd + torch.optim.Adagrad on the host cores (oracle/train_oracle.py)
         from oracle.train_oracle import TorchBackend
