@@ -2423,12 +2423,35 @@ __global__ void mpc_shift_kernel(const MpcShiftArgs<T> a) {
     }
     // cost -= c(x0, u0, x1, t = None) dt + fcost(xN) dt   (the example costs do not use t: evaluated at 0)
     T cost = a.cost[b] - (P::cost(m, x0, u0, x1, T(0)) * a.dt + P::fcost(m, xN) * a.dt);
-    for (int k = 0; k < Ts; k++) {  // np.roll(xx, -1), np.roll(uu, -1)
+    // np.roll(xx, -1), np.roll(uu, -1), in place.  Eight intervals are loaded before they are stored one slot down: loads and
+    // stores may alias, so an interval-by-interval loop is a chain of T dependent L2 round trips (116 us for T = 50: the
+    // longest kernel of a control step); the blocked loop is T / 8 of them.
+    constexpr int SB = 8;
+    for (int k0 = 0; k0 < Ts; k0 += SB) {
+        T xs8[SB][N], us8[SB][M];
 #pragma unroll
-        for (int i = 0; i < N; i++) a.xbar[((int64_t)k * N + i) * B + b] = a.xbar[((int64_t)(k + 1) * N + i) * B + b];
-        if (k + 1 < Ts) {
+        for (int s = 0; s < SB; s++) {
+            const int k = k0 + s;
+            if (k < Ts) {
 #pragma unroll
-            for (int r = 0; r < M; r++) a.ubar[((int64_t)k * M + r) * B + b] = a.ubar[((int64_t)(k + 1) * M + r) * B + b];
+                for (int i = 0; i < N; i++) xs8[s][i] = a.xbar[((int64_t)(k + 1) * N + i) * B + b];
+                if (k + 1 < Ts) {
+#pragma unroll
+                    for (int r = 0; r < M; r++) us8[s][r] = a.ubar[((int64_t)(k + 1) * M + r) * B + b];
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < SB; s++) {
+            const int k = k0 + s;
+            if (k < Ts) {
+#pragma unroll
+                for (int i = 0; i < N; i++) a.xbar[((int64_t)k * N + i) * B + b] = xs8[s][i];
+                if (k + 1 < Ts) {
+#pragma unroll
+                    for (int r = 0; r < M; r++) a.ubar[((int64_t)k * M + r) * B + b] = us8[s][r];
+                }
+            }
         }
     }
 #pragma unroll
