@@ -154,9 +154,27 @@ class iLQR(Algorithm):
         self._x0 = self.environment._to_dev(self.environment._x0_host, n)
         u8 = lambda *s: torch.zeros(s, dtype=torch.uint8, device=dev)
         i32 = lambda *s: torch.zeros(s, dtype=torch.int32, device=dev)
-        self._st = {"cost": z(B), "mu": z(B) + self.mu0, "mu_d": z(B) + 1.0, "dcost": z(B),
-                    "success_gradient": u8(B), "status": i32(B), "iters": i32(B), "alpha_best": z(B) + 1.0,
-                    "accept": u8(B), "active": u8(B) + 1}
+        # Everything a new solve re-arms lives in ONE block with a template beside it: status, iters, the first work list and
+        # its count, active, success_gradient (and, in a second block, mu / mu_d, which reset_mu=False keeps) -- a solve
+        # starts with one or two device copies instead of eight fill kernels (a receding-horizon control step is ~20 launches)
+        Bp = (B + 15) // 16 * 16
+        self._arm = torch.zeros(4 * (3 * Bp + 16) + 2 * Bp, dtype=torch.uint8, device=dev)
+        i32v = lambda off, cnt: self._arm[4 * off:4 * (off + cnt)].view(torch.int32)
+        status_, iters_, idx0_, cnt0_ = i32v(0, B), i32v(Bp, B), i32v(2 * Bp, B), i32v(3 * Bp, 1)
+        active_ = self._arm[4 * (3 * Bp + 16):4 * (3 * Bp + 16) + B]
+        sgrad_ = self._arm[4 * (3 * Bp + 16) + Bp:4 * (3 * Bp + 16) + Bp + B]
+        idx0_.copy_(torch.arange(B, dtype=torch.int32, device=dev))
+        cnt0_.fill_(B)
+        active_.fill_(1)
+        self._arm_template = self._arm.clone()
+        self._mu_block = z(2, B)
+        self._mu_block[0] = self.mu0
+        self._mu_block[1] = 1.0
+        self._mu_template = self._mu_block.clone()
+        self._mu_template_mu0 = float(self.mu0)
+        self._st = {"cost": z(B), "mu": self._mu_block[0], "mu_d": self._mu_block[1], "dcost": z(B),
+                    "success_gradient": sgrad_, "status": status_, "iters": iters_, "alpha_best": z(B) + 1.0,
+                    "accept": u8(B), "active": active_}
         A = len(self.alphas)
         self._bw = {"KK": self._KKc, "kk": self._kkc, "dV": z(2, B), "gnorm": z(B), "success": u8(B)}
         self._fw = {"cost": z(A, B), "diverged": u8(A, B), "terminated": u8(A, B), "xN": z(A, n, B)}
@@ -166,8 +184,8 @@ class iLQR(Algorithm):
             self._fw["xS"] = z(A, self._n_snap, n, B)
         self._last_tried = i32(B) - 1   # last alpha evaluated per trajectory (MPC plan shift)
         # compacted work lists (ping-pong): trajectories still running, written by the select kernel
-        self._idx = [torch.arange(B, dtype=torch.int32, device=dev), i32(B)]
-        self._cnt = [i32(1) + B, i32(1)]
+        self._idx = [idx0_, i32(B)]
+        self._cnt = [cnt0_, i32(1)]
         self._cur = 0
         self._n_active = self._cnt[1]
         self._have_gains = False
@@ -274,12 +292,7 @@ class iLQR(Algorithm):
         self._have_gains = False
         self._KK.zero_()
         self._kk.zero_()
-        self._st["mu"].fill_(self.mu0)
-        self._st["mu_d"].fill_(1.0)
-        self._st["status"].zero_()
-        self._st["iters"].zero_()
-        self._st["active"].fill_(1)
-        self._st["success_gradient"].zero_()
+        self._arm_state(True)
         if self.init or not getattr(self, "_have_nominal", False):  # the reference also initialises when it has no plan yet
             self.init_trajectory()
 
@@ -453,11 +466,26 @@ class iLQR(Algorithm):
         return p
 
     def _rearm(self):
-        """Every trajectory back on the work list (start of run_optim)."""
+        """Every trajectory back on the work list, nothing else touched (tests and tools that drive `iterate()` themselves)."""
+        Bp = (self.B + 15) // 16 * 16
+        tmpl = self._arm_template[4 * 2 * Bp:4 * (3 * Bp + 1)].view(torch.int32)
+        self._idx[0].copy_(tmpl[:self.B])
+        self._cnt[0].copy_(tmpl[Bp:Bp + 1])
         self._cur = 0
         self._tail = False
-        self._idx[0].copy_(torch.arange(self.B, dtype=torch.int32, device=self._idx[0].device))
-        self._cnt[0].fill_(self.B)
+        self._n_active = self._cnt[0]
+
+    def _arm_state(self, reset_mu):
+        """Start of a solve (`for _ in range(1, max_iters + 1)` starts over): status, iteration counts, stopping flags, every
+        trajectory back on the work list -- one device copy of the template block; mu, mu_d with `reset_mu` -- a second."""
+        self._arm.copy_(self._arm_template)
+        if reset_mu:
+            if float(self._mu_template_mu0) != float(self.mu0):  # mu0 is a public attribute: follow it
+                self._mu_template[0] = self.mu0
+                self._mu_template_mu0 = float(self.mu0)
+            self._mu_block.copy_(self._mu_template)
+        self._cur = 0
+        self._tail = False
         self._n_active = self._cnt[0]
 
     def iterate(self):
@@ -519,15 +547,7 @@ class iLQR(Algorithm):
     def run_iterations(self, n):
         """`n` loop bodies of run_optim for every trajectory, device only: no host synchronisation, nothing copied
         back (the receding-horizon agent calls this once per control step)."""
-        st = self._st
-        if self.reset_mu:
-            st["mu"].fill_(self.mu0)
-            st["mu_d"].fill_(1.0)
-        st["status"].zero_()
-        st["iters"].zero_()
-        st["active"].fill_(1)
-        st["success_gradient"].zero_()
-        self._rearm()
+        self._arm_state(self.reset_mu)
         self._sel = self._select_params()
         self._sel.max_iters = int(n)
         for _ in range(int(n)):
@@ -651,15 +671,8 @@ class iLQR(Algorithm):
         `cost` fetch them on demand) and None is returned -- a 16,384-trajectory batch otherwise copies 66 MB per call."""
         start_time = time.time()
         st = self._st
-        if self.reset_mu:
-            st["mu"].fill_(self.mu0)
-            st["mu_d"].fill_(1.0)
         # a new call re-arms every trajectory: `for _ in range(1, max_iters + 1)` starts over
-        st["status"].zero_()
-        st["iters"].zero_()
-        st["active"].fill_(1)
-        st["success_gradient"].zero_()
-        self._rearm()
+        self._arm_state(self.reset_mu)
         self._sel = self._select_params()
         self._iterate_until_done()
         if self.final_backpass:
