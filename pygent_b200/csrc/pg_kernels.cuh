@@ -1939,13 +1939,30 @@ struct SelectArgs {
 template <typename T>
 __device__ __forceinline__ int select_one(const SelectArgs<T>& a, const int64_t b) {
     const int64_t B = a.B;
-    a.accept[b] = 0;
-    if (a.status[b] != 0) {
-        a.active[b] = 0;
-        return a.status[b];
-    }
     const SelectParams& p = a.p;
-    T mu = a.mu[b], mu_d = a.mu_d[b];
+    // Everything the decision may read is loaded up front, in one batch of independent loads: taken in program order -- status,
+    // then mu, then the backward pass's flag, then one candidate after the other until the search stops -- the same reads are
+    // a chain of ~15 dependent L2 round trips (17 us per launch, 10 us of every iteration of the fused solver).  Slots of
+    // alphas a split line search did not evaluate hold older values; they are read, never used (same loop, same exits).
+    const int status_in = a.status[b];
+    const T mu_in = a.mu[b], mu_d_in = a.mu_d[b];
+    const int iters_in = a.iters[b];
+    const bool bw_ok = a.bw_success[b] != 0, sg_in = a.success_gradient[b] != 0;
+    const T gnorm_in = a.gnorm[b], cost_in = a.cost[b], sV1_in = a.dV[b], sV2_in = a.dV[B + b], dcost_in = a.dcost[b];
+    T cc[MAX_ALPHAS];
+    bool dvg[MAX_ALPHAS];
+#pragma unroll
+    for (int i = 0; i < MAX_ALPHAS; i++) {
+        const bool in = i < p.n_alpha;
+        cc[i] = in ? a.cost_cand[(int64_t)i * B + b] : T(0);
+        dvg[i] = in ? a.diverged[(int64_t)i * B + b] != 0 : true;
+    }
+    a.accept[b] = 0;
+    if (status_in != 0) {
+        a.active[b] = 0;
+        return status_in;
+    }
+    T mu = mu_in, mu_d = mu_d_in;
     const T mu_d0 = T(p.mu_d0), mu_min = T(p.mu_min), mu_max = T(p.mu_max);
     auto increase_mu = [&]() {  // ilqr.py:618-622
         mu_d = fmax(mu_d0, mu_d0 * mu_d);
@@ -1956,34 +1973,40 @@ __device__ __forceinline__ int select_one(const SelectArgs<T>& a, const int64_t 
         mu = mu * mu_d * (mu > mu_min ? T(1) : T(0));
     };
     int status = 0;
-    const int it = a.iters[b] + 1;
+    const int it = iters_in + 1;
     a.iters[b] = it;
     if (a.last_tried) a.last_tried[b] = -1;
-    if (!a.bw_success[b]) {
+    if (!bw_ok) {
         increase_mu();  // ilqr.py:411-413
         increase_mu();  // ... and again on the "forward not successful" branch (ilqr.py:478-479)
         if (mu > mu_max) status = 3;
     } else {
-        bool sg = a.success_gradient[b] != 0;
-        if (a.gnorm[b] < T(p.tol_grad) && mu < T(1e-5)) {  // ilqr.py:421-423
+        bool sg = sg_in;
+        if (gnorm_in < T(p.tol_grad) && mu < T(1e-5)) {  // ilqr.py:421-423
             decrease_mu();
             sg = true;
         }
-        const T cost_old = a.cost[b];
-        const T sV1 = a.dV[b], sV2 = a.dV[B + b];
-        T dcost = a.dcost[b];
-        bool success_fw = false;
+        const T cost_old = cost_in;
+        const T sV1 = sV1_in, sV2 = sV2_in;
+        T dcost = dcost_in;
+        bool success_fw = false, searching = true;
         int n_tried = 0;
-        for (int i = 0; i < p.n_alpha; i++) {
-            n_tried = i + 1;
-            if (a.diverged[(int64_t)i * B + b]) break;  // 'forward diverged.' (ilqr.py:435-437)
-            const T alpha = T(p.alphas[i]);
-            dcost = cost_old - a.cost_cand[(int64_t)i * B + b];
-            const T expected = -alpha * (sV1 + alpha * sV2);
-            const T z = expected > T(0) ? dcost / expected : pg::sign(dcost);
-            if (z > T(p.zmin)) {
-                success_fw = true;
-                if (!p.parallel) break;
+#pragma unroll
+        for (int i = 0; i < MAX_ALPHAS; i++) {
+            if (searching && i < p.n_alpha) {
+                n_tried = i + 1;
+                if (dvg[i]) {  // 'forward diverged.' (ilqr.py:435-437)
+                    searching = false;
+                } else {
+                    const T alpha = T(p.alphas[i]);
+                    dcost = cost_old - cc[i];
+                    const T expected = -alpha * (sV1 + alpha * sV2);
+                    const T z = expected > T(0) ? dcost / expected : pg::sign(dcost);
+                    if (z > T(p.zmin)) {
+                        success_fw = true;
+                        if (!p.parallel) searching = false;
+                    }
+                }
             }
         }
         if (a.last_tried) a.last_tried[b] = n_tried - 1;
@@ -1993,16 +2016,17 @@ __device__ __forceinline__ int select_one(const SelectArgs<T>& a, const int64_t 
             // beyond |x| >= 2^30 -- a candidate that diverged towards -inf, which the one-sided test x > 1e8 does not flag.
             int best = -1;
             T bc = T(0);
-            for (int i = 0; i < n_tried; i++) {
-                const T c = a.cost_cand[(int64_t)i * B + b];
-                if (c == c && (best < 0 || c < bc)) {
+#pragma unroll
+            for (int i = 0; i < MAX_ALPHAS; i++) {
+                const T c = cc[i];
+                if (i < n_tried && c == c && (best < 0 || c < bc)) {
                     bc = c;
                     best = i;
                 }
             }
             if (best < 0) {  // every tried candidate is NaN (cannot pass the z-test, so this is unreachable): keep alpha 0
                 best = 0;
-                bc = a.cost_cand[b];
+                bc = cc[0];
             }
             a.cost[b] = bc;
             a.alpha_best[b] = T(p.alphas[best]);
