@@ -175,6 +175,7 @@ class DynamicsTrainer(object):
         lens = tuple(len(b) for b in batches)
         st = self._epoch_graphs.get(lens)
         if st is None:
+            self._epoch_graphs.clear()  # a growing data set (MBRL adds transitions every episode) changes the key: keep one graph
             be._sync_weights()
             width = max(lens)
             st = {"idx": torch.zeros((len(lens), width), dtype=torch.int32, device=dev),

@@ -169,4 +169,4 @@ def test_training_epochs_replayed_from_a_graph_equal_the_eager_loop():
         res.append((losses, torch.cat([p.detach().reshape(-1) for p in net.parameters()]).cpu(), tr.steps, tr.backend.launches - l0))
     assert res[0][0] == res[1][0] and torch.equal(res[0][1], res[1][1]) and res[0][2] == res[1][2] == 15
     assert res[0][0][-1] < res[0][0][0]
-    assert len(tr._epoch_graphs) == 0 and res[0][3] < res[1][3]
+    assert len(tr._epoch_graphs) == 0 and res[0][3] < res[1][3]   # (tr: the eager trainer)
