@@ -173,7 +173,8 @@ class DynamicsTrainer(object):
         Same kernels in the same order as the eager loop: identical losses and weights."""
         be, dev = self.backend, self.device
         lens = tuple(len(b) for b in batches)
-        st = self._epoch_graphs.get(lens)
+        key = (lens, float(self.dyn_lr), float(self.weight_decay))  # the step size and decay are baked into the captured launches
+        st = self._epoch_graphs.get(key)
         if st is None:
             self._epoch_graphs.clear()  # a growing data set (MBRL adds transitions every episode) changes the key: keep one graph
             be._sync_weights()
@@ -193,7 +194,7 @@ class DynamicsTrainer(object):
                 finally:
                     st["graph"].capture_end()
             torch.cuda.current_stream(dev).wait_stream(side)
-            self._epoch_graphs[lens] = st
+            self._epoch_graphs[key] = st
         be._sync_weights()
         for it, b in enumerate(batches):
             st["host"][it, :len(b)] = torch.from_numpy(np.ascontiguousarray(b, dtype=np.int32))
