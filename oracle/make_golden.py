@@ -230,12 +230,13 @@ def golden_ilqr(case, T, S, x0=None, max_iters=500, **kw):
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     rng = np.random.default_rng(20261019)
-    t0 = time.time()
-    np.savez_compressed(os.path.join(GOLDEN, "models.npz"), **golden_models(rng))
-    print("models.npz  %.1fs" % (time.time() - t0))
-    t0 = time.time()
-    np.savez_compressed(os.path.join(GOLDEN, "steps.npz"), **golden_steps(rng))
-    print("steps.npz   %.1fs" % (time.time() - t0))
+    if not sys.argv[1:]:  # (named runs only: leave the model / step fixtures alone)
+        t0 = time.time()
+        np.savez_compressed(os.path.join(GOLDEN, "models.npz"), **golden_models(rng))
+        print("models.npz  %.1fs" % (time.time() - t0))
+        t0 = time.time()
+        np.savez_compressed(os.path.join(GOLDEN, "steps.npz"), **golden_steps(rng))
+        print("steps.npz   %.1fs" % (time.time() - t0))
     runs = [
         ("ilqr_cart_pole_rk4x4", "cart_pole", 100, 4, {}),
         ("ilqr_cart_pole_rk45", "cart_pole", 100, 0, {}),
@@ -253,8 +254,16 @@ def main():
         ("ilqr_cart_pole_costfd_rk4x4", "cart_pole", 100, 4, {"finite_diff": True}),
         ("ilqr_cart_pole_tv_costfd_rk4x4", "cart_pole_tv", 100, 4, {"finite_diff": True}),
         ("ilqr_pendulum_fd_costfd_rk4x4", "pendulum", 60, 4, {"finite_diff": True}),
+        # constrained=True (ilqr.py:303-327; every shipped examples/ilqr/*.py): the reference's own code around its box QP, the
+        # QP itself solved by the BVLS stand-in for the absent cvxopt (ref_harness.install_qp_standin)
+        ("ilqr_cart_pole_constrained_rk4x4", "cart_pole", 100, 4, {"constrained": True}),
+        ("ilqr_cart_pole_tv_constrained_rk4x4", "cart_pole_tv", 100, 4, {"constrained": True}),
+        ("ilqr_double_parallel_constrained_rk4x4", "double_parallel", 100, 4, {"constrained": True}),
+        ("ilqr_pendulum_fd_constrained_rk4x4", "pendulum", 60, 4, {"constrained": True}),
     ]
     only = sys.argv[1:]
+    rh.load_reference()
+    rh.install_qp_standin()
     for name, case, T, S, kw in runs:
         if only and name not in only:
             continue

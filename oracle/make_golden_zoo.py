@@ -10,6 +10,7 @@ instrumented iLQR solve of the Car and of the AngularPendulum -> tests/golden/il
 no analytic Jacobians, so the reference linearises them with helpers.system_linearization (central differences, eps = 1e-3).  TEST TOOLING ONLY.
 """
 import os
+import sys
 import time
 
 import numpy as np
@@ -69,14 +70,22 @@ def main():
     mg.CASES.update(ZOO)
     try:
         rng = np.random.default_rng(20261020)
-        t0 = time.time()
-        np.savez_compressed(os.path.join(mg.GOLDEN, "steps_zoo.npz"), **mg.golden_steps(rng))
-        print("steps_zoo.npz %.1fs" % (time.time() - t0))
+        if not sys.argv[1:]:
+            t0 = time.time()
+            np.savez_compressed(os.path.join(mg.GOLDEN, "steps_zoo.npz"), **mg.golden_steps(rng))
+            print("steps_zoo.npz %.1fs" % (time.time() - t0))
         # MarBot.ode returns a list: the reference's FD linearisation (helpers.py:144) and fast_step (environments.py:314)
         # fail on it, so the reference itself can only STEP a MarBot (as its DDPG example does) -- no iLQR golden exists
-        for name, case, T in (("ilqr_car_rk4x4", "car", 100), ("ilqr_angular_pendulum_rk4x4", "angular_pendulum", 100)):
+        only = sys.argv[1:]
+        from . import ref_harness as rh
+        rh.load_reference()
+        rh.install_qp_standin()
+        for name, case, T, kw in (("ilqr_car_rk4x4", "car", 100, {}), ("ilqr_angular_pendulum_rk4x4", "angular_pendulum", 100, {}),
+                                  ("ilqr_car_constrained_rk4x4", "car", 100, {"constrained": True})):  # m = 2 box QP
+            if only and name not in only:
+                continue
             t0 = time.time()
-            g = mg.golden_ilqr(case, T, 4)
+            g = mg.golden_ilqr(case, T, 4, **kw)
             np.savez_compressed(os.path.join(mg.GOLDEN, name + ".npz"), **g)
             print("%-24s iters=%-4d cost=%.12f  %.1fs" % (name, g["iters"], g["cost"], time.time() - t0))
     finally:

@@ -181,3 +181,36 @@ def fixed_step(substeps):
         yield
     finally:
         cls.step = orig
+
+
+def install_qp_standin():
+    """cvxopt is absent from this image, and `constrained=True` -- the branch every shipped examples/ilqr/*.py uses -- solves
+    its box QP with it (ilqr.py:303-316).  This installs a stand-in module with exactly the three names the reference touches:
+    `matrix`, `solvers.options` and `solvers.qp(P, q, G, h)` = argmin 1/2 x'Px + q'x subject to G x <= h, returned as
+    {'x': column}.  The reference only ever passes the box pattern G = [I; -I], h = [up; lo]; the stand-in checks that and
+    solves the bounded least-squares form of the problem with scipy's BVLS (an active-set method: exact to rounding, where
+    cvxopt's interior point stops ~1e-8 inside the bounds).  Everything around the QP -- regularisation, the clamp detection
+    with its lower-bound sign quirk, the zeroed feedback rows -- is the reference's own code, so goldens made with this pin the
+    constrained branch up to the QP solver's tolerance.  Generator-side only."""
+    import numpy as np
+    from scipy.optimize import lsq_linear
+
+    def qp(P, q, G, h, *a, **k):
+        P, q = np.atleast_2d(np.asarray(P, dtype=float)), np.asarray(q, dtype=float).reshape(-1)
+        G, h = np.atleast_2d(np.asarray(G, dtype=float)), np.asarray(h, dtype=float).reshape(-1)
+        m = len(q)
+        if G.shape != (2 * m, m) or not (np.array_equal(G[:m], np.eye(m)) and np.array_equal(G[m:], -np.eye(m))):
+            raise NotImplementedError("qp stand-in: box constraints only (the reference's G = [I; -I])")
+        L = np.linalg.cholesky(P)                      # 1/2 x'Px + q'x = 1/2 |L'x + L^-1 q|^2 + const
+        r = lsq_linear(L.T, -np.linalg.solve(L, q), bounds=(-h[m:], h[:m]), method="bvls", tol=1e-15, max_iter=200)
+        return {"x": r.x.reshape(m, 1), "status": "optimal"}
+    mod, solvers = types.ModuleType("cvxopt"), types.ModuleType("cvxopt.solvers")
+    mod.matrix = lambda a, *x, **k: np.array(a, dtype=float)
+    solvers.options, solvers.qp = {}, qp
+    mod.solvers = solvers
+    sys.modules["cvxopt"], sys.modules["cvxopt.solvers"] = mod, solvers
+    for name, m_ in list(sys.modules.items()):  # modules of the reference that were imported with the permissive stub
+        if name.startswith("pygent") and getattr(m_, "opt", None) is not None and hasattr(m_, "iLQR"):
+            m_.opt = mod
+    return mod
+

