@@ -68,5 +68,47 @@ def main():
         len(data), stub.episode_steps, np.round(stub.meanCost, 6), out["pred_loss"][0]))
 
 
+def schedule_trace(MBRL, n, aggregation_interval, use_mpc, warm_up, batch_size, check_interval, samples_per_episode=60):
+    """The call sequence of `MBRL.run_learning(n)` (mbrl.py:275-310) on a recording stand-in `self`: which of
+    run_random_episode / train_dynamics / run_episode / traj_optimizer.save / learning_curve / save / plot it calls, in order."""
+    calls = []
+    stub = types.SimpleNamespace(batch_size=batch_size, warm_up=warm_up, dynamics_first_trained=False, use_mpc=use_mpc,
+                                 aggregation_interval=aggregation_interval, checkInterval=check_interval, episode=1,
+                                 D_rand=types.SimpleNamespace(data=[]), D_RL=types.SimpleNamespace(data=[]))
+
+    def episode(kind):
+        def f():
+            calls.append(kind)
+            if kind == "random":
+                stub.D_rand.data.extend([0] * samples_per_episode)
+            stub.episode += 1
+        return f
+    stub.run_random_episode, stub.run_episode = episode("random"), episode("episode")
+    stub.train_dynamics = lambda: calls.append("train")
+    stub.agent = types.SimpleNamespace(traj_optimizer=types.SimpleNamespace(save=lambda: calls.append("ilqr_save"), saving=True))
+    stub.learning_curve = lambda: calls.append("curve")
+    stub.save = lambda: calls.append("save")
+    stub.plot = lambda: calls.append("plot")
+    stub.animation = lambda: calls.append("animation")
+    with rh.quiet():
+        MBRL.run_learning(stub, n)
+    return calls
+
+
+def main_schedule():
+    rh.load_reference()
+    from pygent.algorithms.mbrl import MBRL
+    import json
+    cases = []
+    for agg in (1, 2, 3):
+        for use_mpc in (False, True):
+            kw = dict(n=12, aggregation_interval=agg, use_mpc=use_mpc, warm_up=150, batch_size=128, check_interval=4)
+            cases.append({"kw": kw, "calls": schedule_trace(MBRL, **kw)})
+    with open(os.path.join(GOLDEN, "mbrl_schedule.json"), "w") as fh:
+        json.dump(cases, fh, indent=0)
+    print("mbrl_schedule.json:", len(cases), "cases;", cases[2]["calls"][:14])
+
+
 if __name__ == "__main__":
     main()
+    main_schedule()

@@ -109,3 +109,39 @@ def test_data_parallel_training_equals_single_process(golden):
         assert np.allclose(W3, net.layer3.weight.detach().numpy(), rtol=1e-4, atol=1e-6)
         assert abs(w2sum - float(net.layer2.weight.detach().double().sum())) < 1e-3
     assert np.array_equal(res[0][2], res[1][2]) and res[0][3] == res[1][3]  # ranks stay bit-identical
+
+
+def test_run_learning_schedule_matches_reference():
+    """The outer loop's schedule -- warm-up episodes until D_rand holds max(batch_size, warm_up) samples, the first training,
+    then `train_dynamics` every `aggregation_interval`-th step (the reference's `steps % interval == 0 & flag`, i.e.
+    `steps % interval == (0 & flag)`), the planner's `save()` unless MPC is used, a checkpoint whenever `episode` is a multiple
+    of `checkInterval` -- as the call sequences of the UNMODIFIED `MBRL.run_learning` on a recording stand-in
+    (oracle/make_golden_mbrl.py -> tests/golden/mbrl_schedule.json; plotting calls are out of scope and ignored)."""
+    import json
+    import os
+    import types
+    from pygent_b200.algorithms.mbrl import MBRL
+    with open(os.path.join(os.path.dirname(__file__), "golden", "mbrl_schedule.json")) as fh:
+        cases = json.load(fh)
+    assert len(cases) == 6
+    for case in cases:
+        kw, calls = case["kw"], []
+        stub = types.SimpleNamespace(batch_size=kw["batch_size"], warm_up=kw["warm_up"], dynamics_first_trained=False,
+                                     use_mpc=kw["use_mpc"], aggregation_interval=kw["aggregation_interval"],
+                                     checkInterval=kw["check_interval"], episode=1, D_rand=types.SimpleNamespace(data=[]),
+                                     D_RL=types.SimpleNamespace(data=[]))
+
+        def episode(kind, stub=stub, calls=calls):
+            def f():
+                calls.append(kind)
+                if kind == "random":
+                    stub.D_rand.data.extend([0] * 60)
+                stub.episode += 1
+            return f
+        stub.run_random_episode, stub.run_episode = episode("random"), episode("episode")
+        stub.train_dynamics = lambda calls=calls: calls.append("train")
+        stub.agent = types.SimpleNamespace(traj_optimizer=types.SimpleNamespace(save=lambda calls=calls: calls.append("ilqr_save"), saving=True))
+        stub.save = lambda calls=calls: calls.append("save")
+        MBRL.run_learning(stub, kw["n"])
+        want = [c for c in case["calls"] if c not in ("plot", "curve", "animation")]
+        assert calls == want, (kw, calls, want)
