@@ -2193,13 +2193,14 @@ __global__ void __launch_bounds__(128) ilqr_solve_kernel(const SolveArgs<T> a) {
         for (int e = lane; e < N; e += 32) px0[e] = a.fw.x0[(int64_t)e * B + b];
         for (int e = lane; e < nX; e += 32) pX[e] = a.xbar[(int64_t)e * B + b];
         for (int e = lane; e < nU; e += 32) pU[e] = a.ubar[(int64_t)e * B + b];
-        bool any_accept = false, running = false;
+        bool any_accept = false, running = false, last_is_accepted = false;
         __syncwarp();
         for (int it = 0;; it++) {
             if (it == round_iters) {  // this launch's share is done: the next launch deals the trajectory again
                 running = true;
                 break;
             }
+            last_is_accepted = false;
             if constexpr (M == 1) {  // the sweep laid over the lanes (backward_lanes)
                 bw.mu = a.sel.mu + b;
                 backward_lanes<P, T, LIN>(m, bw, sm, lane);
@@ -2237,8 +2238,19 @@ __global__ void __launch_bounds__(128) ilqr_solve_kernel(const SolveArgs<T> a) {
                     if (T(a.sel.p.alphas[i]) == ab) best = i;
                 for (int e = lane; e < nX; e += 32) pX[e] = Xc[(size_t)e * 16 + best];
                 for (int e = lane; e < nU; e += 32) pU[e] = Uc[(size_t)e * 16 + best];
-                for (int e = lane; e < nK; e += 32) pKa[e] = pKc[e];
-                for (int e = lane; e < nU; e += 32) pka[e] = pkc[e];
+                {  // self.KK, self.kk = KK, kk: the candidate gains become the accepted ones by exchanging the two buffers
+                    T* t1 = pKa;
+                    pKa = pKc;
+                    pKc = t1;
+                    T* t2 = pka;
+                    pka = pkc;
+                    pkc = t2;
+                    bw.KK = pKc;
+                    bw.kk = pkc;
+                    fw.KK = pKc;
+                    fw.kk = pkc;
+                    last_is_accepted = true;
+                }
                 any_accept = true;
             }
             __syncwarp();
@@ -2250,8 +2262,12 @@ __global__ void __launch_bounds__(128) ilqr_solve_kernel(const SolveArgs<T> a) {
             for (int e = lane; e < nK; e += 32) a.KK_acc[(int64_t)e * B + b] = pKa[e];
             for (int e = lane; e < nU; e += 32) a.kk_acc[(int64_t)e * B + b] = pka[e];
         }
-        for (int e = lane; e < nK; e += 32) a.bw.KK[(int64_t)e * B + b] = pKc[e];  // the last candidate gains (as K3 leaves them)
-        for (int e = lane; e < nU; e += 32) a.bw.kk[(int64_t)e * B + b] = pkc[e];
+        {  // the last candidate gains (as K3 leaves them): the accepted buffer if the last iteration was accepted
+            const T* lK = last_is_accepted ? pKa : pKc;
+            const T* lk = last_is_accepted ? pka : pkc;
+            for (int e = lane; e < nK; e += 32) a.bw.KK[(int64_t)e * B + b] = lK[e];
+            for (int e = lane; e < nU; e += 32) a.bw.kk[(int64_t)e * B + b] = lk[e];
+        }
         if (running && lane == 0) a.index_out[atomicAdd(a.count_out, 1)] = (int32_t)b;
         __syncwarp();
     }
